@@ -1,0 +1,382 @@
+// tcgen05 GEMM for sm_100a: every Linear / Conv1d on the Whisper hot path.
+//
+//   C[M, N] = epilogue( A[M, K] * W[N, K]^T )      A, W 16-bit K-major; fp32 accumulate in TMEM
+//
+// Replaces the cuBLAS / cuDNN call sites of the reference: Linear (model.py:44-50), Conv1d
+// (model.py:53-59, used at :193-194), the MLP (model.py:155-157) and the tied-embedding logits
+// product (model.py:245-247).  Conv1d(k=3) is run as three accumulated GEMM "taps" whose A tiles
+// are the same activation matrix shifted by one row; the zero padding comes from TMA's
+// out-of-bounds fill, the stride-2 of conv2 from a tensor map with a doubled row stride.
+//
+// Structure (persistent, one CTA per SM, 256 threads):
+//   warp 0   : TMA producer (one elected thread) - A tile 128x64, W tile BNx64, 128B swizzle
+//   warp 1   : tcgen05.mma issuer (one thread)   - UMMA 128 x BN x 16, accumulators in TMEM
+//   warp 2   : TMEM allocator / deallocator
+//   warps 4-7: epilogue - tcgen05.ld -> bias / GELU / positional add / residual -> global
+// Pipelines: smem ring (full/empty mbarriers) between TMA and MMA; two TMEM accumulator
+// stages (tmem_full/tmem_empty) between MMA and epilogue so tile i+1's main loop overlaps
+// tile i's epilogue.
+#include "kernels.h"
+#include "ptx.cuh"
+#include "tmap.cuh"
+
+namespace wb {
+
+constexpr int kBM = 128;
+constexpr int kBK = 64;  // 64 x 16-bit = 128 B = one swizzle row
+constexpr int kGemmThreads = 256;
+
+struct GemmParams {
+  int batch, rows_per_batch, m_tiles_per_batch;
+  int N, n_tiles, k_blocks_per_tap, taps, K_tap;
+  int a_row_off[3];
+  int a_map_sel[3];
+  void* C;
+  long long ldc;
+  const void* bias;
+  const void* residual;
+  long long ldr;
+  const float* pos;
+  int gelu;
+};
+
+template <int BN>
+struct GemmCfg {
+  static constexpr int kStages = BN == 256 ? 4 : (BN == 128 ? 6 : 8);
+  static constexpr int kABytes = kBM * kBK * 2;
+  static constexpr int kBBytes = BN * kBK * 2;
+  static constexpr int kStageBytes = kABytes + kBBytes;
+  static constexpr int kTmemCols = (2 * BN < 32) ? 32 : 2 * BN;  // BN in {64,128,256} -> pow2
+  static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align*/ + 256 /*barriers*/;
+};
+
+__device__ __forceinline__ float gelu_erf(float x) {
+  return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f));
+}
+
+template <typename T, int BN, bool OUT_F32>
+__global__ void __launch_bounds__(kGemmThreads, 1)
+gemm_tcgen05_kernel(const GemmParams p, const __grid_constant__ CUtensorMap mapA0,
+                    const __grid_constant__ CUtensorMap mapA1,
+                    const __grid_constant__ CUtensorMap mapB) {
+  using Cfg = GemmCfg<BN>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
+                                             ~static_cast<uintptr_t>(1023));
+  uint8_t* tiles = smem;
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + Cfg::kStages * Cfg::kStageBytes);
+  uint64_t* empty_bar = full_bar + Cfg::kStages;
+  uint64_t* tmem_full = empty_bar + Cfg::kStages;
+  uint64_t* tmem_empty = tmem_full + 2;
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int total_tiles = p.batch * p.m_tiles_per_batch * p.n_tiles;
+  const int k_blocks = p.taps * p.k_blocks_per_tap;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&mapA0);
+    tma_prefetch_desc(&mapA1);
+    tma_prefetch_desc(&mapB);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int i = 0; i < Cfg::kStages; ++i) {
+      mbar_init(&full_bar[i], 1);
+      mbar_init(&empty_bar[i], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&tmem_full[i], 1);
+      mbar_init(&tmem_empty[i], 128);
+    }
+    mbar_fence_init();
+  }
+  if (warp == 2) {
+    tmem_alloc(tmem_ptr_smem, Cfg::kTmemCols);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr_smem;
+
+  if (warp == 0 && lane == 0) {
+    // ===================== TMA producer =====================
+    int stage = 0;
+    uint32_t phase = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      const int m_tile = tile / p.n_tiles;
+      const int n0 = (tile % p.n_tiles) * BN;
+      const int b = m_tile / p.m_tiles_per_batch;
+      const int t0 = (m_tile % p.m_tiles_per_batch) * kBM;
+      for (int tap = 0; tap < p.taps; ++tap) {
+        const CUtensorMap* ma = p.a_map_sel[tap] ? &mapA1 : &mapA0;
+        const int row0 = t0 + p.a_row_off[tap];
+        for (int kb = 0; kb < p.k_blocks_per_tap; ++kb) {
+          mbar_wait(&empty_bar[stage], phase ^ 1);
+          uint8_t* sa = tiles + stage * Cfg::kStageBytes;
+          uint8_t* sb = sa + Cfg::kABytes;
+          mbar_expect_tx(&full_bar[stage], Cfg::kStageBytes);
+          tma_load_3d(sa, ma, &full_bar[stage], kb * kBK, row0, b);
+          tma_load_2d(sb, &mapB, &full_bar[stage], tap * p.K_tap + kb * kBK, n0);
+          if (++stage == Cfg::kStages) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+      }
+    }
+  } else if (warp == 1 && lane == 0) {
+    // ===================== MMA issuer =====================
+    constexpr uint32_t idesc = umma_idesc(Cvt<T>::kUmmaFmt, kBM, BN, 0, 0);
+    int stage = 0;
+    uint32_t phase = 0;
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
+      tc_fence_after();
+      const uint32_t d_tmem = tmem_base + acc * BN;
+      for (int kb = 0; kb < k_blocks; ++kb) {
+        mbar_wait(&full_bar[stage], phase);
+        tc_fence_after();
+        const uint32_t sa = smem_u32(tiles + stage * Cfg::kStageBytes);
+        const uint32_t sb = sa + Cfg::kABytes;
+        const uint64_t adesc = umma_desc_sw128(sa, 16, 1024);
+        const uint64_t bdesc = umma_desc_sw128(sb, 16, 1024);
+#pragma unroll
+        for (int k = 0; k < kBK / 16; ++k) {
+          // advance 16 elements (32 B) along K inside the 128 B swizzle row: +2 in 16 B units
+          umma_f16(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0);
+        }
+        umma_commit(&empty_bar[stage]);
+        if (++stage == Cfg::kStages) {
+          stage = 0;
+          phase ^= 1;
+        }
+      }
+      umma_commit(&tmem_full[acc]);
+      acc ^= 1;
+      if (acc == 0) acc_phase ^= 1;
+    }
+  } else if (warp >= 4) {
+    // ===================== epilogue =====================
+    const int quad = warp & 3;  // TMEM lane quadrant this warp may access
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    const T* bias = reinterpret_cast<const T*>(p.bias);
+    const T* resid = reinterpret_cast<const T*>(p.residual);
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      const int m_tile = tile / p.n_tiles;
+      const int n0 = (tile % p.n_tiles) * BN;
+      const int b = m_tile / p.m_tiles_per_batch;
+      const int t = (m_tile % p.m_tiles_per_batch) * kBM + quad * 32 + lane;
+      const bool row_ok = t < p.rows_per_batch;
+      const long long grow = static_cast<long long>(b) * p.rows_per_batch + t;
+
+      mbar_wait(&tmem_full[acc], acc_phase);
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + acc * BN;
+#pragma unroll 1
+      for (int c = 0; c < BN / 32; ++c) {
+        uint32_t r[32];
+        tmem_ld32(taddr + c * 32, r);
+        tmem_ld_wait();
+        const int nb = n0 + c * 32;
+        if (row_ok && nb < p.N) {
+          float v[32];
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
+          const bool full = nb + 32 <= p.N;
+          if (bias) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j)
+              if (full || nb + j < p.N) v[j] += Cvt<T>::to_f(bias[nb + j]);
+          }
+          if (p.gelu) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] = gelu_erf(round_to<T>(v[j]));
+          }
+          if (p.pos) {
+            const float* pr = p.pos + static_cast<long long>(t) * p.N + nb;
+#pragma unroll
+            for (int j = 0; j < 32; ++j)
+              if (full || nb + j < p.N) v[j] = round_to<T>(v[j]) + pr[j];
+          }
+          if (resid) {
+            const T* rr = resid + grow * p.ldr + nb;
+            if (full) {
+#pragma unroll
+              for (int q = 0; q < 4; ++q) {
+                uint4 u = *reinterpret_cast<const uint4*>(rr + q * 8);
+                const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                  float2 f = Cvt<T>::unpack2(w[e]);
+                  v[q * 8 + e * 2] = round_to<T>(v[q * 8 + e * 2]) + f.x;
+                  v[q * 8 + e * 2 + 1] = round_to<T>(v[q * 8 + e * 2 + 1]) + f.y;
+                }
+              }
+            } else {
+#pragma unroll
+              for (int j = 0; j < 32; ++j)
+                if (nb + j < p.N) v[j] = round_to<T>(v[j]) + Cvt<T>::to_f(rr[j]);
+            }
+          }
+          if constexpr (OUT_F32) {
+            float* out = reinterpret_cast<float*>(p.C) + grow * p.ldc + nb;
+            if (full) {
+#pragma unroll
+              for (int q = 0; q < 8; ++q)
+                *reinterpret_cast<float4*>(out + q * 4) =
+                    make_float4(v[q * 4], v[q * 4 + 1], v[q * 4 + 2], v[q * 4 + 3]);
+            } else {
+#pragma unroll
+              for (int j = 0; j < 32; ++j)
+                if (nb + j < p.N) out[j] = v[j];
+            }
+          } else {
+            T* out = reinterpret_cast<T*>(p.C) + grow * p.ldc + nb;
+            if (full) {
+#pragma unroll
+              for (int q = 0; q < 4; ++q) {
+                uint4 u;
+                u.x = Cvt<T>::pack2(v[q * 8 + 0], v[q * 8 + 1]);
+                u.y = Cvt<T>::pack2(v[q * 8 + 2], v[q * 8 + 3]);
+                u.z = Cvt<T>::pack2(v[q * 8 + 4], v[q * 8 + 5]);
+                u.w = Cvt<T>::pack2(v[q * 8 + 6], v[q * 8 + 7]);
+                *reinterpret_cast<uint4*>(out + q * 8) = u;
+              }
+            } else {
+#pragma unroll
+              for (int j = 0; j < 32; ++j)
+                if (nb + j < p.N) out[j] = Cvt<T>::from_f(v[j]);
+            }
+          }
+        }
+      }
+      tc_fence_before();
+      mbar_arrive(&tmem_empty[acc]);
+      acc ^= 1;
+      if (acc == 0) acc_phase ^= 1;
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) tmem_dealloc(tmem_base, Cfg::kTmemCols);
+}
+
+template <typename T, int BN, bool OUT_F32>
+static int launch_impl(const GemmParams& p, const CUtensorMap& a0, const CUtensorMap& a1,
+                       const CUtensorMap& b, cudaStream_t s) {
+  using Cfg = GemmCfg<BN>;
+  static bool attr_set = false;
+  auto kern = gemm_tcgen05_kernel<T, BN, OUT_F32>;
+  if (!attr_set) {
+    cudaError_t e =
+        cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes);
+    if (e != cudaSuccess) return 10;
+    attr_set = true;
+  }
+  static int num_sms = 0;
+  if (!num_sms) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev);
+  }
+  const int total = p.batch * p.m_tiles_per_batch * p.n_tiles;
+  const int grid = total < num_sms ? total : num_sms;
+  kern<<<grid, kGemmThreads, Cfg::kSmemBytes, s>>>(p, a0, a1, b);
+  count_launch();
+  return cudaGetLastError() == cudaSuccess ? 0 : 11;
+}
+
+int launch_linear(const LinearArgs& a, cudaStream_t s) {
+  if (a.rows_per_batch <= 0 || a.batch <= 0 || a.N <= 0 || a.K_tap <= 0) return 0;
+  if (a.taps < 1 || a.taps > 3) return 3;
+  // TMA / vector-store alignment requirements
+  const long long esz = 2;
+  if ((reinterpret_cast<uintptr_t>(a.A) & 15) || (reinterpret_cast<uintptr_t>(a.W) & 15) ||
+      (a.lda * esz) % 16 || (a.ldw * esz) % 16 || (a.a_batch_stride * esz) % 16)
+    return 4;
+  const long long osz = a.out_f32 ? 4 : 2;
+  if ((reinterpret_cast<uintptr_t>(a.C) & 15) || (a.ldc * osz) % 16) return 5;
+  if (a.residual && ((reinterpret_cast<uintptr_t>(a.residual) & 15) || (a.ldr * esz) % 16)) return 6;
+
+  int bn = a.block_n;
+  const long long rows = static_cast<long long>(a.batch) * a.rows_per_batch;
+  if (bn == 0) bn = rows >= 4096 ? 256 : 64;
+  if (bn == 256 && a.N < 256) bn = a.N >= 128 ? 128 : 64;
+
+  GemmParams p;
+  p.batch = a.batch;
+  p.rows_per_batch = a.rows_per_batch;
+  p.m_tiles_per_batch = (a.rows_per_batch + kBM - 1) / kBM;
+  p.N = a.N;
+  p.n_tiles = (a.N + bn - 1) / bn;
+  p.k_blocks_per_tap = (a.K_tap + kBK - 1) / kBK;
+  p.taps = a.taps;
+  p.K_tap = a.K_tap;
+  p.C = a.C;
+  p.ldc = a.ldc;
+  p.bias = a.bias;
+  p.residual = a.residual;
+  p.ldr = a.ldr;
+  p.pos = a.pos;
+  p.gelu = a.gelu;
+
+  // A maps: distinct base offsets -> at most two tensor maps
+  CUtensorMap mapA[2];
+  long long base_of[2] = {a.a_base_off[0], a.a_base_off[0]};
+  int n_maps = 1;
+  for (int t = 0; t < 3; ++t) {
+    p.a_row_off[t] = t < a.taps ? a.a_row_off[t] : 0;
+    p.a_map_sel[t] = 0;
+    if (t >= a.taps) continue;
+    if (a.a_base_off[t] == base_of[0]) {
+      p.a_map_sel[t] = 0;
+    } else if (n_maps == 2 && a.a_base_off[t] == base_of[1]) {
+      p.a_map_sel[t] = 1;
+    } else if (n_maps == 1) {
+      base_of[1] = a.a_base_off[t];
+      n_maps = 2;
+      p.a_map_sel[t] = 1;
+    } else {
+      return 7;
+    }
+  }
+  for (int i = 0; i < 2; ++i) {
+    const uint8_t* base = reinterpret_cast<const uint8_t*>(a.A) + base_of[i] * esz;
+    if (reinterpret_cast<uintptr_t>(base) & 15) return 4;
+    uint64_t dims[3] = {static_cast<uint64_t>(a.K_tap), static_cast<uint64_t>(a.a_rows_per_batch),
+                        static_cast<uint64_t>(a.batch)};
+    uint64_t strides[2] = {static_cast<uint64_t>(a.lda * esz),
+                           static_cast<uint64_t>((a.batch > 1 ? a.a_batch_stride : a.lda * a.a_rows_per_batch) * esz)};
+    uint32_t box[3] = {kBK, kBM, 1};
+    if (make_tmap_16bit(&mapA[i], a.dtype, base, 3, dims, strides, box)) return 8;
+  }
+  CUtensorMap mapB;
+  {
+    uint64_t dims[2] = {static_cast<uint64_t>(a.taps) * a.K_tap, static_cast<uint64_t>(a.N)};
+    uint64_t strides[1] = {static_cast<uint64_t>(a.ldw * esz)};
+    uint32_t box[2] = {kBK, static_cast<uint32_t>(bn)};
+    if (make_tmap_16bit(&mapB, a.dtype, a.W, 2, dims, strides, box)) return 9;
+  }
+
+#define WB_DISPATCH(TT, BNN)                                                              \
+  return a.out_f32 ? launch_impl<TT, BNN, true>(p, mapA[0], mapA[1], mapB, s)             \
+                   : launch_impl<TT, BNN, false>(p, mapA[0], mapA[1], mapB, s)
+  if (a.dtype == DT_BF16) {
+    if (bn == 256) { WB_DISPATCH(__nv_bfloat16, 256); }
+    if (bn == 128) { WB_DISPATCH(__nv_bfloat16, 128); }
+    WB_DISPATCH(__nv_bfloat16, 64);
+  } else {
+    if (bn == 256) { WB_DISPATCH(__half, 256); }
+    if (bn == 128) { WB_DISPATCH(__half, 128); }
+    WB_DISPATCH(__half, 64);
+  }
+#undef WB_DISPATCH
+}
+
+}  // namespace wb
