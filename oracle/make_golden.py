@@ -1,0 +1,196 @@
+"""Generate the golden fixtures under tests/golden/ by RUNNING THE REFERENCE (openai/whisper,
+imported read-only from /root/reference) on deterministic synthetic weights and audio.
+
+    python -m oracle.make_golden            # from the repo root, in the build container
+
+The reference cannot travel to the GPU box, so its outputs are committed as small fixtures; the
+script is committed so they can be regenerated and audited.  Nothing is copied from the reference
+except DATA it ships or computes: the mel filterbank asset, integer token-id tables, and its
+numerical outputs on our inputs.
+
+Fixtures:
+  mel_filters.npz          whisper/assets/mel_filters.npz re-saved (audio.py:91-107)
+  token_ids.json           special ids, non-speech suppress lists, " " encoding, language codes
+  timing.npz               median_filter / dtw_cpu outputs (timing.py:19-105) on seeded inputs
+  mel_<kind>.npz           log_mel_spectrogram outputs (sub-sampled) + global statistics
+  model_<name>.npz/.json   encoder features (sub-sampled), prefill logits probes, and decode()
+                           results (tokens, avg_logprob, no_speech_prob) for several DecodingOptions
+"""
+from __future__ import annotations
+
+import json
+import os
+import sys
+import time
+
+import numpy as np
+import torch
+
+REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+REF = os.environ.get("WHISPER_REFERENCE", "/root/reference")
+GOLD = os.path.join(REPO, "tests", "golden")
+sys.path.insert(0, REPO)
+sys.path.insert(0, REF)
+
+import whisper  # noqa: E402  (the reference)
+from whisper.audio import log_mel_spectrogram, mel_filters  # noqa: E402
+from whisper.decoding import DecodingOptions  # noqa: E402
+from whisper.model import ModelDimensions, Whisper  # noqa: E402
+from whisper.timing import dtw_cpu, median_filter  # noqa: E402
+from whisper.tokenizer import LANGUAGES, get_tokenizer  # noqa: E402
+
+from whisper_b200 import synthetic  # noqa: E402
+
+# decode cases: name -> (DecodingOptions kwargs, n_audio)
+DECODE_CASES = {
+    "greedy": (dict(sample_len=48), 2),
+    "greedy_notimestamps": (dict(sample_len=48, without_timestamps=True), 2),
+    "greedy_prompt": (dict(sample_len=24, prompt=[1000 + 7 * i for i in range(40)]), 1),
+    "greedy_prefix": (dict(sample_len=24, prefix=[2000 + 3 * i for i in range(5)]), 1),
+    "greedy_nosuppress": (dict(sample_len=24, suppress_tokens="", suppress_blank=False), 1),
+    "beam5": (dict(sample_len=40, beam_size=5), 2),
+    "beam5_patience2": (dict(sample_len=40, beam_size=5, patience=2.0), 1),
+    "beam3_lenpen": (dict(sample_len=32, beam_size=3, length_penalty=0.6), 1),
+    "beam2_notimestamps": (dict(sample_len=32, beam_size=2, without_timestamps=True), 1),
+}
+FULL_LENGTH_CASE = ("greedy_full", dict(), 1)   # default sample_len = 224
+
+
+# weight-generator settings per fixture model: "confident" = heavy-tailed logits (large top-1/top-2
+# margins, the regime of a trained model); "diverse" = Gaussian logits (many near-ties, EOT and
+# timestamp events everywhere - the hard case for selection logic)
+SYNTH = {
+    "confident": dict(),
+    "diverse": dict(row_sigma=0.0, eot_scale=2.5, timestamp_scale=1.3),
+}
+
+
+def build_reference_model(name: str, seed: int, regime: str):
+    dims = synthetic.dims_dict(name)
+    sd = synthetic.synthetic_state_dict(dims, seed=seed, **SYNTH[regime])
+    model = Whisper(ModelDimensions(**dims))
+    missing = model.load_state_dict({k: torch.from_numpy(v) for k, v in sd.items()}, strict=True)
+    assert not missing.missing_keys and not missing.unexpected_keys
+    return model.eval(), dims
+
+
+def gen_static():
+    os.makedirs(GOLD, exist_ok=True)
+    np.savez_compressed(os.path.join(GOLD, "mel_filters.npz"),
+                        mel_80=mel_filters("cpu", 80).numpy(), mel_128=mel_filters("cpu", 128).numpy())
+    table = {"languages": list(LANGUAGES.keys())}
+    for key, multilingual, nl in (("gpt2", False, 99), ("multilingual", True, 99)):
+        tok = get_tokenizer(multilingual, num_languages=nl, language="en", task="transcribe")
+        table[key] = {"non_speech_tokens": list(tok.non_speech_tokens), "blank": tok.encode(" ")}
+    specials = {}
+    for n_vocab, multilingual, nl in ((51864, False, 99), (51865, True, 99), (51866, True, 100)):
+        tok = get_tokenizer(multilingual, num_languages=nl, language="en", task="transcribe")
+        specials[str(n_vocab)] = dict(
+            eot=tok.eot, sot=tok.sot, translate=tok.translate, transcribe=tok.transcribe,
+            sot_lm=tok.sot_lm, sot_prev=tok.sot_prev, no_speech=tok.no_speech,
+            no_timestamps=tok.no_timestamps, timestamp_begin=tok.timestamp_begin,
+            sot_sequence=list(tok.sot_sequence), all_language_tokens=list(tok.all_language_tokens),
+            n_non_speech=len(tok.non_speech_tokens))
+    table["specials"] = specials
+    with open(os.path.join(GOLD, "token_ids.json"), "w") as f:
+        json.dump(table, f)
+
+
+def gen_timing():
+    rng = np.random.Generator(np.random.PCG64(7))
+    out = {}
+    for i, shape in enumerate([(10,), (1, 15), (4, 5, 345), (3, 7, 1500)]):       # tests/test_timing.py:14-19
+        x = rng.standard_normal(shape).astype(np.float32)
+        out[f"med_in_{i}"] = x
+        for w in (3, 5, 7, 13):                                                  # tests/test_timing.py:71
+            out[f"med_out_{i}_{w}"] = median_filter(torch.from_numpy(x), w).numpy()
+    for i, (N, M) in enumerate([(10, 20), (32, 16), (123, 1500), (234, 189)]):    # tests/test_timing.py:8-13
+        x = rng.standard_normal((N, M)).astype(np.float32)
+        out[f"dtw_in_{i}"] = x
+        out[f"dtw_out_{i}"] = dtw_cpu(x.astype(np.float64)).astype(np.int32)
+    np.savez_compressed(os.path.join(GOLD, "timing.npz"), **out)
+
+
+def gen_mel():
+    for kind in ("noise", "speechlike"):
+        audio = synthetic.synthetic_audio(2, 480000, seed=1234, kind=kind)
+        out = {}
+        for n_mels in (80, 128):
+            batch = log_mel_spectrogram(torch.from_numpy(audio), n_mels=n_mels).numpy()   # global max over batch
+            single = log_mel_spectrogram(torch.from_numpy(audio[1, :160000]), n_mels=n_mels,
+                                         padding=480000).numpy()                           # transcribe.py:139 usage
+            out[f"batch_{n_mels}"] = batch[:, :, ::8].astype(np.float32)                  # every 8th frame
+            out[f"batch_{n_mels}_head"] = batch[:, :, :64]
+            out[f"batch_{n_mels}_tail"] = batch[:, :, -64:]
+            out[f"single_{n_mels}"] = single[:, ::8]
+            out[f"single_{n_mels}_shape"] = np.array(single.shape)
+            out[f"batch_{n_mels}_sum"] = np.array([batch.astype(np.float64).sum(), batch.max(), batch.min()])
+        np.savez_compressed(os.path.join(GOLD, f"mel_{kind}.npz"), **out)
+
+
+def decode_case(model, mel, opts, n_audio):
+    beam = opts.get("beam_size")
+    options = DecodingOptions(language="en", fp16=False, temperature=0.0, **opts)
+    results = []
+    if beam:                      # reference raises for beam search with n_audio > 1 (decoding.py:734,740)
+        for a in range(n_audio):
+            results.append(model.decode(mel[a], options))
+    else:
+        results = model.decode(mel[:n_audio], options)
+    return [dict(tokens=list(map(int, r.tokens)), avg_logprob=float(r.avg_logprob),
+                 no_speech_prob=float(r.no_speech_prob)) for r in results]
+
+
+def gen_model(name: str, seed: int, audio_kind: str, full_length: bool, regime: str):
+    t0 = time.time()
+    model, dims = build_reference_model(name, seed, regime)
+    audio = synthetic.synthetic_audio(2, 480000, seed=4321, kind=audio_kind)
+    with torch.no_grad():
+        mel = torch.stack([log_mel_spectrogram(torch.from_numpy(a), n_mels=dims["n_mels"]) for a in audio])
+        feats = model.encoder(mel)
+        tok = get_tokenizer(model.is_multilingual, num_languages=model.num_languages, language="en",
+                            task="transcribe")
+        init = torch.tensor([list(tok.sot_sequence)] * 2)
+        logits0 = model.decoder(init, feats)                       # prefill, all positions (model.py:245)
+    arrays = {
+        "feats_sub": feats[:, ::25, :].numpy(),                   # 60 of 1500 positions
+        "feats_stats": np.array([float(feats.mean()), float(feats.std()), float(feats.abs().max())]),
+        "logits0_last_top_idx": logits0[:, -1].topk(16).indices.numpy(),
+        "logits0_last_top_val": logits0[:, -1].topk(16).values.numpy(),
+        "logits0_last_sub": logits0[:, -1, ::97].numpy(),
+        "logits0_sot_sub": logits0[:, 0, ::97].numpy(),
+    }
+    meta = {"name": name, "seed": seed, "audio_seed": 4321, "audio_kind": audio_kind, "dims": dims,
+            "regime": regime, "synth_kwargs": SYNTH[regime], "decode": {}}
+    cases = dict(DECODE_CASES)
+    if full_length:
+        cases[FULL_LENGTH_CASE[0]] = (FULL_LENGTH_CASE[1], FULL_LENGTH_CASE[2])
+    for cname, (opts, n_audio) in cases.items():
+        meta["decode"][cname] = {"options": opts, "n_audio": n_audio,
+                                 "results": decode_case(model, mel, opts, n_audio)}
+        print(f"  {name}/{cname}: {[len(r['tokens']) for r in meta['decode'][cname]['results']]} tokens "
+              f"({time.time() - t0:.1f}s)", flush=True)
+    if model.is_multilingual:
+        with torch.no_grad():
+            lang_tokens, lang_probs = model.detect_language(feats)
+        meta["detect_language"] = {"tokens": lang_tokens.tolist(),
+                                   "top": [max(p, key=p.get) for p in lang_probs],
+                                   "top_prob": [max(p.values()) for p in lang_probs]}
+    np.savez_compressed(os.path.join(GOLD, f"model_{name}.npz"), **arrays)
+    with open(os.path.join(GOLD, f"model_{name}.json"), "w") as f:
+        json.dump(meta, f)
+
+
+def main():
+    torch.set_num_threads(os.cpu_count() or 1)
+    gen_static()
+    gen_timing()
+    gen_mel()
+    gen_model("test-en", seed=11, audio_kind="speechlike", full_length=True, regime="confident")
+    gen_model("test-multi", seed=12, audio_kind="noise", full_length=True, regime="diverse")
+    gen_model("tiny.en", seed=13, audio_kind="speechlike", full_length=False, regime="confident")
+    print("golden fixtures written to", GOLD)
+
+
+if __name__ == "__main__":
+    main()

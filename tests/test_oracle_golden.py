@@ -1,0 +1,115 @@
+"""CPU: the oracle (oracle/) against the golden vectors produced by running the reference
+(oracle/make_golden.py).  This is what pins the oracle: every stage of the hot path, on the same
+synthetic inputs, must reproduce the reference's outputs - token ids exactly, floating-point
+values to the stated tolerances."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from helpers import GOLD, load_model_fixture, oracle_features, oracle_options
+
+MEL_TOL = 1e-4          # fp32 mel, post-scaling range <= 2.0
+
+
+@pytest.mark.parametrize("kind", ["noise", "speechlike"])
+@pytest.mark.parametrize("n_mels", [80, 128])
+def test_log_mel(kind, n_mels):
+    from oracle import audio as OA
+    from whisper_b200 import synthetic
+
+    g = np.load(os.path.join(GOLD, f"mel_{kind}.npz"))
+    audio = synthetic.synthetic_audio(2, 480000, seed=1234, kind=kind)
+    mel = OA.log_mel_spectrogram(audio, n_mels)                  # one global max over the batch
+    assert mel.shape == (2, n_mels, 3000)
+    assert np.abs(mel[:, :, ::8] - g[f"batch_{n_mels}"]).max() < MEL_TOL
+    assert np.abs(mel[:, :, :64] - g[f"batch_{n_mels}_head"]).max() < MEL_TOL
+    assert np.abs(mel[:, :, -64:] - g[f"batch_{n_mels}_tail"]).max() < MEL_TOL
+    s, mx, mn = g[f"batch_{n_mels}_sum"]
+    assert abs(mel.astype(np.float64).sum() - s) < 1e-6 * abs(s) + 5.0
+    assert abs(mel.max() - mx) < MEL_TOL and abs(mel.min() - mn) < MEL_TOL
+    single = OA.log_mel_spectrogram(audio[1, :160000], n_mels, padding=480000)   # transcribe.py:139
+    assert tuple(single.shape) == tuple(g[f"single_{n_mels}_shape"])
+    assert np.abs(single[:, ::8] - g[f"single_{n_mels}"]).max() < MEL_TOL
+
+
+def test_mel_dynamic_range_property():
+    """tests/test_audio.py:19 of the reference: mel.max() - mel.min() <= 2.0."""
+    from oracle import audio as OA
+    from whisper_b200 import synthetic
+
+    mel = OA.log_mel_spectrogram(synthetic.synthetic_audio(1, 176000, seed=5, kind="speechlike")[0], 80)
+    assert mel.max() - mel.min() <= 2.0
+
+
+def test_timing_golden():
+    from oracle import timing as OT
+
+    g = np.load(os.path.join(GOLD, "timing.npz"))
+    for i in range(4):
+        x = g[f"med_in_{i}"]
+        for w in (3, 5, 7, 13):
+            assert np.array_equal(OT.median_filter(x, w), g[f"med_out_{i}_{w}"]), (i, w)
+        assert np.array_equal(OT.dtw(g[f"dtw_in_{i}"]), g[f"dtw_out_{i}"]), i
+
+
+def test_token_ids_table():
+    import json
+
+    from oracle import decoding as OD
+
+    with open(os.path.join(GOLD, "token_ids.json")) as f:
+        table = json.load(f)
+    for n_vocab, spec in table["specials"].items():
+        ids = OD.token_ids(int(n_vocab))
+        for k in ("eot", "sot", "translate", "transcribe", "sot_lm", "sot_prev", "no_speech",
+                  "no_timestamps", "timestamp_begin"):
+            assert getattr(ids, k) == spec[k], (n_vocab, k)
+        assert list(ids.sot_sequence("en", "transcribe")) == spec["sot_sequence"]
+        # the reference enumerates a Python set (tokenizer.py:222-228): order is arbitrary, compare as sets
+        assert sorted(ids.all_language_tokens) == sorted(spec["all_language_tokens"])
+        assert len(ids.non_speech) == spec["n_non_speech"]
+
+
+@pytest.mark.parametrize("name", ["test-en", "test-multi"])
+def test_encoder_and_prefill(name):
+    from oracle import decoding as OD
+    from oracle import model as OM
+
+    meta, arrays, dims, W, mel, feats = oracle_features(name)
+    assert np.abs(feats[:, ::25].numpy() - arrays["feats_sub"]).max() < 2e-4
+    ids = OD.token_ids(dims["n_vocab"])
+    init = torch.tensor([list(ids.sot_sequence("en", "transcribe"))] * 2)
+    logits = OM.decoder_forward(W, dims, init, feats)
+    assert np.array_equal(logits[:, -1].topk(16).indices.numpy(), arrays["logits0_last_top_idx"])
+    assert np.abs(logits[:, -1, ::97].numpy() - arrays["logits0_last_sub"]).max() < 2e-3
+    assert np.abs(logits[:, 0, ::97].numpy() - arrays["logits0_sot_sub"]).max() < 2e-3
+
+
+def _decode_cases(name):
+    meta, _ = load_model_fixture(name)
+    return sorted(meta["decode"].keys())
+
+
+@pytest.mark.parametrize("name,case", [(n, c) for n in ("test-en", "test-multi") for c in _decode_cases(n)])
+def test_decode_matches_reference(name, case):
+    """Token ids bit-identical to the reference's decode(); avg_logprob / no_speech_prob to 1e-5."""
+    from oracle import decoding as OD
+
+    meta, arrays, dims, W, mel, feats = oracle_features(name)
+    c = meta["decode"][case]
+    res = OD.decode(W, dims, feats[: c["n_audio"]], oracle_options(c["options"]))
+    for r, g in zip(res, c["results"]):
+        assert r.tokens == g["tokens"]
+        assert abs(r.avg_logprob - g["avg_logprob"]) < 1e-5
+        assert abs(r.no_speech_prob - g["no_speech_prob"]) <= 1e-5 * max(g["no_speech_prob"], 1e-30) + 1e-12
+
+
+def test_detect_language():
+    from oracle import decoding as OD
+
+    meta, arrays, dims, W, mel, feats = oracle_features("test-multi")
+    toks, probs = OD.detect_language(W, dims, feats)
+    assert toks.tolist() == meta["detect_language"]["tokens"]
+    assert np.allclose(probs.max(dim=-1).values.numpy(), meta["detect_language"]["top_prob"], atol=1e-5)

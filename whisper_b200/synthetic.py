@@ -122,17 +122,32 @@ def _rng(seed: int, name: str) -> np.random.Generator:
     return np.random.Generator(np.random.PCG64([seed, zlib.crc32(name.encode())]))
 
 
-def synthetic_state_dict(dims: Dict[str, int], seed: int = 0, embed_std: float = 0.6) -> Dict[str, np.ndarray]:
-    """Random weights at the given dims.  Scales keep activations O(1) through the residual stream
-    and give logits a standard deviation of roughly embed_std * sqrt(d) (peaky enough that greedy /
-    beam decisions have margins well above 16-bit rounding noise most of the time)."""
+def synthetic_state_dict(dims: Dict[str, int], seed: int = 0, linear_gain: float = 2.0,
+                         logit_std: float = 8.0, eot_scale: float = 8.0,
+                         timestamp_scale: float = 3.5, row_sigma: float = 0.5) -> Dict[str, np.ndarray]:
+    """Random weights at the given dims, shaped so that decoding is NOT degenerate:
+
+    * Linear layers have gain `linear_gain` (> 1), so the residual stream is dominated by what the
+      blocks compute (attention over the audio, MLPs) rather than by the input token embedding -
+      with tied embeddings a weak network would just echo its last token for ever.
+    * The token embedding has std logit_std / sqrt(d): logits are ~N(0, logit_std^2), peaky enough
+      that greedy / beam decisions usually have margins far above 16-bit rounding noise.
+    * The <|endoftext|> row is scaled by `eot_scale` and the 1501 timestamp rows by
+      `timestamp_scale`, so sequences end naturally after tens of tokens and the timestamp rules
+      (pairs, monotonicity, "timestamp mass beats best text token") actually fire.
+    """
     sd: Dict[str, np.ndarray] = {}
+    n_vocab = dims["n_vocab"]
+    multilingual = n_vocab >= 51865
+    eot = 50257 if multilingual else 50256
+    ts_begin = n_vocab - 1501
+    embed_std = logit_std / np.sqrt(dims["n_text_state"])
     for name, shape, kind in state_dict_spec(dims):
         g = _rng(seed, name)
         if kind == "sinusoid":
             w = sinusoid_table(*shape)
         elif kind == "linear":
-            w = g.standard_normal(shape, dtype=np.float32) * np.float32(0.7 / np.sqrt(shape[1]))
+            w = g.standard_normal(shape, dtype=np.float32) * np.float32(linear_gain / np.sqrt(shape[1]))
             w = round_to_16bit_common(w)
         elif kind == "conv":
             w = g.standard_normal(shape, dtype=np.float32) * np.float32(1.0 / np.sqrt(shape[1] * shape[2]))
@@ -141,12 +156,22 @@ def synthetic_state_dict(dims: Dict[str, int], seed: int = 0, embed_std: float =
             w = round_to_16bit_common(g.standard_normal(shape, dtype=np.float32) * np.float32(0.05))
         elif kind == "ln_w":
             w = (1.0 + 0.1 * g.standard_normal(shape, dtype=np.float32)).astype(np.float32)
+            if name == "decoder.ln.weight":
+                # random signs: with tied embeddings, an all-positive final gain makes the logit of
+                # the token just fed in systematically the largest (the model echoes itself)
+                w = w * np.where(g.random(shape) < 0.5, -1.0, 1.0).astype(np.float32)
         elif kind == "ln_b":
             w = (0.05 * g.standard_normal(shape, dtype=np.float32)).astype(np.float32)
         elif kind == "embed":
-            w = round_to_16bit_common(g.standard_normal(shape, dtype=np.float32) * np.float32(embed_std))
+            w = g.standard_normal(shape, dtype=np.float32) * np.float32(embed_std)
+            # log-normal row norms: a heavy-tailed logit distribution, like a trained LM's (the
+            # top-1 / top-2 gap is then O(1) relative to the top logit instead of O(1/ln V))
+            w *= np.exp(row_sigma * g.standard_normal((shape[0], 1), dtype=np.float32))
+            w[eot] *= np.float32(eot_scale)
+            w[ts_begin:] *= np.float32(timestamp_scale)
+            w = round_to_16bit_common(w)
         elif kind == "pos":
-            w = round_to_16bit_common(g.standard_normal(shape, dtype=np.float32) * np.float32(0.3))
+            w = round_to_16bit_common(g.standard_normal(shape, dtype=np.float32) * np.float32(1.0))
         else:  # pragma: no cover
             raise ValueError(kind)
         sd[name] = w
