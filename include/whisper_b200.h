@@ -67,6 +67,127 @@ int wb200_transpose_to16(int dtype, const float* x, void* y, int B, int C, int T
 int wb200_encoder_attention(int dtype, const void* qkv, void* out, int B, int T, int n_head,
                             void* stream);
 
+/* ---------------------------------------------------------------------------------------------
+ * audio front-end
+ * ------------------------------------------------------------------------------------------- */
+
+/* log_mel_spectrogram, whisper/audio.py:110-157 (after any right-padding, which the caller does by
+ * allocating zeros): audio [n_audio, n_samples] fp32 -> out [n_audio, n_mels, n_samples / 160] fp32.
+ * filters: the dense (n_mels x 201) fp32 mel matrix of audio.py:91-107 (device).  per_row_max = 0
+ * reproduces the reference exactly (ONE max over the whole call, audio.py:155); 1 clamps each
+ * waveform against its own max (== calling the reference once per waveform). */
+size_t wb200_log_mel_workspace_bytes(int n_audio);
+int wb200_log_mel(const float* audio, int n_audio, int64_t n_samples, int n_mels, const float* filters,
+                  float* out, void* workspace, size_t workspace_bytes, int per_row_max, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * model handle: a table of caller-owned device tensors (weights already converted to `dtype`).
+ * dims order = ModelDimensions of whisper/model.py:25-36:
+ *   n_mels, n_audio_ctx, n_audio_state, n_audio_head, n_audio_layer,
+ *   n_vocab, n_text_ctx, n_text_state, n_text_head, n_text_layer
+ * Tensor slots (T = 16-bit `dtype`, F = fp32), reference state-dict names in brackets:
+ *   global (12): conv1.w T[d,3*n_mels] tap-major, conv1.b T, conv2.w T[d,3*d] tap-major, conv2.b T,
+ *                enc.pos F[1500,d], ln_post.w F, ln_post.b F, tok_emb T[V,d], tok_emb F[V,d],
+ *                dec.pos F[448,d], dec.ln.w F, dec.ln.b F
+ *   per encoder layer (12): attn_ln.w F, attn_ln.b F, qkv.w T[3d,d] (query|key|value), qkv.b T[3d]
+ *                (key part zero: model.py:88), out.w T, out.b T, mlp_ln.w F, mlp_ln.b F,
+ *                fc1.w T[4d,d], fc1.b T, fc2.w T[d,4d], fc2.b T
+ *   per decoder layer (20): attn_ln.w/b F, qkv.w T, qkv.b T, out.w T, out.b T, cross_ln.w/b F,
+ *                cq.w T[d,d], cq.b T, ckv.w T[2d,d] (key|value), ckv.b T[2d] (key part zero),
+ *                cout.w T, cout.b T, mlp_ln.w/b F, fc1.w T, fc1.b T, fc2.w T, fc2.b T
+ * The handle stores the pointers only; the caller keeps the tensors alive until destroy.
+ * Replaces the nn.Module state of whisper/model.py:252-276 (and the per-call weight casts of
+ * model.py:44-59). */
+typedef struct wb200_model wb200_model;
+int wb200_model_num_tensors(const int32_t dims[10]);
+int wb200_model_create(const int32_t dims[10], int dtype, const void* const* tensors, int n_tensors,
+                       wb200_model** out);
+void wb200_model_destroy(wb200_model* model);
+
+/* AudioEncoder.forward, whisper/model.py:188-204: mel [n_audio, n_mels, 3000] fp32 ->
+ * features [n_audio, 1500, d] 16-bit.  workspace: wb200_encoder_workspace_bytes(). */
+size_t wb200_encoder_workspace_bytes(const wb200_model* model, int n_audio);
+int wb200_encoder_forward(const wb200_model* model, const float* mel, int n_audio, void* features,
+                          void* workspace, size_t workspace_bytes, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * decoder session: kv-cache, logit filters and token selection of whisper/decoding.py:144-176
+ * (PyTorchInference), :272-404 (GreedyDecoder / BeamSearchDecoder), :423-505 (logit filters) and the
+ * body of DecodingTask._main_loop (:680-710), resident on the device.
+ * ------------------------------------------------------------------------------------------- */
+typedef struct {
+  int32_t n_audio;                      /* segments decoded together */
+  int32_t n_group;                      /* beam_size (beam search) or 1 (greedy)   decoding.py:527 */
+  int32_t beam_search;                  /* 1: BeamSearchDecoder, 0: GreedyDecoder (temperature 0) */
+  int32_t max_candidates;               /* round(beam_size * patience)             decoding.py:313 */
+  int32_t n_init;                       /* len(initial_tokens)                     decoding.py:535 */
+  int32_t sample_begin;                 /* == n_init                               decoding.py:536 */
+  int32_t sot_index;                    /* position of <|startoftranscript|>       decoding.py:537 */
+  int32_t eot, no_speech, no_timestamps, timestamp_begin;   /* ids; no_speech < 0: none */
+  int32_t suppress_blank;               /* SuppressBlank installed                 decoding.py:555 */
+  int32_t timestamp_rules;              /* ApplyTimestampRules installed           decoding.py:559 */
+  int32_t max_initial_timestamp_index;  /* < 0: none                               decoding.py:561 */
+  int32_t n_suppress, n_blank;
+  const int32_t* suppress_ids;          /* host: sorted SuppressTokens ids         decoding.py:615 */
+  const int32_t* blank_ids;             /* host: tokenizer.encode(" ")             decoding.py:430 */
+} wb200_decode_config;
+
+typedef struct wb200_decoder wb200_decoder;
+size_t wb200_decoder_workspace_bytes(const wb200_model* model, const wb200_decode_config* cfg);
+int wb200_decoder_create(const wb200_model* model, const wb200_decode_config* cfg, void* workspace,
+                         size_t workspace_bytes, wb200_decoder** out, void* stream);
+void wb200_decoder_destroy(wb200_decoder* dec);
+/* cross-attention K/V of every layer from features [n_audio, 1500, d] (model.py:104-109) */
+int wb200_decoder_set_audio(wb200_decoder* dec, const void* features, void* stream);
+/* reset the session and run the n_init-token first pass (decoding.py:687-696 at i == 0):
+ * initial_tokens: HOST int32 [n_audio, n_init].  Leaves the logits of the last prompt position
+ * current and stores no_speech_prob per audio. */
+int wb200_decoder_prefill(wb200_decoder* dec, const int32_t* initial_tokens, void* stream);
+/* logit filters + GreedyDecoder.update / BeamSearchDecoder.update on the current logits
+ * (decoding.py:699-703), including the beam kv-cache reorder (a parent-table update). */
+int wb200_decoder_select(wb200_decoder* dec, void* stream);
+/* one TextDecoder step on the last token of every row with kv-cache append (decoding.py:687) */
+int wb200_decoder_step(wb200_decoder* dec, void* stream);
+/* up to max_steps x (step, select); stops early once the device-side completion flag is seen
+ * (decoding.py:705).  steps_issued (host, optional) receives the number of iterations launched. */
+int wb200_decoder_run(wb200_decoder* dec, int max_steps, int32_t* steps_issued, void* stream);
+/* teacher forcing for parity tests: append HOST int32 tokens [n_audio*n_group] instead of selecting */
+int wb200_decoder_force_tokens(wb200_decoder* dec, const int32_t* next_tokens, void* stream);
+
+/* state access: copies between the session and caller memory (host or device), asynchronously on
+ * `stream`.  Element types: int32 except LOGITS / SUM_LOGPROBS / NO_SPEECH / TOP_VAL / FIN_SCORE (fp32). */
+#define WB200_STATE_TOKENS 0        /* [R, n_text_ctx]                                   */
+#define WB200_STATE_LENGTH 1        /* [1]                                               */
+#define WB200_STATE_SUM_LOGPROBS 2  /* [R]                                               */
+#define WB200_STATE_NO_SPEECH 3     /* [n_audio]                                         */
+#define WB200_STATE_LOGITS 4        /* [R (or n_audio after prefill), ld]; ld = logits row stride */
+#define WB200_STATE_TOP_VAL 5       /* [R, K]                                            */
+#define WB200_STATE_TOP_IDX 6       /* [R, K]                                            */
+#define WB200_STATE_SOURCES 7       /* [R] beam parents of the last select                */
+#define WB200_STATE_FIN_TOKENS 8    /* [n_audio, max_candidates, n_text_ctx]              */
+#define WB200_STATE_FIN_LEN 9       /* [n_audio, max_candidates]                          */
+#define WB200_STATE_FIN_SCORE 10    /* [n_audio, max_candidates]                          */
+#define WB200_STATE_FIN_COUNT 11    /* [n_audio]                                          */
+#define WB200_STATE_DONE 12         /* [1]                                               */
+int64_t wb200_decoder_logits_ld(const wb200_decoder* dec);
+int wb200_decoder_get_state(wb200_decoder* dec, int what, void* dst, size_t bytes, void* stream);
+int wb200_decoder_set_state(wb200_decoder* dec, int what, const void* src, size_t bytes, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * word timing
+ * ------------------------------------------------------------------------------------------- */
+/* median_filter, whisper/timing.py:19-54 (+ triton_ops.py:43-117): x, y [rows, T] fp32, reflect
+ * padding of width/2, odd width <= 21, T > width/2 (shorter inputs are returned unchanged by the
+ * caller, timing.py:22-24). */
+int wb200_median_filter(const float* x, float* y, int64_t rows, int T, int width, void* stream);
+/* dtw, whisper/timing.py:82-151 (+ triton_ops.py:13-40): x [N, M] fp32 cost matrix (device) ->
+ * path [2, N + M + 1] int32 (device; row 0 text indices, row 1 time indices, first *path_len
+ * entries valid).  tie_mode 0 = the rule the reference applies to CUDA tensors (triton_ops.py:38-40),
+ * 1 = its CPU rule (timing.py:95-100). */
+size_t wb200_dtw_workspace_bytes(int N, int M);
+int wb200_dtw(const float* x, int N, int M, int32_t* path, int32_t* path_len, void* workspace,
+              size_t workspace_bytes, int tie_mode, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

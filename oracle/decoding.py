@@ -172,6 +172,7 @@ class BeamState:
         self.max_candidates = round(beam_size * (patience or 1.0))          # decoding.py:312-313
         assert self.max_candidates > 0
         self.finished: Optional[List[Dict[tuple, float]]] = None
+        self.min_gap = float("inf")     # diagnostics: smallest score gap that could reorder candidates
 
     def update(self, tokens: List[List[int]], logits: torch.Tensor, sum_logprobs: torch.Tensor):
         G = self.beam
@@ -188,13 +189,20 @@ class BeamState:
             origin: Dict[tuple, int] = {}
             for j in range(G):                                               # decoding.py:339-346
                 r = a * G + j
-                vals, idxs = logprobs[r].topk(G + 1)
+                vals, idxs = logprobs[r].topk(G + 2)
+                if torch.isfinite(vals[G + 1]):
+                    self.min_gap = min(self.min_gap, float(vals[G] - vals[G + 1]))   # top-(G+1) boundary
+                vals, idxs = vals[: G + 1], idxs[: G + 1]
                 for lp, tok in zip(vals, idxs):
                     seq = tuple(tokens[r] + [int(tok)])
                     score[seq] = float((sum_logprobs[r] + lp).item())        # fp32 add, then widen
                     origin[seq] = r
             done: Dict[tuple, float] = {}
             kept = 0
+            ranked = sorted(score.values(), reverse=True)[: 2 * G]
+            for hi, lo in zip(ranked, ranked[1:]):
+                if np.isfinite(lo):
+                    self.min_gap = min(self.min_gap, hi - lo)
             for seq in sorted(score, key=score.get, reverse=True):           # stable; decoding.py:350-360
                 if seq[-1] == self.eot:
                     done[seq] = score[seq]
@@ -351,6 +359,7 @@ def decode(W: M.Weights, dims: Dict[str, int], mel_or_features: torch.Tensor, op
                           step_margins=margins[a * G]))
     if record is not None:
         record["all_margins"] = margins
+        record["beam_min_gap"] = beam.min_gap if beam is not None else None
     return out
 
 

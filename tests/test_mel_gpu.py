@@ -1,0 +1,73 @@
+"""GPU: fused log-mel kernel (wb200_log_mel) vs the reference's golden vectors and the oracle.
+Tolerance (fp32 path): max abs error 1e-4 on the (x+4)/4-scaled output."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from helpers import GOLD
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-4
+
+
+@pytest.mark.parametrize("kind", ["noise", "speechlike"])
+@pytest.mark.parametrize("n_mels", [80, 128])
+def test_log_mel_vs_reference_golden(kind, n_mels):
+    import whisper_b200 as wb
+    from whisper_b200 import synthetic
+
+    g = np.load(os.path.join(GOLD, f"mel_{kind}.npz"))
+    audio = synthetic.synthetic_audio(2, 480000, seed=1234, kind=kind)
+    mel = wb.log_mel_spectrogram(torch.from_numpy(audio).cuda(), n_mels).cpu().numpy()
+    assert mel.shape == (2, n_mels, 3000)
+    for key, sl in ((f"batch_{n_mels}", np.s_[:, :, ::8]), (f"batch_{n_mels}_head", np.s_[:, :, :64]),
+                    (f"batch_{n_mels}_tail", np.s_[:, :, -64:])):
+        err = np.abs(mel[sl] - g[key]).max()
+        assert err < TOL, f"{key}: max abs err {err}"
+    single = wb.log_mel_spectrogram(audio[1, :160000], n_mels, padding=480000).cpu().numpy()   # transcribe.py:139
+    assert tuple(single.shape) == tuple(g[f"single_{n_mels}_shape"])
+    assert np.abs(single[:, ::8] - g[f"single_{n_mels}"]).max() < TOL
+
+
+@pytest.mark.parametrize("n_samples", [201, 1000, 16000, 47999, 160000 + 37])
+def test_log_mel_ragged_lengths_vs_oracle(n_samples):
+    import whisper_b200 as wb
+    from oracle import audio as OA
+    from whisper_b200 import synthetic
+
+    audio = synthetic.synthetic_audio(3, n_samples, seed=9, kind="speechlike")
+    got = wb.log_mel_spectrogram(torch.from_numpy(audio).cuda(), 80).cpu().numpy()
+    ref = OA.log_mel_spectrogram(audio, 80)
+    assert got.shape == ref.shape
+    assert np.abs(got - ref).max() < TOL
+    # per-waveform clamp == the reference called once per waveform
+    got1 = wb.log_mel_spectrogram(torch.from_numpy(audio).cuda(), 80, per_waveform_max=True).cpu().numpy()
+    ref1 = np.stack([OA.log_mel_spectrogram(a, 80) for a in audio])
+    assert np.abs(got1 - ref1).max() < TOL
+
+
+def test_log_mel_properties_full_size():
+    """BASELINE config size (64 x 30 s): size-independent properties - dynamic range <= 2.0
+    (reference tests/test_audio.py:19), batch result == per-row results when maxima agree, silence."""
+    import whisper_b200 as wb
+    from whisper_b200 import synthetic
+
+    audio = torch.from_numpy(synthetic.synthetic_audio(64, 480000, seed=3, kind="noise")).cuda()
+    mel = wb.log_mel_spectrogram(audio, 128)
+    assert mel.shape == (64, 128, 3000)
+    assert float(mel.max() - mel.min()) <= 2.0 + 1e-6
+    row = wb.log_mel_spectrogram(audio[5], 128, per_waveform_max=True)
+    batch_pw = wb.log_mel_spectrogram(audio, 128, per_waveform_max=True)
+    assert torch.equal(row, batch_pw[5])
+    silent = wb.log_mel_spectrogram(torch.zeros(2, 48000, device="cuda"), 80)
+    assert torch.all(silent == (np.log10(1e-10) + 4.0) / 4.0)
+
+
+def test_mel_filters_match_reference_asset():
+    from whisper_b200.audio import mel_filters
+
+    g = np.load(os.path.join(GOLD, "mel_filters.npz"))
+    for n in (80, 128):
+        assert np.array_equal(mel_filters("cpu", n).numpy(), g[f"mel_{n}"])

@@ -42,7 +42,15 @@ def lib() -> ctypes.CDLL:
         _lib.wb200_launch_count.restype = c_uint64
         for name in header_symbols():
             fn = getattr(_lib, name)  # raises AttributeError if the export is missing
-            if name not in ("wb200_version", "wb200_last_error", "wb200_launch_count"):
+            if name in ("wb200_version", "wb200_last_error", "wb200_launch_count"):
+                continue
+            if name.endswith("_bytes"):
+                fn.restype = ctypes.c_size_t
+            elif name == "wb200_decoder_logits_ld":
+                fn.restype = c_int64
+            elif name.endswith("_destroy"):
+                fn.restype = None
+            else:
                 fn.restype = c_int
     return _lib
 

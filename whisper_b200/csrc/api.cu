@@ -5,6 +5,7 @@
 #include <string.h>
 
 #include "../../include/whisper_b200.h"
+#include "engine.h"
 #include "kernels.h"
 
 namespace wb {
@@ -123,6 +124,143 @@ int wb200_encoder_attention(int dtype, const void* qkv, void* out, int B, int T,
   WB_CHECK_DTYPE(dtype);
   int r = launch_enc_attention(dtype, qkv, out, B, T, n_head, static_cast<cudaStream_t>(stream));
   return r ? set_error(r, "wb200_encoder_attention: failed (%d): %s", r, cudaGetErrorString(cudaGetLastError())) : 0;
+}
+
+size_t wb200_log_mel_workspace_bytes(int n_audio) { return log_mel_workspace_bytes(n_audio); }
+
+int wb200_log_mel(const float* audio, int n_audio, int64_t n_samples, int n_mels, const float* filters,
+                  float* out, void* workspace, size_t workspace_bytes, int per_row_max, void* stream) {
+  if (n_mels != 80 && n_mels != 128) return set_error(110, "Unsupported n_mels: %d", n_mels);  // audio.py:103
+  if (workspace_bytes < log_mel_workspace_bytes(n_audio)) return set_error(111, "wb200_log_mel: workspace too small");
+  int r = launch_log_mel(audio, n_audio, n_samples, n_mels, filters, out, workspace, per_row_max,
+                         static_cast<cudaStream_t>(stream));
+  return r ? set_error(r, "wb200_log_mel: failed (%d): %s", r, cudaGetErrorString(cudaGetLastError())) : 0;
+}
+
+struct wb200_model { Model m; };
+struct wb200_decoder { Decoder* d; };
+
+static Dims dims_from(const int32_t d[10]) {
+  Dims o;
+  o.n_mels = d[0]; o.n_audio_ctx = d[1]; o.n_audio_state = d[2]; o.n_audio_head = d[3]; o.n_audio_layer = d[4];
+  o.n_vocab = d[5]; o.n_text_ctx = d[6]; o.n_text_state = d[7]; o.n_text_head = d[8]; o.n_text_layer = d[9];
+  return o;
+}
+
+int wb200_model_num_tensors(const int32_t dims[10]) { return Model::num_tensors(dims_from(dims)); }
+
+int wb200_model_create(const int32_t dims[10], int dtype, const void* const* tensors, int n_tensors,
+                       wb200_model** out) {
+  WB_CHECK_DTYPE(dtype);
+  Dims d = dims_from(dims);
+  if (d.n_audio_state != d.n_audio_head * 64 || d.n_text_state != d.n_text_head * 64)
+    return set_error(120, "model: head dim must be 64 (state %d/%d heads %d/%d)", d.n_audio_state, d.n_text_state,
+                     d.n_audio_head, d.n_text_head);
+  if (d.n_audio_state != d.n_text_state) return set_error(121, "model: audio/text widths must match");
+  if (d.n_audio_state % 64 || d.n_audio_state > 2048) return set_error(122, "model: unsupported width %d", d.n_audio_state);
+  if (n_tensors != Model::num_tensors(d)) return set_error(123, "model: expected %d tensors, got %d", Model::num_tensors(d), n_tensors);
+  for (int i = 0; i < n_tensors; ++i)
+    if (!tensors[i]) return set_error(124, "model: tensor slot %d is null", i);
+  wb200_model* h = new wb200_model();
+  h->m.dims = d;
+  h->m.dtype = dtype;
+  h->m.t.assign(tensors, tensors + n_tensors);
+  *out = h;
+  return 0;
+}
+
+void wb200_model_destroy(wb200_model* model) { delete model; }
+
+size_t wb200_encoder_workspace_bytes(const wb200_model* model, int n_audio) {
+  return encoder_workspace_bytes(&model->m, n_audio);
+}
+
+int wb200_encoder_forward(const wb200_model* model, const float* mel, int n_audio, void* features,
+                          void* workspace, size_t workspace_bytes, void* stream) {
+  return encoder_forward(&model->m, mel, n_audio, features, workspace, workspace_bytes,
+                         static_cast<cudaStream_t>(stream));
+}
+
+size_t wb200_decoder_workspace_bytes(const wb200_model* model, const wb200_decode_config* cfg) {
+  return decoder_workspace_bytes(&model->m, cfg);
+}
+
+int wb200_decoder_create(const wb200_model* model, const wb200_decode_config* cfg, void* workspace,
+                         size_t workspace_bytes, wb200_decoder** out, void* stream) {
+  Decoder* d = nullptr;
+  int r = decoder_create(&model->m, cfg, workspace, workspace_bytes, &d, static_cast<cudaStream_t>(stream));
+  if (r) return r;
+  wb200_decoder* h = new wb200_decoder();
+  h->d = d;
+  *out = h;
+  return 0;
+}
+
+void wb200_decoder_destroy(wb200_decoder* dec) {
+  if (!dec) return;
+  if (dec->d) {
+    if (dec->d->pinned) cudaFreeHost(dec->d->pinned);
+    delete dec->d;
+  }
+  delete dec;
+}
+
+int wb200_decoder_set_audio(wb200_decoder* dec, const void* features, void* stream) {
+  return decoder_set_audio(dec->d, features, static_cast<cudaStream_t>(stream));
+}
+int wb200_decoder_prefill(wb200_decoder* dec, const int32_t* initial_tokens, void* stream) {
+  return decoder_prefill(dec->d, initial_tokens, static_cast<cudaStream_t>(stream));
+}
+int wb200_decoder_select(wb200_decoder* dec, void* stream) {
+  return decoder_select(dec->d, static_cast<cudaStream_t>(stream));
+}
+int wb200_decoder_step(wb200_decoder* dec, void* stream) {
+  return decoder_step(dec->d, static_cast<cudaStream_t>(stream));
+}
+int wb200_decoder_run(wb200_decoder* dec, int max_steps, int32_t* steps_issued, void* stream) {
+  int n = 0;
+  int r = decoder_run(dec->d, max_steps, &n, static_cast<cudaStream_t>(stream));
+  if (steps_issued) *steps_issued = n;
+  return r;
+}
+int wb200_decoder_force_tokens(wb200_decoder* dec, const int32_t* next_tokens, void* stream) {
+  return decoder_append(dec->d, next_tokens, static_cast<cudaStream_t>(stream));
+}
+int64_t wb200_decoder_logits_ld(const wb200_decoder* dec) { return dec->d->ldv; }
+
+int wb200_decoder_get_state(wb200_decoder* dec, int what, void* dst, size_t bytes, void* stream) {
+  void* p = nullptr;
+  size_t n = 0;
+  int r = decoder_state_ptr(dec->d, what, &p, &n, static_cast<cudaStream_t>(stream));
+  if (r) return r;
+  if (bytes > n) return set_error(271, "get_state(%d): asked for %zu bytes, have %zu", what, bytes, n);
+  if (cudaMemcpyAsync(dst, p, bytes, cudaMemcpyDefault, static_cast<cudaStream_t>(stream)) != cudaSuccess)
+    return set_error(272, "get_state(%d): copy failed", what);
+  return 0;
+}
+int wb200_decoder_set_state(wb200_decoder* dec, int what, const void* src, size_t bytes, void* stream) {
+  void* p = nullptr;
+  size_t n = 0;
+  int r = decoder_state_ptr(dec->d, what, &p, &n, static_cast<cudaStream_t>(stream));
+  if (r) return r;
+  if (bytes > n) return set_error(273, "set_state(%d): %zu bytes given, room for %zu", what, bytes, n);
+  if (cudaMemcpyAsync(p, src, bytes, cudaMemcpyDefault, static_cast<cudaStream_t>(stream)) != cudaSuccess)
+    return set_error(274, "set_state(%d): copy failed", what);
+  return 0;
+}
+
+int wb200_median_filter(const float* x, float* y, int64_t rows, int T, int width, void* stream) {
+  int r = launch_median_filter(x, y, rows, T, width, static_cast<cudaStream_t>(stream));
+  return r ? set_error(r, "wb200_median_filter: failed (%d) rows=%lld T=%d width=%d", r, (long long)rows, T, width) : 0;
+}
+
+size_t wb200_dtw_workspace_bytes(int N, int M) { return dtw_workspace_bytes(N, M); }
+
+int wb200_dtw(const float* x, int N, int M, int32_t* path, int32_t* path_len, void* workspace,
+              size_t workspace_bytes, int tie_mode, void* stream) {
+  if (workspace_bytes < dtw_workspace_bytes(N, M)) return set_error(130, "wb200_dtw: workspace too small");
+  int r = launch_dtw(x, N, M, path, path_len, workspace, tie_mode, static_cast<cudaStream_t>(stream));
+  return r ? set_error(r, "wb200_dtw: failed (%d) N=%d M=%d", r, N, M) : 0;
 }
 
 }  // extern "C"

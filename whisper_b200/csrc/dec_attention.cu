@@ -1,0 +1,550 @@
+// Decoder attention for the autoregressive step (and its n_init-token prefill): the HBM-bound
+// part of TextDecoder.forward (reference whisper/model.py:81-139 as driven by the kv-cache hooks
+// of model.py:310-341 and decoding.py:144-176).
+//
+// Both kernels stream K/V rows (64 x 16-bit = 128 B per head per position) through a 4-stage
+// cp.async ring in shared memory and do the (tiny) math on mma.sync m16n8k16 with fp32
+// accumulation and an online softmax: the "query" side of the tile is the <= 16 queries that
+// share one K/V stream, so every K/V byte is read from HBM once per step.
+//
+//   cross_attention_kernel : queries = the G beams (step) or n_init prompt positions (prefill) of
+//                            ONE audio; K/V = that audio's 1500 encoder positions, shared by all
+//                            of them ("each audio's K/V counted once").  The 1500
+//                            keys are split across CTAs (flash-decoding); the last CTA to finish a
+//                            (audio, head, q-tile) combines the partials - no second launch.
+//   self_attention_kernel  : one query per (row, head); keys are gathered through the beam
+//                            indirection table (position p of row r lives in physical row
+//                            indir[r][p]), so a beam reorder is a table update, not the physical
+//                            gather of every cache tensor that decoding.py:172-176 performs.  In
+//                            step mode the kernel also APPENDS the new token's K/V to the cache
+//                            (the torch.cat of model.py:327-333).
+#include "kernels.h"
+#include "ptx.cuh"
+
+namespace wb {
+
+constexpr int kDaThreads = 128;  // 4 warps, each owns 16 keys of every 64-key tile
+constexpr int kDaStages = 4;
+constexpr int kDaTileKeys = 64;
+constexpr int kDaTileBytes = kDaTileKeys * 128;                 // K or V tile
+constexpr int kDaSmem = kDaStages * 2 * kDaTileBytes;           // 64 KB
+constexpr float kScaleLog2 = 0.125f * 1.4426950408889634f;      // (1/sqrt(64)) * log2(e)
+
+struct RowSrc {
+  const uint8_t* k;
+  const uint8_t* v;
+};
+
+// Per-warp online-softmax state for a 16-query tile: rows g and g+8 of the mma fragment.
+struct WarpAcc {
+  float o[8][4];
+  float m[2];
+  float l[2];
+};
+
+__device__ __forceinline__ void acc_init(WarpAcc& a) {
+#pragma unroll
+  for (int i = 0; i < 8; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) a.o[i][j] = 0.f;
+  a.m[0] = a.m[1] = -INFINITY;
+  a.l[0] = a.l[1] = 0.f;
+}
+
+// One warp consumes its 16 keys (rows wrow0..wrow0+15) of the staged K/V tile.
+// n_valid: number of valid keys among those 16 (<= 0 means none).
+template <typename T>
+__device__ __forceinline__ void warp_tile(const uint8_t* sK, const uint8_t* sV, int wrow0,
+                                          const uint32_t (&qa)[4][4], int n_valid, WarpAcc& acc) {
+  const int lane = threadIdx.x & 31;
+  const int t = lane & 3;
+  if (n_valid <= 0) return;
+  // ---- S = Q K^T for 16 keys: two n-tiles of 8 keys, four k-steps over dh = 64
+  float s[2][4];
+#pragma unroll
+  for (int i = 0; i < 2; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) s[i][j] = 0.f;
+  {
+    const int m = lane >> 3;                       // matrix id for ldmatrix.x4
+    const int krow = wrow0 + (m >> 1) * 8 + (lane & 7);
+#pragma unroll
+    for (int ks = 0; ks < 4; ++ks) {
+      const int chunk = ks * 2 + (m & 1);          // 16-byte chunk index along dh
+      uint32_t kb[4];
+      ldmatrix_x4(kb, sK + krow * 128 + ((chunk ^ (krow & 7)) << 4));
+      mma16816<T>(s[0], qa[ks], kb[0], kb[1]);
+      mma16816<T>(s[1], qa[ks], kb[2], kb[3]);
+    }
+  }
+  // ---- mask keys beyond n_valid, online softmax (rows g -> idx 0,1 ; g+8 -> idx 2,3)
+  if (n_valid < 16) {
+#pragma unroll
+    for (int nt = 0; nt < 2; ++nt)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int key = nt * 8 + 2 * t + (j & 1);
+        if (key >= n_valid) s[nt][j] = -INFINITY;
+      }
+  }
+  float mx0 = fmaxf(fmaxf(s[0][0], s[0][1]), fmaxf(s[1][0], s[1][1]));
+  float mx1 = fmaxf(fmaxf(s[0][2], s[0][3]), fmaxf(s[1][2], s[1][3]));
+  mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 1));
+  mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 2));
+  mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 1));
+  mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 2));
+  const float mn0 = fmaxf(acc.m[0], mx0 * kScaleLog2);
+  const float mn1 = fmaxf(acc.m[1], mx1 * kScaleLog2);
+  const float al0 = fast_exp2(acc.m[0] - mn0);     // mn finite here (>=1 valid key)
+  const float al1 = fast_exp2(acc.m[1] - mn1);
+  acc.m[0] = mn0;
+  acc.m[1] = mn1;
+  float p[2][4];
+#pragma unroll
+  for (int nt = 0; nt < 2; ++nt) {
+    p[nt][0] = fast_exp2(s[nt][0] * kScaleLog2 - mn0);
+    p[nt][1] = fast_exp2(s[nt][1] * kScaleLog2 - mn0);
+    p[nt][2] = fast_exp2(s[nt][2] * kScaleLog2 - mn1);
+    p[nt][3] = fast_exp2(s[nt][3] * kScaleLog2 - mn1);
+  }
+  acc.l[0] = acc.l[0] * al0 + (p[0][0] + p[0][1] + p[1][0] + p[1][1]);
+  acc.l[1] = acc.l[1] * al1 + (p[0][2] + p[0][3] + p[1][2] + p[1][3]);
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    acc.o[i][0] *= al0;
+    acc.o[i][1] *= al0;
+    acc.o[i][2] *= al1;
+    acc.o[i][3] *= al1;
+  }
+  // ---- O += P V : A = P (16 q x 16 keys) from the S fragments, B = V via ldmatrix.trans
+  uint32_t pa[4];
+  pa[0] = Cvt<T>::pack2(p[0][0], p[0][1]);
+  pa[1] = Cvt<T>::pack2(p[0][2], p[0][3]);
+  pa[2] = Cvt<T>::pack2(p[1][0], p[1][1]);
+  pa[3] = Cvt<T>::pack2(p[1][2], p[1][3]);
+  {
+    const int m = lane >> 3;
+    const int vrow = wrow0 + (m & 1) * 8 + (lane & 7);
+#pragma unroll
+    for (int np = 0; np < 4; ++np) {               // pairs of dh n-tiles
+      const int chunk = np * 2 + (m >> 1);
+      uint32_t vb[4];
+      ldmatrix_x4_trans(vb, sV + vrow * 128 + ((chunk ^ (vrow & 7)) << 4));
+      mma16816<T>(acc.o[np * 2], pa, vb[0], vb[1]);
+      mma16816<T>(acc.o[np * 2 + 1], pa, vb[2], vb[3]);
+    }
+  }
+}
+
+// Q fragments (A operand, 16 queries x 64 dh) straight from global memory; rows >= n_q are zero.
+template <typename T>
+__device__ __forceinline__ void load_q_frags(uint32_t (&qa)[4][4], const T* q0, long long ldq, int n_q) {
+  const int lane = threadIdx.x & 31;
+  const int g = lane >> 2, t = lane & 3;
+#pragma unroll
+  for (int ks = 0; ks < 4; ++ks) {
+    const int c = ks * 16 + 2 * t;
+    qa[ks][0] = g < n_q ? *reinterpret_cast<const uint32_t*>(q0 + g * ldq + c) : 0u;
+    qa[ks][1] = g + 8 < n_q ? *reinterpret_cast<const uint32_t*>(q0 + (g + 8) * ldq + c) : 0u;
+    qa[ks][2] = g < n_q ? *reinterpret_cast<const uint32_t*>(q0 + g * ldq + c + 8) : 0u;
+    qa[ks][3] = g + 8 < n_q ? *reinterpret_cast<const uint32_t*>(q0 + (g + 8) * ldq + c + 8) : 0u;
+  }
+}
+
+// Merge the four warps' (m, l, O) through shared memory into warp 0's registers.
+// red: float[4][32][36+]; uses 4*32*40 floats.
+__device__ __forceinline__ void cta_merge(WarpAcc& acc, float* red) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  // finish the row sums inside each quad first
+#pragma unroll
+  for (int r = 0; r < 2; ++r) {
+    acc.l[r] += __shfl_xor_sync(0xffffffffu, acc.l[r], 1);
+    acc.l[r] += __shfl_xor_sync(0xffffffffu, acc.l[r], 2);
+  }
+  float* mine = red + (warp * 32 + lane) * 40;
+#pragma unroll
+  for (int i = 0; i < 8; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) mine[i * 4 + j] = acc.o[i][j];
+  mine[32] = acc.m[0];
+  mine[33] = acc.m[1];
+  mine[34] = acc.l[0];
+  mine[35] = acc.l[1];
+  __syncthreads();
+  if (warp == 0) {
+    float m0 = -INFINITY, m1 = -INFINITY;
+#pragma unroll
+    for (int w = 0; w < 4; ++w) {
+      m0 = fmaxf(m0, red[(w * 32 + lane) * 40 + 32]);
+      m1 = fmaxf(m1, red[(w * 32 + lane) * 40 + 33]);
+    }
+    float l0 = 0.f, l1 = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) acc.o[i][j] = 0.f;
+#pragma unroll
+    for (int w = 0; w < 4; ++w) {
+      const float* o = red + (w * 32 + lane) * 40;
+      const float f0 = o[32] == -INFINITY ? 0.f : fast_exp2(o[32] - m0);
+      const float f1 = o[33] == -INFINITY ? 0.f : fast_exp2(o[33] - m1);
+      l0 += o[34] * f0;
+      l1 += o[35] * f1;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        acc.o[i][0] += o[i * 4 + 0] * f0;
+        acc.o[i][1] += o[i * 4 + 1] * f0;
+        acc.o[i][2] += o[i * 4 + 2] * f1;
+        acc.o[i][3] += o[i * 4 + 3] * f1;
+      }
+    }
+    acc.m[0] = m0;
+    acc.m[1] = m1;
+    acc.l[0] = l0;
+    acc.l[1] = l1;
+  }
+}
+
+// Stage one 64-key tile: thread i copies 16-byte chunk (i % 8) of rows (i / 8) + {0,16,32,48}.
+template <typename F>
+__device__ __forceinline__ void stage_tile(uint8_t* sK, uint8_t* sV, int key0, int kv_len, F src_of) {
+  const int tid = threadIdx.x;
+  const int chunk = tid & 7;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int row = (tid >> 3) + i * 16;
+    const int key = key0 + row;
+    const bool ok = key < kv_len;
+    RowSrc s = src_of(ok ? key : 0);
+    const int off = row * 128 + ((chunk ^ (row & 7)) << 4);
+    cp_async16_zfill(sK + off, s.k + chunk * 16, ok);
+    cp_async16_zfill(sV + off, s.v + chunk * 16, ok);
+  }
+}
+
+// Shared main loop: stream keys [key_begin, key_end) in 64-key tiles through the cp.async ring.
+template <typename T, typename F>
+__device__ __forceinline__ void stream_keys(uint8_t* smem, int key_begin, int key_end, int kv_len,
+                                            const uint32_t (&qa)[4][4], WarpAcc& acc, F src_of) {
+  const int warp = threadIdx.x >> 5;
+  const int n_tiles = (key_end - key_begin + kDaTileKeys - 1) / kDaTileKeys;
+#pragma unroll
+  for (int s = 0; s < kDaStages - 1; ++s) {
+    if (s < n_tiles)
+      stage_tile(smem + s * 2 * kDaTileBytes, smem + s * 2 * kDaTileBytes + kDaTileBytes,
+                 key_begin + s * kDaTileKeys, min(kv_len, key_end), src_of);
+    cp_async_commit();
+  }
+  for (int it = 0; it < n_tiles; ++it) {
+    cp_async_wait<kDaStages - 2>();
+    __syncthreads();
+    const int nx = it + kDaStages - 1;
+    if (nx < n_tiles) {
+      const int st = nx % kDaStages;
+      stage_tile(smem + st * 2 * kDaTileBytes, smem + st * 2 * kDaTileBytes + kDaTileBytes,
+                 key_begin + nx * kDaTileKeys, min(kv_len, key_end), src_of);
+    }
+    cp_async_commit();
+    const int st = it % kDaStages;
+    const int k0 = key_begin + it * kDaTileKeys + warp * 16;
+    warp_tile<T>(smem + st * 2 * kDaTileBytes, smem + st * 2 * kDaTileBytes + kDaTileBytes, warp * 16,
+                 qa, min(kv_len, key_end) - k0, acc);
+  }
+  cp_async_wait<0>();
+  __syncthreads();
+}
+
+// =================================================================================================
+// cross attention
+// =================================================================================================
+struct CrossParams {
+  const void* q;        // [n_audio * n_q, d] queries (already projected)
+  const void* k;        // [n_audio, T, d]
+  const void* v;        // [n_audio, T, d]
+  void* out;            // [n_audio * n_q, d]
+  float* partial;       // [n_audio * q_tiles, H, splits, 16, 66]
+  int* counters;        // [n_audio * q_tiles * H], zero on entry, zero on exit
+  const int* skip_flag; // optional device flag: non-zero -> kernel does nothing
+  int n_q, q_tiles, T, d, splits, keys_per_split, kv_ld;
+};
+
+template <typename T>
+__global__ void __launch_bounds__(kDaThreads) cross_attention_kernel(const CrossParams p) {
+  if (p.skip_flag && *p.skip_flag) return;
+  extern __shared__ __align__(1024) uint8_t da_smem[];
+  __shared__ int s_last;
+  const int split = blockIdx.x, h = blockIdx.y;
+  const int audio = blockIdx.z / p.q_tiles, qt = blockIdx.z % p.q_tiles;
+  const int q_first = qt * 16;
+  const int n_q = min(16, p.n_q - q_first);
+  const T* q0 = reinterpret_cast<const T*>(p.q) + (static_cast<long long>(audio) * p.n_q + q_first) * p.d + h * 64;
+  uint32_t qa[4][4];
+  load_q_frags<T>(qa, q0, p.d, n_q);
+
+  const uint8_t* kbase = reinterpret_cast<const uint8_t*>(p.k) + (static_cast<long long>(audio) * p.T * p.kv_ld + h * 64) * 2;
+  const uint8_t* vbase = reinterpret_cast<const uint8_t*>(p.v) + (static_cast<long long>(audio) * p.T * p.kv_ld + h * 64) * 2;
+  const long long row_bytes = static_cast<long long>(p.kv_ld) * 2;
+  auto src_of = [&](int key) {
+    RowSrc s;
+    s.k = kbase + key * row_bytes;
+    s.v = vbase + key * row_bytes;
+    return s;
+  };
+  WarpAcc acc;
+  acc_init(acc);
+  const int kb = split * p.keys_per_split;
+  const int ke = min(p.T, kb + p.keys_per_split);
+  stream_keys<T>(da_smem, kb, ke, p.T, qa, acc, src_of);
+
+  float* red = reinterpret_cast<float*>(da_smem);
+  cta_merge(acc, red);
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int g = lane >> 2, t = lane & 3;
+  const long long tile_id = (static_cast<long long>(blockIdx.z) * gridDim.y + h);
+  float* part = p.partial + (tile_id * p.splits + split) * (16 * 66);
+  if (warp == 0) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      part[g * 66 + i * 8 + 2 * t] = acc.o[i][0];
+      part[g * 66 + i * 8 + 2 * t + 1] = acc.o[i][1];
+      part[(g + 8) * 66 + i * 8 + 2 * t] = acc.o[i][2];
+      part[(g + 8) * 66 + i * 8 + 2 * t + 1] = acc.o[i][3];
+    }
+    if (t == 0) {
+      part[g * 66 + 64] = acc.m[0];
+      part[g * 66 + 65] = acc.l[0];
+      part[(g + 8) * 66 + 64] = acc.m[1];
+      part[(g + 8) * 66 + 65] = acc.l[1];
+    }
+  }
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const int prev = atomicAdd(&p.counters[tile_id], 1);
+    s_last = (prev == p.splits - 1);
+    if (s_last) p.counters[tile_id] = 0;          // ready for the next launch
+  }
+  __syncthreads();
+  if (!s_last) return;
+  __threadfence();
+  // ---- combine the splits: 128 threads = 16 rows x 8 column groups of 8
+  const int row = threadIdx.x >> 3, cg = threadIdx.x & 7;
+  if (row < n_q) {
+    const float* base = p.partial + tile_id * p.splits * (16 * 66) + row * 66;
+    float m = -INFINITY;
+    for (int s = 0; s < p.splits; ++s) m = fmaxf(m, __ldcg(base + s * 16 * 66 + 64));
+    float l = 0.f, o[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) o[e] = 0.f;
+    for (int s = 0; s < p.splits; ++s) {
+      const float* ps = base + s * 16 * 66;
+      const float ms = __ldcg(ps + 64);
+      const float f = ms == -INFINITY ? 0.f : fast_exp2(ms - m);
+      l += __ldcg(ps + 65) * f;
+#pragma unroll
+      for (int e = 0; e < 8; ++e) o[e] += __ldcg(ps + cg * 8 + e) * f;
+    }
+    const float inv = 1.0f / l;
+    T* orow = reinterpret_cast<T*>(p.out) + (static_cast<long long>(audio) * p.n_q + q_first + row) * p.d + h * 64 + cg * 8;
+    uint4 u;
+    u.x = Cvt<T>::pack2(o[0] * inv, o[1] * inv);
+    u.y = Cvt<T>::pack2(o[2] * inv, o[3] * inv);
+    u.z = Cvt<T>::pack2(o[4] * inv, o[5] * inv);
+    u.w = Cvt<T>::pack2(o[6] * inv, o[7] * inv);
+    *reinterpret_cast<uint4*>(orow) = u;
+  }
+}
+
+// =================================================================================================
+// self attention (+ kv-cache append)
+// =================================================================================================
+struct SelfParams {
+  const void* qkv;      // [n_rows, 3*d]: q | k | v of the NEW position(s)
+  void* kcache;         // [phys_rows, max_ctx, d]
+  void* vcache;
+  void* out;            // [n_rows, d]
+  const int* indir;     // step mode: [R, max_ctx] position -> physical row; null in prefill mode
+  const int* len_ptr;   // step mode: device int, current token count L (new token is position L-1)
+  const int* skip_flag;
+  int d, max_ctx;
+  int n_init;           // prefill mode: tokens per audio (query row = audio * n_init + i)
+  int group;            // prefill mode: physical row of audio a is a * group
+};
+
+template <typename T>
+__global__ void __launch_bounds__(kDaThreads) self_attention_kernel(const SelfParams p) {
+  if (p.skip_flag && *p.skip_flag) return;
+  extern __shared__ __align__(1024) uint8_t da_smem[];
+  const int h = blockIdx.x;
+  const int row = blockIdx.y;
+  const bool step = p.indir != nullptr;
+  int kv_len, phys_fixed = 0;
+  if (step) {
+    kv_len = *p.len_ptr;
+  } else {
+    kv_len = row % p.n_init + 1;
+    phys_fixed = (row / p.n_init) * p.group;
+  }
+  const int pos_new = kv_len - 1;
+  const T* qrow = reinterpret_cast<const T*>(p.qkv) + static_cast<long long>(row) * 3 * p.d + h * 64;
+  const uint8_t* knew = reinterpret_cast<const uint8_t*>(qrow + p.d);
+  const uint8_t* vnew = reinterpret_cast<const uint8_t*>(qrow + 2 * p.d);
+  uint8_t* kc = reinterpret_cast<uint8_t*>(p.kcache);
+  uint8_t* vc = reinterpret_cast<uint8_t*>(p.vcache);
+  const long long row_bytes = static_cast<long long>(p.d) * 2;
+  if (step && threadIdx.x < 16) {
+    // append: the new token's K/V (this head's 128 B each) into physical row `row`, position L-1
+    const long long off = (static_cast<long long>(row) * p.max_ctx + pos_new) * row_bytes + h * 128;
+    const int c = threadIdx.x & 7;
+    if (threadIdx.x < 8)
+      *reinterpret_cast<uint4*>(kc + off + c * 16) = *reinterpret_cast<const uint4*>(knew + c * 16);
+    else
+      *reinterpret_cast<uint4*>(vc + off + c * 16) = *reinterpret_cast<const uint4*>(vnew + c * 16);
+  }
+  uint32_t qa[4][4];
+  load_q_frags<T>(qa, qrow, 0, 1);
+  const int* ind = step ? p.indir + static_cast<long long>(row) * p.max_ctx : nullptr;
+  auto src_of = [&](int key) {
+    RowSrc s;
+    if (step && key == pos_new) {   // not yet visible through the cache: read it from qkv
+      s.k = knew;
+      s.v = vnew;
+    } else {
+      const int phys = step ? __ldg(ind + key) : phys_fixed;
+      const long long off = (static_cast<long long>(phys) * p.max_ctx + key) * row_bytes + h * 128;
+      s.k = kc + off;
+      s.v = vc + off;
+    }
+    return s;
+  };
+  WarpAcc acc;
+  acc_init(acc);
+  stream_keys<T>(da_smem, 0, kv_len, kv_len, qa, acc, src_of);
+  float* red = reinterpret_cast<float*>(da_smem);
+  cta_merge(acc, red);
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  if (warp == 0 && (lane >> 2) == 0) {
+    const int t = lane & 3;
+    const float inv = 1.0f / acc.l[0];
+    T* orow = reinterpret_cast<T*>(p.out) + static_cast<long long>(row) * p.d + h * 64;
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+      *reinterpret_cast<uint32_t*>(orow + i * 8 + 2 * t) = Cvt<T>::pack2(acc.o[i][0] * inv, acc.o[i][1] * inv);
+  }
+}
+
+// Prefill-mode append: copy k|v of qkv[(a, i)] into cache[(a*group, i)].  One warp per (row, k/v).
+template <typename T>
+__global__ void kv_append_kernel(const T* __restrict__ qkv, T* __restrict__ kcache, T* __restrict__ vcache,
+                                 int n_rows, int n_init, int group, int d, int max_ctx) {
+  const int w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (w >= n_rows * 2) return;
+  const int row = w >> 1, which = w & 1;
+  const int a = row / n_init, i = row % n_init;
+  const T* src = qkv + static_cast<long long>(row) * 3 * d + (1 + which) * d;
+  T* dst = (which ? vcache : kcache) + (static_cast<long long>(a) * group * max_ctx + i) * d;
+  for (int c = lane * 8; c < d; c += 256)
+    *reinterpret_cast<uint4*>(dst + c) = *reinterpret_cast<const uint4*>(src + c);
+}
+
+// -------------------------------------------------------------------------------------------------
+// launchers
+// -------------------------------------------------------------------------------------------------
+int cross_attention_splits(int T) { return T >= 1024 ? 4 : (T >= 256 ? 2 : 1); }
+
+size_t cross_attention_partial_floats(int n_audio, int n_q, int n_head, int T) {
+  const int q_tiles = (n_q + 15) / 16;
+  return static_cast<size_t>(n_audio) * q_tiles * n_head * cross_attention_splits(T) * 16 * 66;
+}
+
+int launch_cross_attention(int dtype, const void* q, const void* k, const void* v, void* out,
+                           float* partial, int* counters, const int* skip_flag, int n_audio, int n_q,
+                           int T, int n_head, int kv_ld, cudaStream_t s) {
+  if (n_audio <= 0 || n_q <= 0) return 0;
+  CrossParams p;
+  p.q = q;
+  p.k = k;
+  p.v = v;
+  p.out = out;
+  p.partial = partial;
+  p.counters = counters;
+  p.skip_flag = skip_flag;
+  p.n_q = n_q;
+  p.q_tiles = (n_q + 15) / 16;
+  p.T = T;
+  p.d = n_head * 64;
+  p.kv_ld = kv_ld;
+  p.splits = cross_attention_splits(T);
+  p.keys_per_split = ((T + p.splits - 1) / p.splits + 63) / 64 * 64;
+  dim3 grid(p.splits, n_head, n_audio * p.q_tiles);
+  static bool attr[2] = {false, false};
+  if (dtype == DT_BF16) {
+    auto kern = cross_attention_kernel<__nv_bfloat16>;
+    if (!attr[0]) {
+      if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kDaSmem) != cudaSuccess) return 40;
+      attr[0] = true;
+    }
+    kern<<<grid, kDaThreads, kDaSmem, s>>>(p);
+  } else {
+    auto kern = cross_attention_kernel<__half>;
+    if (!attr[1]) {
+      if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kDaSmem) != cudaSuccess) return 40;
+      attr[1] = true;
+    }
+    kern<<<grid, kDaThreads, kDaSmem, s>>>(p);
+  }
+  count_launch();
+  return cudaGetLastError() == cudaSuccess ? 0 : 41;
+}
+
+int launch_self_attention(int dtype, const void* qkv, void* kcache, void* vcache, void* out,
+                          const int* indir, const int* len_ptr, const int* skip_flag, int n_rows,
+                          int n_head, int max_ctx, int n_init, int group, cudaStream_t s) {
+  if (n_rows <= 0) return 0;
+  SelfParams p;
+  p.qkv = qkv;
+  p.kcache = kcache;
+  p.vcache = vcache;
+  p.out = out;
+  p.indir = indir;
+  p.len_ptr = len_ptr;
+  p.skip_flag = skip_flag;
+  p.d = n_head * 64;
+  p.max_ctx = max_ctx;
+  p.n_init = n_init > 0 ? n_init : 1;
+  p.group = group;
+  dim3 grid(n_head, n_rows);
+  static bool attr[2] = {false, false};
+  if (dtype == DT_BF16) {
+    if (!indir) {
+      kv_append_kernel<__nv_bfloat16><<<(n_rows * 2 * 32 + 255) / 256, 256, 0, s>>>(
+          static_cast<const __nv_bfloat16*>(qkv), static_cast<__nv_bfloat16*>(kcache),
+          static_cast<__nv_bfloat16*>(vcache), n_rows, p.n_init, group, p.d, max_ctx);
+      count_launch();
+    }
+    auto kern = self_attention_kernel<__nv_bfloat16>;
+    if (!attr[0]) {
+      if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kDaSmem) != cudaSuccess) return 42;
+      attr[0] = true;
+    }
+    kern<<<grid, kDaThreads, kDaSmem, s>>>(p);
+  } else {
+    if (!indir) {
+      kv_append_kernel<__half><<<(n_rows * 2 * 32 + 255) / 256, 256, 0, s>>>(
+          static_cast<const __half*>(qkv), static_cast<__half*>(kcache), static_cast<__half*>(vcache),
+          n_rows, p.n_init, group, p.d, max_ctx);
+      count_launch();
+    }
+    auto kern = self_attention_kernel<__half>;
+    if (!attr[1]) {
+      if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kDaSmem) != cudaSuccess) return 42;
+      attr[1] = true;
+    }
+    kern<<<grid, kDaThreads, kDaSmem, s>>>(p);
+  }
+  count_launch();
+  return cudaGetLastError() == cudaSuccess ? 0 : 43;
+}
+
+}  // namespace wb

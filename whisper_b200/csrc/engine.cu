@@ -1,0 +1,557 @@
+// Model / encoder / decoder orchestration behind the C ABI: which kernels run, in what order, on
+// which slices of the caller-provided workspace.  No allocation happens here except the small
+// host-side handle structs; every device byte belongs to the caller (PyTorch).
+#include <stdio.h>
+#include <string.h>
+
+#include <vector>
+
+#include "../../include/whisper_b200.h"
+#include "engine.h"
+#include "kernels.h"
+#include "ptx.cuh"
+
+namespace wb {
+
+int set_error(int code, const char* fmt, ...);
+
+// -------------------------------------------------------------------------------------------------
+// small kernels: embedding gather, row gather, state initialisation
+// -------------------------------------------------------------------------------------------------
+// x[row] = T(token_embedding[tok] + positional_embedding[pos])   (reference model.py:235-239)
+template <typename T>
+__global__ void embed_kernel(const int* __restrict__ tokens, int max_ctx, const int* __restrict__ len_ptr,
+                             int n_init, int group, const float* __restrict__ emb, const float* __restrict__ pos,
+                             T* __restrict__ x, int d, const int* skip_flag) {
+  if (skip_flag && *skip_flag) return;
+  const int row = blockIdx.x;
+  int tok, p;
+  if (len_ptr) {            // step: the last token of every row
+    p = *len_ptr - 1;
+    tok = tokens[static_cast<long long>(row) * max_ctx + p];
+  } else {                  // prefill: token i of audio a (read from the audio's first beam row)
+    const int a = row / n_init;
+    p = row % n_init;
+    tok = tokens[static_cast<long long>(a) * group * max_ctx + p];
+  }
+  const float* e = emb + static_cast<long long>(tok) * d;
+  const float* pp = pos + static_cast<long long>(p) * d;
+  T* xr = x + static_cast<long long>(row) * d;
+  for (int c = threadIdx.x * 2; c < d; c += blockDim.x * 2) {
+    const float2 a = *reinterpret_cast<const float2*>(e + c);
+    const float2 b = *reinterpret_cast<const float2*>(pp + c);
+    *reinterpret_cast<uint32_t*>(xr + c) = Cvt<T>::pack2(a.x + b.x, a.y + b.y);
+  }
+}
+
+// dst[i] = src[idx(i)] for the two prefill positions whose logits are needed (decoding.py:692,696)
+template <typename T>
+__global__ void gather_prefill_rows_kernel(const T* __restrict__ x, T* __restrict__ dst, int n_audio, int n_init,
+                                           int sot_index, int d) {
+  const int i = blockIdx.x;  // [0, 2*n_audio)
+  const int a = i % n_audio;
+  const int src = a * n_init + (i < n_audio ? sot_index : n_init - 1);
+  for (int c = threadIdx.x * 8; c < d; c += blockDim.x * 8)
+    *reinterpret_cast<uint4*>(dst + static_cast<long long>(i) * d + c) =
+        *reinterpret_cast<const uint4*>(x + static_cast<long long>(src) * d + c);
+}
+
+__global__ void decoder_init_state_kernel(int* tokens0, int* tokens1, int* indir0, int* indir1, int max_ctx, int R,
+                                          int group, int n_init, const int* __restrict__ init_tokens /*[n_audio,n_init]*/,
+                                          float* sum_lp, int* len_ptr, int* done, int* cur, int* fin_count, int* fin_len,
+                                          int n_audio, int max_cand, int* counters, int n_counters) {
+  const int tid = blockIdx.x * blockDim.x + threadIdx.x;
+  const int stride = gridDim.x * blockDim.x;
+  for (long long i = tid; i < static_cast<long long>(R) * max_ctx; i += stride) {
+    const int r = static_cast<int>(i / max_ctx), p = static_cast<int>(i % max_ctx);
+    const int a = r / group;
+    const int t = p < n_init ? init_tokens[a * n_init + p] : 0;
+    tokens0[i] = t;
+    tokens1[i] = t;
+    const int ph = p < n_init ? a * group : r;
+    indir0[i] = ph;
+    indir1[i] = ph;
+  }
+  for (int i = tid; i < R; i += stride) sum_lp[i] = 0.f;
+  for (int i = tid; i < n_audio; i += stride) fin_count[i] = 0;
+  for (int i = tid; i < n_audio * max_cand; i += stride) fin_len[i] = 0;
+  for (int i = tid; i < n_counters; i += stride) counters[i] = 0;
+  if (tid == 0) {
+    *len_ptr = n_init;
+    *done = 0;
+    *cur = 0;
+  }
+}
+
+// teacher forcing: append given tokens (tests)
+__global__ void append_tokens_kernel(int* tokens, int max_ctx, int R, const int* __restrict__ next, int* len_ptr) {
+  const int L = *len_ptr;
+  for (int r = threadIdx.x; r < R; r += blockDim.x) tokens[static_cast<long long>(r) * max_ctx + L] = next[r];
+  __syncthreads();
+  if (threadIdx.x == 0) *len_ptr = L + 1;
+}
+
+// -------------------------------------------------------------------------------------------------
+// workspace carving
+// -------------------------------------------------------------------------------------------------
+struct Arena {
+  uint8_t* base;
+  size_t off, cap;
+  void* take(size_t bytes) {
+    off = (off + 255) & ~static_cast<size_t>(255);
+    void* p = base ? base + off : nullptr;
+    off += bytes;
+    return p;
+  }
+};
+
+#define WB_TRY(expr)                                  \
+  do {                                                \
+    int _r = (expr);                                  \
+    if (_r) return set_error(_r, "%s failed (%d) at %s:%d", #expr, _r, __FILE__, __LINE__); \
+  } while (0)
+
+static int linear(const Model* m, const void* A, long long lda, int M, const void* W, int N, int K, const void* bias,
+                  const void* residual, void* C, long long ldc, int gelu, int out_f32, cudaStream_t s,
+                  const int* skip = nullptr) {
+  LinearArgs a;
+  a.dtype = m->dtype;
+  a.batch = 1;
+  a.rows_per_batch = M;
+  a.a_rows_per_batch = M;
+  a.lda = lda;
+  a.N = N;
+  a.K_tap = K;
+  a.taps = 1;
+  a.A = A;
+  a.W = W;
+  a.ldw = K;
+  a.bias = bias;
+  a.residual = residual;
+  a.ldr = ldc;
+  a.C = C;
+  a.ldc = ldc;
+  a.gelu = gelu;
+  a.out_f32 = out_f32;
+  a.skip_flag = skip;
+  return launch_linear(a, s);
+}
+
+// -------------------------------------------------------------------------------------------------
+// encoder (reference model.py:174-204)
+// -------------------------------------------------------------------------------------------------
+struct EncBufs {
+  void *x, *ln, *qkv, *att, *hid;
+};
+static size_t enc_carve(const Model* m, int B, Arena& ar, EncBufs& b) {
+  const size_t es = 2;
+  const size_t d = m->dims.n_audio_state, T = m->dims.n_audio_ctx;
+  b.x = ar.take(B * T * d * es);
+  b.ln = ar.take(B * T * d * es);
+  b.att = ar.take(B * T * d * es);
+  b.qkv = ar.take(B * T * 3 * d * es);            // also holds the time-major mel (B*2T*n_mels)
+  b.hid = ar.take(B * T * 4 * d * es);            // also holds conv1's output (B*2T*d)
+  return ar.off;
+}
+
+size_t encoder_workspace_bytes(const Model* m, int B) {
+  Arena ar{nullptr, 0, 0};
+  EncBufs b;
+  return enc_carve(m, B, ar, b) + 256;
+}
+
+int encoder_forward(const Model* m, const float* mel, int B, void* out, void* ws, size_t ws_bytes, cudaStream_t s) {
+  if (B <= 0) return 0;
+  if (ws_bytes < encoder_workspace_bytes(m, B)) return set_error(200, "encoder workspace too small");
+  Arena ar{static_cast<uint8_t*>(ws), 0, ws_bytes};
+  EncBufs b;
+  enc_carve(m, B, ar, b);
+  const int d = m->dims.n_audio_state, T = m->dims.n_audio_ctx, H = m->dims.n_audio_head;
+  const int n_mels = m->dims.n_mels, T2 = 2 * T;
+  const int dt = m->dtype;
+  void* melT = b.qkv;
+  void* h1 = b.hid;
+  WB_TRY(launch_transpose_to16(dt, mel, melT, B, n_mels, T2, s));
+  {
+    LinearArgs a;   // conv1 + GELU (model.py:193)
+    a.dtype = dt; a.batch = B; a.rows_per_batch = T2; a.a_rows_per_batch = T2;
+    a.a_batch_stride = static_cast<long long>(T2) * n_mels; a.lda = n_mels;
+    a.N = d; a.K_tap = n_mels; a.taps = 3; a.a_row_off[0] = -1; a.a_row_off[1] = 0; a.a_row_off[2] = 1;
+    a.A = melT; a.W = m->t[G_CONV1_W]; a.ldw = 3LL * n_mels; a.bias = m->t[G_CONV1_B];
+    a.C = h1; a.ldc = d; a.gelu = 1;
+    WB_TRY(launch_linear(a, s));
+  }
+  {
+    LinearArgs a;   // conv2 (stride 2) + GELU + positional embedding (model.py:194-198)
+    a.dtype = dt; a.batch = B; a.rows_per_batch = T; a.a_rows_per_batch = T;
+    a.a_batch_stride = static_cast<long long>(T2) * d; a.lda = 2LL * d;
+    a.N = d; a.K_tap = d; a.taps = 3;
+    a.a_base_off[0] = d; a.a_row_off[0] = -1; a.a_base_off[1] = 0; a.a_row_off[1] = 0;
+    a.a_base_off[2] = d; a.a_row_off[2] = 0;
+    a.A = h1; a.W = m->t[G_CONV2_W]; a.ldw = 3LL * d; a.bias = m->t[G_CONV2_B];
+    a.pos = static_cast<const float*>(m->t[G_ENC_POS]);
+    a.C = b.x; a.ldc = d; a.gelu = 1;
+    WB_TRY(launch_linear(a, s));
+  }
+  const int rows = B * T;
+  for (int l = 0; l < m->dims.n_audio_layer; ++l) {
+    const void* const* L = m->enc_layer(l);
+    WB_TRY(launch_layernorm(dt, b.x, d, b.ln, d, (const float*)L[E_ATTN_LN_W], (const float*)L[E_ATTN_LN_B], rows, d, s));
+    WB_TRY(linear(m, b.ln, d, rows, L[E_QKV_W], 3 * d, d, L[E_QKV_B], nullptr, b.qkv, 3 * d, 0, 0, s));
+    WB_TRY(launch_enc_attention(dt, b.qkv, b.att, B, T, H, s));
+    WB_TRY(linear(m, b.att, d, rows, L[E_OUT_W], d, d, L[E_OUT_B], b.x, b.x, d, 0, 0, s));
+    WB_TRY(launch_layernorm(dt, b.x, d, b.ln, d, (const float*)L[E_MLP_LN_W], (const float*)L[E_MLP_LN_B], rows, d, s));
+    WB_TRY(linear(m, b.ln, d, rows, L[E_FC1_W], 4 * d, d, L[E_FC1_B], nullptr, b.hid, 4 * d, 1, 0, s));
+    WB_TRY(linear(m, b.hid, 4 * d, rows, L[E_FC2_W], d, 4 * d, L[E_FC2_B], b.x, b.x, d, 0, 0, s));
+  }
+  WB_TRY(launch_layernorm(dt, b.x, d, out, d, (const float*)m->t[G_ENC_LN_POST_W], (const float*)m->t[G_ENC_LN_POST_B],
+                          rows, d, s));
+  return 0;
+}
+
+// -------------------------------------------------------------------------------------------------
+// decoder
+// -------------------------------------------------------------------------------------------------
+static void dec_carve(const Model* m, const wb200_decode_config& c, Arena& ar, Decoder* D) {
+  const size_t es = 2;
+  const size_t d = m->dims.n_text_state, V = m->dims.n_vocab, ctx = m->dims.n_text_ctx;
+  const size_t Ta = m->dims.n_audio_ctx, NL = m->dims.n_text_layer, H = m->dims.n_text_head;
+  const size_t B = c.n_audio, G = c.n_group, R = B * G;
+  const size_t P = B * c.n_init;
+  const size_t rows = R > P ? R : P;
+  const size_t ldv = (V + 31) / 32 * 32;
+  Decoder dd;
+  Decoder* o = D ? D : &dd;
+  o->ldv = static_cast<long long>(ldv);
+  o->cross_kv = ar.take(NL * B * Ta * 2 * d * es);
+  o->self_k = ar.take(NL * R * ctx * d * es);
+  o->self_v = ar.take(NL * R * ctx * d * es);
+  o->x = ar.take(rows * d * es);
+  o->ln = ar.take(rows * d * es);
+  o->qkv = ar.take(rows * 3 * d * es);
+  o->att = ar.take(rows * d * es);
+  o->q = ar.take(rows * d * es);
+  o->hid = ar.take(rows * 4 * d * es);
+  o->sel = ar.take(2 * B * d * es);
+  const size_t logit_rows = R > 2 * B ? R : 2 * B;
+  o->logits = static_cast<float*>(ar.take(logit_rows * ldv * 4));
+  const size_t nq = c.n_init > (int)G ? c.n_init : G;
+  o->partial = static_cast<float*>(ar.take(cross_attention_partial_floats((int)B, (int)nq, (int)H, (int)Ta) * 4));
+  o->n_counters = static_cast<int>(B * ((nq + 15) / 16) * H);
+  o->counters = static_cast<int*>(ar.take(o->n_counters * 4));
+  for (int i = 0; i < 2; ++i) {
+    o->tokens[i] = static_cast<int*>(ar.take(R * ctx * 4));
+    o->indir[i] = static_cast<int*>(ar.take(R * ctx * 4));
+  }
+  o->sum_lp = static_cast<float*>(ar.take(R * 4));
+  o->no_speech = static_cast<float*>(ar.take(B * 4));
+  const size_t K = c.beam_search ? G + 1 : 1;
+  o->top_val = static_cast<float*>(ar.take(R * K * 4));
+  o->top_idx = static_cast<int*>(ar.take(R * K * 4));
+  o->sources = static_cast<int*>(ar.take(R * 4));
+  const size_t mc = c.max_candidates > 0 ? c.max_candidates : 1;
+  o->fin_tokens = static_cast<int*>(ar.take(B * mc * ctx * 4));
+  o->fin_len = static_cast<int*>(ar.take(B * mc * 4));
+  o->fin_score = static_cast<float*>(ar.take(B * mc * 4));
+  o->fin_count = static_cast<int*>(ar.take(B * 4));
+  o->suppress_mask = static_cast<uint32_t*>(ar.take(ldv / 8 + 64));
+  o->blank_mask = static_cast<uint32_t*>(ar.take(ldv / 8 + 64));
+  o->init_tokens = static_cast<int*>(ar.take(P * 4 + 64));
+  o->scalars = static_cast<int*>(ar.take(256));
+}
+
+size_t decoder_workspace_bytes(const Model* m, const wb200_decode_config* c) {
+  Arena ar{nullptr, 0, 0};
+  dec_carve(m, *c, ar, nullptr);
+  return ar.off + 512;
+}
+
+int decoder_create(const Model* m, const wb200_decode_config* c, void* ws, size_t ws_bytes, Decoder** out,
+                   cudaStream_t s) {
+  if (c->n_audio <= 0 || c->n_group <= 0) return set_error(210, "decoder: n_audio/n_group must be positive");
+  if (c->n_group > 16) return set_error(211, "decoder: at most 16 beams / samples per audio");
+  if (c->n_init < 1 || c->n_init + 1 > m->dims.n_text_ctx) return set_error(212, "decoder: bad n_init %d", c->n_init);
+  if (c->sot_index < 0 || c->sot_index >= c->n_init) return set_error(213, "decoder: bad sot_index");
+  if (ws_bytes < decoder_workspace_bytes(m, c)) return set_error(214, "decoder workspace too small");
+  Decoder* D = new Decoder();
+  D->m = m;
+  D->cfg = *c;
+  D->cfg.suppress_ids = nullptr;
+  D->cfg.blank_ids = nullptr;
+  Arena ar{static_cast<uint8_t*>(ws), 0, ws_bytes};
+  dec_carve(m, *c, ar, D);
+  D->len_ptr = D->scalars;
+  D->done_ptr = D->scalars + 8;
+  D->cur_ptr = D->scalars + 16;
+  D->cur = 0;
+  if (cudaMallocHost(reinterpret_cast<void**>(&D->pinned), 64) != cudaSuccess) {
+    delete D;
+    return set_error(216, "decoder: pinned scratch allocation failed");
+  }
+  D->host_len = 0;
+  // suppress / blank bit masks (decoding.py:423-438, 454-455)
+  const size_t words = static_cast<size_t>(D->ldv) / 32 + 1;
+  std::vector<uint32_t> sup(words, 0u), blank(words, 0u);
+  const int V = m->dims.n_vocab;
+  for (int i = 0; i < c->n_suppress; ++i) {
+    const int t = c->suppress_ids[i];
+    if (t >= 0 && t < V) sup[t >> 5] |= 1u << (t & 31);
+  }
+  if (c->timestamp_rules && c->no_timestamps >= 0 && c->no_timestamps < V)
+    sup[c->no_timestamps >> 5] |= 1u << (c->no_timestamps & 31);
+  for (int i = 0; i < c->n_blank; ++i) {
+    const int t = c->blank_ids[i];
+    if (t >= 0 && t < V) blank[t >> 5] |= 1u << (t & 31);
+  }
+  if (c->eot >= 0 && c->eot < V) blank[c->eot >> 5] |= 1u << (c->eot & 31);
+  if (cudaMemcpyAsync(D->suppress_mask, sup.data(), words * 4, cudaMemcpyHostToDevice, s) != cudaSuccess ||
+      cudaMemcpyAsync(D->blank_mask, blank.data(), words * 4, cudaMemcpyHostToDevice, s) != cudaSuccess ||
+      cudaStreamSynchronize(s) != cudaSuccess) {
+    delete D;
+    return set_error(215, "decoder: mask upload failed");
+  }
+  *out = D;
+  return 0;
+}
+
+// cross-attention K/V for every layer, once per segment (model.py:104-109 first-call branch)
+int decoder_set_audio(Decoder* D, const void* features, cudaStream_t s) {
+  const Model* m = D->m;
+  const int d = m->dims.n_text_state, Ta = m->dims.n_audio_ctx, B = D->cfg.n_audio;
+  if (m->dims.n_audio_state != d) return set_error(220, "audio/text widths differ");
+  const size_t per_layer = static_cast<size_t>(B) * Ta * 2 * d * 2;
+  for (int l = 0; l < m->dims.n_text_layer; ++l) {
+    const void* const* L = m->dec_layer(l);
+    void* kv = static_cast<uint8_t*>(D->cross_kv) + l * per_layer;
+    WB_TRY(linear(m, features, d, B * Ta, L[D_CKV_W], 2 * d, d, L[D_CKV_B], nullptr, kv, 2 * d, 0, 0, s));
+  }
+  return 0;
+}
+
+// the transformer stack for `rows` new positions; step mode when `step` is true
+static int decoder_stack(Decoder* D, int rows, bool step, cudaStream_t s) {
+  const Model* m = D->m;
+  const int d = m->dims.n_text_state, H = m->dims.n_text_head, ctx = m->dims.n_text_ctx;
+  const int Ta = m->dims.n_audio_ctx, B = D->cfg.n_audio, G = D->cfg.n_group, dt = m->dtype;
+  const int R = B * G;
+  const int* skip = step ? D->done_ptr : nullptr;
+  const size_t cross_per_layer = static_cast<size_t>(B) * Ta * 2 * d * 2;
+  const size_t self_per_layer = static_cast<size_t>(R) * ctx * d * 2;
+  const int n_q = step ? G : D->cfg.n_init;
+  for (int l = 0; l < m->dims.n_text_layer; ++l) {
+    const void* const* L = m->dec_layer(l);
+    void* kc = static_cast<uint8_t*>(D->self_k) + l * self_per_layer;
+    void* vc = static_cast<uint8_t*>(D->self_v) + l * self_per_layer;
+    const uint8_t* ckv = static_cast<const uint8_t*>(D->cross_kv) + l * cross_per_layer;
+    WB_TRY(launch_layernorm(dt, D->x, d, D->ln, d, (const float*)L[D_ATTN_LN_W], (const float*)L[D_ATTN_LN_B], rows, d, s, skip));
+    WB_TRY(linear(m, D->ln, d, rows, L[D_QKV_W], 3 * d, d, L[D_QKV_B], nullptr, D->qkv, 3 * d, 0, 0, s, skip));
+    WB_TRY(launch_self_attention(dt, D->qkv, kc, vc, D->att, step ? D->indir[D->cur] : nullptr, D->len_ptr, skip, rows, H,
+                                 ctx, D->cfg.n_init, G, s));
+    WB_TRY(linear(m, D->att, d, rows, L[D_OUT_W], d, d, L[D_OUT_B], D->x, D->x, d, 0, 0, s, skip));
+    WB_TRY(launch_layernorm(dt, D->x, d, D->ln, d, (const float*)L[D_CROSS_LN_W], (const float*)L[D_CROSS_LN_B], rows, d, s, skip));
+    WB_TRY(linear(m, D->ln, d, rows, L[D_CQ_W], d, d, L[D_CQ_B], nullptr, D->q, d, 0, 0, s, skip));
+    WB_TRY(launch_cross_attention(dt, D->q, ckv, ckv + static_cast<size_t>(d) * 2, D->att, D->partial, D->counters, skip, B,
+                                  n_q, Ta, H, 2 * d, s));
+    WB_TRY(linear(m, D->att, d, rows, L[D_COUT_W], d, d, L[D_COUT_B], D->x, D->x, d, 0, 0, s, skip));
+    WB_TRY(launch_layernorm(dt, D->x, d, D->ln, d, (const float*)L[D_MLP_LN_W], (const float*)L[D_MLP_LN_B], rows, d, s, skip));
+    WB_TRY(linear(m, D->ln, d, rows, L[D_FC1_W], 4 * d, d, L[D_FC1_B], nullptr, D->hid, 4 * d, 1, 0, s, skip));
+    WB_TRY(linear(m, D->hid, 4 * d, rows, L[D_FC2_W], d, 4 * d, L[D_FC2_B], D->x, D->x, d, 0, 0, s, skip));
+  }
+  return 0;
+}
+
+template <typename T>
+static void launch_embed(Decoder* D, int rows, bool step, cudaStream_t s) {
+  const Model* m = D->m;
+  embed_kernel<T><<<rows, 128, 0, s>>>(D->tokens[D->cur], m->dims.n_text_ctx, step ? D->len_ptr : nullptr, D->cfg.n_init,
+                                       D->cfg.n_group, (const float*)m->t[G_TOK_EMB32], (const float*)m->t[G_DEC_POS],
+                                       static_cast<T*>(D->x), m->dims.n_text_state, step ? D->done_ptr : nullptr);
+  count_launch();
+}
+
+int decoder_prefill(Decoder* D, const int32_t* init_tokens_host, cudaStream_t s) {
+  const Model* m = D->m;
+  const wb200_decode_config& c = D->cfg;
+  const int B = c.n_audio, G = c.n_group, R = B * G, P = B * c.n_init;
+  const int d = m->dims.n_text_state, V = m->dims.n_vocab, ctx = m->dims.n_text_ctx, dt = m->dtype;
+  if (cudaMemcpyAsync(D->init_tokens, init_tokens_host, static_cast<size_t>(P) * 4, cudaMemcpyHostToDevice, s) != cudaSuccess)
+    return set_error(230, "prefill: token upload failed");
+  D->cur = 0;
+  decoder_init_state_kernel<<<256, 256, 0, s>>>(D->tokens[0], D->tokens[1], D->indir[0], D->indir[1], ctx, R, G, c.n_init,
+                                                D->init_tokens, D->sum_lp, D->len_ptr, D->done_ptr, D->cur_ptr, D->fin_count, D->fin_len,
+                                                B, c.max_candidates > 0 ? c.max_candidates : 1, D->counters, D->n_counters);
+  count_launch();
+  if (dt == DT_BF16) launch_embed<__nv_bfloat16>(D, P, false, s); else launch_embed<__half>(D, P, false, s);
+  WB_TRY(decoder_stack(D, P, false, s));
+  if (dt == DT_BF16)
+    gather_prefill_rows_kernel<__nv_bfloat16><<<2 * B, 128, 0, s>>>((const __nv_bfloat16*)D->x, (__nv_bfloat16*)D->sel, B, c.n_init, c.sot_index, d);
+  else
+    gather_prefill_rows_kernel<__half><<<2 * B, 128, 0, s>>>((const __half*)D->x, (__half*)D->sel, B, c.n_init, c.sot_index, d);
+  count_launch();
+  WB_TRY(launch_layernorm(dt, D->sel, d, D->ln, d, (const float*)m->t[G_DEC_LN_W], (const float*)m->t[G_DEC_LN_B], 2 * B, d, s, nullptr));
+  WB_TRY(linear(m, D->ln, d, 2 * B, m->t[G_TOK_EMB16], V, d, nullptr, nullptr, D->logits, D->ldv, 0, 1, s));
+  if (c.no_speech >= 0) WB_TRY(launch_no_speech(D->logits, D->ldv, V, c.no_speech, D->no_speech, B, s));
+  D->logits_cur = D->logits + static_cast<size_t>(B) * D->ldv;   // rows [B, 2B): last prompt position
+  D->logits_row_div = G;
+  D->host_len = c.n_init;
+  if (cudaGetLastError() != cudaSuccess) return set_error(231, "prefill: launch error");
+  return 0;
+}
+
+int decoder_step(Decoder* D, cudaStream_t s) {
+  const Model* m = D->m;
+  const int R = D->cfg.n_audio * D->cfg.n_group;
+  const int d = m->dims.n_text_state, V = m->dims.n_vocab, dt = m->dtype;
+  if (D->host_len >= m->dims.n_text_ctx) return set_error(240, "step: context full");
+  if (dt == DT_BF16) launch_embed<__nv_bfloat16>(D, R, true, s); else launch_embed<__half>(D, R, true, s);
+  WB_TRY(decoder_stack(D, R, true, s));
+  WB_TRY(launch_layernorm(dt, D->x, d, D->ln, d, (const float*)m->t[G_DEC_LN_W], (const float*)m->t[G_DEC_LN_B], R, d, s, D->done_ptr));
+  WB_TRY(linear(m, D->ln, d, R, m->t[G_TOK_EMB16], V, d, nullptr, nullptr, D->logits, D->ldv, 0, 1, s, D->done_ptr));
+  D->logits_cur = D->logits;
+  D->logits_row_div = 1;
+  return 0;
+}
+
+int decoder_select(Decoder* D, cudaStream_t s) {
+  const Model* m = D->m;
+  const wb200_decode_config& c = D->cfg;
+  const int B = c.n_audio, G = c.n_group, R = B * G, ctx = m->dims.n_text_ctx;
+  FilterParams f;
+  f.logits = D->logits_cur;
+  f.ld = D->ldv;
+  f.V = m->dims.n_vocab;
+  f.row_div = D->logits_row_div;
+  f.tokens = D->tokens[D->cur];
+  f.max_ctx = ctx;
+  f.len_ptr = D->len_ptr;
+  f.skip_flag = D->done_ptr;
+  f.suppress_mask = D->suppress_mask;
+  f.blank_mask = D->blank_mask;
+  f.sample_begin = c.sample_begin;
+  f.eot = c.eot;
+  f.timestamp_begin = c.timestamp_begin;
+  f.max_initial_ts = c.max_initial_timestamp_index;
+  f.suppress_blank = c.suppress_blank;
+  f.ts_rules = c.timestamp_rules;
+  f.K = c.beam_search ? G + 1 : 1;
+  f.top_val = D->top_val;
+  f.top_idx = D->top_idx;
+  WB_TRY(launch_filter_topk(f, R, s));
+  if (!c.beam_search) {
+    GreedyParams g;
+    g.tokens = D->tokens[D->cur];
+    g.max_ctx = ctx;
+    g.R = R;
+    g.eot = c.eot;
+    g.len_ptr = D->len_ptr;
+    g.sum_logprobs = D->sum_lp;
+    g.top_val = D->top_val;
+    g.top_idx = D->top_idx;
+    g.done_flag = D->done_ptr;
+    g.skip_flag = D->done_ptr;
+    WB_TRY(launch_greedy_update(g, s));
+  } else {
+    BeamParams b;
+    b.tokens_in = D->tokens[D->cur];
+    b.tokens_out = D->tokens[D->cur ^ 1];
+    b.indir_in = D->indir[D->cur];
+    b.indir_out = D->indir[D->cur ^ 1];
+    b.max_ctx = ctx;
+    b.n_audio = B;
+    b.G = G;
+    b.eot = c.eot;
+    b.max_candidates = c.max_candidates;
+    b.len_ptr = D->len_ptr;
+    b.sum_logprobs = D->sum_lp;
+    b.top_val = D->top_val;
+    b.top_idx = D->top_idx;
+    b.fin_tokens = D->fin_tokens;
+    b.fin_len = D->fin_len;
+    b.fin_score = D->fin_score;
+    b.fin_count = D->fin_count;
+    b.source_out = D->sources;
+    b.done_flag = D->done_ptr;
+    b.skip_flag = D->done_ptr;
+    b.cur_out_ptr = D->cur_ptr;       // the device records which buffer is current: once the done
+    b.out_index = D->cur ^ 1;         // flag is up later launches are no-ops and the host view goes stale
+    WB_TRY(launch_beam_update(b, s));
+    D->cur ^= 1;
+  }
+  D->host_len += 1;
+  return 0;
+}
+
+int decoder_append(Decoder* D, const int32_t* next_host, cudaStream_t s) {
+  const int R = D->cfg.n_audio * D->cfg.n_group;
+  if (cudaMemcpyAsync(D->sources, next_host, static_cast<size_t>(R) * 4, cudaMemcpyHostToDevice, s) != cudaSuccess)
+    return set_error(250, "append: upload failed");
+  append_tokens_kernel<<<1, 256, 0, s>>>(D->tokens[D->cur], D->m->dims.n_text_ctx, R, D->sources, D->len_ptr);
+  count_launch();
+  D->host_len += 1;
+  return 0;
+}
+
+static int poll_int(Decoder* D, const int* dev, int* value, cudaStream_t s) {
+  if (cudaMemcpyAsync(D->pinned, dev, 4, cudaMemcpyDeviceToHost, s) != cudaSuccess ||
+      cudaStreamSynchronize(s) != cudaSuccess)
+    return set_error(260, "decoder: flag read failed: %s", cudaGetErrorString(cudaGetLastError()));
+  *value = D->pinned[0];
+  return 0;
+}
+
+// DecodingTask._main_loop for i >= 1 (decoding.py:686-706): step, filters, update; the completion
+// flag lives on the device and is polled every 8 iterations (kernels become no-ops once it is set,
+// so overshooting leaves the state exactly as it was when the flag went up).
+int decoder_run(Decoder* D, int max_steps, int* steps_issued, cudaStream_t s) {
+  const int ctx = D->m->dims.n_text_ctx;
+  int issued = 0;
+  for (int i = 0; i < max_steps; ++i) {
+    if (D->host_len >= ctx) break;
+    int r = decoder_step(D, s);
+    if (r) return r;
+    r = decoder_select(D, s);
+    if (r) return r;
+    ++issued;
+    if ((i & 7) == 7) {
+      int done = 0;
+      r = poll_int(D, D->done_ptr, &done, s);
+      if (r) return r;
+      if (done) break;
+    }
+  }
+  if (steps_issued) *steps_issued = issued;
+  return 0;
+}
+
+int decoder_state_ptr(Decoder* D, int what, void** ptr, size_t* bytes, cudaStream_t s) {
+  const Model* m = D->m;
+  const wb200_decode_config& c = D->cfg;
+  const size_t B = c.n_audio, R = B * c.n_group, ctx = m->dims.n_text_ctx;
+  const size_t K = c.beam_search ? c.n_group + 1 : 1;
+  const size_t mc = c.max_candidates > 0 ? c.max_candidates : 1;
+  int cur = 0;
+  if (what == WB200_STATE_TOKENS && c.beam_search) {
+    int r = poll_int(D, D->cur_ptr, &cur, s);
+    if (r) return r;
+  }
+  switch (what) {
+    case WB200_STATE_TOKENS: *ptr = D->tokens[cur]; *bytes = R * ctx * 4; break;
+    case WB200_STATE_LENGTH: *ptr = D->len_ptr; *bytes = 4; break;
+    case WB200_STATE_SUM_LOGPROBS: *ptr = D->sum_lp; *bytes = R * 4; break;
+    case WB200_STATE_NO_SPEECH: *ptr = D->no_speech; *bytes = B * 4; break;
+    case WB200_STATE_LOGITS: *ptr = const_cast<float*>(D->logits_cur);
+      *bytes = (D->logits_row_div > 1 ? B : R) * static_cast<size_t>(D->ldv) * 4; break;
+    case WB200_STATE_TOP_VAL: *ptr = D->top_val; *bytes = R * K * 4; break;
+    case WB200_STATE_TOP_IDX: *ptr = D->top_idx; *bytes = R * K * 4; break;
+    case WB200_STATE_SOURCES: *ptr = D->sources; *bytes = R * 4; break;
+    case WB200_STATE_FIN_TOKENS: *ptr = D->fin_tokens; *bytes = B * mc * ctx * 4; break;
+    case WB200_STATE_FIN_LEN: *ptr = D->fin_len; *bytes = B * mc * 4; break;
+    case WB200_STATE_FIN_SCORE: *ptr = D->fin_score; *bytes = B * mc * 4; break;
+    case WB200_STATE_FIN_COUNT: *ptr = D->fin_count; *bytes = B * 4; break;
+    case WB200_STATE_DONE: *ptr = D->done_ptr; *bytes = 4; break;
+    default: return set_error(270, "decoder: unknown state id %d", what);
+  }
+  return 0;
+}
+
+}  // namespace wb

@@ -38,6 +38,7 @@ struct GemmParams {
   long long ldr;
   const float* pos;
   int gelu;
+  const int* skip_flag;
 };
 
 template <int BN>
@@ -60,6 +61,7 @@ gemm_tcgen05_kernel(const GemmParams p, const __grid_constant__ CUtensorMap mapA
                     const __grid_constant__ CUtensorMap mapA1,
                     const __grid_constant__ CUtensorMap mapB) {
   using Cfg = GemmCfg<BN>;
+  if (p.skip_flag && *p.skip_flag) return;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
                                              ~static_cast<uintptr_t>(1023));
@@ -325,6 +327,7 @@ int launch_linear(const LinearArgs& a, cudaStream_t s) {
   p.ldr = a.ldr;
   p.pos = a.pos;
   p.gelu = a.gelu;
+  p.skip_flag = a.skip_flag;
 
   // A maps: distinct base offsets -> at most two tensor maps
   CUtensorMap mapA[2];

@@ -38,12 +38,13 @@ struct LinearArgs {
   int gelu = 0;
   int out_f32 = 0;
   int block_n = 0;  // 0 = choose (256 for large M, 64 for skinny M)
+  const int* skip_flag = nullptr;  // optional device int: non-zero -> the kernel is a no-op
 };
 int launch_linear(const LinearArgs& a, cudaStream_t s);
 
 // Row LayerNorm in fp32 (reference model.py:39-41): y = (x - mean) / sqrt(var + 1e-5) * g + b
 int launch_layernorm(int dtype, const void* x, long long ldx, void* y, long long ldy, const float* g,
-                     const float* b, int rows, int d, cudaStream_t s);
+                     const float* b, int rows, int d, cudaStream_t s, const int* skip_flag = nullptr);
 
 // (B, C, T) fp32 -> (B, T, C) 16-bit.  Used to put the mel spectrogram time-major for the conv GEMM.
 int launch_transpose_to16(int dtype, const float* x, void* y, int B, int C, int T, cudaStream_t s);
@@ -51,5 +52,83 @@ int launch_transpose_to16(int dtype, const float* x, void* y, int B, int C, int 
 // Encoder (non-causal) multi-head attention over packed qkv [B*T, 3*d] -> out [B*T, d]
 int launch_enc_attention(int dtype, const void* qkv, void* out, int B, int T, int n_head,
                          cudaStream_t s);
+
+// ---- decoder attention (dec_attention.cu)
+int cross_attention_splits(int T);
+size_t cross_attention_partial_floats(int n_audio, int n_q, int n_head, int T);
+// q: [n_audio*n_q, d]; k/v: [n_audio, T, kv_ld] row stride kv_ld elements; out: [n_audio*n_q, d]
+int launch_cross_attention(int dtype, const void* q, const void* k, const void* v, void* out,
+                           float* partial, int* counters, const int* skip_flag, int n_audio, int n_q,
+                           int T, int n_head, int kv_ld, cudaStream_t s);
+// step mode (indir != null): one new position per row, appended to the cache; prefill mode
+// (indir == null): n_init positions per audio, causal, cache rows a*group.
+int launch_self_attention(int dtype, const void* qkv, void* kcache, void* vcache, void* out,
+                          const int* indir, const int* len_ptr, const int* skip_flag, int n_rows,
+                          int n_head, int max_ctx, int n_init, int group, cudaStream_t s);
+
+// ---- token selection (select.cu)
+struct FilterParams {
+  const float* logits;      // [n_logit_rows, ld]
+  long long ld;
+  int V;
+  int row_div;              // row r reads logits row r / row_div (G on the first step, else 1)
+  const int* tokens;        // [R, max_ctx] current sequences
+  int max_ctx;
+  const int* len_ptr;       // device: current length L
+  const int* skip_flag;
+  const uint32_t* suppress_mask;  // V bits: SuppressTokens set (+ no_timestamps when rules are on)
+  const uint32_t* blank_mask;     // V bits: SuppressBlank set (" " ids + eot)
+  int sample_begin, eot, timestamp_begin, max_initial_ts;  // max_initial_ts < 0: none
+  int suppress_blank, ts_rules;
+  int K;
+  float* top_val;           // [R, K] log-probabilities, best first
+  int* top_idx;             // [R, K]
+};
+struct GreedyParams {
+  int* tokens;            // [R, max_ctx], appended in place
+  int max_ctx, R, eot;
+  int* len_ptr;           // incremented
+  float* sum_logprobs;    // [R]
+  const float* top_val;   // [R, 1]
+  const int* top_idx;
+  int* done_flag;         // set when every row's last token is EOT
+  const int* skip_flag;
+};
+struct BeamParams {
+  const int* tokens_in;   // [R, max_ctx]
+  int* tokens_out;        // [R, max_ctx]
+  const int* indir_in;    // [R, max_ctx]
+  int* indir_out;
+  int max_ctx, n_audio, G, eot, max_candidates;
+  int* len_ptr;
+  float* sum_logprobs;    // [R] in/out
+  const float* top_val;   // [R, G+1]
+  const int* top_idx;
+  int* fin_tokens;        // [n_audio, max_candidates, max_ctx]
+  int* fin_len;           // [n_audio, max_candidates]
+  float* fin_score;       // [n_audio, max_candidates]
+  int* fin_count;         // [n_audio]
+  int* source_out;        // [R] parent row of each new beam (diagnostics / parity tests)
+  int* done_flag;
+  const int* skip_flag;
+  int* cur_out_ptr;       // device int: receives out_index (which ping-pong buffer is current)
+  int out_index;
+};
+int launch_filter_topk(const FilterParams& p, int R, cudaStream_t s);
+int launch_no_speech(const float* logits, long long ld, int V, int no_speech, float* out, int rows,
+                     cudaStream_t s);
+int launch_greedy_update(const GreedyParams& p, cudaStream_t s);
+int launch_beam_update(const BeamParams& p, cudaStream_t s);
+
+// ---- audio front-end (mel.cu)
+size_t log_mel_workspace_bytes(int n_audio);
+int launch_log_mel(const float* audio, int n_audio, long long n_samples, int n_mels, const float* filters,
+                   float* out, void* workspace, int per_row_max, cudaStream_t s);
+
+// ---- word timing (timing.cu)
+int launch_median_filter(const float* x, float* y, long long rows, int T, int width, cudaStream_t s);
+size_t dtw_workspace_bytes(int N, int M);
+int launch_dtw(const float* x, int N, int M, int* path, int* path_len, void* workspace, int tie_mode,
+               cudaStream_t s);
 
 }  // namespace wb

@@ -12,7 +12,9 @@ template <typename T, int MAX_STEPS>
 __global__ void __launch_bounds__(256) layernorm_kernel(const T* __restrict__ x, long long ldx,
                                                         T* __restrict__ y, long long ldy,
                                                         const float* __restrict__ g,
-                                                        const float* __restrict__ b, int rows, int d) {
+                                                        const float* __restrict__ b, int rows, int d,
+                                                        const int* skip_flag) {
+  if (skip_flag && *skip_flag) return;
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
   if (warp >= rows) return;
@@ -77,17 +79,17 @@ __global__ void __launch_bounds__(256) layernorm_kernel(const T* __restrict__ x,
 }
 
 int launch_layernorm(int dtype, const void* x, long long ldx, void* y, long long ldy, const float* g,
-                     const float* b, int rows, int d, cudaStream_t s) {
+                     const float* b, int rows, int d, cudaStream_t s, const int* skip_flag) {
   if (rows <= 0) return 0;
   if (d % 8 || d > 2048 || ldx % 8 || ldy % 8) return 20;
   const int threads = 256;
   const int blocks = (rows * 32 + threads - 1) / threads;
   if (dtype == DT_BF16)
     layernorm_kernel<__nv_bfloat16, 8><<<blocks, threads, 0, s>>>(
-        static_cast<const __nv_bfloat16*>(x), ldx, static_cast<__nv_bfloat16*>(y), ldy, g, b, rows, d);
+        static_cast<const __nv_bfloat16*>(x), ldx, static_cast<__nv_bfloat16*>(y), ldy, g, b, rows, d, skip_flag);
   else
     layernorm_kernel<__half, 8><<<blocks, threads, 0, s>>>(static_cast<const __half*>(x), ldx,
-                                                           static_cast<__half*>(y), ldy, g, b, rows, d);
+                                                           static_cast<__half*>(y), ldy, g, b, rows, d, skip_flag);
   count_launch();
   return cudaGetLastError() == cudaSuccess ? 0 : 21;
 }

@@ -1,0 +1,446 @@
+// Token selection on the device: the logit filters, log-softmax, top-k and the greedy / beam
+// bookkeeping of reference whisper/decoding.py:272-505, which the reference runs as Python loops
+// with a host sync per row and per beam candidate.
+//
+//   filter_topk_kernel : one CTA per row.  Applies SuppressBlank (decoding.py:423-430),
+//                        SuppressTokens (:433-438) and ApplyTimestampRules (:441-505) as masks
+//                        computed on the fly (the logits buffer is never rewritten), then the
+//                        log-softmax normaliser and the top-K (K = 1 greedy, beam+1 beam search)
+//                        by warp/CTA reductions.  Integer rules are exact; ties in the top-K go
+//                        to the lower token id.
+//   greedy_update_kernel / beam_update_kernel : one CTA.  Append the chosen tokens, update
+//                        sum_logprobs, EOT bookkeeping / finished-hypothesis store, beam parent
+//                        table (the kv-cache "reorder"), completion flag.
+#include "kernels.h"
+#include "ptx.cuh"
+
+namespace wb {
+
+constexpr int kSelThreads = 512;
+constexpr int kMaxTopK = 17;  // beam <= 16
+
+struct TopK {
+  float v[kMaxTopK];
+  int i[kMaxTopK];
+};
+
+// total order used everywhere: larger value first, then smaller index
+__device__ __forceinline__ bool better(float va, int ia, float vb, int ib) {
+  return va > vb || (va == vb && ia < ib);
+}
+
+__device__ __forceinline__ void lse_merge(float& m, float& s, float m2, float s2) {
+  if (m2 == -INFINITY) return;
+  if (m == -INFINITY) {
+    m = m2;
+    s = s2;
+    return;
+  }
+  if (m2 > m) {
+    s = s * __expf(m - m2) + s2;
+    m = m2;
+  } else {
+    s += s2 * __expf(m2 - m);
+  }
+}
+
+
+__global__ void __launch_bounds__(kSelThreads) filter_topk_kernel(const FilterParams p) {
+  if (p.skip_flag && *p.skip_flag) return;
+  const int r = blockIdx.x;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int L = *p.len_ptr;
+  const float* x = p.logits + static_cast<long long>(r / p.row_div) * p.ld;
+  const int tb = p.timestamp_begin;
+
+  __shared__ int s_rule[4];      // ts_lo (mask [tb, ts_lo)), mask_all_ts, mask_text_below_eot, first_step
+  __shared__ float s_red[kSelThreads / 32][6];
+  __shared__ float s_fin[4];
+  __shared__ TopK s_top[kSelThreads / 32];
+
+  const bool first = (L == p.sample_begin);
+  if (tid == 0) {
+    int ts_lo = tb, all_ts = 0, text_lt_eot = 0;
+    if (p.ts_rules) {
+      const int* row = p.tokens + static_cast<long long>(r) * p.max_ctx;
+      const int n = L - p.sample_begin;                       // sampled tokens so far
+      const bool last_ts = n >= 1 && row[L - 1] >= tb;        // decoding.py:461-463
+      const bool pen_ts = n < 2 || row[L - 2] >= tb;          // decoding.py:464-466
+      if (last_ts) {
+        if (pen_ts) all_ts = 1; else text_lt_eot = 1;         // decoding.py:468-472
+      }
+      int last_stamp = -1;                                    // decoding.py:474-484
+      for (int i = L - 1; i >= p.sample_begin; --i)
+        if (row[i] >= tb) { last_stamp = row[i]; break; }
+      if (last_stamp >= 0) ts_lo = (last_ts && !pen_ts) ? last_stamp : last_stamp + 1;
+    }
+    s_rule[0] = ts_lo;
+    s_rule[1] = all_ts;
+    s_rule[2] = text_lt_eot;
+  }
+  __syncthreads();
+  const int ts_lo = s_rule[0];
+  const bool all_ts = s_rule[1], text_lt_eot = s_rule[2];
+  const int ts_hi = (p.ts_rules && first && p.max_initial_ts >= 0) ? tb + p.max_initial_ts : p.V - 1;
+
+  auto masked = [&](int v) -> bool {
+    if ((p.suppress_mask[v >> 5] >> (v & 31)) & 1u) return true;
+    if (p.suppress_blank && first && ((p.blank_mask[v >> 5] >> (v & 31)) & 1u)) return true;
+    if (p.ts_rules) {
+      if (v >= tb) {
+        if (all_ts || v < ts_lo || v > ts_hi) return true;
+      } else {
+        if (first) return true;                               // decoding.py:486-488
+        if (text_lt_eot && v < p.eot) return true;
+      }
+    }
+    return false;
+  };
+
+  // ---- pass 1: (max, sum-exp) of the text part [0, tb) and the timestamp part [tb, V); text max
+  float m_txt = -INFINITY, s_txt = 0.f, m_ts = -INFINITY, s_ts = 0.f;
+  for (int v = tid; v < p.V; v += kSelThreads) {
+    if (masked(v)) continue;
+    const float val = x[v];
+    if (val == -INFINITY) continue;
+    if (v < tb) lse_merge(m_txt, s_txt, val, 1.f); else lse_merge(m_ts, s_ts, val, 1.f);
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    lse_merge(m_txt, s_txt, __shfl_xor_sync(0xffffffffu, m_txt, o), __shfl_xor_sync(0xffffffffu, s_txt, o));
+    lse_merge(m_ts, s_ts, __shfl_xor_sync(0xffffffffu, m_ts, o), __shfl_xor_sync(0xffffffffu, s_ts, o));
+  }
+  if (lane == 0) {
+    s_red[warp][0] = m_txt;
+    s_red[warp][1] = s_txt;
+    s_red[warp][2] = m_ts;
+    s_red[warp][3] = s_ts;
+  }
+  __syncthreads();
+  if (tid == 0) {
+    float a = -INFINITY, b = 0.f, c = -INFINITY, d = 0.f;
+    for (int w = 0; w < kSelThreads / 32; ++w) {
+      lse_merge(a, b, s_red[w][0], s_red[w][1]);
+      lse_merge(c, d, s_red[w][2], s_red[w][3]);
+    }
+    float mt = a, st = b;
+    lse_merge(mt, st, c, d);                                   // everything
+    const float lse_all = mt + __logf(st);
+    const float lse_ts = c == -INFINITY ? -INFINITY : c + __logf(d);
+    int drop_text = 0;
+    if (p.ts_rules) {
+      // decoding.py:498-505: logsumexp(logprobs[tb:]) > max(logprobs[:tb])
+      const float ts_lp = lse_ts - lse_all;
+      const float txt_lp = a - lse_all;
+      drop_text = ts_lp > txt_lp;
+    }
+    s_fin[0] = drop_text ? lse_ts : lse_all;
+    s_rule[3] = drop_text;
+  }
+  __syncthreads();
+  const float lse = s_fin[0];
+  const bool drop_text = s_rule[3];
+
+  // ---- pass 2: top-K of the surviving logits
+  TopK mine;
+#pragma unroll
+  for (int k = 0; k < kMaxTopK; ++k) {
+    mine.v[k] = -INFINITY;
+    mine.i[k] = 0x7fffffff;
+  }
+  const int K = p.K;
+  for (int v = tid; v < p.V; v += kSelThreads) {
+    float val = x[v];
+    if (masked(v) || (drop_text && v < tb)) val = -INFINITY;
+    if (better(val, v, mine.v[K - 1], mine.i[K - 1])) {
+      int k = K - 1;
+      while (k > 0 && better(val, v, mine.v[k - 1], mine.i[k - 1])) {
+        mine.v[k] = mine.v[k - 1];
+        mine.i[k] = mine.i[k - 1];
+        --k;
+      }
+      mine.v[k] = val;
+      mine.i[k] = v;
+    }
+  }
+  // warp merge: K rounds of "pop the best head among lanes"
+  TopK wtop;
+  {
+    int head = 0;
+    for (int k = 0; k < K; ++k) {
+      float bv = head < K ? mine.v[head] : -INFINITY;
+      int bi = head < K ? mine.i[head] : 0x7fffffff;
+      float cv = bv;
+      int ci = bi;
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        const float ov = __shfl_xor_sync(0xffffffffu, cv, o);
+        const int oi = __shfl_xor_sync(0xffffffffu, ci, o);
+        if (better(ov, oi, cv, ci)) {
+          cv = ov;
+          ci = oi;
+        }
+      }
+      if (ci == bi && cv == bv && head < K) ++head;             // this lane's head was taken
+      wtop.v[k] = cv;
+      wtop.i[k] = ci;
+    }
+  }
+  if (lane == 0) s_top[warp] = wtop;
+  __syncthreads();
+  if (warp == 0) {
+    // lane w holds warp w's sorted list; same pop-the-best merge across lanes
+    TopK l;
+    if (lane < kSelThreads / 32) l = s_top[lane];
+    int head = 0;
+    const bool have = lane < kSelThreads / 32;
+    for (int k = 0; k < K; ++k) {
+      float bv = (have && head < K) ? l.v[head] : -INFINITY;
+      int bi = (have && head < K) ? l.i[head] : 0x7fffffff;
+      float cv = bv;
+      int ci = bi;
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        const float ov = __shfl_xor_sync(0xffffffffu, cv, o);
+        const int oi = __shfl_xor_sync(0xffffffffu, ci, o);
+        if (better(ov, oi, cv, ci)) {
+          cv = ov;
+          ci = oi;
+        }
+      }
+      if (have && head < K && ci == bi && cv == bv) ++head;
+      if (lane == 0) {
+        p.top_val[static_cast<long long>(r) * K + k] = cv - lse;   // log-probability
+        p.top_idx[static_cast<long long>(r) * K + k] = ci;
+      }
+    }
+  }
+}
+
+// -------------------------------------------------------------------------------------------------
+// no-speech probability at the <|startoftranscript|> position (decoding.py:689-693)
+// -------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kSelThreads) no_speech_kernel(const float* logits, long long ld, int V,
+                                                                int no_speech, float* out) {
+  const float* x = logits + static_cast<long long>(blockIdx.x) * ld;
+  __shared__ float s_red[kSelThreads / 32][2];
+  float m = -INFINITY, s = 0.f;
+  for (int v = threadIdx.x; v < V; v += kSelThreads) lse_merge(m, s, x[v], 1.f);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1)
+    lse_merge(m, s, __shfl_xor_sync(0xffffffffu, m, o), __shfl_xor_sync(0xffffffffu, s, o));
+  if ((threadIdx.x & 31) == 0) {
+    s_red[threadIdx.x >> 5][0] = m;
+    s_red[threadIdx.x >> 5][1] = s;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float a = -INFINITY, b = 0.f;
+    for (int w = 0; w < kSelThreads / 32; ++w) lse_merge(a, b, s_red[w][0], s_red[w][1]);
+    out[blockIdx.x] = __expf(x[no_speech] - a) / b;
+  }
+}
+
+// -------------------------------------------------------------------------------------------------
+// greedy update (decoding.py:277-293, temperature 0)
+// -------------------------------------------------------------------------------------------------
+
+__global__ void __launch_bounds__(1024) greedy_update_kernel(const GreedyParams p) {
+  if (p.skip_flag && *p.skip_flag) return;
+  __shared__ int s_all;
+  if (threadIdx.x == 0) s_all = 1;
+  __syncthreads();
+  const int L = *p.len_ptr;
+  int all_eot = 1;
+  for (int r = threadIdx.x; r < p.R; r += blockDim.x) {
+    int* row = p.tokens + static_cast<long long>(r) * p.max_ctx;
+    const int last = row[L - 1];
+    int nxt = p.top_idx[r];
+    if (last != p.eot) p.sum_logprobs[r] += p.top_val[r];      // decoding.py:287
+    else nxt = p.eot;                                          // decoding.py:289
+    row[L] = nxt;
+    if (nxt != p.eot) all_eot = 0;
+  }
+  if (!all_eot) atomicAnd(&s_all, 0);
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    *p.len_ptr = L + 1;
+    if (s_all) *p.done_flag = 1;
+  }
+}
+
+// -------------------------------------------------------------------------------------------------
+// beam-search update (decoding.py:323-382); one warp per audio, lane 0 runs the (tiny) sequential
+// candidate logic, all lanes help with prefix comparison and row copies.
+// -------------------------------------------------------------------------------------------------
+
+constexpr int kMaxBeam = 16;
+constexpr int kMaxCand = kMaxBeam * (kMaxBeam + 1);
+
+constexpr int kBeamWarps = 8;
+
+__global__ void __launch_bounds__(kBeamWarps * 32) beam_update_kernel(const BeamParams p) {
+  if (p.skip_flag && *p.skip_flag) return;
+  __shared__ int s_all_done;
+  __shared__ float s_score[kBeamWarps][kMaxCand];
+  __shared__ short s_tok_row[kBeamWarps][kMaxCand];   // owning beam j
+  __shared__ int s_tok[kBeamWarps][kMaxCand];
+  __shared__ short s_order[kBeamWarps][kMaxCand];
+  __shared__ unsigned char s_same[kBeamWarps][kMaxBeam][kMaxBeam];
+  __shared__ int s_newsrc[kBeamWarps][kMaxBeam];
+  __shared__ int s_newtok[kBeamWarps][kMaxBeam];
+  if (threadIdx.x == 0) s_all_done = 1;
+  __syncthreads();
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int n_warps = blockDim.x >> 5;
+  const int L = *p.len_ptr;
+  const int G = p.G, K = G + 1, N = G * K;
+  for (int a = warp; a < p.n_audio; a += n_warps) {
+    const int r0 = a * G;
+    // prefix equality between beams (needed for the dict de-duplication of decoding.py:344-346)
+    for (int pair = 0; pair < G * G; ++pair) {
+      const int j1 = pair / G, j2 = pair % G;
+      if (j2 <= j1) {
+        if (lane == 0) s_same[warp][j1][j2] = (j1 == j2);
+        continue;
+      }
+      const int* a1 = p.tokens_in + static_cast<long long>(r0 + j1) * p.max_ctx;
+      const int* a2 = p.tokens_in + static_cast<long long>(r0 + j2) * p.max_ctx;
+      int diff = 0;
+      for (int i = lane; i < L; i += 32) diff |= (a1[i] != a2[i]);
+      diff = __any_sync(0xffffffffu, diff);
+      if (lane == 0) s_same[warp][j1][j2] = !diff;
+    }
+    __syncwarp();
+    int n_kept = 0;
+    if (lane == 0) {
+      // candidates in insertion order (j, then top-k rank); score = fp32(sum_lp + lp)
+      for (int c = 0; c < N; ++c) {
+        const int j = c / K;
+        s_score[warp][c] = p.sum_logprobs[r0 + j] + p.top_val[static_cast<long long>(r0 + j) * K + c % K];
+        s_tok[warp][c] = p.top_idx[static_cast<long long>(r0 + j) * K + c % K];
+        s_tok_row[warp][c] = static_cast<short>(j);
+      }
+      // dict semantics: a later duplicate (same prefix, same token) overwrites value and source but
+      // keeps the FIRST insertion position.  dead[c] marks removed later duplicates.
+      bool dead[kMaxCand];
+      for (int c = 0; c < N; ++c) dead[c] = false;
+      for (int c = 0; c < N; ++c) {
+        if (dead[c]) continue;
+        for (int c2 = c + 1; c2 < N; ++c2) {
+          if (dead[c2]) continue;
+          const int j1 = s_tok_row[warp][c], j2 = s_tok_row[warp][c2];
+          const int lo = j1 < j2 ? j1 : j2, hi = j1 < j2 ? j2 : j1;
+          const bool same_prefix = (lo == hi) ? true : s_same[warp][lo][hi];
+          if (same_prefix && s_tok[warp][c] == s_tok[warp][c2] && j1 != j2) {
+            s_score[warp][c] = s_score[warp][c2];       // last writer's value ...
+            s_tok_row[warp][c] = s_tok_row[warp][c2];   // ... and source
+            dead[c2] = true;
+          }
+        }
+      }
+      // stable descending sort of the live candidates (insertion sort; N <= 272)
+      int n_live = 0;
+      for (int c = 0; c < N; ++c) {
+        if (dead[c]) continue;
+        int pos = n_live++;
+        while (pos > 0 && s_score[warp][s_order[warp][pos - 1]] < s_score[warp][c]) {
+          s_order[warp][pos] = s_order[warp][pos - 1];
+          --pos;
+        }
+        s_order[warp][pos] = static_cast<short>(c);
+      }
+      // decoding.py:349-360: walk the ranking; EOT candidates met before the beam is full are finished
+      int fin_n = p.fin_count[a];
+      for (int q = 0; q < n_live && n_kept < G; ++q) {
+        const int c = s_order[warp][q];
+        const int tok = s_tok[warp][c];
+        const int src = r0 + s_tok_row[warp][c];
+        if (tok == p.eot) {
+          if (fin_n < p.max_candidates) {                    // decoding.py:372-375
+            const long long slot = static_cast<long long>(a) * p.max_candidates + fin_n;
+            p.fin_len[slot] = -(src + 1);                    // marks "copy prefix of row src" for the lanes below
+            p.fin_score[slot] = s_score[warp][c];
+            ++fin_n;
+          }
+        } else {
+          s_newsrc[warp][n_kept] = src;
+          s_newtok[warp][n_kept] = tok;
+          p.sum_logprobs[r0 + n_kept] = s_score[warp][c];    // decoding.py:354 (safe: scores were read above)
+          ++n_kept;
+        }
+      }
+      p.fin_count[a] = fin_n;
+      if (fin_n < p.max_candidates) atomicAnd(&s_all_done, 0);
+    }
+    __syncwarp();
+    // materialise newly finished hypotheses: prefix of the source row + EOT
+    for (int f = 0; f < p.max_candidates; ++f) {
+      const long long slot = static_cast<long long>(a) * p.max_candidates + f;
+      const int mark = p.fin_len[slot];
+      if (mark < 0) {
+        const int src = -mark - 1;
+        const int* srow = p.tokens_in + static_cast<long long>(src) * p.max_ctx;
+        int* drow = p.fin_tokens + slot * p.max_ctx;
+        for (int i = lane; i < L; i += 32) drow[i] = srow[i];
+        if (lane == 0) {
+          drow[L] = p.eot;
+          p.fin_len[slot] = L + 1;
+        }
+        __syncwarp();
+      }
+    }
+    // new beams: token rows and the kv-cache parent table
+    for (int j = 0; j < G; ++j) {
+      const int src = s_newsrc[warp][j];
+      const int* srow = p.tokens_in + static_cast<long long>(src) * p.max_ctx;
+      const int* sind = p.indir_in + static_cast<long long>(src) * p.max_ctx;
+      int* drow = p.tokens_out + static_cast<long long>(r0 + j) * p.max_ctx;
+      int* dind = p.indir_out + static_cast<long long>(r0 + j) * p.max_ctx;
+      for (int i = lane; i < L; i += 32) {
+        drow[i] = srow[i];
+        dind[i] = (i == L - 1) ? src : sind[i];               // position L-1 was just written by row src
+      }
+      if (lane == 0) {
+        drow[L] = s_newtok[warp][j];
+        p.source_out[r0 + j] = src;
+      }
+    }
+    __syncwarp();
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    *p.len_ptr = L + 1;
+    *p.cur_out_ptr = p.out_index;
+    if (s_all_done) *p.done_flag = 1;                          // decoding.py:377-381
+  }
+}
+
+// -------------------------------------------------------------------------------------------------
+// launchers
+// -------------------------------------------------------------------------------------------------
+int launch_filter_topk(const FilterParams& p, int R, cudaStream_t s) {
+  if (p.K < 1 || p.K > kMaxTopK) return 50;
+  filter_topk_kernel<<<R, kSelThreads, 0, s>>>(p);
+  count_launch();
+  return cudaGetLastError() == cudaSuccess ? 0 : 51;
+}
+int launch_no_speech(const float* logits, long long ld, int V, int no_speech, float* out, int rows,
+                     cudaStream_t s) {
+  no_speech_kernel<<<rows, kSelThreads, 0, s>>>(logits, ld, V, no_speech, out);
+  count_launch();
+  return cudaGetLastError() == cudaSuccess ? 0 : 52;
+}
+int launch_greedy_update(const GreedyParams& p, cudaStream_t s) {
+  greedy_update_kernel<<<1, 1024, 0, s>>>(p);
+  count_launch();
+  return cudaGetLastError() == cudaSuccess ? 0 : 53;
+}
+int launch_beam_update(const BeamParams& p, cudaStream_t s) {
+  if (p.G > kMaxBeam) return 54;
+  beam_update_kernel<<<1, kBeamWarps * 32, 0, s>>>(p);
+  count_launch();
+  return cudaGetLastError() == cudaSuccess ? 0 : 55;
+}
+
+}  // namespace wb
