@@ -34,6 +34,19 @@ const char* wb200_last_error(void);
 /* number of kernels this library has launched since load (bench.py's gpu_launches) */
 uint64_t wb200_launch_count(void);
 
+/* Per-kernel device timing for roofline reports: after wb200_profile_enable(id) every launch of
+ * that kernel is bracketed by CUDA events on its own stream; wb200_profile_read() waits for them,
+ * returns the summed duration and launch count, and clears the record.  id 0 disables. */
+#define WB200_KERNEL_CROSS_ATTENTION 1
+#define WB200_KERNEL_SELF_ATTENTION 2
+#define WB200_KERNEL_GEMM 3
+#define WB200_KERNEL_ENCODER_ATTENTION 4
+#define WB200_KERNEL_LAYERNORM 5
+#define WB200_KERNEL_SELECT 6
+#define WB200_KERNEL_LOG_MEL 7
+int wb200_profile_enable(int kernel_id);
+int wb200_profile_read(double* total_ms, int64_t* launches);
+
 /* ---------------------------------------------------------------------------------------------
  * primitive operators (each is a hand-written sm_100a kernel; exposed for parity tests)
  * ------------------------------------------------------------------------------------------- */

@@ -277,8 +277,11 @@ def suppress_list(ids: TokenIds, opt: Options) -> Tuple[int, ...]:
 
 
 def decode(W: M.Weights, dims: Dict[str, int], mel_or_features: torch.Tensor, opt: Options = Options(),
-           record: Optional[dict] = None, max_steps: Optional[int] = None) -> List[Result]:
-    """DecodingTask.run (decoding.py:713-789) for a batch; beam search is per audio."""
+           record: Optional[dict] = None, max_steps: Optional[int] = None,
+           timings: Optional[list] = None) -> List[Result]:
+    """DecodingTask.run (decoding.py:713-789) for a batch; beam search is per audio.
+    `timings`, if given, receives the wall-clock seconds of every loop iteration (bench.py's CPU baseline)."""
+    import time as _time
     ids = token_ids(dims["n_vocab"])
     n_ctx = dims["n_text_ctx"]
     G = opt.beam_size or 1
@@ -308,6 +311,7 @@ def decode(W: M.Weights, dims: Dict[str, int], mel_or_features: torch.Tensor, op
     margins: List[List[float]] = [[] for _ in range(R)]
     steps = sample_len if max_steps is None else min(sample_len, max_steps)
     for i in range(steps):                                                   # decoding.py:686
+        _t0 = _time.perf_counter()
         new = torch.tensor([t[cache.length:] for t in tokens])               # decoding.py:159-161
         logits_all = M.decoder_forward(W, dims, new, xa, cache)
         if i == 0:                                                           # decoding.py:689-693
@@ -339,6 +343,8 @@ def decode(W: M.Weights, dims: Dict[str, int], mel_or_features: torch.Tensor, op
         if record is not None:
             record.setdefault("tokens_out", []).append([list(t) for t in tokens])
             record.setdefault("sum_logprobs_out", []).append(sum_lp.clone())
+        if timings is not None:
+            timings.append(_time.perf_counter() - _t0)
         if completed or len(tokens[0]) > n_ctx:                              # decoding.py:705
             break
     grouped = [[tokens[a * G + j] for j in range(G)] for a in range(B)]

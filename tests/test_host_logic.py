@@ -1,0 +1,167 @@
+"""CPU: host-side logic of the product package (no GPU, no kernels): option handling, initial tokens,
+suppress lists, hypothesis finalisation / ranking, window splitting, padding, id tables."""
+import json
+import os
+from types import SimpleNamespace
+
+import numpy as np
+import pytest
+import torch
+
+from helpers import GOLD
+
+
+def fake_model(name):
+    from whisper_b200 import synthetic
+    from whisper_b200.model import ModelDimensions
+
+    dims = ModelDimensions(**synthetic.dims_dict(name))
+    return SimpleNamespace(dims=dims, is_multilingual=dims.n_vocab >= 51865,
+                           num_languages=dims.n_vocab - 51765 - int(dims.n_vocab >= 51865),
+                           device=torch.device("cpu"), dtype=torch.float16)
+
+
+def test_mel_filterbank_regenerated_bit_exact():
+    from whisper_b200.audio import _slaney_mel_filterbank
+
+    g = np.load(os.path.join(GOLD, "mel_filters.npz"))
+    for n in (80, 128):
+        assert np.array_equal(_slaney_mel_filterbank(n), g[f"mel_{n}"])
+
+
+def test_tokenizer_ids_match_reference_table():
+    from whisper_b200.tokenizer import get_tokenizer
+
+    with open(os.path.join(GOLD, "token_ids.json")) as f:
+        table = json.load(f)
+    for n_vocab, spec in table["specials"].items():
+        n_vocab = int(n_vocab)
+        multi = n_vocab >= 51865
+        tk = get_tokenizer(multi, num_languages=n_vocab - 51765 - int(multi), language="en", task="transcribe")
+        for k in ("eot", "sot", "translate", "transcribe", "sot_lm", "sot_prev", "no_speech", "no_timestamps",
+                  "timestamp_begin"):
+            assert getattr(tk, k) == spec[k], (n_vocab, k)
+        assert list(tk.sot_sequence) == spec["sot_sequence"]
+        assert tk.n_vocab == n_vocab
+        assert sorted(tk.all_language_tokens) == sorted(spec["all_language_tokens"])
+        assert len(tk.non_speech_tokens) == spec["n_non_speech"]
+
+
+@pytest.mark.parametrize("name", ["test-en", "test-multi"])
+@pytest.mark.parametrize("opts", [
+    dict(), dict(without_timestamps=True), dict(prompt=list(range(1000, 1300))), dict(prefix=[5, 6, 7], sample_len=100),
+    dict(suppress_tokens="", suppress_blank=False), dict(suppress_tokens="-1,17,23"), dict(beam_size=5, patience=2.0),
+    dict(max_initial_timestamp=None), dict(prompt=[1, 2, 3], prefix=[9, 9]),
+])
+def test_task_setup_matches_oracle(name, opts):
+    from oracle import decoding as OD
+    from whisper_b200.decoding import DecodingOptions, DecodingTask
+
+    model = fake_model(name)
+    task = DecodingTask(model, DecodingOptions(language="en", **opts))
+    o = dict(opts)
+    st = o.get("suppress_tokens", "-1")
+    if isinstance(st, str):
+        o["suppress_tokens"] = tuple(int(t) for t in st.split(",")) if st else ()
+    oopt = OD.Options(**o)
+    ids = OD.token_ids(model.dims.n_vocab)
+    sample_len = oopt.sample_len or model.dims.n_text_ctx // 2
+    assert task.initial_tokens == OD.initial_tokens(ids, oopt, model.dims.n_text_ctx, sample_len)
+    assert tuple(task.suppress) == (OD.suppress_list(ids, oopt) if oopt.suppress_tokens else ())
+    cfg = task.session_config(3)
+    assert cfg["n_init"] == len(task.initial_tokens) and cfg["sot_index"] == task.initial_tokens.index(ids.sot)
+    assert cfg["timestamp_rules"] == int(not oopt.without_timestamps)
+    if oopt.beam_size:
+        assert cfg["max_candidates"] == round(oopt.beam_size * (oopt.patience or 1.0)) and cfg["n_group"] == oopt.beam_size
+    exp_mits = -1
+    if not oopt.without_timestamps and oopt.max_initial_timestamp:
+        exp_mits = round(oopt.max_initial_timestamp / 0.02)
+    assert cfg["max_initial_timestamp_index"] == exp_mits
+
+
+def test_option_validation_errors():
+    from whisper_b200.decoding import DecodingOptions, DecodingTask
+
+    m = fake_model("test-en")
+    for bad in (dict(beam_size=5, best_of=5), dict(best_of=3), dict(patience=1.0), dict(length_penalty=1.5)):
+        with pytest.raises(ValueError):                        # decoding.py:572-585
+            DecodingTask(m, DecodingOptions(language="en", **bad))
+    with pytest.raises(NotImplementedError):
+        DecodingTask(m, DecodingOptions(language="en", temperature=0.4))
+
+
+def test_finalize_and_rank_match_oracle():
+    from oracle import decoding as OD
+    from whisper_b200.decoding import DecodingOptions, DecodingTask
+
+    m = fake_model("test-en")
+    rng = np.random.RandomState(3)
+    for alpha in (None, 0.6):
+        task = DecodingTask(m, DecodingOptions(language="en", beam_size=4, length_penalty=alpha))
+        ids = OD.token_ids(m.dims.n_vocab)
+        B, G, L, ctx, mc = 3, 4, 9, m.dims.n_text_ctx, 4
+        tokens = rng.randint(0, 50000, size=(B, G, L))
+        lp = rng.randn(B, G).astype(np.float32)
+        fin_count = np.array([0, 2, 4])
+        fin_tokens = np.zeros((B, mc, ctx), dtype=np.int32)
+        fin_len = np.zeros((B, mc), dtype=np.int32)
+        fin_score = rng.randn(B, mc).astype(np.float32)
+        beam = OD.BeamState(G, ids.eot, None)
+        beam.finished = [dict() for _ in range(B)]
+        for a in range(B):
+            for k in range(fin_count[a]):
+                n = 4 + k
+                seq = rng.randint(0, 50000, size=n).tolist() + [ids.eot]
+                fin_tokens[a, k, : n + 1] = seq
+                fin_len[a, k] = n + 1
+                beam.finished[a][tuple(seq)] = float(fin_score[a, k])
+        cands, scores = task._finalize(tokens, lp, (fin_tokens, fin_len, fin_score, fin_count))
+        o_c, o_s = beam.finalize([[tokens[a, j].tolist() for j in range(G)] for a in range(B)], torch.from_numpy(lp))
+        assert cands == o_c and scores == o_s
+        sb = 1
+        sliced = [[s[sb: s.index(ids.eot)] for s in grp] for grp in cands]
+        assert task._rank(sliced, scores) == OD.rank(sliced, scores, alpha)
+
+
+def test_pad_or_trim():
+    from oracle import audio as OA
+    from whisper_b200.audio import pad_or_trim
+
+    x = np.arange(10, dtype=np.float32).reshape(2, 5)
+    for n in (3, 5, 8):
+        assert np.array_equal(pad_or_trim(x, n), OA.pad_or_trim(x, n))
+        assert np.array_equal(pad_or_trim(torch.from_numpy(x), n).numpy(), OA.pad_or_trim(x, n))
+        assert np.array_equal(pad_or_trim(torch.from_numpy(x), n, axis=0).numpy(), OA.pad_or_trim(x, n, axis=0))
+
+
+def test_window_splitting_rules():
+    """transcribe.py:339-399 on handcrafted token rows (tb = timestamp_begin)."""
+    from whisper_b200.decoding import DecodingResult
+    from whisper_b200.tokenizer import get_tokenizer
+    from whisper_b200.transcribe import _WindowLoop
+
+    tk = get_tokenizer(False)
+    tb = tk.timestamp_begin
+    loop = _WindowLoop.__new__(_WindowLoop)
+    loop.tokenizer, loop.input_stride, loop.time_precision = tk, 2, 0.02
+
+    def res(tokens):
+        return DecodingResult(audio_features=None, language="en", tokens=tokens, temperature=0.0, avg_logprob=-0.1,
+                              compression_ratio=1.0, no_speech_prob=0.0)
+
+    # two complete segments then an unfinished one: seek advances to the last consecutive pair's timestamp
+    toks = [tb, 11, 12, tb + 100, tb + 100, 13, tb + 250, tb + 250, 14]
+    segs, seek = loop.split_window(0, 3000, 30.0, res(toks))
+    assert [s["tokens"] for s in segs] == [[tb, 11, 12, tb + 100], [tb + 100, 13, tb + 250]]
+    assert (segs[0]["start"], segs[0]["end"]) == (0.0, 2.0) and segs[1]["end"] == 5.0
+    assert seek == 250 * 2
+    # single timestamp ending: the tail is kept and the whole window is consumed
+    toks = [tb, 11, tb + 100, tb + 100, 12, tb + 400]
+    segs, seek = loop.split_window(1000, 3000, 30.0, res(toks))
+    assert [s["tokens"] for s in segs] == [[tb, 11, tb + 100], [tb + 100, 12, tb + 400]] and seek == 4000
+    assert segs[1]["start"] == pytest.approx(10.0 + 2.0) and segs[1]["end"] == pytest.approx(10.0 + 8.0)
+    # no consecutive timestamps: one segment, duration from the last timestamp
+    segs, seek = loop.split_window(0, 2000, 20.0, res([tb, 11, 12, tb + 300]))
+    assert len(segs) == 1 and segs[0]["end"] == pytest.approx(6.0) and seek == 2000
+    segs, seek = loop.split_window(0, 2000, 20.0, res([11, 12]))
+    assert segs[0]["end"] == pytest.approx(20.0)

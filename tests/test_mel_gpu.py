@@ -9,7 +9,11 @@ import torch
 from helpers import GOLD
 
 pytestmark = pytest.mark.gpu
-TOL = 1e-4
+TOL = 1e-4          # against exact arithmetic (the fp64-internal oracle)
+# The reference's own fp32 torch.stft pipeline sits up to 9e-5 from exact arithmetic on the quiet bins of
+# the "speechlike" signal (tests/test_oracle_golden.py measures oracle-vs-reference), so two independent
+# fp32 pipelines can differ by the sum of both errors.
+TOL_VS_FP32_REFERENCE = 2e-4
 
 
 @pytest.mark.parametrize("kind", ["noise", "speechlike"])
@@ -25,10 +29,13 @@ def test_log_mel_vs_reference_golden(kind, n_mels):
     for key, sl in ((f"batch_{n_mels}", np.s_[:, :, ::8]), (f"batch_{n_mels}_head", np.s_[:, :, :64]),
                     (f"batch_{n_mels}_tail", np.s_[:, :, -64:])):
         err = np.abs(mel[sl] - g[key]).max()
-        assert err < TOL, f"{key}: max abs err {err}"
+        assert err < TOL_VS_FP32_REFERENCE, f"{key}: max abs err {err}"
     single = wb.log_mel_spectrogram(audio[1, :160000], n_mels, padding=480000).cpu().numpy()   # transcribe.py:139
     assert tuple(single.shape) == tuple(g[f"single_{n_mels}_shape"])
-    assert np.abs(single[:, ::8] - g[f"single_{n_mels}"]).max() < TOL
+    assert np.abs(single[:, ::8] - g[f"single_{n_mels}"]).max() < TOL_VS_FP32_REFERENCE
+    from oracle import audio as OA
+
+    assert np.abs(mel - OA.log_mel_spectrogram(audio, n_mels)).max() < TOL      # vs exact arithmetic
 
 
 @pytest.mark.parametrize("n_samples", [201, 1000, 16000, 47999, 160000 + 37])

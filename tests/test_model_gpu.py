@@ -23,7 +23,8 @@ DTYPES = [torch.float16, torch.bfloat16]
 # max |logit error| allowed under teacher forcing, and the decision-margin gate for e2e equality.
 # logits of the synthetic models have std ~8-40; 16-bit activations give ~2^-11 (fp16) / 2^-8 (bf16)
 # relative error per layer.
-LOGIT_TOL = {torch.float16: 0.06, torch.bfloat16: 0.5}
+# LOGIT_TOL is relative to the largest |logit| of the step (the synthetic models have heavy-tailed logits)
+LOGIT_TOL = {torch.float16: 2.5e-3, torch.bfloat16: 2.5e-2}
 TAU = {torch.float16: 0.12, torch.bfloat16: 1.0}
 FEAT_TOL = {torch.float16: 0.02, torch.bfloat16: 0.12}
 
@@ -83,7 +84,8 @@ def test_decoder_logits_teacher_forced(name, dtype):
         for i in range(len(rec["raw_logits"])):
             got = sess.get_logits(2).float().cpu()
             ref = rec["raw_logits"][i]
-            err = float((got - ref).abs().max())
+            assert bool(torch.isfinite(got).all()), f"step {i}: non-finite logits"
+            err = float((got - ref).abs().max() / ref.abs().max())
             worst = max(worst, err)
             top2 = ref.topk(2, dim=-1)
             margin = top2.values[:, 0] - top2.values[:, 1]
@@ -93,8 +95,9 @@ def test_decoder_logits_teacher_forced(name, dtype):
                 nxt = [t[-1] for t in rec["tokens_out"][i]]
                 sess.force_tokens(nxt)
                 sess.step()
-        print(f"{name} {dtype}: teacher-forced max |logit err| = {worst:.4f} (logit std {float(ref.std()):.2f})")
-        assert worst < LOGIT_TOL[dtype] * max(1.0, float(ref.std()) / 8.0)
+        print(f"{name} {dtype}: teacher-forced max |logit err| / max|logit| = {worst:.5f} "
+              f"(logit std {float(ref.std()):.2f}, max {float(ref.abs().max()):.1f})")
+        assert worst < LOGIT_TOL[dtype]
         ns = sess.get("no_speech").cpu().numpy()
         ref_ns = np.array([r["no_speech_prob"] for r in meta["decode"]["greedy"]["results"]])
         assert np.allclose(ns, ref_ns, rtol=0.2, atol=1e-12)
@@ -184,6 +187,7 @@ def test_decode_end_to_end(name, case, dtype):
     beam = c["options"].get("beam_size")
     for a, (g, ref) in enumerate(zip(got, c["results"])):
         assert o_res[a].tokens == ref["tokens"]                      # the oracle itself is pinned
+        assert np.isfinite(g.avg_logprob), f"audio {a}: non-finite avg_logprob, tokens {g.tokens[:8]}"
         if beam:
             risky = rec["beam_min_gap"] < TAU[dtype]
             if not risky:

@@ -8,8 +8,22 @@
 #include "engine.h"
 #include "kernels.h"
 
+#include <vector>
+
 namespace wb {
 unsigned long long g_launch_count = 0;
+int g_profile_kernel = 0;
+static std::vector<cudaEvent_t> g_prof_events;   // begin/end pairs
+static size_t g_prof_used = 0;
+void profile_mark(cudaStream_t s, bool begin) {
+  (void)begin;
+  if (g_prof_used == g_prof_events.size()) {
+    cudaEvent_t e;
+    if (cudaEventCreate(&e) != cudaSuccess) return;
+    g_prof_events.push_back(e);
+  }
+  cudaEventRecord(g_prof_events[g_prof_used++], s);
+}
 static thread_local char g_err[512] = "";
 int set_error(int code, const char* fmt, ...) {
   va_list ap;
@@ -30,6 +44,29 @@ extern "C" {
 const char* wb200_version(void) { return "whisper_b200 0.1 (sm_100a)"; }
 const char* wb200_last_error(void) { return g_err; }
 uint64_t wb200_launch_count(void) { return g_launch_count; }
+
+int wb200_profile_enable(int kernel_id) {
+  g_profile_kernel = kernel_id;
+  g_prof_used = 0;
+  return 0;
+}
+
+int wb200_profile_read(double* total_ms, int64_t* launches) {
+  double tot = 0.0;
+  int64_t n = 0;
+  for (size_t i = 0; i + 1 < g_prof_used; i += 2) {
+    float ms = 0.f;
+    if (cudaEventSynchronize(g_prof_events[i + 1]) != cudaSuccess) return set_error(140, "profile: event sync failed");
+    if (cudaEventElapsedTime(&ms, g_prof_events[i], g_prof_events[i + 1]) != cudaSuccess)
+      return set_error(141, "profile: elapsed time failed");
+    tot += ms;
+    ++n;
+  }
+  g_prof_used = 0;
+  if (total_ms) *total_ms = tot;
+  if (launches) *launches = n;
+  return 0;
+}
 
 int wb200_linear(int dtype, int M, int N, int K, const void* A, int64_t lda, const void* W,
                  int64_t ldw, const void* bias, const void* residual, int64_t ldr, void* C,

@@ -478,6 +478,7 @@ int launch_cross_attention(int dtype, const void* q, const void* k, const void* 
   p.splits = cross_attention_splits(T);
   p.keys_per_split = ((T + p.splits - 1) / p.splits + 63) / 64 * 64;
   dim3 grid(p.splits, n_head, n_audio * p.q_tiles);
+  ProfileScope prof(PROF_CROSS_ATTN, s);
   static bool attr[2] = {false, false};
   if (dtype == DT_BF16) {
     auto kern = cross_attention_kernel<__nv_bfloat16>;
@@ -515,6 +516,7 @@ int launch_self_attention(int dtype, const void* qkv, void* kcache, void* vcache
   p.n_init = n_init > 0 ? n_init : 1;
   p.group = group;
   dim3 grid(n_head, n_rows);
+  ProfileScope prof(PROF_SELF_ATTN, s);
   static bool attr[2] = {false, false};
   if (dtype == DT_BF16) {
     if (!indir) {

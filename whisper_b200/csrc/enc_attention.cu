@@ -276,6 +276,7 @@ int launch_enc_attention(int dtype, const void* qkv, void* out, int B, int T, in
   if (reinterpret_cast<uintptr_t>(qkv) & 15) return 30;
   if (make_tmap_16bit(&map, dtype, qkv, 3, dims, strides, box)) return 31;
   dim3 grid((T + 255) / 256, n_head, B);
+  ProfileScope prof(PROF_ENC_ATTN, s);
   static bool attr[2] = {false, false};
   if (dtype == DT_BF16) {
     auto kern = enc_attention_kernel<__nv_bfloat16>;

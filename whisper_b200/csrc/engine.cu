@@ -474,6 +474,7 @@ int decoder_select(Decoder* D, cudaStream_t s) {
     b.skip_flag = D->done_ptr;
     b.cur_out_ptr = D->cur_ptr;       // the device records which buffer is current: once the done
     b.out_index = D->cur ^ 1;         // flag is up later launches are no-ops and the host view goes stale
+    b.n_init = c.n_init;
     WB_TRY(launch_beam_update(b, s));
     D->cur ^= 1;
   }

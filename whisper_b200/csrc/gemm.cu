@@ -289,6 +289,7 @@ static int launch_impl(const GemmParams& p, const CUtensorMap& a0, const CUtenso
   }
   const int total = p.batch * p.m_tiles_per_batch * p.n_tiles;
   const int grid = total < num_sms ? total : num_sms;
+  ProfileScope prof(PROF_GEMM, s);
   kern<<<grid, kGemmThreads, Cfg::kSmemBytes, s>>>(p, a0, a1, b);
   count_launch();
   return cudaGetLastError() == cudaSuccess ? 0 : 11;

@@ -12,6 +12,23 @@ enum { DT_BF16 = 0, DT_F16 = 1 };
 extern unsigned long long g_launch_count;
 inline void count_launch(int n = 1) { g_launch_count += static_cast<unsigned long long>(n); }
 
+// Optional per-kernel timing for bench.py's roofline: when profiling is enabled for a kernel id,
+// every launch of that kernel is bracketed by CUDA events on its own stream (api.cu owns the pool).
+enum { PROF_NONE = 0, PROF_CROSS_ATTN = 1, PROF_SELF_ATTN = 2, PROF_GEMM = 3, PROF_ENC_ATTN = 4,
+       PROF_LAYERNORM = 5, PROF_SELECT = 6, PROF_MEL = 7 };
+extern int g_profile_kernel;
+void profile_mark(cudaStream_t s, bool begin);
+struct ProfileScope {
+  cudaStream_t s;
+  bool on;
+  ProfileScope(int id, cudaStream_t st) : s(st), on(g_profile_kernel == id) {
+    if (on) profile_mark(s, true);
+  }
+  ~ProfileScope() {
+    if (on) profile_mark(s, false);
+  }
+};
+
 // C[b*rows_per_batch + t, n] = epilogue( sum_tap sum_k A_tap[b, t + a_row_off[tap], k] * W[n, tap*K_tap + k] )
 // A_tap is the 3-D view {K_tap, a_rows_per_batch, batch} at A + a_base_off[tap] with row stride lda and
 // batch stride a_batch_stride (elements).  Rows outside [0, a_rows_per_batch) read as zero (TMA OOB fill),
@@ -113,6 +130,7 @@ struct BeamParams {
   const int* skip_flag;
   int* cur_out_ptr;       // device int: receives out_index (which ping-pong buffer is current)
   int out_index;
+  int n_init;             // prompt length: positions < n_init were written by the prefill
 };
 int launch_filter_topk(const FilterParams& p, int R, cudaStream_t s);
 int launch_no_speech(const float* logits, long long ld, int V, int no_speech, float* out, int rows,

@@ -269,6 +269,7 @@ int launch_log_mel(const float* audio, int n_audio, long long n_samples, int n_m
     attr = true;
   }
   dim3 grid((n_frames + kFramesPerCta - 1) / kFramesPerCta, n_audio);
+  ProfileScope prof(PROF_MEL, s);
   kern<<<grid, kMelThreads, smem, s>>>(audio, n_samples, n_frames, n_mels, sp, out, gmax, per_row_max);
   const long long per_row = static_cast<long long>(n_mels) * n_frames;
   const long long total = per_row * n_audio;

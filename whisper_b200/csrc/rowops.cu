@@ -84,6 +84,7 @@ int launch_layernorm(int dtype, const void* x, long long ldx, void* y, long long
   if (d % 8 || d > 2048 || ldx % 8 || ldy % 8) return 20;
   const int threads = 256;
   const int blocks = (rows * 32 + threads - 1) / threads;
+  ProfileScope prof(PROF_LAYERNORM, s);
   if (dtype == DT_BF16)
     layernorm_kernel<__nv_bfloat16, 8><<<blocks, threads, 0, s>>>(
         static_cast<const __nv_bfloat16*>(x), ldx, static_cast<__nv_bfloat16*>(y), ldy, g, b, rows, d, skip_flag);

@@ -399,7 +399,9 @@ __global__ void __launch_bounds__(kBeamWarps * 32) beam_update_kernel(const Beam
       int* dind = p.indir_out + static_cast<long long>(r0 + j) * p.max_ctx;
       for (int i = lane; i < L; i += 32) {
         drow[i] = srow[i];
-        dind[i] = (i == L - 1) ? src : sind[i];               // position L-1 was just written by row src
+        // position L-1 was written by row `src` in the step that produced these logits - unless it is
+        // still a prompt position (first select after the prefill), which lives in the audio's row 0
+        dind[i] = (i == L - 1 && i >= p.n_init) ? src : sind[i];
       }
       if (lane == 0) {
         drow[L] = s_newtok[warp][j];
@@ -421,6 +423,7 @@ __global__ void __launch_bounds__(kBeamWarps * 32) beam_update_kernel(const Beam
 // -------------------------------------------------------------------------------------------------
 int launch_filter_topk(const FilterParams& p, int R, cudaStream_t s) {
   if (p.K < 1 || p.K > kMaxTopK) return 50;
+  ProfileScope prof(PROF_SELECT, s);
   filter_topk_kernel<<<R, kSelThreads, 0, s>>>(p);
   count_launch();
   return cudaGetLastError() == cudaSuccess ? 0 : 51;
