@@ -237,6 +237,10 @@ void wb200_decoder_destroy(wb200_decoder* dec) {
   if (!dec) return;
   if (dec->d) {
     if (dec->d->pinned) cudaFreeHost(dec->d->pinned);
+    if (dec->d->pair_graph) cudaGraphExecDestroy(dec->d->pair_graph);
+    if (dec->d->ev_in) cudaEventDestroy(dec->d->ev_in);
+    if (dec->d->ev_out) cudaEventDestroy(dec->d->ev_out);
+    if (dec->d->gstream) cudaStreamDestroy(dec->d->gstream);
     delete dec->d;
   }
   delete dec;

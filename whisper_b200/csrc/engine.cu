@@ -2,6 +2,7 @@
 // which slices of the caller-provided workspace.  No allocation happens here except the small
 // host-side handle structs; every device byte belongs to the caller (PyTorch).
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <vector>
@@ -503,7 +504,7 @@ static int poll_int(Decoder* D, const int* dev, int* value, cudaStream_t s) {
 // DecodingTask._main_loop for i >= 1 (decoding.py:686-706): step, filters, update; the completion
 // flag lives on the device and is polled every 8 iterations (kernels become no-ops once it is set,
 // so overshooting leaves the state exactly as it was when the flag went up).
-int decoder_run(Decoder* D, int max_steps, int* steps_issued, cudaStream_t s) {
+static int run_direct(Decoder* D, int max_steps, int* issued_out, cudaStream_t s) {
   const int ctx = D->m->dims.n_text_ctx;
   int issued = 0;
   for (int i = 0; i < max_steps; ++i) {
@@ -520,6 +521,100 @@ int decoder_run(Decoder* D, int max_steps, int* steps_issued, cudaStream_t s) {
       if (done) break;
     }
   }
+  *issued_out = issued;
+  return 0;
+}
+
+static bool graphs_enabled() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("WB200_NO_GRAPH");
+    v = (e && e[0] && e[0] != '0') ? 0 : 1;
+  }
+  return v == 1 && g_profile_kernel == 0;   // per-kernel event timing needs real launches
+}
+
+int decoder_run(Decoder* D, int max_steps, int* steps_issued, cudaStream_t s) {
+  const int ctx = D->m->dims.n_text_ctx;
+  int issued = 0;
+  if (!graphs_enabled() || max_steps < 6) {
+    int r = run_direct(D, max_steps, &issued, s);
+    if (steps_issued) *steps_issued = issued;
+    return r;
+  }
+  // ---- graph mode: everything runs on the session's private stream, fenced against the caller's
+  if (!D->gstream) {
+    if (cudaStreamCreateWithFlags(&D->gstream, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaEventCreateWithFlags(&D->ev_in, cudaEventDisableTiming) != cudaSuccess ||
+        cudaEventCreateWithFlags(&D->ev_out, cudaEventDisableTiming) != cudaSuccess)
+      return set_error(280, "decoder: stream/event creation failed");
+  }
+  cudaStream_t g = D->gstream;
+  cudaEventRecord(D->ev_in, s);
+  cudaStreamWaitEvent(g, D->ev_in, 0);
+  int remaining = max_steps;
+  // first iteration directly: warms every kernel (function attributes) before capture
+  {
+    int n = 0;
+    int r = run_direct(D, 1, &n, g);
+    if (r) return r;
+    issued += n;
+    remaining -= n;
+    if (n == 0) remaining = 0;
+  }
+  if (remaining >= 2 && D->host_len + 2 <= ctx && (!D->pair_graph || D->pair_graph_cur != D->cur)) {
+    if (D->pair_graph) {
+      cudaGraphExecDestroy(D->pair_graph);
+      D->pair_graph = nullptr;
+    }
+    const int cur0 = D->cur, len0 = D->host_len;
+    cudaGraph_t graph = nullptr;
+    if (cudaStreamBeginCapture(g, cudaStreamCaptureModeThreadLocal) != cudaSuccess)
+      return set_error(281, "decoder: stream capture failed to start");
+    const unsigned long long launches0 = g_launch_count;
+    int r = 0;
+    for (int k = 0; k < 2 && !r; ++k) {
+      r = decoder_step(D, g);
+      if (!r) r = decoder_select(D, g);
+    }
+    cudaError_t ce = cudaStreamEndCapture(g, &graph);
+    D->launches_per_pair = static_cast<int>(g_launch_count - launches0);
+    g_launch_count = launches0;                    // capture records launches, it does not run them
+    D->host_len = len0;
+    D->cur = cur0;
+    if (r || ce != cudaSuccess || !graph) return set_error(282, "decoder: graph capture failed (%d, %s)", r, cudaGetErrorString(ce));
+    ce = cudaGraphInstantiate(&D->pair_graph, graph, 0);
+    cudaGraphDestroy(graph);
+    if (ce != cudaSuccess) return set_error(283, "decoder: graph instantiate failed: %s", cudaGetErrorString(ce));
+    D->pair_graph_cur = cur0;
+  }
+  int pairs_since_poll = 0;
+  bool done_seen = false;
+  while (remaining >= 2 && D->host_len + 2 <= ctx && D->pair_graph) {
+    if (cudaGraphLaunch(D->pair_graph, g) != cudaSuccess) return set_error(284, "decoder: graph launch failed");
+    count_launch(D->launches_per_pair);
+    D->host_len += 2;
+    issued += 2;
+    remaining -= 2;
+    if (++pairs_since_poll == 4) {
+      pairs_since_poll = 0;
+      int done = 0;
+      int r = poll_int(D, D->done_ptr, &done, g);
+      if (r) return r;
+      if (done) {
+        done_seen = true;
+        break;
+      }
+    }
+  }
+  if (!done_seen && remaining > 0) {
+    int n = 0;
+    int r = run_direct(D, remaining, &n, g);
+    if (r) return r;
+    issued += n;
+  }
+  cudaEventRecord(D->ev_out, g);
+  cudaStreamWaitEvent(s, D->ev_out, 0);
   if (steps_issued) *steps_issued = issued;
   return 0;
 }

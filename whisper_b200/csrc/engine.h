@@ -75,6 +75,13 @@ struct Decoder {
   const float* logits_cur = nullptr;
   int logits_row_div = 1;
   int* pinned = nullptr;       // pinned host scratch for flag polling
+  // CUDA-graph replay of the decode loop: two iterations (step, select, step, select) per graph so
+  // the ping-pong token / parent-table buffers are back where they started after every replay.
+  cudaStream_t gstream = nullptr;   // private capture / replay stream (capture is illegal on the legacy stream)
+  cudaEvent_t ev_in = nullptr, ev_out = nullptr;
+  cudaGraphExec_t pair_graph = nullptr;
+  int pair_graph_cur = -1;          // value of `cur` the graph was captured at
+  int launches_per_pair = 0;        // kernels inside one replay (for wb200_launch_count)
 };
 
 size_t encoder_workspace_bytes(const Model* m, int B);
