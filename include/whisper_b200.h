@@ -59,6 +59,14 @@ int wb200_linear(int dtype, int M, int N, int K, const void* A, int64_t lda, con
                  int64_t ldw, const void* bias, const void* residual, int64_t ldr, void* C,
                  int64_t ldc, int gelu, int out_f32, void* stream);
 
+/* Same operator with split-K enabled for skinny problems (the 320-row decode-step GEMMs): `workspace`
+ * holds fp32 partial slabs (up to 8 * M * N floats are used), `tickets` is an int32 array of n_tickets
+ * entries that must be zero on entry and is zero again on exit. */
+int wb200_linear_splitk(int dtype, int M, int N, int K, const void* A, int64_t lda, const void* W,
+                        int64_t ldw, const void* bias, const void* residual, int64_t ldr, void* C,
+                        int64_t ldc, int gelu, int out_f32, void* workspace, size_t workspace_bytes,
+                        int32_t* tickets, int n_tickets, void* stream);
+
 /* Conv1d(kernel=3, padding=1, stride in {1,2}) + GELU on time-major activations; replaces
  * whisper/model.py:53-59 + F.gelu at model.py:193-194.  x: [B, T_in, C_in] 16-bit, w: [C_out, 3*C_in]
  * tap-major (w[o, k*C_in + c] = weight[o, c, k]), bias [C_out], pos (optional fp32 [T_out, C_out],

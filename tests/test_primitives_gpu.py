@@ -77,6 +77,28 @@ def test_linear_epilogues(dtype, M):
 
 
 @pytest.mark.parametrize("dtype", DTYPES)
+@pytest.mark.parametrize("M,N,K", [(320, 1280, 1280), (320, 1280, 5120), (320, 3840, 1280), (5, 1280, 5120),
+                                   (64, 384, 1536), (200, 512, 2048)])
+def test_linear_splitk_decode_shapes(dtype, M, N, K):
+    """The skinny decode-step GEMMs (C3: 320 rows) run split-K: same result as the plain kernel up to
+    fp32 summation order, epilogues included, and the per-tile tickets return to zero."""
+    from whisper_b200 import ops
+    torch.manual_seed(7)
+    x = (torch.randn(M, K, device="cuda") * 0.5).to(dtype)
+    w = (torch.randn(N, K, device="cuda") * (1.0 / math.sqrt(K))).to(dtype)
+    b = (torch.randn(N, device="cuda") * 0.3).to(dtype)
+    r = torch.randn(M, N, device="cuda").to(dtype)
+    acc = x.float() @ w.float().T
+    report("splitk plain", ops.linear_splitk(x, w), rt(acc, dtype), dtype)
+    report("splitk bias+gelu", ops.linear_splitk(x, w, bias=b, gelu=True),
+           rt(torch.nn.functional.gelu(rt(acc + b.float(), dtype)), dtype), dtype)
+    report("splitk bias+residual", ops.linear_splitk(x, w, bias=b, residual=r),
+           rt(rt(acc + b.float(), dtype) + r.float(), dtype), dtype)
+    got = ops.linear_splitk(x, w, out_f32=True)
+    assert float((got - acc).abs().max()) < 2e-3 * math.sqrt(K) / 30 + 1e-3
+
+
+@pytest.mark.parametrize("dtype", DTYPES)
 def test_linear_f32_out_ragged_n(dtype):
     """Logits-shaped product: N not a multiple of the tile, fp32 output with a padded row stride."""
     from whisper_b200 import ops

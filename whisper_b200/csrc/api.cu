@@ -97,6 +97,39 @@ int wb200_linear(int dtype, int M, int N, int K, const void* A, int64_t lda, con
   return r ? set_error(r, "wb200_linear: launch failed (%d): %s", r, cudaGetErrorString(cudaGetLastError())) : 0;
 }
 
+int wb200_linear_splitk(int dtype, int M, int N, int K, const void* A, int64_t lda, const void* W,
+                        int64_t ldw, const void* bias, const void* residual, int64_t ldr, void* C,
+                        int64_t ldc, int gelu, int out_f32, void* workspace, size_t workspace_bytes,
+                        int32_t* tickets, int n_tickets, void* stream) {
+  WB_CHECK_DTYPE(dtype);
+  if (M <= 0 || N <= 0 || K <= 0) return set_error(101, "wb200_linear_splitk: bad shape M=%d N=%d K=%d", M, N, K);
+  LinearArgs a;
+  a.dtype = dtype;
+  a.batch = 1;
+  a.rows_per_batch = M;
+  a.a_rows_per_batch = M;
+  a.lda = lda;
+  a.N = N;
+  a.K_tap = K;
+  a.taps = 1;
+  a.A = A;
+  a.W = W;
+  a.ldw = ldw;
+  a.bias = bias;
+  a.residual = residual;
+  a.ldr = ldr;
+  a.C = C;
+  a.ldc = ldc;
+  a.gelu = gelu;
+  a.out_f32 = out_f32;
+  a.splitk_ws = static_cast<float*>(workspace);
+  a.splitk_ws_bytes = workspace_bytes;
+  a.splitk_counters = tickets;
+  a.splitk_max_tiles = n_tickets;
+  int r = launch_linear(a, static_cast<cudaStream_t>(stream));
+  return r ? set_error(r, "wb200_linear_splitk: launch failed (%d): %s", r, cudaGetErrorString(cudaGetLastError())) : 0;
+}
+
 int wb200_conv1d_k3_gelu(int dtype, int B, int T_in, int C_in, int C_out, int stride, const void* x,
                          const void* w, const void* bias, const float* pos, void* y, void* stream) {
   WB_CHECK_DTYPE(dtype);

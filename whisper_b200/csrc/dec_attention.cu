@@ -12,7 +12,8 @@
 //                            of them ("each audio's K/V counted once").  The 1500
 //                            keys are split across CTAs (flash-decoding); the last CTA to finish a
 //                            (audio, head, q-tile) combines the partials - no second launch.
-//   self_attention_kernel  : one query per (row, head); keys are gathered through the beam
+//   self_attention_kernel  : one WARP per (row, head), plain streaming reduction (no tensor-core
+//                            tile: a single query has nothing to share); keys are gathered through the beam
 //                            indirection table (position p of row r lives in physical row
 //                            indir[r][p]), so a beam reorder is a table update, not the physical
 //                            gather of every cache tensor that decoding.py:172-176 performs.  In
@@ -371,12 +372,24 @@ struct SelfParams {
   int group;            // prefill mode: physical row of audio a is a * group
 };
 
+// One WARP per (row, head): with a single query there is nothing for a tensor-core tile to share, so
+// the kernel is a pure streaming reduction.  Lane = (key sub-index g = lane / 8, 16-byte chunk
+// c = lane % 8): every load instruction fetches four complete 128-byte K (or V) rows, fully
+// coalesced; the 64-dim dot product is finished with three xor-shuffles inside the 8-lane group, and
+// each group keeps its own online-softmax state (m, l, o[8]) that is merged across the four groups
+// once at the end.  No shared memory and no block barrier, so dozens of warps per SM keep ~4 KB of
+// loads in flight each - the short sequences of the first decode steps are latency-bound and this
+// is what hides it.
+constexpr int kSaWarps = 8;
+
 template <typename T>
-__global__ void __launch_bounds__(kDaThreads) self_attention_kernel(const SelfParams p) {
+__global__ void __launch_bounds__(kSaWarps * 32) self_attention_kernel(const SelfParams p, int n_pairs, int n_head) {
   if (p.skip_flag && *p.skip_flag) return;
-  extern __shared__ __align__(1024) uint8_t da_smem[];
-  const int h = blockIdx.x;
-  const int row = blockIdx.y;
+  const int w = blockIdx.x * kSaWarps + (threadIdx.x >> 5);
+  if (w >= n_pairs) return;
+  const int lane = threadIdx.x & 31;
+  const int g = lane >> 3, c = lane & 7;
+  const int row = w / n_head, h = w % n_head;
   const bool step = p.indir != nullptr;
   int kv_len, phys_fixed = 0;
   if (step) {
@@ -386,50 +399,114 @@ __global__ void __launch_bounds__(kDaThreads) self_attention_kernel(const SelfPa
     phys_fixed = (row / p.n_init) * p.group;
   }
   const int pos_new = kv_len - 1;
-  const T* qrow = reinterpret_cast<const T*>(p.qkv) + static_cast<long long>(row) * 3 * p.d + h * 64;
-  const uint8_t* knew = reinterpret_cast<const uint8_t*>(qrow + p.d);
-  const uint8_t* vnew = reinterpret_cast<const uint8_t*>(qrow + 2 * p.d);
+  const long long row_bytes = static_cast<long long>(p.d) * 2;
+  const uint8_t* qrow = reinterpret_cast<const uint8_t*>(p.qkv) + static_cast<long long>(row) * 3 * row_bytes + h * 128;
+  const uint8_t* knew = qrow + row_bytes;
+  const uint8_t* vnew = qrow + 2 * row_bytes;
   uint8_t* kc = reinterpret_cast<uint8_t*>(p.kcache);
   uint8_t* vc = reinterpret_cast<uint8_t*>(p.vcache);
-  const long long row_bytes = static_cast<long long>(p.d) * 2;
-  if (step && threadIdx.x < 16) {
-    // append: the new token's K/V (this head's 128 B each) into physical row `row`, position L-1
-    const long long off = (static_cast<long long>(row) * p.max_ctx + pos_new) * row_bytes + h * 128;
-    const int c = threadIdx.x & 7;
-    if (threadIdx.x < 8)
-      *reinterpret_cast<uint4*>(kc + off + c * 16) = *reinterpret_cast<const uint4*>(knew + c * 16);
+  if (step && lane < 16) {
+    // append the new token's K/V (this head's 128 B each) to physical row `row`, position L-1
+    const long long off = (static_cast<long long>(row) * p.max_ctx + pos_new) * row_bytes + h * 128 + c * 16;
+    if (lane < 8)
+      *reinterpret_cast<uint4*>(kc + off) = *reinterpret_cast<const uint4*>(knew + c * 16);
     else
-      *reinterpret_cast<uint4*>(vc + off + c * 16) = *reinterpret_cast<const uint4*>(vnew + c * 16);
+      *reinterpret_cast<uint4*>(vc + off) = *reinterpret_cast<const uint4*>(vnew + c * 16);
   }
-  uint32_t qa[4][4];
-  load_q_frags<T>(qa, qrow, 0, 1);
-  const int* ind = step ? p.indir + static_cast<long long>(row) * p.max_ctx : nullptr;
-  auto src_of = [&](int key) {
-    RowSrc s;
-    if (step && key == pos_new) {   // not yet visible through the cache: read it from qkv
-      s.k = knew;
-      s.v = vnew;
-    } else {
-      const int phys = step ? __ldg(ind + key) : phys_fixed;
-      const long long off = (static_cast<long long>(phys) * p.max_ctx + key) * row_bytes + h * 128;
-      s.k = kc + off;
-      s.v = vc + off;
-    }
-    return s;
-  };
-  WarpAcc acc;
-  acc_init(acc);
-  stream_keys<T>(da_smem, 0, kv_len, kv_len, qa, acc, src_of);
-  float* red = reinterpret_cast<float*>(da_smem);
-  cta_merge(acc, red);
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  if (warp == 0 && (lane >> 2) == 0) {
-    const int t = lane & 3;
-    const float inv = 1.0f / acc.l[0];
-    T* orow = reinterpret_cast<T*>(p.out) + static_cast<long long>(row) * p.d + h * 64;
+  float q[8];
+  {
+    const uint4 u = *reinterpret_cast<const uint4*>(qrow + c * 16);
+    const uint32_t wq[4] = {u.x, u.y, u.z, u.w};
 #pragma unroll
-    for (int i = 0; i < 8; ++i)
-      *reinterpret_cast<uint32_t*>(orow + i * 8 + 2 * t) = Cvt<T>::pack2(acc.o[i][0] * inv, acc.o[i][1] * inv);
+    for (int e = 0; e < 4; ++e) {
+      const float2 f = Cvt<T>::unpack2(wq[e]);
+      q[2 * e] = f.x * kScaleLog2;
+      q[2 * e + 1] = f.y * kScaleLog2;
+    }
+  }
+  const int* ind = step ? p.indir + static_cast<long long>(row) * p.max_ctx : nullptr;
+  float m = -INFINITY, l = 0.f, o[8];
+#pragma unroll
+  for (int e = 0; e < 8; ++e) o[e] = 0.f;
+
+  constexpr int UNROLL = 4;
+  for (int base = 0; base < kv_len; base += 4 * UNROLL) {
+    uint4 kk[UNROLL], vv[UNROLL];
+    bool ok[UNROLL];
+#pragma unroll
+    for (int j = 0; j < UNROLL; ++j) {
+      const int key = base + j * 4 + g;
+      ok[j] = key < kv_len;
+      kk[j] = make_uint4(0, 0, 0, 0);
+      vv[j] = make_uint4(0, 0, 0, 0);
+      if (ok[j]) {
+        const uint8_t *ks, *vs;
+        if (step && key == pos_new) {       // not yet visible through the cache: read it from qkv
+          ks = knew;
+          vs = vnew;
+        } else {
+          const int phys = step ? __ldg(ind + key) : phys_fixed;
+          const long long off = (static_cast<long long>(phys) * p.max_ctx + key) * row_bytes + h * 128;
+          ks = kc + off;
+          vs = vc + off;
+        }
+        kk[j] = *reinterpret_cast<const uint4*>(ks + c * 16);
+        vv[j] = *reinterpret_cast<const uint4*>(vs + c * 16);
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < UNROLL; ++j) {
+      const uint32_t wk[4] = {kk[j].x, kk[j].y, kk[j].z, kk[j].w};
+      float sdot = 0.f;
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const float2 f = Cvt<T>::unpack2(wk[e]);
+        sdot = fmaf(q[2 * e], f.x, sdot);
+        sdot = fmaf(q[2 * e + 1], f.y, sdot);
+      }
+      sdot += __shfl_xor_sync(0xffffffffu, sdot, 1);
+      sdot += __shfl_xor_sync(0xffffffffu, sdot, 2);
+      sdot += __shfl_xor_sync(0xffffffffu, sdot, 4);
+      if (ok[j]) {                          // uniform within the 8-lane group
+        const float mn = fmaxf(m, sdot);
+        const float al = fast_exp2(m - mn);
+        const float pr = fast_exp2(sdot - mn);
+        m = mn;
+        l = l * al + pr;
+        const uint32_t wv[4] = {vv[j].x, vv[j].y, vv[j].z, vv[j].w};
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const float2 f = Cvt<T>::unpack2(wv[e]);
+          o[2 * e] = o[2 * e] * al + pr * f.x;
+          o[2 * e + 1] = o[2 * e + 1] * al + pr * f.y;
+        }
+      }
+    }
+  }
+  // merge the four key groups (lanes differing in bits 3 and 4)
+#pragma unroll
+  for (int sh = 8; sh <= 16; sh <<= 1) {
+    const float m2 = __shfl_xor_sync(0xffffffffu, m, sh);
+    const float l2 = __shfl_xor_sync(0xffffffffu, l, sh);
+    const float mn = fmaxf(m, m2);
+    const float a1 = m == -INFINITY ? 0.f : fast_exp2(m - mn);
+    const float a2 = m2 == -INFINITY ? 0.f : fast_exp2(m2 - mn);
+    l = l * a1 + l2 * a2;
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      const float o2 = __shfl_xor_sync(0xffffffffu, o[e], sh);
+      o[e] = o[e] * a1 + o2 * a2;
+    }
+    m = mn;
+  }
+  if (lane < 8) {
+    const float inv = 1.0f / l;
+    uint4 u;
+    u.x = Cvt<T>::pack2(o[0] * inv, o[1] * inv);
+    u.y = Cvt<T>::pack2(o[2] * inv, o[3] * inv);
+    u.z = Cvt<T>::pack2(o[4] * inv, o[5] * inv);
+    u.w = Cvt<T>::pack2(o[6] * inv, o[7] * inv);
+    *reinterpret_cast<uint4*>(reinterpret_cast<uint8_t*>(p.out) + static_cast<long long>(row) * row_bytes + h * 128 + c * 16) = u;
   }
 }
 
@@ -515,9 +592,8 @@ int launch_self_attention(int dtype, const void* qkv, void* kcache, void* vcache
   p.max_ctx = max_ctx;
   p.n_init = n_init > 0 ? n_init : 1;
   p.group = group;
-  dim3 grid(n_head, n_rows);
-  ProfileScope prof(PROF_SELF_ATTN, s);
-  static bool attr[2] = {false, false};
+  const int n_pairs = n_rows * n_head;
+  const int blocks = (n_pairs + kSaWarps - 1) / kSaWarps;
   if (dtype == DT_BF16) {
     if (!indir) {
       kv_append_kernel<__nv_bfloat16><<<(n_rows * 2 * 32 + 255) / 256, 256, 0, s>>>(
@@ -525,12 +601,8 @@ int launch_self_attention(int dtype, const void* qkv, void* kcache, void* vcache
           static_cast<__nv_bfloat16*>(vcache), n_rows, p.n_init, group, p.d, max_ctx);
       count_launch();
     }
-    auto kern = self_attention_kernel<__nv_bfloat16>;
-    if (!attr[0]) {
-      if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kDaSmem) != cudaSuccess) return 42;
-      attr[0] = true;
-    }
-    kern<<<grid, kDaThreads, kDaSmem, s>>>(p);
+    ProfileScope prof(PROF_SELF_ATTN, s);
+    self_attention_kernel<__nv_bfloat16><<<blocks, kSaWarps * 32, 0, s>>>(p, n_pairs, n_head);
   } else {
     if (!indir) {
       kv_append_kernel<__half><<<(n_rows * 2 * 32 + 255) / 256, 256, 0, s>>>(
@@ -538,12 +610,8 @@ int launch_self_attention(int dtype, const void* qkv, void* kcache, void* vcache
           n_rows, p.n_init, group, p.d, max_ctx);
       count_launch();
     }
-    auto kern = self_attention_kernel<__half>;
-    if (!attr[1]) {
-      if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kDaSmem) != cudaSuccess) return 42;
-      attr[1] = true;
-    }
-    kern<<<grid, kDaThreads, kDaSmem, s>>>(p);
+    ProfileScope prof(PROF_SELF_ATTN, s);
+    self_attention_kernel<__half><<<blocks, kSaWarps * 32, 0, s>>>(p, n_pairs, n_head);
   }
   count_launch();
   return cudaGetLastError() == cudaSuccess ? 0 : 43;

@@ -81,6 +81,8 @@ __global__ void decoder_init_state_kernel(int* tokens0, int* tokens1, int* indir
     *len_ptr = n_init;
     *done = 0;
     *cur = 0;
+    cur[8] = 0;      // beam tickets (scalars + 24, + 25)
+    cur[9] = 0;
   }
 }
 
@@ -114,7 +116,7 @@ struct Arena {
 
 static int linear(const Model* m, const void* A, long long lda, int M, const void* W, int N, int K, const void* bias,
                   const void* residual, void* C, long long ldc, int gelu, int out_f32, cudaStream_t s,
-                  const int* skip = nullptr) {
+                  const int* skip = nullptr, const Decoder* D = nullptr) {
   LinearArgs a;
   a.dtype = m->dtype;
   a.batch = 1;
@@ -135,6 +137,12 @@ static int linear(const Model* m, const void* A, long long lda, int M, const voi
   a.gelu = gelu;
   a.out_f32 = out_f32;
   a.skip_flag = skip;
+  if (D) {
+    a.splitk_ws = D->gemm_ws;
+    a.splitk_ws_bytes = D->gemm_ws_bytes;
+    a.splitk_counters = D->gemm_counters;
+    a.splitk_max_tiles = 256;
+  }
   return launch_linear(a, s);
 }
 
@@ -239,7 +247,10 @@ static void dec_carve(const Model* m, const wb200_decode_config& c, Arena& ar, D
   const size_t nq = c.n_init > (int)G ? c.n_init : G;
   o->partial = static_cast<float*>(ar.take(cross_attention_partial_floats((int)B, (int)nq, (int)H, (int)Ta) * 4));
   o->n_counters = static_cast<int>(B * ((nq + 15) / 16) * H);
-  o->counters = static_cast<int*>(ar.take(o->n_counters * 4));
+  o->counters = static_cast<int*>(ar.take((o->n_counters + 256) * 4));
+  o->gemm_counters = o->counters ? o->counters + o->n_counters : nullptr;
+  o->gemm_ws_bytes = 40u << 20;
+  o->gemm_ws = static_cast<float*>(ar.take(o->gemm_ws_bytes));
   for (int i = 0; i < 2; ++i) {
     o->tokens[i] = static_cast<int*>(ar.take(R * ctx * 4));
     o->indir[i] = static_cast<int*>(ar.take(R * ctx * 4));
@@ -345,18 +356,18 @@ static int decoder_stack(Decoder* D, int rows, bool step, cudaStream_t s) {
     void* vc = static_cast<uint8_t*>(D->self_v) + l * self_per_layer;
     const uint8_t* ckv = static_cast<const uint8_t*>(D->cross_kv) + l * cross_per_layer;
     WB_TRY(launch_layernorm(dt, D->x, d, D->ln, d, (const float*)L[D_ATTN_LN_W], (const float*)L[D_ATTN_LN_B], rows, d, s, skip));
-    WB_TRY(linear(m, D->ln, d, rows, L[D_QKV_W], 3 * d, d, L[D_QKV_B], nullptr, D->qkv, 3 * d, 0, 0, s, skip));
+    WB_TRY(linear(m, D->ln, d, rows, L[D_QKV_W], 3 * d, d, L[D_QKV_B], nullptr, D->qkv, 3 * d, 0, 0, s, skip, D));
     WB_TRY(launch_self_attention(dt, D->qkv, kc, vc, D->att, step ? D->indir[D->cur] : nullptr, D->len_ptr, skip, rows, H,
                                  ctx, D->cfg.n_init, G, s));
-    WB_TRY(linear(m, D->att, d, rows, L[D_OUT_W], d, d, L[D_OUT_B], D->x, D->x, d, 0, 0, s, skip));
+    WB_TRY(linear(m, D->att, d, rows, L[D_OUT_W], d, d, L[D_OUT_B], D->x, D->x, d, 0, 0, s, skip, D));
     WB_TRY(launch_layernorm(dt, D->x, d, D->ln, d, (const float*)L[D_CROSS_LN_W], (const float*)L[D_CROSS_LN_B], rows, d, s, skip));
-    WB_TRY(linear(m, D->ln, d, rows, L[D_CQ_W], d, d, L[D_CQ_B], nullptr, D->q, d, 0, 0, s, skip));
+    WB_TRY(linear(m, D->ln, d, rows, L[D_CQ_W], d, d, L[D_CQ_B], nullptr, D->q, d, 0, 0, s, skip, D));
     WB_TRY(launch_cross_attention(dt, D->q, ckv, ckv + static_cast<size_t>(d) * 2, D->att, D->partial, D->counters, skip, B,
                                   n_q, Ta, H, 2 * d, s));
-    WB_TRY(linear(m, D->att, d, rows, L[D_COUT_W], d, d, L[D_COUT_B], D->x, D->x, d, 0, 0, s, skip));
+    WB_TRY(linear(m, D->att, d, rows, L[D_COUT_W], d, d, L[D_COUT_B], D->x, D->x, d, 0, 0, s, skip, D));
     WB_TRY(launch_layernorm(dt, D->x, d, D->ln, d, (const float*)L[D_MLP_LN_W], (const float*)L[D_MLP_LN_B], rows, d, s, skip));
-    WB_TRY(linear(m, D->ln, d, rows, L[D_FC1_W], 4 * d, d, L[D_FC1_B], nullptr, D->hid, 4 * d, 1, 0, s, skip));
-    WB_TRY(linear(m, D->hid, 4 * d, rows, L[D_FC2_W], d, 4 * d, L[D_FC2_B], D->x, D->x, d, 0, 0, s, skip));
+    WB_TRY(linear(m, D->ln, d, rows, L[D_FC1_W], 4 * d, d, L[D_FC1_B], nullptr, D->hid, 4 * d, 1, 0, s, skip, D));
+    WB_TRY(linear(m, D->hid, 4 * d, rows, L[D_FC2_W], d, 4 * d, L[D_FC2_B], D->x, D->x, d, 0, 0, s, skip, D));
   }
   return 0;
 }
@@ -380,7 +391,7 @@ int decoder_prefill(Decoder* D, const int32_t* init_tokens_host, cudaStream_t s)
   D->cur = 0;
   decoder_init_state_kernel<<<256, 256, 0, s>>>(D->tokens[0], D->tokens[1], D->indir[0], D->indir[1], ctx, R, G, c.n_init,
                                                 D->init_tokens, D->sum_lp, D->len_ptr, D->done_ptr, D->cur_ptr, D->fin_count, D->fin_len,
-                                                B, c.max_candidates > 0 ? c.max_candidates : 1, D->counters, D->n_counters);
+                                                B, c.max_candidates > 0 ? c.max_candidates : 1, D->counters, D->n_counters + 256);
   count_launch();
   if (dt == DT_BF16) launch_embed<__nv_bfloat16>(D, P, false, s); else launch_embed<__half>(D, P, false, s);
   WB_TRY(decoder_stack(D, P, false, s));
@@ -407,7 +418,7 @@ int decoder_step(Decoder* D, cudaStream_t s) {
   if (dt == DT_BF16) launch_embed<__nv_bfloat16>(D, R, true, s); else launch_embed<__half>(D, R, true, s);
   WB_TRY(decoder_stack(D, R, true, s));
   WB_TRY(launch_layernorm(dt, D->x, d, D->ln, d, (const float*)m->t[G_DEC_LN_W], (const float*)m->t[G_DEC_LN_B], R, d, s, D->done_ptr));
-  WB_TRY(linear(m, D->ln, d, R, m->t[G_TOK_EMB16], V, d, nullptr, nullptr, D->logits, D->ldv, 0, 1, s, D->done_ptr));
+  WB_TRY(linear(m, D->ln, d, R, m->t[G_TOK_EMB16], V, d, nullptr, nullptr, D->logits, D->ldv, 0, 1, s, D->done_ptr, D));
   D->logits_cur = D->logits;
   D->logits_row_div = 1;
   return 0;
@@ -476,6 +487,7 @@ int decoder_select(Decoder* D, cudaStream_t s) {
     b.cur_out_ptr = D->cur_ptr;       // the device records which buffer is current: once the done
     b.out_index = D->cur ^ 1;         // flag is up later launches are no-ops and the host view goes stale
     b.n_init = c.n_init;
+    b.tickets = D->scalars + 24;
     WB_TRY(launch_beam_update(b, s));
     D->cur ^= 1;
   }

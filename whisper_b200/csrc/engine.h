@@ -51,6 +51,9 @@ struct Decoder {
   float* partial = nullptr;
   int* counters = nullptr;
   int n_counters = 0;
+  float* gemm_ws = nullptr;        // split-K slabs for the skinny decode-step GEMMs
+  size_t gemm_ws_bytes = 0;
+  int* gemm_counters = nullptr;    // per-tile tickets, zero between launches
   int* tokens[2] = {nullptr, nullptr};
   int* indir[2] = {nullptr, nullptr};
   float* sum_lp = nullptr;

@@ -10,9 +10,10 @@
 //
 // Structure (persistent, one CTA per SM, 256 threads):
 //   warp 0   : TMA producer (one elected thread) - A tile 128x64, W tile BNx64, 128B swizzle
+//   (384 threads: warps 0-3 control, warps 4-11 epilogue)
 //   warp 1   : tcgen05.mma issuer (one thread)   - UMMA 128 x BN x 16, accumulators in TMEM
 //   warp 2   : TMEM allocator / deallocator
-//   warps 4-7: epilogue - tcgen05.ld -> bias / GELU / positional add / residual -> global
+//   warps 4-11: epilogue - tcgen05.ld -> bias / GELU / positional add / residual -> global
 // Pipelines: smem ring (full/empty mbarriers) between TMA and MMA; two TMEM accumulator
 // stages (tmem_full/tmem_empty) between MMA and epilogue so tile i+1's main loop overlaps
 // tile i's epilogue.
@@ -24,7 +25,7 @@ namespace wb {
 
 constexpr int kBM = 128;
 constexpr int kBK = 64;  // 64 x 16-bit = 128 B = one swizzle row
-constexpr int kGemmThreads = 256;
+constexpr int kGemmThreads = 384;  // 4 control warps + 8 epilogue warps
 
 struct GemmParams {
   int batch, rows_per_batch, m_tiles_per_batch;
@@ -39,6 +40,12 @@ struct GemmParams {
   const float* pos;
   int gelu;
   const int* skip_flag;
+  // split-K (skinny decode-step GEMMs): work item = (tile, split); partial fp32 tiles go to
+  // `partial[split][row][n]`, the last CTA to finish a tile sums them in split order and runs the epilogue
+  int splits, k_per_split;
+  float* partial;
+  long long partial_stride;   // floats per split slab
+  int* tile_counters;
 };
 
 template <int BN>
@@ -53,6 +60,79 @@ struct GemmCfg {
 
 __device__ __forceinline__ float gelu_erf(float x) {
   return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f));
+}
+
+// bias / GELU / positional add / residual, then the store of 32 consecutive columns of one row
+template <typename T, bool OUT_F32>
+__device__ __forceinline__ void epilogue_store(float (&v)[32], const GemmParams& p, int t, long long grow, int nb) {
+  const T* bias = reinterpret_cast<const T*>(p.bias);
+  const T* resid = reinterpret_cast<const T*>(p.residual);
+  const bool full = nb + 32 <= p.N;
+  if (bias) {
+#pragma unroll
+    for (int j = 0; j < 32; ++j)
+      if (full || nb + j < p.N) v[j] += Cvt<T>::to_f(bias[nb + j]);
+  }
+  if (p.gelu) {
+#pragma unroll
+    for (int j = 0; j < 32; ++j) v[j] = gelu_erf(round_to<T>(v[j]));
+  }
+  if (p.pos) {
+    const float* pr = p.pos + static_cast<long long>(t) * p.N + nb;
+#pragma unroll
+    for (int j = 0; j < 32; ++j)
+      if (full || nb + j < p.N) v[j] = round_to<T>(v[j]) + pr[j];
+  }
+  if (resid) {
+    const T* rr = resid + grow * p.ldr + nb;
+    if (full) {
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        uint4 u = *reinterpret_cast<const uint4*>(rr + q * 8);
+        const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          float2 f = Cvt<T>::unpack2(w[e]);
+          v[q * 8 + e * 2] = round_to<T>(v[q * 8 + e * 2]) + f.x;
+          v[q * 8 + e * 2 + 1] = round_to<T>(v[q * 8 + e * 2 + 1]) + f.y;
+        }
+      }
+    } else {
+#pragma unroll
+      for (int j = 0; j < 32; ++j)
+        if (nb + j < p.N) v[j] = round_to<T>(v[j]) + Cvt<T>::to_f(rr[j]);
+    }
+  }
+  if constexpr (OUT_F32) {
+    float* out = reinterpret_cast<float*>(p.C) + grow * p.ldc + nb;
+    if (full) {
+#pragma unroll
+      for (int q = 0; q < 8; ++q)
+        *reinterpret_cast<float4*>(out + q * 4) =
+            make_float4(v[q * 4], v[q * 4 + 1], v[q * 4 + 2], v[q * 4 + 3]);
+    } else {
+#pragma unroll
+      for (int j = 0; j < 32; ++j)
+        if (nb + j < p.N) out[j] = v[j];
+    }
+  } else {
+    T* out = reinterpret_cast<T*>(p.C) + grow * p.ldc + nb;
+    if (full) {
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        uint4 u;
+        u.x = Cvt<T>::pack2(v[q * 8 + 0], v[q * 8 + 1]);
+        u.y = Cvt<T>::pack2(v[q * 8 + 2], v[q * 8 + 3]);
+        u.z = Cvt<T>::pack2(v[q * 8 + 4], v[q * 8 + 5]);
+        u.w = Cvt<T>::pack2(v[q * 8 + 6], v[q * 8 + 7]);
+        *reinterpret_cast<uint4*>(out + q * 8) = u;
+      }
+    } else {
+#pragma unroll
+      for (int j = 0; j < 32; ++j)
+        if (nb + j < p.N) out[j] = Cvt<T>::from_f(v[j]);
+    }
+  }
 }
 
 template <typename T, int BN, bool OUT_F32>
@@ -75,7 +155,9 @@ gemm_tcgen05_kernel(const GemmParams p, const __grid_constant__ CUtensorMap mapA
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   const int total_tiles = p.batch * p.m_tiles_per_batch * p.n_tiles;
+  const int total_items = total_tiles * p.splits;
   const int k_blocks = p.taps * p.k_blocks_per_tap;
+  __shared__ int s_ticket;
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&mapA0);
@@ -89,7 +171,7 @@ gemm_tcgen05_kernel(const GemmParams p, const __grid_constant__ CUtensorMap mapA
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&tmem_full[i], 1);
-      mbar_init(&tmem_empty[i], 128);
+      mbar_init(&tmem_empty[i], 256);
     }
     mbar_fence_init();
   }
@@ -106,15 +188,19 @@ gemm_tcgen05_kernel(const GemmParams p, const __grid_constant__ CUtensorMap mapA
     // ===================== TMA producer =====================
     int stage = 0;
     uint32_t phase = 0;
-    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+    for (int item = blockIdx.x; item < total_items; item += gridDim.x) {
+      const int tile = item / p.splits, split = item % p.splits;
       const int m_tile = tile / p.n_tiles;
       const int n0 = (tile % p.n_tiles) * BN;
       const int b = m_tile / p.m_tiles_per_batch;
       const int t0 = (m_tile % p.m_tiles_per_batch) * kBM;
+      const int kb_lo = split * p.k_per_split, kb_hi = min(k_blocks, kb_lo + p.k_per_split);
       for (int tap = 0; tap < p.taps; ++tap) {
         const CUtensorMap* ma = p.a_map_sel[tap] ? &mapA1 : &mapA0;
         const int row0 = t0 + p.a_row_off[tap];
         for (int kb = 0; kb < p.k_blocks_per_tap; ++kb) {
+          const int kidx = tap * p.k_blocks_per_tap + kb;
+          if (kidx < kb_lo || kidx >= kb_hi) continue;
           mbar_wait(&empty_bar[stage], phase ^ 1);
           uint8_t* sa = tiles + stage * Cfg::kStageBytes;
           uint8_t* sb = sa + Cfg::kABytes;
@@ -135,11 +221,13 @@ gemm_tcgen05_kernel(const GemmParams p, const __grid_constant__ CUtensorMap mapA
     uint32_t phase = 0;
     int acc = 0;
     uint32_t acc_phase = 0;
-    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+    for (int item = blockIdx.x; item < total_items; item += gridDim.x) {
+      const int split = item % p.splits;
+      const int kb_lo = split * p.k_per_split, kb_hi = min(k_blocks, kb_lo + p.k_per_split);
       mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
       tc_fence_after();
       const uint32_t d_tmem = tmem_base + acc * BN;
-      for (int kb = 0; kb < k_blocks; ++kb) {
+      for (int kb = kb_lo; kb < kb_hi; ++kb) {
         mbar_wait(&full_bar[stage], phase);
         tc_fence_after();
         const uint32_t sa = smem_u32(tiles + stage * Cfg::kStageBytes);
@@ -149,7 +237,7 @@ gemm_tcgen05_kernel(const GemmParams p, const __grid_constant__ CUtensorMap mapA
 #pragma unroll
         for (int k = 0; k < kBK / 16; ++k) {
           // advance 16 elements (32 B) along K inside the 128 B swizzle row: +2 in 16 B units
-          umma_f16(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0);
+          umma_f16(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (kb != kb_lo) || (k != 0));
         }
         umma_commit(&empty_bar[stage]);
         if (++stage == Cfg::kStages) {
@@ -163,12 +251,18 @@ gemm_tcgen05_kernel(const GemmParams p, const __grid_constant__ CUtensorMap mapA
     }
   } else if (warp >= 4) {
     // ===================== epilogue =====================
-    const int quad = warp & 3;  // TMEM lane quadrant this warp may access
+    // Eight epilogue warps: two per TMEM lane quadrant (a warp may only touch lanes 32*(warp%4)..+31),
+    // each owning half of the tile's columns.  With K = 1280 the main loop of a 128x256 tile lasts
+    // ~10k cycles; four warps needed longer than that for the bias/GELU/residual epilogue and stalled it.
+    const int quad = warp & 3;
+    const int half = (warp - 4) >> 2;
+    constexpr int kColsPerWarp = BN / 2;
     int acc = 0;
     uint32_t acc_phase = 0;
     const T* bias = reinterpret_cast<const T*>(p.bias);
     const T* resid = reinterpret_cast<const T*>(p.residual);
-    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+    for (int item = blockIdx.x; item < total_items; item += gridDim.x) {
+      const int tile = item / p.splits, split = item % p.splits;
       const int m_tile = tile / p.n_tiles;
       const int n0 = (tile % p.n_tiles) * BN;
       const int b = m_tile / p.m_tiles_per_batch;
@@ -178,82 +272,25 @@ gemm_tcgen05_kernel(const GemmParams p, const __grid_constant__ CUtensorMap mapA
 
       mbar_wait(&tmem_full[acc], acc_phase);
       tc_fence_after();
-      const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + acc * BN;
+      const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + acc * BN + half * kColsPerWarp;
 #pragma unroll 1
-      for (int c = 0; c < BN / 32; ++c) {
+      for (int c = 0; c < kColsPerWarp / 32; ++c) {
         uint32_t r[32];
         tmem_ld32(taddr + c * 32, r);
         tmem_ld_wait();
-        const int nb = n0 + c * 32;
+        const int nb = n0 + half * kColsPerWarp + c * 32;
         if (row_ok && nb < p.N) {
           float v[32];
 #pragma unroll
           for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
-          const bool full = nb + 32 <= p.N;
-          if (bias) {
-#pragma unroll
-            for (int j = 0; j < 32; ++j)
-              if (full || nb + j < p.N) v[j] += Cvt<T>::to_f(bias[nb + j]);
-          }
-          if (p.gelu) {
-#pragma unroll
-            for (int j = 0; j < 32; ++j) v[j] = gelu_erf(round_to<T>(v[j]));
-          }
-          if (p.pos) {
-            const float* pr = p.pos + static_cast<long long>(t) * p.N + nb;
-#pragma unroll
-            for (int j = 0; j < 32; ++j)
-              if (full || nb + j < p.N) v[j] = round_to<T>(v[j]) + pr[j];
-          }
-          if (resid) {
-            const T* rr = resid + grow * p.ldr + nb;
-            if (full) {
-#pragma unroll
-              for (int q = 0; q < 4; ++q) {
-                uint4 u = *reinterpret_cast<const uint4*>(rr + q * 8);
-                const uint32_t w[4] = {u.x, u.y, u.z, u.w};
-#pragma unroll
-                for (int e = 0; e < 4; ++e) {
-                  float2 f = Cvt<T>::unpack2(w[e]);
-                  v[q * 8 + e * 2] = round_to<T>(v[q * 8 + e * 2]) + f.x;
-                  v[q * 8 + e * 2 + 1] = round_to<T>(v[q * 8 + e * 2 + 1]) + f.y;
-                }
-              }
-            } else {
-#pragma unroll
-              for (int j = 0; j < 32; ++j)
-                if (nb + j < p.N) v[j] = round_to<T>(v[j]) + Cvt<T>::to_f(rr[j]);
-            }
-          }
-          if constexpr (OUT_F32) {
-            float* out = reinterpret_cast<float*>(p.C) + grow * p.ldc + nb;
-            if (full) {
-#pragma unroll
-              for (int q = 0; q < 8; ++q)
-                *reinterpret_cast<float4*>(out + q * 4) =
-                    make_float4(v[q * 4], v[q * 4 + 1], v[q * 4 + 2], v[q * 4 + 3]);
-            } else {
-#pragma unroll
-              for (int j = 0; j < 32; ++j)
-                if (nb + j < p.N) out[j] = v[j];
-            }
+          if (p.splits == 1) {
+            epilogue_store<T, OUT_F32>(v, p, t, grow, nb);
           } else {
-            T* out = reinterpret_cast<T*>(p.C) + grow * p.ldc + nb;
-            if (full) {
+            // raw fp32 partial sums of this K-slice (only in-range columns exist in the slab)
+            float* ps = p.partial + split * p.partial_stride + grow * p.N + nb;
 #pragma unroll
-              for (int q = 0; q < 4; ++q) {
-                uint4 u;
-                u.x = Cvt<T>::pack2(v[q * 8 + 0], v[q * 8 + 1]);
-                u.y = Cvt<T>::pack2(v[q * 8 + 2], v[q * 8 + 3]);
-                u.z = Cvt<T>::pack2(v[q * 8 + 4], v[q * 8 + 5]);
-                u.w = Cvt<T>::pack2(v[q * 8 + 6], v[q * 8 + 7]);
-                *reinterpret_cast<uint4*>(out + q * 8) = u;
-              }
-            } else {
-#pragma unroll
-              for (int j = 0; j < 32; ++j)
-                if (nb + j < p.N) out[j] = Cvt<T>::from_f(v[j]);
-            }
+            for (int j = 0; j < 32; ++j)
+              if (nb + j < p.N) __stcg(ps + j, v[j]);
           }
         }
       }
@@ -261,6 +298,36 @@ gemm_tcgen05_kernel(const GemmParams p, const __grid_constant__ CUtensorMap mapA
       mbar_arrive(&tmem_empty[acc]);
       acc ^= 1;
       if (acc == 0) acc_phase ^= 1;
+      if (p.splits > 1) {
+        // ticket: the last of the tile's `splits` CTAs reduces the slabs (in split order, so the sum does
+        // not depend on arrival order) and applies the epilogue
+        __threadfence();
+        asm volatile("bar.sync 1, 256;" ::: "memory");
+        if (threadIdx.x == 128) s_ticket = atomicAdd(&p.tile_counters[tile], 1);
+        asm volatile("bar.sync 1, 256;" ::: "memory");
+        const bool last = (s_ticket == p.splits - 1);
+        if (last) {
+          __threadfence();
+          if (threadIdx.x == 128) p.tile_counters[tile] = 0;
+#pragma unroll 1
+          for (int c = 0; c < kColsPerWarp / 32; ++c) {
+            const int nb = n0 + half * kColsPerWarp + c * 32;
+            if (row_ok && nb < p.N) {
+              float v[32];
+#pragma unroll
+              for (int j = 0; j < 32; ++j) v[j] = 0.f;
+              for (int sp = 0; sp < p.splits; ++sp) {
+                const float* ps = p.partial + sp * p.partial_stride + grow * p.N + nb;
+#pragma unroll
+                for (int j = 0; j < 32; ++j)
+                  if (nb + j < p.N) v[j] += __ldcg(ps + j);
+              }
+              epilogue_store<T, OUT_F32>(v, p, t, grow, nb);
+            }
+          }
+        }
+        asm volatile("bar.sync 1, 256;" ::: "memory");   // s_ticket is reused by the next item
+      }
     }
   }
 
@@ -287,7 +354,7 @@ static int launch_impl(const GemmParams& p, const CUtensorMap& a0, const CUtenso
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev);
   }
-  const int total = p.batch * p.m_tiles_per_batch * p.n_tiles;
+  const int total = p.batch * p.m_tiles_per_batch * p.n_tiles * p.splits;
   const int grid = total < num_sms ? total : num_sms;
   ProfileScope prof(PROF_GEMM, s);
   kern<<<grid, kGemmThreads, Cfg::kSmemBytes, s>>>(p, a0, a1, b);
@@ -309,7 +376,9 @@ int launch_linear(const LinearArgs& a, cudaStream_t s) {
 
   int bn = a.block_n;
   const long long rows = static_cast<long long>(a.batch) * a.rows_per_batch;
-  if (bn == 0) bn = rows >= 4096 ? 256 : 64;
+  // wide tiles when M is large (encoder) or N is huge (logits: fewer passes over the A tile);
+  // 64-wide tiles for the skinny decode-step GEMMs so that more CTAs pull weights concurrently
+  if (bn == 0) bn = (rows >= 4096 || a.N >= 16384) ? 256 : 64;
   if (bn == 256 && a.N < 256) bn = a.N >= 128 ? 128 : 64;
 
   GemmParams p;
@@ -329,6 +398,28 @@ int launch_linear(const LinearArgs& a, cudaStream_t s) {
   p.pos = a.pos;
   p.gelu = a.gelu;
   p.skip_flag = a.skip_flag;
+  // split-K only for skinny problems that would otherwise leave most SMs idle
+  p.splits = 1;
+  p.k_per_split = p.taps * p.k_blocks_per_tap;
+  p.partial = nullptr;
+  p.partial_stride = rows * static_cast<long long>(a.N);
+  p.tile_counters = a.splitk_counters;
+  {
+    const int tiles = p.batch * p.m_tiles_per_batch * p.n_tiles;
+    const int kblocks = p.taps * p.k_blocks_per_tap;
+    if (a.splitk_ws && a.splitk_counters && a.taps == 1 && tiles < 148 && kblocks >= 8 && tiles <= a.splitk_max_tiles) {
+      int sp = (2 * 148 + tiles - 1) / tiles;          // aim at ~2 work items per SM
+      if (sp > kblocks / 4) sp = kblocks / 4;          // keep >= 4 k-blocks (256 of K) per item
+      if (sp > 8) sp = 8;
+      while (sp > 1 && static_cast<size_t>(sp) * p.partial_stride * 4 > a.splitk_ws_bytes) --sp;
+      if (sp > 1) {
+        p.splits = sp;
+        p.k_per_split = (kblocks + sp - 1) / sp;
+        p.splits = (kblocks + p.k_per_split - 1) / p.k_per_split;   // no empty slices
+        p.partial = a.splitk_ws;
+      }
+    }
+  }
 
   // A maps: distinct base offsets -> at most two tensor maps
   CUtensorMap mapA[2];

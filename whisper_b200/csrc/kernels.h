@@ -56,6 +56,11 @@ struct LinearArgs {
   int out_f32 = 0;
   int block_n = 0;  // 0 = choose (256 for large M, 64 for skinny M)
   const int* skip_flag = nullptr;  // optional device int: non-zero -> the kernel is a no-op
+  // optional split-K scratch (decode-step GEMMs): fp32 slabs + per-tile tickets (zero between launches)
+  float* splitk_ws = nullptr;
+  size_t splitk_ws_bytes = 0;
+  int* splitk_counters = nullptr;
+  int splitk_max_tiles = 0;
 };
 int launch_linear(const LinearArgs& a, cudaStream_t s);
 
@@ -131,6 +136,7 @@ struct BeamParams {
   int* cur_out_ptr;       // device int: receives out_index (which ping-pong buffer is current)
   int out_index;
   int n_init;             // prompt length: positions < n_init were written by the prefill
+  int* tickets;           // device int[2], zero between launches: arrival ticket, count of full audios
 };
 int launch_filter_topk(const FilterParams& p, int R, cudaStream_t s);
 int launch_no_speech(const float* logits, long long ld, int V, int no_speech, float* out, int rows,

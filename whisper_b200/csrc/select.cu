@@ -277,7 +277,7 @@ __global__ void __launch_bounds__(1024) greedy_update_kernel(const GreedyParams 
 constexpr int kMaxBeam = 16;
 constexpr int kMaxCand = kMaxBeam * (kMaxBeam + 1);
 
-constexpr int kBeamWarps = 8;
+constexpr int kBeamWarps = 1;   // one warp = one audio = one CTA; completion is reduced through a ticket
 
 __global__ void __launch_bounds__(kBeamWarps * 32) beam_update_kernel(const BeamParams p) {
   if (p.skip_flag && *p.skip_flag) return;
@@ -291,11 +291,11 @@ __global__ void __launch_bounds__(kBeamWarps * 32) beam_update_kernel(const Beam
   __shared__ int s_newtok[kBeamWarps][kMaxBeam];
   if (threadIdx.x == 0) s_all_done = 1;
   __syncthreads();
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int n_warps = blockDim.x >> 5;
+  const int warp = 0, lane = threadIdx.x & 31;
   const int L = *p.len_ptr;
   const int G = p.G, K = G + 1, N = G * K;
-  for (int a = warp; a < p.n_audio; a += n_warps) {
+  {
+    const int a = blockIdx.x;
     const int r0 = a * G;
     // prefix equality between beams (needed for the dict de-duplication of decoding.py:344-346)
     for (int pair = 0; pair < G * G; ++pair) {
@@ -412,9 +412,20 @@ __global__ void __launch_bounds__(kBeamWarps * 32) beam_update_kernel(const Beam
   }
   __syncthreads();
   if (threadIdx.x == 0) {
-    *p.len_ptr = L + 1;
-    *p.cur_out_ptr = p.out_index;
-    if (s_all_done) *p.done_flag = 1;                          // decoding.py:377-381
+    // last CTA to arrive publishes the new length / buffer index and the completion flag: every CTA
+    // read *len_ptr before taking its ticket, so bumping it here cannot race with them.
+    if (s_all_done) atomicAdd(&p.tickets[1], 1);
+    __threadfence();
+    const int t = atomicAdd(&p.tickets[0], 1);
+    if (t == p.n_audio - 1) {
+      __threadfence();
+      const int n_full = atomicAdd(&p.tickets[1], 0);
+      p.tickets[0] = 0;
+      p.tickets[1] = 0;
+      *p.len_ptr = L + 1;
+      *p.cur_out_ptr = p.out_index;
+      if (n_full == p.n_audio) *p.done_flag = 1;               // decoding.py:377-381
+    }
   }
 }
 
@@ -441,7 +452,7 @@ int launch_greedy_update(const GreedyParams& p, cudaStream_t s) {
 }
 int launch_beam_update(const BeamParams& p, cudaStream_t s) {
   if (p.G > kMaxBeam) return 54;
-  beam_update_kernel<<<1, kBeamWarps * 32, 0, s>>>(p);
+  beam_update_kernel<<<p.n_audio, kBeamWarps * 32, 0, s>>>(p);
   count_launch();
   return cudaGetLastError() == cudaSuccess ? 0 : 55;
 }
