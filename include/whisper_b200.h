@@ -149,6 +149,9 @@ typedef struct {
   int32_t timestamp_rules;              /* ApplyTimestampRules installed           decoding.py:559 */
   int32_t max_initial_timestamp_index;  /* < 0: none                               decoding.py:561 */
   int32_t n_suppress, n_blank;
+  int32_t all_logits;                   /* 1: the prefill keeps logits of ALL n_init positions (the
+                                           un-cached forward of model.py:293-296); such a session is
+                                           forward-only (no select / step) */
   const int32_t* suppress_ids;          /* host: sorted SuppressTokens ids         decoding.py:615 */
   const int32_t* blank_ids;             /* host: tokenizer.encode(" ")             decoding.py:430 */
 } wb200_decode_config;
@@ -174,6 +177,20 @@ int wb200_decoder_step(wb200_decoder* dec, void* stream);
 int wb200_decoder_run(wb200_decoder* dec, int max_steps, int32_t* steps_issued, void* stream);
 /* teacher forcing for parity tests: append HOST int32 tokens [n_audio*n_group] instead of selecting */
 int wb200_decoder_force_tokens(wb200_decoder* dec, const int32_t* next_tokens, void* stream);
+
+/* find_alignment support (timing.py:185-197): before wb200_decoder_prefill, ask for the PRE-softmax
+ * cross-attention scores (q k^T / 8, fp32) of selected heads.  heads: HOST int32 [n_heads][2] =
+ * (layer, head); qk_out: device fp32 [n_heads, n_init, 1500] of audio 0, filled by the next prefill.
+ * n_heads = 0 cancels. */
+int wb200_decoder_set_alignment(wb200_decoder* dec, const int32_t* heads, int n_heads, float* qk_out);
+
+/* timing.py:207-214 on the exported scores: softmax over the first n_frames frames of qk * qk_scale,
+ * z-score over the token axis (population std), median filter of odd `medfilt_width` along frames,
+ * mean over heads.  qk: [n_heads, n_tokens, t_stride]; out: [n_tokens, n_frames] (negated when
+ * `negate` != 0, ready for DTW); scratch: 2 * n_heads * n_tokens * n_frames floats. */
+int wb200_alignment_weights(const float* qk, int n_heads, int n_tokens, int t_stride, int n_frames,
+                            float qk_scale, int medfilt_width, int negate, float* out, float* scratch,
+                            void* stream);
 
 /* state access: copies between the session and caller memory (host or device), asynchronously on
  * `stream`.  Element types: int32 except LOGITS / SUM_LOGPROBS / NO_SPEECH / TOP_VAL / FIN_SCORE (fp32). */

@@ -13,6 +13,7 @@ Fixtures:
   token_ids.json           special ids, non-speech suppress lists, " " encoding, language codes
   timing.npz               median_filter / dtw_cpu outputs (timing.py:19-105) on seeded inputs
   mel_<kind>.npz           log_mel_spectrogram outputs (sub-sampled) + global statistics
+  alignment_<name>.npz     find_alignment tensor part: alignment matrix, DTW path, token probabilities
   model_<name>.npz/.json   encoder features (sub-sampled), prefill logits probes, and decode()
                            results (tokens, avg_logprob, no_speech_prob) for several DecodingOptions
 """
@@ -181,6 +182,46 @@ def gen_model(name: str, seed: int, audio_kind: str, full_length: bool, regime: 
         json.dump(meta, f)
 
 
+def gen_alignment(name: str, seed: int, regime: str):
+    """The tensor part of find_alignment (timing.py:176-216) executed with the reference's own model,
+    hooks, median_filter and dtw on a fixed token row; word splitting (BPE strings) is left out."""
+    from whisper.model import disable_sdpa
+    from whisper.timing import dtw as ref_dtw
+
+    model, dims = build_reference_model(name, seed, regime)
+    audio = synthetic.synthetic_audio(1, 480000, seed=4321, kind="speechlike")
+    tok = get_tokenizer(model.is_multilingual, num_languages=model.num_languages, language="en", task="transcribe")
+    rng = np.random.Generator(np.random.PCG64(99))
+    text_tokens = [int(t) for t in rng.integers(1000, 40000, size=37)]
+    num_frames = 2400
+    with torch.no_grad():
+        mel = log_mel_spectrogram(torch.from_numpy(audio[0]), n_mels=dims["n_mels"])
+        tokens = torch.tensor([*tok.sot_sequence, tok.no_timestamps, *text_tokens, tok.eot])
+        QKs = [None] * model.dims.n_text_layer
+        hooks = [blk.cross_attn.register_forward_hook(lambda _, ins, outs, index=i: QKs.__setitem__(index, outs[-1][0]))
+                 for i, blk in enumerate(model.decoder.blocks)]
+        with disable_sdpa():
+            logits = model(mel.unsqueeze(0), tokens.unsqueeze(0))[0]
+        for h in hooks:
+            h.remove()
+        sampled = logits[len(tok.sot_sequence):, : tok.eot]
+        probs = sampled.softmax(dim=-1)[np.arange(len(text_tokens)), text_tokens]
+        heads = model.alignment_heads.indices().T
+        weights = torch.stack([QKs[_l][_h] for _l, _h in heads])
+        weights = weights[:, :, : num_frames // 2]
+        weights = weights.softmax(dim=-1)
+        std, mean = torch.std_mean(weights, dim=-2, keepdim=True, unbiased=False)
+        weights = (weights - mean) / std
+        weights = median_filter(weights, 7)
+        matrix = weights.mean(axis=0)
+        matrix = matrix[len(tok.sot_sequence): -1]
+        text_idx, time_idx = ref_dtw(-matrix)
+    np.savez_compressed(os.path.join(GOLD, f"alignment_{name}.npz"), text_tokens=np.array(text_tokens),
+                        num_frames=np.array(num_frames), heads=heads.numpy(), matrix=matrix.numpy().astype(np.float32),
+                        text_indices=np.asarray(text_idx), time_indices=np.asarray(time_idx),
+                        token_probs=probs.numpy().astype(np.float32), seed=np.array(seed))
+
+
 def main():
     torch.set_num_threads(os.cpu_count() or 1)
     gen_static()
@@ -189,6 +230,7 @@ def main():
     gen_model("test-en", seed=11, audio_kind="speechlike", full_length=True, regime="confident")
     gen_model("test-multi", seed=12, audio_kind="noise", full_length=True, regime="diverse")
     gen_model("tiny.en", seed=13, audio_kind="speechlike", full_length=False, regime="confident")
+    gen_alignment("test-en", seed=11, regime="confident")
     print("golden fixtures written to", GOLD)
 
 

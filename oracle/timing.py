@@ -78,3 +78,18 @@ def dtw(x: np.ndarray) -> np.ndarray:
 def dtw_gpu_tiebreak(x: np.ndarray) -> np.ndarray:
     """dtw_cuda / dtw_kernel semantics (timing.py:108-138, triton_ops.py:13-40)."""
     return _dtw(x, gpu_ties=True)
+
+
+def alignment_matrix(qk: np.ndarray, n_frames: int, qk_scale: float = 1.0, medfilt_width: int = 7) -> np.ndarray:
+    """timing.py:207-214: qk [heads, tokens, 1500] (pre-softmax cross-attention scores of the alignment
+    heads) -> softmax over the first n_frames frames, z-score over the token axis (population std),
+    median filter along frames, mean over heads.  Returns [tokens, n_frames] fp32."""
+    w = qk[:, :, :n_frames].astype(np.float32) * np.float32(qk_scale)
+    w = w - w.max(axis=-1, keepdims=True)
+    w = np.exp(w)
+    w = w / w.sum(axis=-1, keepdims=True)
+    mean = w.mean(axis=-2, keepdims=True)
+    std = np.sqrt(((w - mean) ** 2).mean(axis=-2, keepdims=True))
+    w = (w - mean) / std
+    w = median_filter(w.astype(np.float32), medfilt_width)
+    return w.mean(axis=0).astype(np.float32)

@@ -1,0 +1,108 @@
+"""find_alignment tensor part (reference timing.py:176-216): oracle vs the reference's golden (CPU) and
+the CUDA path vs the oracle (GPU)."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from helpers import GOLD, fixture_inputs, load_model_fixture
+
+
+def _setup():
+    from oracle import audio as OA
+    from oracle import decoding as OD
+    from oracle import model as OM
+    from whisper_b200 import synthetic
+
+    g = np.load(os.path.join(GOLD, "alignment_test-en.npz"))
+    meta, _ = load_model_fixture("test-en")
+    dims, sd, _ = fixture_inputs(meta)
+    audio = synthetic.synthetic_audio(1, 480000, seed=4321, kind="speechlike")
+    ids = OD.token_ids(dims["n_vocab"])
+    text_tokens = g["text_tokens"].tolist()
+    tokens = [*ids.sot_sequence("en"), ids.no_timestamps, *text_tokens, ids.eot]
+    return g, dims, sd, audio, ids, text_tokens, tokens, OA, OM
+
+
+def test_oracle_alignment_matches_reference():
+    from oracle import timing as OT
+
+    g, dims, sd, audio, ids, text_tokens, tokens, OA, OM = _setup()
+    W = OM.to_weights(sd)
+    mel = torch.from_numpy(OA.log_mel_spectrogram(audio, dims["n_mels"]))
+    feats = OM.encoder_forward(W, dims, mel)
+    qks = []
+    logits = OM.decoder_forward(W, dims, torch.tensor([tokens]), feats, collect_qk=qks)[0]
+    heads = g["heads"]                      # rows are (layer, head) pairs
+    qk = np.stack([qks[l][0, h].numpy() for l, h in heads])
+    n_frames = int(g["num_frames"]) // 2
+    matrix = OT.alignment_matrix(qk, n_frames)[len(ids.sot_sequence("en")): -1]
+    assert np.abs(matrix - g["matrix"]).max() < 2e-4
+    path = OT.dtw(-matrix)
+    assert np.array_equal(path[0], g["text_indices"]) and np.array_equal(path[1], g["time_indices"])
+    probs = torch.softmax(logits[1:, : ids.eot], dim=-1)[np.arange(len(text_tokens)), text_tokens].numpy()
+    assert np.allclose(probs, g["token_probs"], rtol=1e-3, atol=1e-7)
+
+
+@pytest.mark.gpu
+def test_gpu_alignment_vs_oracle():
+    import whisper_b200 as wb
+    from oracle import timing as OT
+    from whisper_b200 import timing as WT
+
+    g, dims, sd, audio, ids, text_tokens, tokens, OA, OM = _setup()
+    W = OM.to_weights(sd)
+    o_mel = torch.from_numpy(OA.log_mel_spectrogram(audio, dims["n_mels"]))
+    o_feats = OM.encoder_forward(W, dims, o_mel)
+    qks = []
+    o_logits = OM.decoder_forward(W, dims, torch.tensor([tokens]), o_feats, collect_qk=qks)[0]
+    heads = [tuple(x) for x in g["heads"].tolist()]
+    o_qk = np.stack([qks[l][0, h].numpy() for l, h in heads])
+
+    model = wb.Whisper(wb.ModelDimensions(**dims), sd, device="cuda", dtype=torch.float16)
+    assert model.alignment_heads.indices().T.tolist() == [list(h) for h in heads]     # default heads, model.py:268-276
+    feats = model.embed_audio(wb.log_mel_spectrogram(torch.from_numpy(audio).cuda(), dims["n_mels"]))
+    logits, qk = model.logits(torch.tensor([tokens]), feats, alignment_heads=heads)
+    # un-cached full-sequence forward: logits at every position, scores of the alignment heads
+    lerr = float((logits[0].cpu() - o_logits).abs().max() / o_logits.abs().max())
+    assert lerr < 2.5e-3, f"full-forward logits rel err {lerr}"
+    qerr = float(np.abs(qk.cpu().numpy() - o_qk).max())
+    assert qerr < 0.05 * max(1.0, float(np.abs(o_qk).max()) / 10), f"qk max err {qerr} (max |qk| {np.abs(o_qk).max():.2f})"
+
+    n_frames = int(g["num_frames"]) // 2
+    # the post-processing kernels on the ORACLE's scores: tight tolerance, then bit-exact DTW on that matrix
+    m_gpu = WT.alignment_matrix(torch.from_numpy(o_qk).cuda().contiguous(), n_frames).cpu().numpy()
+    assert np.abs(m_gpu - OT.alignment_matrix(o_qk, n_frames)).max() < 2e-4
+    sub = np.ascontiguousarray(-m_gpu[1:-1])
+    assert np.array_equal(WT.dtw(torch.from_numpy(sub).cuda()), OT.dtw_gpu_tiebreak(sub))
+    # negate flag == negating afterwards
+    m_neg = WT.alignment_matrix(torch.from_numpy(o_qk).cuda().contiguous(), n_frames, negate=True).cpu().numpy()
+    assert np.array_equal(m_neg, -m_gpu)
+
+    # end to end through find_alignment (ids-only tokenizer: word splitting degenerates, timings still come out)
+    tk = wb.tokenizer.get_tokenizer(False)
+    words = WT.find_alignment(model, tk, text_tokens, None, int(g["num_frames"]), audio_features=feats)
+    assert len(words) >= 1 and all(w.end >= w.start for w in words)
+    assert sum(len(w.tokens) for w in words) == len(text_tokens) + 1
+
+
+@pytest.mark.gpu
+def test_gpu_logits_method_matches_prefill_session():
+    """Whisper.logits (all positions) agrees with the last-position logits the decode session produces."""
+    import whisper_b200 as wb
+    from whisper_b200.decoding import DecodingOptions, DecodingTask
+
+    g, dims, sd, audio, ids, text_tokens, tokens, OA, OM = _setup()
+    model = wb.Whisper(wb.ModelDimensions(**dims), sd, device="cuda", dtype=torch.float16)
+    feats = model.embed_audio(wb.log_mel_spectrogram(torch.from_numpy(audio).cuda(), dims["n_mels"]))
+    task = DecodingTask(model, DecodingOptions(language="en", prompt=text_tokens[:9]))
+    sess = task.open_session(1)
+    try:
+        sess.set_audio(feats)
+        sess.prefill(np.asarray([task.initial_tokens], dtype=np.int32))
+        last = sess.get_logits(1)[0].clone()
+    finally:
+        sess.close()
+    full = model.logits(torch.tensor([list(task.initial_tokens)]), feats)[0]
+    assert torch.equal(full[-1], last)

@@ -300,6 +300,32 @@ int wb200_decoder_run(wb200_decoder* dec, int max_steps, int32_t* steps_issued, 
 int wb200_decoder_force_tokens(wb200_decoder* dec, const int32_t* next_tokens, void* stream) {
   return decoder_append(dec->d, next_tokens, static_cast<cudaStream_t>(stream));
 }
+int wb200_decoder_set_alignment(wb200_decoder* dec, const int32_t* heads, int n_heads, float* qk_out) {
+  Decoder* D = dec->d;
+  D->align_heads.clear();
+  D->align_qk = nullptr;
+  if (n_heads <= 0) return 0;
+  if (!heads || !qk_out) return set_error(150, "set_alignment: null argument");
+  for (int i = 0; i < n_heads; ++i) {
+    const int l = heads[2 * i], h = heads[2 * i + 1];
+    if (l < 0 || l >= D->m->dims.n_text_layer || h < 0 || h >= D->m->dims.n_text_head)
+      return set_error(151, "set_alignment: head (%d, %d) out of range", l, h);
+    D->align_heads.push_back(l);
+    D->align_heads.push_back(h);
+  }
+  D->align_qk = qk_out;
+  return 0;
+}
+
+int wb200_alignment_weights(const float* qk, int n_heads, int n_tokens, int t_stride, int n_frames,
+                            float qk_scale, int medfilt_width, int negate, float* out, float* scratch,
+                            void* stream) {
+  if (medfilt_width < 1 || (medfilt_width & 1) == 0) return set_error(152, "alignment_weights: filter width must be odd");
+  int r = launch_alignment_weights(qk, n_heads, n_tokens, t_stride, n_frames, qk_scale, medfilt_width, negate, out,
+                                   scratch, static_cast<cudaStream_t>(stream));
+  return r ? set_error(r, "wb200_alignment_weights: failed (%d)", r) : 0;
+}
+
 int64_t wb200_decoder_logits_ld(const wb200_decoder* dec) { return dec->d->ldv; }
 
 int wb200_decoder_get_state(wb200_decoder* dec, int what, void* dst, size_t bytes, void* stream) {

@@ -528,11 +528,22 @@ __global__ void kv_append_kernel(const T* __restrict__ qkv, T* __restrict__ kcac
 // -------------------------------------------------------------------------------------------------
 // launchers
 // -------------------------------------------------------------------------------------------------
-int cross_attention_splits(int T) { return T >= 1024 ? 4 : (T >= 256 ? 2 : 1); }
+// Number of key splits per (audio, head, q-tile).  Every CTA pays ~2 us of pipeline fill before its
+// first tile is consumed, so splits are kept as few as still give ~6 CTAs per SM: 2 at C3
+// (64 audios x 20 heads), up to 8 for a single audio.
+int cross_attention_splits(int T, int n_groups) {
+  if (T < 256) return 1;
+  int s = (888 + n_groups - 1) / n_groups;
+  if (s < 2) s = 2;
+  if (s > 8) s = 8;
+  const int max_by_len = T / 128;              // at least two 64-key tiles per split
+  if (s > max_by_len) s = max_by_len;
+  return s < 1 ? 1 : s;
+}
 
 size_t cross_attention_partial_floats(int n_audio, int n_q, int n_head, int T) {
   const int q_tiles = (n_q + 15) / 16;
-  return static_cast<size_t>(n_audio) * q_tiles * n_head * cross_attention_splits(T) * 16 * 66;
+  return static_cast<size_t>(n_audio) * q_tiles * n_head * 8 /* max splits */ * 16 * 66;
 }
 
 int launch_cross_attention(int dtype, const void* q, const void* k, const void* v, void* out,
@@ -552,7 +563,7 @@ int launch_cross_attention(int dtype, const void* q, const void* k, const void* 
   p.T = T;
   p.d = n_head * 64;
   p.kv_ld = kv_ld;
-  p.splits = cross_attention_splits(T);
+  p.splits = cross_attention_splits(T, n_audio * p.q_tiles * n_head);
   p.keys_per_split = ((T + p.splits - 1) / p.splits + 63) / 64 * 64;
   dim3 grid(p.splits, n_head, n_audio * p.q_tiles);
   ProfileScope prof(PROF_CROSS_ATTN, s);

@@ -242,7 +242,8 @@ static void dec_carve(const Model* m, const wb200_decode_config& c, Arena& ar, D
   o->q = ar.take(rows * d * es);
   o->hid = ar.take(rows * 4 * d * es);
   o->sel = ar.take(2 * B * d * es);
-  const size_t logit_rows = R > 2 * B ? R : 2 * B;
+  size_t logit_rows = R > 2 * B ? R : 2 * B;
+  if (c.all_logits && P > logit_rows) logit_rows = P;
   o->logits = static_cast<float*>(ar.take(logit_rows * ldv * 4));
   const size_t nq = c.n_init > (int)G ? c.n_init : G;
   o->partial = static_cast<float*>(ar.take(cross_attention_partial_floats((int)B, (int)nq, (int)H, (int)Ta) * 4));
@@ -362,6 +363,16 @@ static int decoder_stack(Decoder* D, int rows, bool step, cudaStream_t s) {
     WB_TRY(linear(m, D->att, d, rows, L[D_OUT_W], d, d, L[D_OUT_B], D->x, D->x, d, 0, 0, s, skip, D));
     WB_TRY(launch_layernorm(dt, D->x, d, D->ln, d, (const float*)L[D_CROSS_LN_W], (const float*)L[D_CROSS_LN_B], rows, d, s, skip));
     WB_TRY(linear(m, D->ln, d, rows, L[D_CQ_W], d, d, L[D_CQ_B], nullptr, D->q, d, 0, 0, s, skip, D));
+    if (!step && D->align_qk) {
+      // timing.py:186-197: pre-softmax cross-attention scores of the alignment heads (audio 0 only)
+      for (size_t i = 0; i + 1 < D->align_heads.size(); i += 2) {
+        if (D->align_heads[i] != l) continue;
+        const int hh = D->align_heads[i + 1];
+        float* dst = D->align_qk + (i / 2) * static_cast<size_t>(D->cfg.n_init) * Ta;
+        WB_TRY(launch_qk_export(dt, static_cast<const uint8_t*>(D->q) + static_cast<size_t>(hh) * 128, d,
+                                ckv + static_cast<size_t>(hh) * 128, 2 * d, dst, D->cfg.n_init, Ta, s));
+      }
+    }
     WB_TRY(launch_cross_attention(dt, D->q, ckv, ckv + static_cast<size_t>(d) * 2, D->att, D->partial, D->counters, skip, B,
                                   n_q, Ta, H, 2 * d, s));
     WB_TRY(linear(m, D->att, d, rows, L[D_COUT_W], d, d, L[D_COUT_B], D->x, D->x, d, 0, 0, s, skip, D));
@@ -395,6 +406,20 @@ int decoder_prefill(Decoder* D, const int32_t* init_tokens_host, cudaStream_t s)
   count_launch();
   if (dt == DT_BF16) launch_embed<__nv_bfloat16>(D, P, false, s); else launch_embed<__half>(D, P, false, s);
   WB_TRY(decoder_stack(D, P, false, s));
+  if (c.all_logits) {
+    // un-cached full forward (model.py:293-296): logits of every prompt position
+    WB_TRY(launch_layernorm(dt, D->x, d, D->ln, d, (const float*)m->t[G_DEC_LN_W], (const float*)m->t[G_DEC_LN_B], P, d, s, nullptr));
+    WB_TRY(linear(m, D->ln, d, P, m->t[G_TOK_EMB16], V, d, nullptr, nullptr, D->logits, D->ldv, 0, 1, s));
+    if (c.no_speech >= 0) WB_TRY(launch_no_speech(D->logits, D->ldv, V, c.no_speech, D->no_speech, B, c.n_init, c.sot_index, s));
+    D->logits_cur = D->logits;
+    D->logits_row_div = 1;
+    D->logits_rows = P;
+    D->host_len = c.n_init;
+    D->forward_only = true;
+    return 0;
+  }
+  D->forward_only = false;
+  D->logits_rows = B;
   if (dt == DT_BF16)
     gather_prefill_rows_kernel<__nv_bfloat16><<<2 * B, 128, 0, s>>>((const __nv_bfloat16*)D->x, (__nv_bfloat16*)D->sel, B, c.n_init, c.sot_index, d);
   else
@@ -402,7 +427,7 @@ int decoder_prefill(Decoder* D, const int32_t* init_tokens_host, cudaStream_t s)
   count_launch();
   WB_TRY(launch_layernorm(dt, D->sel, d, D->ln, d, (const float*)m->t[G_DEC_LN_W], (const float*)m->t[G_DEC_LN_B], 2 * B, d, s, nullptr));
   WB_TRY(linear(m, D->ln, d, 2 * B, m->t[G_TOK_EMB16], V, d, nullptr, nullptr, D->logits, D->ldv, 0, 1, s));
-  if (c.no_speech >= 0) WB_TRY(launch_no_speech(D->logits, D->ldv, V, c.no_speech, D->no_speech, B, s));
+  if (c.no_speech >= 0) WB_TRY(launch_no_speech(D->logits, D->ldv, V, c.no_speech, D->no_speech, B, 1, 0, s));
   D->logits_cur = D->logits + static_cast<size_t>(B) * D->ldv;   // rows [B, 2B): last prompt position
   D->logits_row_div = G;
   D->host_len = c.n_init;
@@ -415,12 +440,14 @@ int decoder_step(Decoder* D, cudaStream_t s) {
   const int R = D->cfg.n_audio * D->cfg.n_group;
   const int d = m->dims.n_text_state, V = m->dims.n_vocab, dt = m->dtype;
   if (D->host_len >= m->dims.n_text_ctx) return set_error(240, "step: context full");
+  if (D->forward_only) return set_error(241, "step: this session was created with all_logits (forward-only)");
   if (dt == DT_BF16) launch_embed<__nv_bfloat16>(D, R, true, s); else launch_embed<__half>(D, R, true, s);
   WB_TRY(decoder_stack(D, R, true, s));
   WB_TRY(launch_layernorm(dt, D->x, d, D->ln, d, (const float*)m->t[G_DEC_LN_W], (const float*)m->t[G_DEC_LN_B], R, d, s, D->done_ptr));
   WB_TRY(linear(m, D->ln, d, R, m->t[G_TOK_EMB16], V, d, nullptr, nullptr, D->logits, D->ldv, 0, 1, s, D->done_ptr, D));
   D->logits_cur = D->logits;
   D->logits_row_div = 1;
+  D->logits_rows = R;
   return 0;
 }
 
@@ -428,6 +455,7 @@ int decoder_select(Decoder* D, cudaStream_t s) {
   const Model* m = D->m;
   const wb200_decode_config& c = D->cfg;
   const int B = c.n_audio, G = c.n_group, R = B * G, ctx = m->dims.n_text_ctx;
+  if (D->forward_only) return set_error(242, "select: this session was created with all_logits (forward-only)");
   FilterParams f;
   f.logits = D->logits_cur;
   f.ld = D->ldv;
@@ -648,7 +676,7 @@ int decoder_state_ptr(Decoder* D, int what, void** ptr, size_t* bytes, cudaStrea
     case WB200_STATE_SUM_LOGPROBS: *ptr = D->sum_lp; *bytes = R * 4; break;
     case WB200_STATE_NO_SPEECH: *ptr = D->no_speech; *bytes = B * 4; break;
     case WB200_STATE_LOGITS: *ptr = const_cast<float*>(D->logits_cur);
-      *bytes = (D->logits_row_div > 1 ? B : R) * static_cast<size_t>(D->ldv) * 4; break;
+      *bytes = static_cast<size_t>(D->logits_rows) * static_cast<size_t>(D->ldv) * 4; break;
     case WB200_STATE_TOP_VAL: *ptr = D->top_val; *bytes = R * K * 4; break;
     case WB200_STATE_TOP_IDX: *ptr = D->top_idx; *bytes = R * K * 4; break;
     case WB200_STATE_SOURCES: *ptr = D->sources; *bytes = R * 4; break;

@@ -77,7 +77,11 @@ struct Decoder {
   int host_len = 0;            // tokens per row as far as the host has issued work
   const float* logits_cur = nullptr;
   int logits_row_div = 1;
+  int logits_rows = 0;         // rows currently valid at logits_cur
+  bool forward_only = false;   // all_logits sessions cannot step / select
   int* pinned = nullptr;       // pinned host scratch for flag polling
+  std::vector<int> align_heads;     // (layer, head) pairs whose cross-attention scores are exported
+  float* align_qk = nullptr;        // [n_heads, n_init, n_audio_ctx] fp32 (caller memory)
   // CUDA-graph replay of the decode loop: two iterations (step, select, step, select) per graph so
   // the ping-pong token / parent-table buffers are back where they started after every replay.
   cudaStream_t gstream = nullptr;   // private capture / replay stream (capture is illegal on the legacy stream)

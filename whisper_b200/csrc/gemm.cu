@@ -17,6 +17,8 @@
 // Pipelines: smem ring (full/empty mbarriers) between TMA and MMA; two TMEM accumulator
 // stages (tmem_full/tmem_empty) between MMA and epilogue so tile i+1's main loop overlaps
 // tile i's epilogue.
+#include <stdlib.h>
+
 #include "kernels.h"
 #include "ptx.cuh"
 #include "tmap.cuh"
@@ -288,9 +290,15 @@ gemm_tcgen05_kernel(const GemmParams p, const __grid_constant__ CUtensorMap mapA
           } else {
             // raw fp32 partial sums of this K-slice (only in-range columns exist in the slab)
             float* ps = p.partial + split * p.partial_stride + grow * p.N + nb;
+            if (nb + 32 <= p.N && (p.N & 3) == 0) {
 #pragma unroll
-            for (int j = 0; j < 32; ++j)
-              if (nb + j < p.N) __stcg(ps + j, v[j]);
+              for (int q = 0; q < 8; ++q)
+                __stcg(reinterpret_cast<float4*>(ps) + q, make_float4(v[q * 4], v[q * 4 + 1], v[q * 4 + 2], v[q * 4 + 3]));
+            } else {
+#pragma unroll
+              for (int j = 0; j < 32; ++j)
+                if (nb + j < p.N) __stcg(ps + j, v[j]);
+            }
           }
         }
       }
@@ -316,11 +324,23 @@ gemm_tcgen05_kernel(const GemmParams p, const __grid_constant__ CUtensorMap mapA
               float v[32];
 #pragma unroll
               for (int j = 0; j < 32; ++j) v[j] = 0.f;
+              const bool vec = nb + 32 <= p.N && (p.N & 3) == 0;
               for (int sp = 0; sp < p.splits; ++sp) {
                 const float* ps = p.partial + sp * p.partial_stride + grow * p.N + nb;
+                if (vec) {
 #pragma unroll
-                for (int j = 0; j < 32; ++j)
-                  if (nb + j < p.N) v[j] += __ldcg(ps + j);
+                  for (int q = 0; q < 8; ++q) {
+                    const float4 f = __ldcg(reinterpret_cast<const float4*>(ps) + q);
+                    v[q * 4] += f.x;
+                    v[q * 4 + 1] += f.y;
+                    v[q * 4 + 2] += f.z;
+                    v[q * 4 + 3] += f.w;
+                  }
+                } else {
+#pragma unroll
+                  for (int j = 0; j < 32; ++j)
+                    if (nb + j < p.N) v[j] += __ldcg(ps + j);
+                }
               }
               epilogue_store<T, OUT_F32>(v, p, t, grow, nb);
             }
@@ -407,7 +427,13 @@ int launch_linear(const LinearArgs& a, cudaStream_t s) {
   {
     const int tiles = p.batch * p.m_tiles_per_batch * p.n_tiles;
     const int kblocks = p.taps * p.k_blocks_per_tap;
-    if (a.splitk_ws && a.splitk_counters && a.taps == 1 && tiles < 148 && kblocks >= 8 && tiles <= a.splitk_max_tiles) {
+    static int splitk_on = -1;
+    if (splitk_on < 0) {
+      const char* e = getenv("WB200_NO_SPLITK");
+      splitk_on = (e && e[0] && e[0] != '0') ? 0 : 1;
+    }
+    if (splitk_on && a.splitk_ws && a.splitk_counters && a.taps == 1 && tiles < 148 && kblocks >= 8 &&
+        tiles <= a.splitk_max_tiles) {
       int sp = (2 * 148 + tiles - 1) / tiles;          // aim at ~2 work items per SM
       if (sp > kblocks / 4) sp = kblocks / 4;          // keep >= 4 k-blocks (256 of K) per item
       if (sp > 8) sp = 8;

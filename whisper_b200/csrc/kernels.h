@@ -76,7 +76,7 @@ int launch_enc_attention(int dtype, const void* qkv, void* out, int B, int T, in
                          cudaStream_t s);
 
 // ---- decoder attention (dec_attention.cu)
-int cross_attention_splits(int T);
+int cross_attention_splits(int T, int n_groups);
 size_t cross_attention_partial_floats(int n_audio, int n_q, int n_head, int T);
 // q: [n_audio*n_q, d]; k/v: [n_audio, T, kv_ld] row stride kv_ld elements; out: [n_audio*n_q, d]
 int launch_cross_attention(int dtype, const void* q, const void* k, const void* v, void* out,
@@ -140,7 +140,7 @@ struct BeamParams {
 };
 int launch_filter_topk(const FilterParams& p, int R, cudaStream_t s);
 int launch_no_speech(const float* logits, long long ld, int V, int no_speech, float* out, int rows,
-                     cudaStream_t s);
+                     int row_stride, int row_offset, cudaStream_t s);
 int launch_greedy_update(const GreedyParams& p, cudaStream_t s);
 int launch_beam_update(const BeamParams& p, cudaStream_t s);
 
@@ -150,6 +150,12 @@ int launch_log_mel(const float* audio, int n_audio, long long n_samples, int n_m
                    float* out, void* workspace, int per_row_max, cudaStream_t s);
 
 // ---- word timing (timing.cu)
+// qk[i][t] = (q_i . k_t) / 8 for one head: q rows [n_q, ldq], k rows [T, ldk] (16-bit), out fp32 [n_q, T]
+int launch_qk_export(int dtype, const void* q, long long ldq, const void* k, long long ldk, float* out,
+                     int n_q, int T, cudaStream_t s);
+int launch_alignment_weights(const float* qk, int n_heads, int n_tokens, int t_stride, int n_frames,
+                             float qk_scale, int medfilt_width, int negate, float* out, float* scratch,
+                             cudaStream_t s);
 int launch_median_filter(const float* x, float* y, long long rows, int T, int width, cudaStream_t s);
 size_t dtw_workspace_bytes(int N, int M);
 int launch_dtw(const float* x, int N, int M, int* path, int* path_len, void* workspace, int tie_mode,

@@ -221,8 +221,9 @@ __global__ void __launch_bounds__(kSelThreads) filter_topk_kernel(const FilterPa
 // no-speech probability at the <|startoftranscript|> position (decoding.py:689-693)
 // -------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(kSelThreads) no_speech_kernel(const float* logits, long long ld, int V,
-                                                                int no_speech, float* out) {
-  const float* x = logits + static_cast<long long>(blockIdx.x) * ld;
+                                                                int no_speech, float* out, int row_stride,
+                                                                int row_offset) {
+  const float* x = logits + (static_cast<long long>(blockIdx.x) * row_stride + row_offset) * ld;
   __shared__ float s_red[kSelThreads / 32][2];
   float m = -INFINITY, s = 0.f;
   for (int v = threadIdx.x; v < V; v += kSelThreads) lse_merge(m, s, x[v], 1.f);
@@ -440,8 +441,8 @@ int launch_filter_topk(const FilterParams& p, int R, cudaStream_t s) {
   return cudaGetLastError() == cudaSuccess ? 0 : 51;
 }
 int launch_no_speech(const float* logits, long long ld, int V, int no_speech, float* out, int rows,
-                     cudaStream_t s) {
-  no_speech_kernel<<<rows, kSelThreads, 0, s>>>(logits, ld, V, no_speech, out);
+                     int row_stride, int row_offset, cudaStream_t s) {
+  no_speech_kernel<<<rows, kSelThreads, 0, s>>>(logits, ld, V, no_speech, out, row_stride, row_offset);
   count_launch();
   return cudaGetLastError() == cudaSuccess ? 0 : 52;
 }

@@ -159,4 +159,133 @@ int launch_dtw(const float* x, int N, int M, int* path, int* path_len, void* wor
   return cudaGetLastError() == cudaSuccess ? 0 : 77;
 }
 
+// -------------------------------------------------------------------------------------------------
+// find_alignment tensor part (timing.py:185-216)
+// -------------------------------------------------------------------------------------------------
+// Pre-softmax cross-attention scores of ONE head: out[i][t] = (q_i . k_t) / sqrt(64).  The reference
+// gets them by re-running the whole model with SDPA disabled (model.py:129-137); here the decoder
+// prefill exports them for the alignment heads only.  One thread per key, the query row in smem.
+template <typename T>
+__global__ void __launch_bounds__(256) qk_export_kernel(const T* __restrict__ q, long long ldq,
+                                                        const T* __restrict__ k, long long ldk,
+                                                        float* __restrict__ out, int T_keys) {
+  __shared__ float sq[64];
+  const int i = blockIdx.y;
+  if (threadIdx.x < 64) sq[threadIdx.x] = Cvt<T>::to_f(q[i * ldq + threadIdx.x]);
+  __syncthreads();
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= T_keys) return;
+  const uint4* kr = reinterpret_cast<const uint4*>(k + static_cast<long long>(t) * ldk);
+  float acc = 0.f;
+#pragma unroll
+  for (int c = 0; c < 8; ++c) {
+    const uint4 u = kr[c];
+    const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const float2 f = Cvt<T>::unpack2(w[e]);
+      acc = fmaf(sq[c * 8 + 2 * e], f.x, acc);
+      acc = fmaf(sq[c * 8 + 2 * e + 1], f.y, acc);
+    }
+  }
+  out[static_cast<long long>(i) * T_keys + t] = acc * 0.125f;
+}
+
+int launch_qk_export(int dtype, const void* q, long long ldq, const void* k, long long ldk, float* out,
+                     int n_q, int T, cudaStream_t s) {
+  if (n_q <= 0 || T <= 0) return 0;
+  dim3 grid((T + 255) / 256, n_q);
+  if (dtype == DT_BF16)
+    qk_export_kernel<__nv_bfloat16><<<grid, 256, 0, s>>>(static_cast<const __nv_bfloat16*>(q), ldq,
+                                                         static_cast<const __nv_bfloat16*>(k), ldk, out, T);
+  else
+    qk_export_kernel<__half><<<grid, 256, 0, s>>>(static_cast<const __half*>(q), ldq,
+                                                  static_cast<const __half*>(k), ldk, out, T);
+  count_launch();
+  return cudaGetLastError() == cudaSuccess ? 0 : 78;
+}
+
+// softmax over the first n_frames frames of one (head, token) row (timing.py:209)
+__global__ void __launch_bounds__(256) align_softmax_kernel(const float* __restrict__ qk, float* __restrict__ w,
+                                                            int t_stride, int n_frames, float qk_scale) {
+  __shared__ float red[8];
+  const float* x = qk + static_cast<long long>(blockIdx.x) * t_stride;
+  float* y = w + static_cast<long long>(blockIdx.x) * n_frames;
+  float m = -INFINITY;
+  for (int t = threadIdx.x; t < n_frames; t += 256) m = fmaxf(m, x[t] * qk_scale);
+  m = warp_max(m);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = m;
+  __syncthreads();
+  m = red[0];
+  for (int i = 1; i < 8; ++i) m = fmaxf(m, red[i]);
+  __syncthreads();
+  float sum = 0.f;
+  for (int t = threadIdx.x; t < n_frames; t += 256) {
+    const float e = expf(x[t] * qk_scale - m);
+    y[t] = e;
+    sum += e;
+  }
+  sum = warp_sum(sum);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = sum;
+  __syncthreads();
+  sum = 0.f;
+  for (int i = 0; i < 8; ++i) sum += red[i];
+  const float inv = 1.0f / sum;
+  for (int t = threadIdx.x; t < n_frames; t += 256) y[t] *= inv;
+}
+
+// z-score over the token axis for every (head, frame): std_mean(dim=-2, unbiased=False) (timing.py:210-211)
+__global__ void __launch_bounds__(256) align_zscore_kernel(float* __restrict__ w, int n_tokens, int n_frames) {
+  const int h = blockIdx.y;
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= n_frames) return;
+  float* base = w + static_cast<long long>(h) * n_tokens * n_frames + t;
+  float mean = 0.f;
+  for (int i = 0; i < n_tokens; ++i) mean += base[static_cast<long long>(i) * n_frames];
+  mean /= static_cast<float>(n_tokens);
+  float var = 0.f;
+  for (int i = 0; i < n_tokens; ++i) {
+    const float d = base[static_cast<long long>(i) * n_frames] - mean;
+    var += d * d;
+  }
+  const float stdv = sqrtf(var / static_cast<float>(n_tokens));
+  for (int i = 0; i < n_tokens; ++i) {
+    float* p = base + static_cast<long long>(i) * n_frames;
+    *p = (*p - mean) / stdv;
+  }
+}
+
+// mean over heads (timing.py:214), optionally negated for dtw(-matrix) (timing.py:216)
+__global__ void __launch_bounds__(256) align_head_mean_kernel(const float* __restrict__ w, float* __restrict__ out,
+                                                              int n_heads, long long per_head, float scale) {
+  const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= per_head) return;
+  float acc = 0.f;
+  for (int h = 0; h < n_heads; ++h) acc += w[h * per_head + i];
+  out[i] = acc * scale;
+}
+
+int launch_alignment_weights(const float* qk, int n_heads, int n_tokens, int t_stride, int n_frames,
+                             float qk_scale, int medfilt_width, int negate, float* out, float* scratch,
+                             cudaStream_t s) {
+  if (n_heads <= 0 || n_tokens <= 0 || n_frames <= 0 || n_frames > t_stride) return 79;
+  const long long per_head = static_cast<long long>(n_tokens) * n_frames;
+  float* w0 = scratch;
+  float* w1 = scratch + n_heads * per_head;
+  align_softmax_kernel<<<n_heads * n_tokens, 256, 0, s>>>(qk, w0, t_stride, n_frames, qk_scale);
+  dim3 gz((n_frames + 255) / 256, n_heads);
+  align_zscore_kernel<<<gz, 256, 0, s>>>(w0, n_tokens, n_frames);
+  count_launch(2);
+  const float* filtered = w0;
+  if (n_frames > medfilt_width / 2) {                       // timing.py:22-24: shorter rows pass through
+    int r = launch_median_filter(w0, w1, static_cast<long long>(n_heads) * n_tokens, n_frames, medfilt_width, s);
+    if (r) return r;
+    filtered = w1;
+  }
+  const float scale = (negate ? -1.0f : 1.0f) / static_cast<float>(n_heads);
+  align_head_mean_kernel<<<static_cast<unsigned>((per_head + 255) / 256), 256, 0, s>>>(filtered, out, n_heads, per_head, scale);
+  count_launch();
+  return cudaGetLastError() == cudaSuccess ? 0 : 80;
+}
+
 }  // namespace wb

@@ -74,7 +74,7 @@ class _DecodeConfig(Structure):
     _fields_ = [(n, c_int32) for n in (
         "n_audio", "n_group", "beam_search", "max_candidates", "n_init", "sample_begin", "sot_index",
         "eot", "no_speech", "no_timestamps", "timestamp_begin", "suppress_blank", "timestamp_rules",
-        "max_initial_timestamp_index", "n_suppress", "n_blank")] + [
+        "max_initial_timestamp_index", "n_suppress", "n_blank", "all_logits")] + [
         ("suppress_ids", POINTER(c_int32)), ("blank_ids", POINTER(c_int32))]
 
 
@@ -90,6 +90,8 @@ class DecoderSession:
         self.cfg = dict(cfg)
         self._sup = (c_int32 * max(1, len(suppress)))(*suppress)
         self._blank = (c_int32 * max(1, len(blank)))(*blank)
+        cfg = dict(cfg)
+        cfg.setdefault("all_logits", 0)
         c = _DecodeConfig(**cfg, n_suppress=len(suppress), n_blank=len(blank))
         c.suppress_ids = ctypes.cast(self._sup, POINTER(c_int32))
         c.blank_ids = ctypes.cast(self._blank, POINTER(c_int32))
@@ -142,6 +144,20 @@ class DecoderSession:
         n = c_int32(0)
         self._call("wb200_decoder_run", c_int(max_steps), ctypes.byref(n))
         return int(n.value)
+
+    def set_alignment(self, heads: Sequence[Tuple[int, int]]) -> torch.Tensor:
+        """Ask the next prefill to export the pre-softmax cross-attention scores of `heads`
+        ((layer, head) pairs) for audio 0; returns the fp32 tensor [n_heads, n_init, n_audio_ctx]
+        that will receive them (reference timing.py:185-197)."""
+        n = len(heads)
+        flat = np.ascontiguousarray(np.asarray(heads, dtype=np.int32).reshape(-1))
+        self._align_heads = flat
+        self._align_qk = torch.empty((n, self.cfg["n_init"], self.model.dims.n_audio_ctx), device=self.model.device,
+                                     dtype=torch.float32)
+        with torch.cuda.device(self.model.device):
+            check(lib().wb200_decoder_set_alignment(self._h, flat.ctypes.data_as(POINTER(c_int32)), c_int(n),
+                                                    ptr(self._align_qk)), "wb200_decoder_set_alignment")
+        return self._align_qk
 
     def force_tokens(self, next_tokens: Sequence[int]):
         arr = np.ascontiguousarray(next_tokens, dtype=np.int32)

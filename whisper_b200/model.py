@@ -199,9 +199,37 @@ class Whisper:
                                               stream_ptr()), "wb200_encoder_forward")
         return out[0] if single else out
 
-    def logits(self, tokens: torch.Tensor, audio_features: torch.Tensor):
-        raise NotImplementedError("un-cached full-sequence logits (model.py:290) are part of the alignment path "
-                                  "(SURVEY.md 8f.2), not built yet; use decode()/DecodingTask")
+    def logits(self, tokens: torch.Tensor, audio_features: torch.Tensor, alignment_heads=None):
+        """Un-cached decoder forward over whole token rows (reference model.py:290-291 -> :227-249):
+        tokens (B, n) int, audio_features (B, 1500, d) -> fp32 logits (B, n, n_vocab).
+        With `alignment_heads` ((layer, head) pairs) also returns the pre-softmax cross-attention scores
+        of those heads for audio 0, fp32 [n_heads, n, 1500] (what timing.py:186-197 collects with hooks)."""
+        from .decoding import DecoderSession
+        from .tokenizer import get_tokenizer
+
+        tokens = torch.as_tensor(tokens)
+        if tokens.dim() == 1:
+            tokens = tokens[None]
+        B, n = tokens.shape
+        feats = audio_features.to(device=self._device, dtype=self.dtype)
+        if feats.dim() == 2:
+            feats = feats[None]
+        feats = feats.contiguous()
+        tk = get_tokenizer(self.is_multilingual, num_languages=self.num_languages)
+        cfg = dict(n_audio=B, n_group=1, beam_search=0, max_candidates=1, n_init=n, sample_begin=n, sot_index=0,
+                   eot=tk.eot, no_speech=-1, no_timestamps=tk.no_timestamps, timestamp_begin=tk.timestamp_begin,
+                   suppress_blank=0, timestamp_rules=0, max_initial_timestamp_index=-1, all_logits=1)
+        sess = DecoderSession(self, cfg, (), ())
+        try:
+            sess.set_audio(feats)
+            qk = sess.set_alignment(alignment_heads) if alignment_heads is not None and len(alignment_heads) else None
+            sess.prefill(tokens.cpu().numpy().astype(np.int32))
+            out = sess.get_logits(B * n).reshape(B, n, self.dims.n_vocab).clone()
+            if qk is not None:
+                torch.cuda.current_stream(self._device).synchronize()
+        finally:
+            sess.close()
+        return out if alignment_heads is None else (out, qk)
 
     def forward(self, mel: torch.Tensor, tokens: torch.Tensor):
         return self.logits(tokens, self.embed_audio(mel))

@@ -53,3 +53,81 @@ def dtw(x: torch.Tensor, cpu_tie_break: bool = False) -> np.ndarray:
                               c_int(int(cpu_tie_break)), stream_ptr()), "wb200_dtw")
     length = int(n.item())
     return path[:, :length].cpu().numpy().astype(np.int64)
+
+
+# ------------------------------------------------------------------------------------------------
+# token <-> audio-frame alignment (reference timing.py:154-242).  The string heuristics that turn an
+# alignment into per-segment word lists (merge_punctuations / add_word_timestamps, timing.py:245-388)
+# are host-side text post-processing that SURVEY.md section 2 leaves out of scope; they are not rebuilt.
+# ------------------------------------------------------------------------------------------------
+from dataclasses import dataclass as _dataclass
+from typing import TYPE_CHECKING as _TC, List as _List
+
+from .audio import HOP_LENGTH, SAMPLE_RATE, TOKENS_PER_SECOND
+
+if _TC:
+    from .model import Whisper
+    from .tokenizer import Tokenizer
+
+
+@_dataclass
+class WordTiming:
+    word: str
+    tokens: _List[int]
+    start: float
+    end: float
+    probability: float
+
+
+def alignment_matrix(qk: torch.Tensor, n_frames: int, qk_scale: float = 1.0, medfilt_width: int = 7,
+                     negate: bool = False) -> torch.Tensor:
+    """timing.py:207-214 on exported cross-attention scores qk [heads, tokens, 1500] (fp32, CUDA):
+    softmax over the first n_frames frames, z-score over tokens, median filter, mean over heads ->
+    [tokens, n_frames]."""
+    assert qk.is_cuda and qk.dtype == torch.float32 and qk.is_contiguous() and qk.dim() == 3
+    H, N, T = qk.shape
+    out = torch.empty((N, n_frames), device=qk.device, dtype=torch.float32)
+    scratch = torch.empty(2 * H * N * n_frames, device=qk.device, dtype=torch.float32)
+    from ctypes import c_float
+
+    with torch.cuda.device(qk.device):
+        check(lib().wb200_alignment_weights(ptr(qk), c_int(H), c_int(N), c_int(T), c_int(n_frames), c_float(qk_scale),
+                                            c_int(medfilt_width), c_int(int(negate)), ptr(out), ptr(scratch),
+                                            stream_ptr()), "wb200_alignment_weights")
+    return out
+
+
+def find_alignment(model: "Whisper", tokenizer: "Tokenizer", text_tokens: _List[int], mel: torch.Tensor,
+                   num_frames: int, *, medfilt_width: int = 7, qk_scale: float = 1.0,
+                   audio_features: torch.Tensor = None) -> _List[WordTiming]:
+    """Reference timing.py:163-242.  The reference re-runs encoder AND decoder with SDPA disabled to
+    capture every cross-attention matrix through hooks; here one teacher-forced decoder pass exports
+    the scores of the alignment heads only, and `audio_features` (e.g. DecodingResult.audio_features)
+    can be passed to skip the encoder."""
+    if len(text_tokens) == 0:
+        return []
+    tokens = [*tokenizer.sot_sequence, tokenizer.no_timestamps, *text_tokens, tokenizer.eot]
+    if audio_features is None:
+        audio_features = model.embed_audio(mel)
+    heads = model.alignment_heads.indices().T.tolist()                     # (layer, head) pairs, timing.py:207
+    logits, qk = model.logits(torch.tensor([tokens]), audio_features, alignment_heads=heads)
+    logits = logits[0]
+    sampled_logits = logits[len(tokenizer.sot_sequence):, : tokenizer.eot]   # timing.py:198-201
+    token_probs = sampled_logits.softmax(dim=-1)
+    text_token_probs = token_probs[np.arange(len(text_tokens)), text_tokens].tolist()
+
+    matrix = alignment_matrix(qk, num_frames // 2, qk_scale, medfilt_width, negate=True)   # already -matrix
+    matrix = matrix[len(tokenizer.sot_sequence): -1].contiguous()          # timing.py:215
+    text_indices, time_indices = dtw(matrix)                               # timing.py:216
+
+    words, word_tokens = tokenizer.split_to_word_tokens(text_tokens + [tokenizer.eot])
+    if len(word_tokens) <= 1:
+        return []                                                          # timing.py:219-225
+    word_boundaries = np.pad(np.cumsum([len(t) for t in word_tokens[:-1]]), (1, 0))
+    jumps = np.pad(np.diff(text_indices), (1, 0), constant_values=1).astype(bool)
+    jump_times = time_indices[jumps] / TOKENS_PER_SECOND
+    start_times = jump_times[word_boundaries[:-1]]
+    end_times = jump_times[word_boundaries[1:]]
+    word_probabilities = [np.mean(text_token_probs[i:j]) for i, j in zip(word_boundaries[:-1], word_boundaries[1:])]
+    return [WordTiming(w, t, s, e, p) for w, t, s, e, p in zip(words, word_tokens, start_times, end_times,
+                                                               word_probabilities)]

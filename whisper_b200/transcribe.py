@@ -196,7 +196,10 @@ def transcribe(
     first rung; `word_timestamps=True` raises (alignment path).
     """
     if word_timestamps:
-        raise NotImplementedError("word_timestamps needs the alignment forward (SURVEY.md 8f.2); not built yet")
+        raise NotImplementedError(
+            "word_timestamps=True is not wired into transcribe(): the tensor part of word timing is available as "
+            "whisper_b200.timing.find_alignment (cross-attention export + median filter + DTW on the GPU), but the "
+            "punctuation-merging / segment-clamping text heuristics of timing.py:245-388 are out of scope (SURVEY.md 2)")
     decode_options.pop("fp16", None)
     temps = [temperature] if isinstance(temperature, (int, float)) else list(temperature)
     kept = [t for t in temps if t == 0]
