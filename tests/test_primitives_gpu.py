@@ -79,9 +79,11 @@ def test_linear_epilogues(dtype, M):
 @pytest.mark.parametrize("dtype", DTYPES)
 @pytest.mark.parametrize("M,N,K", [(320, 1280, 1280), (320, 1280, 5120), (320, 3840, 1280), (5, 1280, 5120),
                                    (64, 384, 1536), (200, 512, 2048)])
-def test_linear_splitk_decode_shapes(dtype, M, N, K):
-    """The skinny decode-step GEMMs (C3: 320 rows) run split-K: same result as the plain kernel up to
-    fp32 summation order, epilogues included, and the per-tile tickets return to zero."""
+def test_linear_splitk_decode_shapes(dtype, M, N, K, monkeypatch):
+    """The skinny decode-step GEMMs (C3: 320 rows) through the split-K path (opt-in, WB200_SPLITK=1): same
+    result as the plain kernel up to fp32 summation order, epilogues included, tickets back to zero."""
+    import os
+    os.environ["WB200_SPLITK"] = "1"      # read once, at the first GEMM launch of the process
     from whisper_b200 import ops
     torch.manual_seed(7)
     x = (torch.randn(M, K, device="cuda") * 0.5).to(dtype)

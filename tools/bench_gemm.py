@@ -19,8 +19,10 @@ def timeit(fn, n=20):
 for (M, N, K) in [(320, 1280, 1280), (320, 3840, 1280), (320, 5120, 1280), (320, 1280, 5120), (5, 1280, 1280), (5, 1280, 5120)]:
     x = torch.randn(M, K, device="cuda").bfloat16(); w = (torch.randn(N, K, device="cuda") / math.sqrt(K)).bfloat16()
     b = torch.randn(N, device="cuda").bfloat16(); r = torch.randn(M, N, device="cuda").bfloat16()
-    t0 = timeit(lambda: ops.linear(x, w, bias=b, residual=r))
-    t1 = timeit(lambda: ops.linear_splitk(x, w, bias=b, residual=r)) if N < 20000 else float("nan")
+    scratch = (torch.empty(8 * M * N, device="cuda"), torch.zeros(1024, device="cuda", dtype=torch.int32))
+    o0 = torch.empty(M, N, device="cuda", dtype=torch.bfloat16); o1 = torch.empty_like(o0)
+    t0 = timeit(lambda: ops.linear(x, w, bias=b, residual=r, out=o0))
+    t1 = timeit(lambda: ops.linear_splitk(x, w, bias=b, residual=r, scratch=scratch, out=o1))
     t2 = timeit(lambda: torch.nn.functional.linear(x, w, b))
     gb = N * K * 2 / 1e9
     print(f"M={M} N={N} K={K}: plain {t0:7.1f} us  splitk {t1:7.1f} us  (cuBLAS via torch {t2:7.1f} us)  weights {gb*1e3:.1f} MB -> floor {gb/6.5*1e3:.1f} us")

@@ -309,13 +309,17 @@ gemm_tcgen05_kernel(const GemmParams p, const __grid_constant__ CUtensorMap mapA
       if (p.splits > 1) {
         // ticket: the last of the tile's `splits` CTAs reduces the slabs (in split order, so the sum does
         // not depend on arrival order) and applies the epilogue
-        __threadfence();
+        // one gpu-scope fence by the ticket thread AFTER the CTA barrier publishes all 256 threads' slab
+        // stores (fences are cumulative); a fence per thread costs microseconds here (it also drops L1)
         asm volatile("bar.sync 1, 256;" ::: "memory");
-        if (threadIdx.x == 128) s_ticket = atomicAdd(&p.tile_counters[tile], 1);
+        if (threadIdx.x == 128) {
+          __threadfence();
+          s_ticket = atomicAdd(&p.tile_counters[tile], 1);
+          __threadfence();
+        }
         asm volatile("bar.sync 1, 256;" ::: "memory");
         const bool last = (s_ticket == p.splits - 1);
         if (last) {
-          __threadfence();
           if (threadIdx.x == 128) p.tile_counters[tile] = 0;
 #pragma unroll 1
           for (int c = 0; c < kColsPerWarp / 32; ++c) {
@@ -429,14 +433,21 @@ int launch_linear(const LinearArgs& a, cudaStream_t s) {
     const int kblocks = p.taps * p.k_blocks_per_tap;
     static int splitk_on = -1;
     if (splitk_on < 0) {
-      const char* e = getenv("WB200_NO_SPLITK");
-      splitk_on = (e && e[0] && e[0] != '0') ? 0 : 1;
+      // Off by default: as measured on B200 (profiles/r1_summary.md) the slab write + ticket + reduce costs
+      // more than the shorter K chain saves at M = 320; kept behind WB200_SPLITK=1 for the next round.
+      const char* e = getenv("WB200_SPLITK");
+      splitk_on = (e && e[0] && e[0] != '0') ? 1 : 0;
     }
     if (splitk_on && a.splitk_ws && a.splitk_counters && a.taps == 1 && tiles < 148 && kblocks >= 8 &&
         tiles <= a.splitk_max_tiles) {
       int sp = (2 * 148 + tiles - 1) / tiles;          // aim at ~2 work items per SM
       if (sp > kblocks / 4) sp = kblocks / 4;          // keep >= 4 k-blocks (256 of K) per item
-      if (sp > 8) sp = 8;
+      static int sp_cap = 0;
+      if (!sp_cap) {
+        const char* e = getenv("WB200_SPLITK_MAX");
+        sp_cap = (e && atoi(e) > 0) ? atoi(e) : 8;
+      }
+      if (sp > sp_cap) sp = sp_cap;
       while (sp > 1 && static_cast<size_t>(sp) * p.partial_stride * 4 > a.splitk_ws_bytes) --sp;
       if (sp > 1) {
         p.splits = sp;
