@@ -59,6 +59,9 @@ int wb200_linear(int dtype, int M, int N, int K, const void* A, int64_t lda, con
                  int64_t ldw, const void* bias, const void* residual, int64_t ldr, void* C,
                  int64_t ldc, int gelu, int out_f32, void* stream);
 
+/* Split-K for the skinny GEMMs is opt-in (WB200_SPLITK=1 in the environment, or this call). */
+int wb200_set_splitk(int enabled);
+
 /* Same operator with split-K enabled for skinny problems (the 320-row decode-step GEMMs): `workspace`
  * holds fp32 partial slabs (up to 8 * M * N floats are used), `tickets` is an int32 array of n_tickets
  * entries that must be zero on entry and is zero again on exit. */

@@ -82,9 +82,9 @@ def test_linear_epilogues(dtype, M):
 def test_linear_splitk_decode_shapes(dtype, M, N, K, monkeypatch):
     """The skinny decode-step GEMMs (C3: 320 rows) through the split-K path (opt-in, WB200_SPLITK=1): same
     result as the plain kernel up to fp32 summation order, epilogues included, tickets back to zero."""
-    import os
-    os.environ["WB200_SPLITK"] = "1"      # read once, at the first GEMM launch of the process
-    from whisper_b200 import ops
+    from whisper_b200 import _lib, ops
+    _lib.lib().wb200_set_splitk(1)
+    monkeypatch.setattr(ops, "_splitk_restore", True, raising=False)
     torch.manual_seed(7)
     x = (torch.randn(M, K, device="cuda") * 0.5).to(dtype)
     w = (torch.randn(N, K, device="cuda") * (1.0 / math.sqrt(K))).to(dtype)
@@ -97,6 +97,7 @@ def test_linear_splitk_decode_shapes(dtype, M, N, K, monkeypatch):
     report("splitk bias+residual", ops.linear_splitk(x, w, bias=b, residual=r),
            rt(rt(acc + b.float(), dtype) + r.float(), dtype), dtype)
     got = ops.linear_splitk(x, w, out_f32=True)
+    _lib.lib().wb200_set_splitk(0)
     assert float((got - acc).abs().max()) < 2e-3 * math.sqrt(K) / 30 + 1e-3
 
 

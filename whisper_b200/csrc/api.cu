@@ -97,6 +97,11 @@ int wb200_linear(int dtype, int M, int N, int K, const void* A, int64_t lda, con
   return r ? set_error(r, "wb200_linear: launch failed (%d): %s", r, cudaGetErrorString(cudaGetLastError())) : 0;
 }
 
+int wb200_set_splitk(int enabled) {
+  g_splitk_on = enabled ? 1 : 0;
+  return 0;
+}
+
 int wb200_linear_splitk(int dtype, int M, int N, int K, const void* A, int64_t lda, const void* W,
                         int64_t ldw, const void* bias, const void* residual, int64_t ldr, void* C,
                         int64_t ldc, int gelu, int out_f32, void* workspace, size_t workspace_bytes,

@@ -25,6 +25,8 @@
 
 namespace wb {
 
+int g_splitk_on = -1;   // -1: read WB200_SPLITK on first use; wb200_set_splitk() overrides
+
 constexpr int kBM = 128;
 constexpr int kBK = 64;  // 64 x 16-bit = 128 B = one swizzle row
 constexpr int kGemmThreads = 384;  // 4 control warps + 8 epilogue warps
@@ -60,8 +62,23 @@ struct GemmCfg {
   static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align*/ + 256 /*barriers*/;
 };
 
+// Exact (erf) GELU of nn.GELU() / F.gelu (reference model.py:156,193-194).  erf is evaluated with the
+// Abramowitz-Stegun 7.1.26 rational form (|error| <= 1.5e-7, below fp32 round-off of 1 + erf and far below
+// the 16-bit rounding applied to the result); the negative side uses erfc directly so the tail does not
+// cancel.  ~16 instructions (one MUFU.RCP, one MUFU.EX2) against ~40 for erff: the fc1 epilogue of the
+// encoder MLP was instruction-bound on this (profiles/r1_summary.md).
 __device__ __forceinline__ float gelu_erf(float x) {
-  return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f));
+  const float z = fabsf(x) * 0.70710678118654752440f;
+  const float t = __frcp_rn(fmaf(0.3275911f, z, 1.0f));
+  float poly = fmaf(1.061405429f, t, -1.453152027f);
+  poly = fmaf(poly, t, 1.421413741f);
+  poly = fmaf(poly, t, -0.284496736f);
+  poly = fmaf(poly, t, 0.254829592f);
+  poly *= t;
+  const float erfc_z = poly * fast_exp2(-z * z * 1.4426950408889634f);   // erfc(|x| / sqrt 2)
+  // x >= 0: 0.5 x (2 - erfc) ; x < 0: 0.5 x erfc
+  const float phi2 = x >= 0.f ? 2.0f - erfc_z : erfc_z;
+  return 0.5f * x * phi2;
 }
 
 // bias / GELU / positional add / residual, then the store of 32 consecutive columns of one row
@@ -71,9 +88,23 @@ __device__ __forceinline__ void epilogue_store(float (&v)[32], const GemmParams&
   const T* resid = reinterpret_cast<const T*>(p.residual);
   const bool full = nb + 32 <= p.N;
   if (bias) {
+    if (full) {
 #pragma unroll
-    for (int j = 0; j < 32; ++j)
-      if (full || nb + j < p.N) v[j] += Cvt<T>::to_f(bias[nb + j]);
+      for (int q = 0; q < 4; ++q) {
+        const uint4 u = __ldg(reinterpret_cast<const uint4*>(bias + nb) + q);
+        const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const float2 f = Cvt<T>::unpack2(w[e]);
+          v[q * 8 + e * 2] += f.x;
+          v[q * 8 + e * 2 + 1] += f.y;
+        }
+      }
+    } else {
+#pragma unroll
+      for (int j = 0; j < 32; ++j)
+        if (nb + j < p.N) v[j] += Cvt<T>::to_f(bias[nb + j]);
+    }
   }
   if (p.gelu) {
 #pragma unroll
@@ -402,7 +433,25 @@ int launch_linear(const LinearArgs& a, cudaStream_t s) {
   const long long rows = static_cast<long long>(a.batch) * a.rows_per_batch;
   // wide tiles when M is large (encoder) or N is huge (logits: fewer passes over the A tile);
   // 64-wide tiles for the skinny decode-step GEMMs so that more CTAs pull weights concurrently
-  if (bn == 0) bn = (rows >= 4096 || a.N >= 16384) ? 256 : 64;
+  if (bn == 0) {
+    if (rows >= 4096) {
+      bn = 256;
+    } else {
+      // Skinny (decode-step) problems are bound by the ~40 B/clk a single SM's TMA unit can pull
+      // (profiles/r1_summary.md): pick the tile width that minimises rounds x bytes per k-block per CTA.
+      const int m_tiles = static_cast<int>((rows + kBM - 1) / kBM);
+      long long best = -1;
+      for (int cand = 64; cand <= 256; cand *= 2) {
+        const long long tiles = static_cast<long long>(m_tiles) * ((a.N + cand - 1) / cand);
+        const long long rounds = (tiles + 147) / 148;
+        const long long cost = rounds * (16 + cand / 8);
+        if (best < 0 || cost < best) {
+          best = cost;
+          bn = cand;
+        }
+      }
+    }
+  }
   if (bn == 256 && a.N < 256) bn = a.N >= 128 ? 128 : 64;
 
   GemmParams p;
@@ -431,7 +480,7 @@ int launch_linear(const LinearArgs& a, cudaStream_t s) {
   {
     const int tiles = p.batch * p.m_tiles_per_batch * p.n_tiles;
     const int kblocks = p.taps * p.k_blocks_per_tap;
-    static int splitk_on = -1;
+    int& splitk_on = g_splitk_on;
     if (splitk_on < 0) {
       // Off by default: as measured on B200 (profiles/r1_summary.md) the slab write + ticket + reduce costs
       // more than the shorter K chain saves at M = 320; kept behind WB200_SPLITK=1 for the next round.

@@ -63,6 +63,7 @@ struct LinearArgs {
   int splitk_max_tiles = 0;
 };
 int launch_linear(const LinearArgs& a, cudaStream_t s);
+extern int g_splitk_on;
 
 // Row LayerNorm in fp32 (reference model.py:39-41): y = (x - mean) / sqrt(var + 1e-5) * g + b
 int launch_layernorm(int dtype, const void* x, long long ldx, void* y, long long ldy, const float* g,
