@@ -61,6 +61,8 @@ int wb200_linear(int dtype, int M, int N, int K, const void* A, int64_t lda, con
 
 /* Split-K for the skinny GEMMs is opt-in (WB200_SPLITK=1 in the environment, or this call). */
 int wb200_set_splitk(int enabled);
+/* 64-row (UMMA M = 64) tiles for skinny GEMMs are on by default; 0 forces 128-row tiles. */
+int wb200_set_bm64(int enabled);
 
 /* Same operator with split-K enabled for skinny problems (the 320-row decode-step GEMMs): `workspace`
  * holds fp32 partial slabs (up to 8 * M * N floats are used), `tickets` is an int32 array of n_tickets

@@ -25,9 +25,10 @@
 
 namespace wb {
 
+int g_bm64_on = 1;      // wb200_set_option("bm64", 0/1): 64-row tiles for skinny problems
 int g_splitk_on = -1;   // -1: read WB200_SPLITK on first use; wb200_set_splitk() overrides
 
-constexpr int kBM = 128;
+constexpr int kBM = 128;   // default tile height; BM = 64 (UMMA M = 64) is used for skinny problems
 constexpr int kBK = 64;  // 64 x 16-bit = 128 B = one swizzle row
 constexpr int kGemmThreads = 384;  // 4 control warps + 8 epilogue warps
 
@@ -52,10 +53,10 @@ struct GemmParams {
   int* tile_counters;
 };
 
-template <int BN>
+template <int BN, int BM = kBM>
 struct GemmCfg {
-  static constexpr int kStages = BN == 256 ? 4 : (BN == 128 ? 6 : 8);
-  static constexpr int kABytes = kBM * kBK * 2;
+  static constexpr int kABytes = BM * kBK * 2;
+  static constexpr int kStages = BN == 256 ? 4 : (BN == 128 ? 6 : (BM == 64 ? 12 : 8));
   static constexpr int kBBytes = BN * kBK * 2;
   static constexpr int kStageBytes = kABytes + kBBytes;
   static constexpr int kTmemCols = (2 * BN < 32) ? 32 : 2 * BN;  // BN in {64,128,256} -> pow2
@@ -168,12 +169,12 @@ __device__ __forceinline__ void epilogue_store(float (&v)[32], const GemmParams&
   }
 }
 
-template <typename T, int BN, bool OUT_F32>
+template <typename T, int BN, bool OUT_F32, int BM = kBM>
 __global__ void __launch_bounds__(kGemmThreads, 1)
 gemm_tcgen05_kernel(const GemmParams p, const __grid_constant__ CUtensorMap mapA0,
                     const __grid_constant__ CUtensorMap mapA1,
                     const __grid_constant__ CUtensorMap mapB) {
-  using Cfg = GemmCfg<BN>;
+  using Cfg = GemmCfg<BN, BM>;
   if (p.skip_flag && *p.skip_flag) return;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
@@ -226,7 +227,7 @@ gemm_tcgen05_kernel(const GemmParams p, const __grid_constant__ CUtensorMap mapA
       const int m_tile = tile / p.n_tiles;
       const int n0 = (tile % p.n_tiles) * BN;
       const int b = m_tile / p.m_tiles_per_batch;
-      const int t0 = (m_tile % p.m_tiles_per_batch) * kBM;
+      const int t0 = (m_tile % p.m_tiles_per_batch) * BM;
       const int kb_lo = split * p.k_per_split, kb_hi = min(k_blocks, kb_lo + p.k_per_split);
       for (int tap = 0; tap < p.taps; ++tap) {
         const CUtensorMap* ma = p.a_map_sel[tap] ? &mapA1 : &mapA0;
@@ -249,7 +250,7 @@ gemm_tcgen05_kernel(const GemmParams p, const __grid_constant__ CUtensorMap mapA
     }
   } else if (warp == 1 && lane == 0) {
     // ===================== MMA issuer =====================
-    constexpr uint32_t idesc = umma_idesc(Cvt<T>::kUmmaFmt, kBM, BN, 0, 0);
+    constexpr uint32_t idesc = umma_idesc(Cvt<T>::kUmmaFmt, BM, BN, 0, 0);
     int stage = 0;
     uint32_t phase = 0;
     int acc = 0;
@@ -299,8 +300,10 @@ gemm_tcgen05_kernel(const GemmParams p, const __grid_constant__ CUtensorMap mapA
       const int m_tile = tile / p.n_tiles;
       const int n0 = (tile % p.n_tiles) * BN;
       const int b = m_tile / p.m_tiles_per_batch;
-      const int t = (m_tile % p.m_tiles_per_batch) * kBM + quad * 32 + lane;
-      const bool row_ok = t < p.rows_per_batch;
+      // UMMA M = 128: accumulator row i sits in TMEM lane i.  M = 64: the 64 rows use lanes 0-15 of each
+      // 32-lane quadrant (row = 16 * quadrant + lane), the upper 16 lanes of every quadrant are unused.
+      const int t = (m_tile % p.m_tiles_per_batch) * BM + (BM == 128 ? quad * 32 + lane : quad * 16 + lane);
+      const bool row_ok = t < p.rows_per_batch && (BM == 128 || lane < 16);
       const long long grow = static_cast<long long>(b) * p.rows_per_batch + t;
 
       mbar_wait(&tmem_full[acc], acc_phase);
@@ -391,12 +394,12 @@ gemm_tcgen05_kernel(const GemmParams p, const __grid_constant__ CUtensorMap mapA
   if (warp == 2) tmem_dealloc(tmem_base, Cfg::kTmemCols);
 }
 
-template <typename T, int BN, bool OUT_F32>
+template <typename T, int BN, bool OUT_F32, int BM = kBM>
 static int launch_impl(const GemmParams& p, const CUtensorMap& a0, const CUtensorMap& a1,
                        const CUtensorMap& b, cudaStream_t s) {
-  using Cfg = GemmCfg<BN>;
+  using Cfg = GemmCfg<BN, BM>;
   static bool attr_set = false;
-  auto kern = gemm_tcgen05_kernel<T, BN, OUT_F32>;
+  auto kern = gemm_tcgen05_kernel<T, BN, OUT_F32, BM>;
   if (!attr_set) {
     cudaError_t e =
         cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes);
@@ -430,6 +433,7 @@ int launch_linear(const LinearArgs& a, cudaStream_t s) {
   if (a.residual && ((reinterpret_cast<uintptr_t>(a.residual) & 15) || (a.ldr * esz) % 16)) return 6;
 
   int bn = a.block_n;
+  int bm = a.block_m ? a.block_m : kBM;
   const long long rows = static_cast<long long>(a.batch) * a.rows_per_batch;
   // wide tiles when M is large (encoder) or N is huge (logits: fewer passes over the A tile);
   // 64-wide tiles for the skinny decode-step GEMMs so that more CTAs pull weights concurrently
@@ -439,15 +443,19 @@ int launch_linear(const LinearArgs& a, cudaStream_t s) {
     } else {
       // Skinny (decode-step) problems are bound by the ~40 B/clk a single SM's TMA unit can pull
       // (profiles/r1_summary.md): pick the tile width that minimises rounds x bytes per k-block per CTA.
-      const int m_tiles = static_cast<int>((rows + kBM - 1) / kBM);
       long long best = -1;
-      for (int cand = 64; cand <= 256; cand *= 2) {
-        const long long tiles = static_cast<long long>(m_tiles) * ((a.N + cand - 1) / cand);
-        const long long rounds = (tiles + 147) / 148;
-        const long long cost = rounds * (16 + cand / 8);
-        if (best < 0 || cost < best) {
-          best = cost;
-          bn = cand;
+      const bool allow_bm64 = a.block_m == 0 && a.batch == 1 && a.taps == 1 && g_bm64_on;
+      for (int cbm = allow_bm64 ? 64 : kBM; cbm <= kBM; cbm *= 2) {
+        const int m_tiles = static_cast<int>((rows + cbm - 1) / cbm);
+        for (int cand = 64; cand <= (cbm == 64 ? 64 : 256); cand *= 2) {
+          const long long tiles = static_cast<long long>(m_tiles) * ((a.N + cand - 1) / cand);
+          const long long rounds = (tiles + 147) / 148;
+          const long long cost = rounds * (cbm / 8 + cand / 8);      // KB per k-block per CTA
+          if (best < 0 || cost < best) {
+            best = cost;
+            bn = cand;
+            bm = cbm;
+          }
         }
       }
     }
@@ -457,7 +465,8 @@ int launch_linear(const LinearArgs& a, cudaStream_t s) {
   GemmParams p;
   p.batch = a.batch;
   p.rows_per_batch = a.rows_per_batch;
-  p.m_tiles_per_batch = (a.rows_per_batch + kBM - 1) / kBM;
+  if (bm == 64 && bn != 64) bm = kBM;        // only the 64 x 64 variant is instantiated
+  p.m_tiles_per_batch = (a.rows_per_batch + bm - 1) / bm;
   p.N = a.N;
   p.n_tiles = (a.N + bn - 1) / bn;
   p.k_blocks_per_tap = (a.K_tap + kBK - 1) / kBK;
@@ -534,7 +543,7 @@ int launch_linear(const LinearArgs& a, cudaStream_t s) {
                         static_cast<uint64_t>(a.batch)};
     uint64_t strides[2] = {static_cast<uint64_t>(a.lda * esz),
                            static_cast<uint64_t>((a.batch > 1 ? a.a_batch_stride : a.lda * a.a_rows_per_batch) * esz)};
-    uint32_t box[3] = {kBK, kBM, 1};
+    uint32_t box[3] = {kBK, static_cast<uint32_t>(bm), 1};
     if (make_tmap_16bit(&mapA[i], a.dtype, base, 3, dims, strides, box)) return 8;
   }
   CUtensorMap mapB;
@@ -548,6 +557,13 @@ int launch_linear(const LinearArgs& a, cudaStream_t s) {
 #define WB_DISPATCH(TT, BNN)                                                              \
   return a.out_f32 ? launch_impl<TT, BNN, true>(p, mapA[0], mapA[1], mapB, s)             \
                    : launch_impl<TT, BNN, false>(p, mapA[0], mapA[1], mapB, s)
+  if (bm == 64) {
+    if (a.dtype == DT_BF16)
+      return a.out_f32 ? launch_impl<__nv_bfloat16, 64, true, 64>(p, mapA[0], mapA[1], mapB, s)
+                       : launch_impl<__nv_bfloat16, 64, false, 64>(p, mapA[0], mapA[1], mapB, s);
+    return a.out_f32 ? launch_impl<__half, 64, true, 64>(p, mapA[0], mapA[1], mapB, s)
+                     : launch_impl<__half, 64, false, 64>(p, mapA[0], mapA[1], mapB, s);
+  }
   if (a.dtype == DT_BF16) {
     if (bn == 256) { WB_DISPATCH(__nv_bfloat16, 256); }
     if (bn == 128) { WB_DISPATCH(__nv_bfloat16, 128); }

@@ -55,6 +55,7 @@ struct LinearArgs {
   int gelu = 0;
   int out_f32 = 0;
   int block_n = 0;  // 0 = choose (256 for large M, 64 for skinny M)
+  int block_m = 0;  // 0 = choose (128; 64 for skinny plain GEMMs)
   const int* skip_flag = nullptr;  // optional device int: non-zero -> the kernel is a no-op
   // optional split-K scratch (decode-step GEMMs): fp32 slabs + per-tile tickets (zero between launches)
   float* splitk_ws = nullptr;
@@ -64,6 +65,7 @@ struct LinearArgs {
 };
 int launch_linear(const LinearArgs& a, cudaStream_t s);
 extern int g_splitk_on;
+extern int g_bm64_on;
 
 // Row LayerNorm in fp32 (reference model.py:39-41): y = (x - mean) / sqrt(var + 1e-5) * g + b
 int launch_layernorm(int dtype, const void* x, long long ldx, void* y, long long ldy, const float* g,
