@@ -53,11 +53,16 @@ struct GemmParams {
   int* tile_counters;
 };
 
-template <int BN, int BM = kBM>
+// KS = 64-wide K sub-blocks per pipeline stage.  The single MMA-issuing thread pays ~350 cycles of
+// mbarrier wait / fence / commit per stage; with 64x64 tiles a 64-wide stage holds only 128 cycles of
+// tensor work, so the skinny variant moves 256 of K per stage (KS = 4) to amortise it.
+template <int BN, int BM = kBM, int KS = 1>
 struct GemmCfg {
-  static constexpr int kABytes = BM * kBK * 2;
-  static constexpr int kStages = BN == 256 ? 4 : (BN == 128 ? 6 : (BM == 64 ? 12 : 8));
-  static constexpr int kBBytes = BN * kBK * 2;
+  static constexpr int kASub = BM * kBK * 2;
+  static constexpr int kBSub = BN * kBK * 2;
+  static constexpr int kABytes = kASub * KS;
+  static constexpr int kStages = KS > 1 ? 3 : (BN == 256 ? 4 : (BN == 128 ? 6 : (BM == 64 ? 12 : 8)));
+  static constexpr int kBBytes = kBSub * KS;
   static constexpr int kStageBytes = kABytes + kBBytes;
   static constexpr int kTmemCols = (2 * BN < 32) ? 32 : 2 * BN;  // BN in {64,128,256} -> pow2
   static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align*/ + 256 /*barriers*/;
@@ -169,12 +174,12 @@ __device__ __forceinline__ void epilogue_store(float (&v)[32], const GemmParams&
   }
 }
 
-template <typename T, int BN, bool OUT_F32, int BM = kBM>
+template <typename T, int BN, bool OUT_F32, int BM = kBM, int KS = 1>
 __global__ void __launch_bounds__(kGemmThreads, 1)
 gemm_tcgen05_kernel(const GemmParams p, const __grid_constant__ CUtensorMap mapA0,
                     const __grid_constant__ CUtensorMap mapA1,
                     const __grid_constant__ CUtensorMap mapB) {
-  using Cfg = GemmCfg<BN, BM>;
+  using Cfg = GemmCfg<BN, BM, KS>;
   if (p.skip_flag && *p.skip_flag) return;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
@@ -190,7 +195,8 @@ gemm_tcgen05_kernel(const GemmParams p, const __grid_constant__ CUtensorMap mapA
   const int lane = threadIdx.x & 31;
   const int total_tiles = p.batch * p.m_tiles_per_batch * p.n_tiles;
   const int total_items = total_tiles * p.splits;
-  const int k_blocks = p.taps * p.k_blocks_per_tap;
+  const int groups_per_tap = (p.k_blocks_per_tap + KS - 1) / KS;
+  const int k_blocks = p.taps * groups_per_tap;          // pipeline stages per full K sweep
   __shared__ int s_ticket;
 
   if (warp == 0 && lane == 0) {
@@ -232,15 +238,19 @@ gemm_tcgen05_kernel(const GemmParams p, const __grid_constant__ CUtensorMap mapA
       for (int tap = 0; tap < p.taps; ++tap) {
         const CUtensorMap* ma = p.a_map_sel[tap] ? &mapA1 : &mapA0;
         const int row0 = t0 + p.a_row_off[tap];
-        for (int kb = 0; kb < p.k_blocks_per_tap; ++kb) {
-          const int kidx = tap * p.k_blocks_per_tap + kb;
+        for (int kg = 0; kg < groups_per_tap; ++kg) {
+          const int kidx = tap * groups_per_tap + kg;
           if (kidx < kb_lo || kidx >= kb_hi) continue;
           mbar_wait(&empty_bar[stage], phase ^ 1);
           uint8_t* sa = tiles + stage * Cfg::kStageBytes;
           uint8_t* sb = sa + Cfg::kABytes;
           mbar_expect_tx(&full_bar[stage], Cfg::kStageBytes);
-          tma_load_3d(sa, ma, &full_bar[stage], kb * kBK, row0, b);
-          tma_load_2d(sb, &mapB, &full_bar[stage], tap * p.K_tap + kb * kBK, n0);
+#pragma unroll
+          for (int sub = 0; sub < KS; ++sub) {     // sub-blocks past K are zero-filled by TMA
+            const int kb = kg * KS + sub;
+            tma_load_3d(sa + sub * Cfg::kASub, ma, &full_bar[stage], kb * kBK, row0, b);
+            tma_load_2d(sb + sub * Cfg::kBSub, &mapB, &full_bar[stage], tap * p.K_tap + kb * kBK, n0);
+          }
           if (++stage == Cfg::kStages) {
             stage = 0;
             phase ^= 1;
@@ -266,12 +276,15 @@ gemm_tcgen05_kernel(const GemmParams p, const __grid_constant__ CUtensorMap mapA
         tc_fence_after();
         const uint32_t sa = smem_u32(tiles + stage * Cfg::kStageBytes);
         const uint32_t sb = sa + Cfg::kABytes;
-        const uint64_t adesc = umma_desc_sw128(sa, 16, 1024);
-        const uint64_t bdesc = umma_desc_sw128(sb, 16, 1024);
 #pragma unroll
-        for (int k = 0; k < kBK / 16; ++k) {
-          // advance 16 elements (32 B) along K inside the 128 B swizzle row: +2 in 16 B units
-          umma_f16(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (kb != kb_lo) || (k != 0));
+        for (int sub = 0; sub < KS; ++sub) {
+          const uint64_t adesc = umma_desc_sw128(sa + sub * Cfg::kASub, 16, 1024);
+          const uint64_t bdesc = umma_desc_sw128(sb + sub * Cfg::kBSub, 16, 1024);
+#pragma unroll
+          for (int k = 0; k < kBK / 16; ++k) {
+            // advance 16 elements (32 B) along K inside the 128 B swizzle row: +2 in 16 B units
+            umma_f16(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (kb != kb_lo) || (sub != 0) || (k != 0));
+          }
         }
         umma_commit(&empty_bar[stage]);
         if (++stage == Cfg::kStages) {
@@ -394,12 +407,12 @@ gemm_tcgen05_kernel(const GemmParams p, const __grid_constant__ CUtensorMap mapA
   if (warp == 2) tmem_dealloc(tmem_base, Cfg::kTmemCols);
 }
 
-template <typename T, int BN, bool OUT_F32, int BM = kBM>
+template <typename T, int BN, bool OUT_F32, int BM = kBM, int KS = 1>
 static int launch_impl(const GemmParams& p, const CUtensorMap& a0, const CUtensorMap& a1,
                        const CUtensorMap& b, cudaStream_t s) {
-  using Cfg = GemmCfg<BN, BM>;
+  using Cfg = GemmCfg<BN, BM, KS>;
   static bool attr_set = false;
-  auto kern = gemm_tcgen05_kernel<T, BN, OUT_F32, BM>;
+  auto kern = gemm_tcgen05_kernel<T, BN, OUT_F32, BM, KS>;
   if (!attr_set) {
     cudaError_t e =
         cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes);
@@ -482,7 +495,8 @@ int launch_linear(const LinearArgs& a, cudaStream_t s) {
   p.skip_flag = a.skip_flag;
   // split-K only for skinny problems that would otherwise leave most SMs idle
   p.splits = 1;
-  p.k_per_split = p.taps * p.k_blocks_per_tap;
+  const int ks_host = (bm == 64) ? 4 : 1;             // must match the kernel variant dispatched below
+  p.k_per_split = p.taps * ((p.k_blocks_per_tap + ks_host - 1) / ks_host);
   p.partial = nullptr;
   p.partial_stride = rows * static_cast<long long>(a.N);
   p.tile_counters = a.splitk_counters;
@@ -496,7 +510,7 @@ int launch_linear(const LinearArgs& a, cudaStream_t s) {
       const char* e = getenv("WB200_SPLITK");
       splitk_on = (e && e[0] && e[0] != '0') ? 1 : 0;
     }
-    if (splitk_on && a.splitk_ws && a.splitk_counters && a.taps == 1 && tiles < 148 && kblocks >= 8 &&
+    if (splitk_on && bm != 64 && a.splitk_ws && a.splitk_counters && a.taps == 1 && tiles < 148 && kblocks >= 8 &&
         tiles <= a.splitk_max_tiles) {
       int sp = (2 * 148 + tiles - 1) / tiles;          // aim at ~2 work items per SM
       if (sp > kblocks / 4) sp = kblocks / 4;          // keep >= 4 k-blocks (256 of K) per item
@@ -559,10 +573,10 @@ int launch_linear(const LinearArgs& a, cudaStream_t s) {
                    : launch_impl<TT, BNN, false>(p, mapA[0], mapA[1], mapB, s)
   if (bm == 64) {
     if (a.dtype == DT_BF16)
-      return a.out_f32 ? launch_impl<__nv_bfloat16, 64, true, 64>(p, mapA[0], mapA[1], mapB, s)
-                       : launch_impl<__nv_bfloat16, 64, false, 64>(p, mapA[0], mapA[1], mapB, s);
-    return a.out_f32 ? launch_impl<__half, 64, true, 64>(p, mapA[0], mapA[1], mapB, s)
-                     : launch_impl<__half, 64, false, 64>(p, mapA[0], mapA[1], mapB, s);
+      return a.out_f32 ? launch_impl<__nv_bfloat16, 64, true, 64, 4>(p, mapA[0], mapA[1], mapB, s)
+                       : launch_impl<__nv_bfloat16, 64, false, 64, 4>(p, mapA[0], mapA[1], mapB, s);
+    return a.out_f32 ? launch_impl<__half, 64, true, 64, 4>(p, mapA[0], mapA[1], mapB, s)
+                     : launch_impl<__half, 64, false, 64, 4>(p, mapA[0], mapA[1], mapB, s);
   }
   if (a.dtype == DT_BF16) {
     if (bn == 256) { WB_DISPATCH(__nv_bfloat16, 256); }
