@@ -495,7 +495,7 @@ int launch_linear(const LinearArgs& a, cudaStream_t s) {
   p.skip_flag = a.skip_flag;
   // split-K only for skinny problems that would otherwise leave most SMs idle
   p.splits = 1;
-  const int ks_host = (bm == 64) ? 4 : 1;             // must match the kernel variant dispatched below
+  const int ks_host = (bm == 64) ? 4 : (bn == 128 ? 2 : 1);   // must match the kernel variant dispatched below
   p.k_per_split = p.taps * ((p.k_blocks_per_tap + ks_host - 1) / ks_host);
   p.partial = nullptr;
   p.partial_stride = rows * static_cast<long long>(a.N);
@@ -510,7 +510,7 @@ int launch_linear(const LinearArgs& a, cudaStream_t s) {
       const char* e = getenv("WB200_SPLITK");
       splitk_on = (e && e[0] && e[0] != '0') ? 1 : 0;
     }
-    if (splitk_on && bm != 64 && a.splitk_ws && a.splitk_counters && a.taps == 1 && tiles < 148 && kblocks >= 8 &&
+    if (splitk_on && ks_host == 1 && a.splitk_ws && a.splitk_counters && a.taps == 1 && tiles < 148 && kblocks >= 8 &&
         tiles <= a.splitk_max_tiles) {
       int sp = (2 * 148 + tiles - 1) / tiles;          // aim at ~2 work items per SM
       if (sp > kblocks / 4) sp = kblocks / 4;          // keep >= 4 k-blocks (256 of K) per item
@@ -580,11 +580,15 @@ int launch_linear(const LinearArgs& a, cudaStream_t s) {
   }
   if (a.dtype == DT_BF16) {
     if (bn == 256) { WB_DISPATCH(__nv_bfloat16, 256); }
-    if (bn == 128) { WB_DISPATCH(__nv_bfloat16, 128); }
+    if (bn == 128)
+      return a.out_f32 ? launch_impl<__nv_bfloat16, 128, true, 128, 2>(p, mapA[0], mapA[1], mapB, s)
+                       : launch_impl<__nv_bfloat16, 128, false, 128, 2>(p, mapA[0], mapA[1], mapB, s);
     WB_DISPATCH(__nv_bfloat16, 64);
   } else {
     if (bn == 256) { WB_DISPATCH(__half, 256); }
-    if (bn == 128) { WB_DISPATCH(__half, 128); }
+    if (bn == 128)
+      return a.out_f32 ? launch_impl<__half, 128, true, 128, 2>(p, mapA[0], mapA[1], mapB, s)
+                       : launch_impl<__half, 128, false, 128, 2>(p, mapA[0], mapA[1], mapB, s);
     WB_DISPATCH(__half, 64);
   }
 #undef WB_DISPATCH
