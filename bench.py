@@ -49,6 +49,9 @@ def parse():
     ap.add_argument("--dtype", default="bf16", choices=["bf16", "fp16"])
     ap.add_argument("--decode-steps", type=int, default=DECODE_STEPS)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--breakdown", action="store_true",
+                    help="after the timed region, run one extra plain-launch step per kernel class with per-launch "
+                         "CUDA events and report each class's total device time (diagnostic, not part of `value`)")
     return ap.parse_args()
 
 
@@ -215,6 +218,9 @@ def run_reference_arm(args, rank):
     }))
 
 
+NCU_CROSS_ATTN_TRAFFIC = 492.06e6 + 11.95e6   # bytes per launch, C3 shape
+
+
 def main():
     args = parse()
     from whisper_b200 import parallel
@@ -307,11 +313,26 @@ def main():
     lib.wb200_profile_read(ctypes.byref(prof_ms), ctypes.byref(prof_n))
     lib.wb200_profile_enable(0)
 
+    breakdown = None
+    if args.breakdown:
+        names = {1: "cross_attention", 2: "self_attention", 3: "gemm", 4: "encoder_attention", 5: "layernorm",
+                 6: "select", 7: "log_mel"}
+        breakdown = {}
+        for kid, name in names.items():
+            lib.wb200_profile_enable(kid)
+            ms_k, _ = timed(step_resident, 1)
+            t_k, n_k = ctypes.c_double(0), ctypes.c_int64(0)
+            lib.wb200_profile_read(ctypes.byref(t_k), ctypes.byref(n_k))
+            lib.wb200_profile_enable(0)
+            breakdown[name] = {"ms": t_k.value, "launches": int(n_k.value), "step_ms": ms_k}
+
     e2e_steps = max(1, min(args.steps, 3))
     step_e2e()
     ms_e2e, _ = timed(step_e2e, e2e_steps)
 
     if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
         return
     audio_s = world * B * CHUNK_S
     value = audio_s * args.steps / (ms / 1000.0)
@@ -357,10 +378,15 @@ def main():
             "share_of_step": (prof_ms.value / ms_prof) if ms_prof > 0 else None,
             "profiled_step_ms": ms_prof,
             "how": "CUDA events around every launch of the kernel on its stream, one extra (non-graph) step",
-            "traffic": None,
+            # dram__bytes_read.sum + dram__bytes_write.sum of one launch from the committed `ncu --set full` capture
+            # (profiles/r1_dec_attn_v3_ncu_full_selected.csv); only valid for the shape it was captured on
+            "traffic": NCU_CROSS_ATTN_TRAFFIC if (args.model, G, B, args.dtype) == ("large-v3", 5, 64, "bf16") else None,
+            "traffic_source": "profiles/r1_dec_attn_v3_ncu_full_selected.csv (ncu --set full, one launch)",
         },
         "algorithmic": alg,
     }
+    if breakdown is not None:
+        line["breakdown"] = breakdown
     if world == 1 and not args.no_cpu_baseline:
         threads = host_threads()
         s = oracle_sample(args.model, G, 3, threads)
@@ -370,6 +396,8 @@ def main():
                        f"beam-{G} iterations, extrapolated to {DECODE_STEPS} (enc {s['t_enc']:.2f}s, prefill "
                        f"{s['t_prefill']:.2f}s, {s['t_step']:.3f}s/iter; {s['wall']:.1f}s of CPU work)")}
     print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
 
 
 if __name__ == "__main__":

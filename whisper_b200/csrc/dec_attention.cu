@@ -19,13 +19,15 @@
 //                            gather of every cache tensor that decoding.py:172-176 performs.  In
 //                            step mode the kernel also APPENDS the new token's K/V to the cache
 //                            (the torch.cat of model.py:327-333).
+#include <stdlib.h>
+
 #include "kernels.h"
 #include "ptx.cuh"
 
 namespace wb {
 
 constexpr int kDaThreads = 128;  // 4 warps, each owns 16 keys of every 64-key tile
-constexpr int kDaStages = 4;
+constexpr int kDaStages = 4;   // default ring depth; the cross-attention launcher can pick 3 or 6 (WB200_XATTN_STAGES)
 constexpr int kDaTileKeys = 64;
 constexpr int kDaTileBytes = kDaTileKeys * 128;                 // K or V tile
 constexpr int kDaSmem = kDaStages * 2 * kDaTileBytes;           // 64 KB
@@ -224,29 +226,29 @@ __device__ __forceinline__ void stage_tile(uint8_t* sK, uint8_t* sV, int key0, i
 }
 
 // Shared main loop: stream keys [key_begin, key_end) in 64-key tiles through the cp.async ring.
-template <typename T, typename F>
+template <typename T, int STAGES, typename F>
 __device__ __forceinline__ void stream_keys(uint8_t* smem, int key_begin, int key_end, int kv_len,
                                             const uint32_t (&qa)[4][4], WarpAcc& acc, F src_of) {
   const int warp = threadIdx.x >> 5;
   const int n_tiles = (key_end - key_begin + kDaTileKeys - 1) / kDaTileKeys;
 #pragma unroll
-  for (int s = 0; s < kDaStages - 1; ++s) {
+  for (int s = 0; s < STAGES - 1; ++s) {
     if (s < n_tiles)
       stage_tile(smem + s * 2 * kDaTileBytes, smem + s * 2 * kDaTileBytes + kDaTileBytes,
                  key_begin + s * kDaTileKeys, min(kv_len, key_end), src_of);
     cp_async_commit();
   }
   for (int it = 0; it < n_tiles; ++it) {
-    cp_async_wait<kDaStages - 2>();
+    cp_async_wait<STAGES - 2>();
     __syncthreads();
-    const int nx = it + kDaStages - 1;
+    const int nx = it + STAGES - 1;
     if (nx < n_tiles) {
-      const int st = nx % kDaStages;
+      const int st = nx % STAGES;
       stage_tile(smem + st * 2 * kDaTileBytes, smem + st * 2 * kDaTileBytes + kDaTileBytes,
                  key_begin + nx * kDaTileKeys, min(kv_len, key_end), src_of);
     }
     cp_async_commit();
-    const int st = it % kDaStages;
+    const int st = it % STAGES;
     const int k0 = key_begin + it * kDaTileKeys + warp * 16;
     warp_tile<T>(smem + st * 2 * kDaTileBytes, smem + st * 2 * kDaTileBytes + kDaTileBytes, warp * 16,
                  qa, min(kv_len, key_end) - k0, acc);
@@ -269,7 +271,7 @@ struct CrossParams {
   int n_q, q_tiles, T, d, splits, keys_per_split, kv_ld;
 };
 
-template <typename T>
+template <typename T, int STAGES>
 __global__ void __launch_bounds__(kDaThreads) cross_attention_kernel(const CrossParams p) {
   if (p.skip_flag && *p.skip_flag) return;
   extern __shared__ __align__(1024) uint8_t da_smem[];
@@ -295,7 +297,7 @@ __global__ void __launch_bounds__(kDaThreads) cross_attention_kernel(const Cross
   acc_init(acc);
   const int kb = split * p.keys_per_split;
   const int ke = min(p.T, kb + p.keys_per_split);
-  stream_keys<T>(da_smem, kb, ke, p.T, qa, acc, src_of);
+  stream_keys<T, STAGES>(da_smem, kb, ke, p.T, qa, acc, src_of);
 
   float* red = reinterpret_cast<float*>(da_smem);
   cta_merge(acc, red);
@@ -565,24 +567,37 @@ int launch_cross_attention(int dtype, const void* q, const void* k, const void* 
   p.kv_ld = kv_ld;
   p.splits = cross_attention_splits(T, n_audio * p.q_tiles * n_head);
   p.keys_per_split = ((T + p.splits - 1) / p.splits + 63) / 64 * 64;
+  static int stages_opt = 0, splits_opt = -1;
+  if (!stages_opt) {
+    const char* e = getenv("WB200_XATTN_STAGES");
+    stages_opt = (e && (atoi(e) == 3 || atoi(e) == 6)) ? atoi(e) : 4;
+    const char* e2 = getenv("WB200_XATTN_SPLITS");
+    splits_opt = (e2 && atoi(e2) >= 1 && atoi(e2) <= 8) ? atoi(e2) : 0;
+  }
+  if (splits_opt) {
+    p.splits = splits_opt;
+    p.keys_per_split = ((T + p.splits - 1) / p.splits + 63) / 64 * 64;
+  }
   dim3 grid(p.splits, n_head, n_audio * p.q_tiles);
   ProfileScope prof(PROF_CROSS_ATTN, s);
-  static bool attr[2] = {false, false};
-  if (dtype == DT_BF16) {
-    auto kern = cross_attention_kernel<__nv_bfloat16>;
-    if (!attr[0]) {
-      if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kDaSmem) != cudaSuccess) return 40;
-      attr[0] = true;
-    }
-    kern<<<grid, kDaThreads, kDaSmem, s>>>(p);
-  } else {
-    auto kern = cross_attention_kernel<__half>;
-    if (!attr[1]) {
-      if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kDaSmem) != cudaSuccess) return 40;
-      attr[1] = true;
-    }
-    kern<<<grid, kDaThreads, kDaSmem, s>>>(p);
+  const int smem = stages_opt * 2 * kDaTileBytes;
+#define WB_XATTN(TT, ST)                                                                                   \
+  {                                                                                                        \
+    auto kern = cross_attention_kernel<TT, ST>;                                                            \
+    static bool attr = false;                                                                              \
+    if (!attr) {                                                                                           \
+      if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess)    \
+        return 40;                                                                                         \
+      attr = true;                                                                                         \
+    }                                                                                                      \
+    kern<<<grid, kDaThreads, smem, s>>>(p);                                                                \
   }
+  if (dtype == DT_BF16) {
+    if (stages_opt == 3) WB_XATTN(__nv_bfloat16, 3) else if (stages_opt == 6) WB_XATTN(__nv_bfloat16, 6) else WB_XATTN(__nv_bfloat16, 4)
+  } else {
+    if (stages_opt == 3) WB_XATTN(__half, 3) else if (stages_opt == 6) WB_XATTN(__half, 6) else WB_XATTN(__half, 4)
+  }
+#undef WB_XATTN
   count_launch();
   return cudaGetLastError() == cudaSuccess ? 0 : 41;
 }

@@ -174,40 +174,35 @@ enc_attention_kernel(const __grid_constant__ CUtensorMap map_qkv, T* __restrict_
       mbar_wait(&s_full[w], j & 1);
       tc_fence_after();
       const int kvalid = Tn - j * 128;  // keys [0,kvalid) of this block are real
+      const bool full_block = kvalid >= 128;   // every block but the last: no per-element masking
       float mx = -INFINITY;
 #pragma unroll 1
       for (int c = 0; c < 4; ++c) {
         uint32_t r[32];
         tmem_ld32(s_addr + c * 32, r);
         tmem_ld_wait();
+        if (full_block) {
+          // four independent running maxima keep the FMNMX chain short
+          float m0 = __uint_as_float(r[0]), m1 = __uint_as_float(r[1]), m2 = __uint_as_float(r[2]), m3 = __uint_as_float(r[3]);
 #pragma unroll
-        for (int i = 0; i < 32; ++i)
-          if (c * 32 + i < kvalid) mx = fmaxf(mx, __uint_as_float(r[i]));
+          for (int i = 4; i < 32; i += 4) {
+            m0 = fmaxf(m0, __uint_as_float(r[i]));
+            m1 = fmaxf(m1, __uint_as_float(r[i + 1]));
+            m2 = fmaxf(m2, __uint_as_float(r[i + 2]));
+            m3 = fmaxf(m3, __uint_as_float(r[i + 3]));
+          }
+          mx = fmaxf(mx, fmaxf(fmaxf(m0, m1), fmaxf(m2, m3)));
+        } else {
+#pragma unroll
+          for (int i = 0; i < 32; ++i)
+            if (c * 32 + i < kvalid) mx = fmaxf(mx, __uint_as_float(r[i]));
+        }
       }
       const float m_new = fmaxf(m_run, mx * scale_log2);
       const float alpha = fast_exp2(m_run - m_new);
-      uint32_t pk[64];
-      float rs = 0.f;
-#pragma unroll
-      for (int c = 0; c < 4; ++c) {
-        uint32_t r[32];
-        tmem_ld32(s_addr + c * 32, r);
-        tmem_ld_wait();
-#pragma unroll
-        for (int i = 0; i < 32; i += 2) {
-          float p0 = fast_exp2(__uint_as_float(r[i]) * scale_log2 - m_new);
-          float p1 = fast_exp2(__uint_as_float(r[i + 1]) * scale_log2 - m_new);
-          if (c * 32 + i >= kvalid) p0 = 0.f;
-          if (c * 32 + i + 1 >= kvalid) p1 = 0.f;
-          rs += p0 + p1;
-          pk[c * 16 + i / 2] = Cvt<T>::pack2(p0, p1);
-        }
-      }
-      l_run = l_run * alpha + rs;
-      m_run = m_new;
-
+      float rs0 = 0.f, rs1 = 0.f;
       if (j > 0) {
-        // fold in the previous block's P V (its MMA has had this whole softmax to finish)
+        // fold in the previous block's P V before P's smem buffer is overwritten below
         mbar_wait(&o_full[w], (j - 1) & 1);
         tc_fence_after();
 #pragma unroll
@@ -221,14 +216,45 @@ enc_attention_kernel(const __grid_constant__ CUtensorMap map_qkv, T* __restrict_
         }
       }
       alpha_prev = alpha;
-
-      // P (this row, 128 keys) -> smem, 16-byte chunks XOR-swizzled by (row % 8)
+      // P = exp2(S * scale - m) for this row, 32 keys at a time, packed to 16 bits and stored straight into
+      // the 128B-swizzled K-major smem tile (16-byte chunks XOR-ed with row % 8) the PV MMA reads
 #pragma unroll
-      for (int ch = 0; ch < 16; ++ch) {
-        uint4 u = make_uint4(pk[ch * 4], pk[ch * 4 + 1], pk[ch * 4 + 2], pk[ch * 4 + 3]);
-        const int sub = ch >> 3, c16 = ch & 7;
-        *reinterpret_cast<uint4*>(myP + sub * kTileBytes + ((c16 ^ (row & 7)) << 4)) = u;
+      for (int c = 0; c < 4; ++c) {
+        uint32_t r[32];
+        tmem_ld32(s_addr + c * 32, r);
+        tmem_ld_wait();
+        uint32_t pk[16];
+        if (full_block) {
+#pragma unroll
+          for (int i = 0; i < 32; i += 2) {
+            const float p0 = fast_exp2(fmaf(__uint_as_float(r[i]), scale_log2, -m_new));
+            const float p1 = fast_exp2(fmaf(__uint_as_float(r[i + 1]), scale_log2, -m_new));
+            rs0 += p0;
+            rs1 += p1;
+            pk[i / 2] = Cvt<T>::pack2(p0, p1);
+          }
+        } else {
+#pragma unroll
+          for (int i = 0; i < 32; i += 2) {
+            float p0 = fast_exp2(fmaf(__uint_as_float(r[i]), scale_log2, -m_new));
+            float p1 = fast_exp2(fmaf(__uint_as_float(r[i + 1]), scale_log2, -m_new));
+            if (c * 32 + i >= kvalid) p0 = 0.f;
+            if (c * 32 + i + 1 >= kvalid) p1 = 0.f;
+            rs0 += p0;
+            rs1 += p1;
+            pk[i / 2] = Cvt<T>::pack2(p0, p1);
+          }
+        }
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const int ch = c * 4 + q;
+          const int sub = ch >> 3, c16 = ch & 7;
+          *reinterpret_cast<uint4*>(myP + sub * kTileBytes + ((c16 ^ (row & 7)) << 4)) =
+              make_uint4(pk[q * 4], pk[q * 4 + 1], pk[q * 4 + 2], pk[q * 4 + 3]);
+        }
       }
+      l_run = l_run * alpha + (rs0 + rs1);
+      m_run = m_new;
       fence_proxy_async_smem();
       tc_fence_before();
       mbar_arrive(&p_full[w]);

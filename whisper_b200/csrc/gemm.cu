@@ -74,14 +74,15 @@ struct GemmCfg {
 // cancel.  ~16 instructions (one MUFU.RCP, one MUFU.EX2) against ~40 for erff: the fc1 epilogue of the
 // encoder MLP was instruction-bound on this (profiles/r1_summary.md).
 __device__ __forceinline__ float gelu_erf(float x) {
-  const float z = fabsf(x) * 0.70710678118654752440f;
-  const float t = __frcp_rn(fmaf(0.3275911f, z, 1.0f));
+  // w = |x| * sqrt(log2(e) / 2): then exp(-x^2 / 2) = 2^(-w^2) and p * |x| / sqrt(2) = p' * w
+  const float w = fabsf(x) * 0.84932180028801904272f;
+  float t;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(t) : "f"(fmaf(0.27274054f, w, 1.0f)));   // 0.3275911 / sqrt(log2 e)
   float poly = fmaf(1.061405429f, t, -1.453152027f);
   poly = fmaf(poly, t, 1.421413741f);
   poly = fmaf(poly, t, -0.284496736f);
   poly = fmaf(poly, t, 0.254829592f);
-  poly *= t;
-  const float erfc_z = poly * fast_exp2(-z * z * 1.4426950408889634f);   // erfc(|x| / sqrt 2)
+  const float erfc_z = poly * t * fast_exp2(-w * w);          // erfc(|x| / sqrt 2)
   // x >= 0: 0.5 x (2 - erfc) ; x < 0: 0.5 x erfc
   const float phi2 = x >= 0.f ? 2.0f - erfc_z : erfc_z;
   return 0.5f * x * phi2;
