@@ -52,6 +52,7 @@ def parse():
     ap.add_argument("--breakdown", action="store_true",
                     help="after the timed region, run one extra plain-launch step per kernel class with per-launch "
                          "CUDA events and report each class's total device time (diagnostic, not part of `value`)")
+    ap.add_argument("--breakdown-ids", default="1,2,3,4,5,6,7", help="kernel classes for --breakdown")
     return ap.parse_args()
 
 
@@ -319,6 +320,8 @@ def main():
                  6: "select", 7: "log_mel"}
         breakdown = {}
         for kid, name in names.items():
+            if str(kid) not in args.breakdown_ids.split(","):
+                continue
             lib.wb200_profile_enable(kid)
             ms_k, _ = timed(step_resident, 1)
             t_k, n_k = ctypes.c_double(0), ctypes.c_int64(0)

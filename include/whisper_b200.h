@@ -63,6 +63,10 @@ int wb200_linear(int dtype, int M, int N, int K, const void* A, int64_t lda, con
 int wb200_set_splitk(int enabled);
 /* 64-row (UMMA M = 64) tiles for skinny GEMMs are on by default; 0 forces 128-row tiles. */
 int wb200_set_bm64(int enabled);
+/* Programmatic dependent launch for the decoder-layer kernels (layer norm, GEMM, self- / cross-attention): on by
+ * default (WB200_PDL=0 in the environment or this call turns it off).  Each of those kernels may be scheduled while
+ * its predecessor drains and waits (griddepcontrol.wait) before it touches global memory. */
+int wb200_set_pdl(int enabled);
 
 /* Same operator with split-K enabled for skinny problems (the 320-row decode-step GEMMs): `workspace`
  * holds fp32 partial slabs (up to 8 * M * N floats are used), `tickets` is an int32 array of n_tickets

@@ -107,6 +107,11 @@ int wb200_set_bm64(int enabled) {
   return 0;
 }
 
+int wb200_set_pdl(int enabled) {
+  g_pdl_on = enabled ? 1 : 0;
+  return 0;
+}
+
 int wb200_linear_splitk(int dtype, int M, int N, int K, const void* A, int64_t lda, const void* W,
                         int64_t ldw, const void* bias, const void* residual, int64_t ldr, void* C,
                         int64_t ldc, int gelu, int out_f32, void* workspace, size_t workspace_bytes,

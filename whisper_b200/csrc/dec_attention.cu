@@ -12,13 +12,15 @@
 //                            of them ("each audio's K/V counted once").  The 1500
 //                            keys are split across CTAs (flash-decoding); the last CTA to finish a
 //                            (audio, head, q-tile) combines the partials - no second launch.
-//   self_attention_kernel  : one WARP per (row, head), plain streaming reduction (no tensor-core
-//                            tile: a single query has nothing to share); keys are gathered through the beam
+//   self_attention_kernel  : one WARP per (row, head), plain streaming reduction through a per-lane
+//                            cp.async ring (no tensor-core tile: a single query has nothing to
+//                            share); keys are gathered through the beam
 //                            indirection table (position p of row r lives in physical row
 //                            indir[r][p]), so a beam reorder is a table update, not the physical
 //                            gather of every cache tensor that decoding.py:172-176 performs.  In
 //                            step mode the kernel also APPENDS the new token's K/V to the cache
 //                            (the torch.cat of model.py:327-333).
+#include <stdio.h>
 #include <stdlib.h>
 
 #include "kernels.h"
@@ -27,10 +29,9 @@
 namespace wb {
 
 constexpr int kDaThreads = 128;  // 4 warps, each owns 16 keys of every 64-key tile
-constexpr int kDaStages = 4;   // default ring depth; the cross-attention launcher can pick 3 or 6 (WB200_XATTN_STAGES)
 constexpr int kDaTileKeys = 64;
 constexpr int kDaTileBytes = kDaTileKeys * 128;                 // K or V tile
-constexpr int kDaSmem = kDaStages * 2 * kDaTileBytes;           // 64 KB
+
 constexpr float kScaleLog2 = 0.125f * 1.4426950408889634f;      // (1/sqrt(64)) * log2(e)
 
 struct RowSrc {
@@ -273,6 +274,8 @@ struct CrossParams {
 
 template <typename T, int STAGES>
 __global__ void __launch_bounds__(kDaThreads) cross_attention_kernel(const CrossParams p) {
+  pdl_launch_dependents();
+  pdl_wait();
   if (p.skip_flag && *p.skip_flag) return;
   extern __shared__ __align__(1024) uint8_t da_smem[];
   __shared__ int s_last;
@@ -376,21 +379,30 @@ struct SelfParams {
 
 // One WARP per (row, head): with a single query there is nothing for a tensor-core tile to share, so
 // the kernel is a pure streaming reduction.  Lane = (key sub-index g = lane / 8, 16-byte chunk
-// c = lane % 8): every load instruction fetches four complete 128-byte K (or V) rows, fully
+// c = lane % 8): every copy instruction fetches four complete 128-byte K (or V) rows, fully
 // coalesced; the 64-dim dot product is finished with three xor-shuffles inside the 8-lane group, and
-// each group keeps its own online-softmax state (m, l, o[8]) that is merged across the four groups
-// once at the end.  No shared memory and no block barrier, so dozens of warps per SM keep ~4 KB of
-// loads in flight each - the short sequences of the first decode steps are latency-bound and this
-// is what hides it.
-constexpr int kSaWarps = 8;
-
-template <typename T>
-__global__ void __launch_bounds__(kSaWarps * 32) self_attention_kernel(const SelfParams p, int n_pairs, int n_head) {
+// each group keeps its own online-softmax state (m, l, o[8]) - rescaled once per block of U keys -
+// that is merged across the four groups once at the end.
+//
+// The kernel is latency-bound (short sequences, a dependent indirection lookup in front of every
+// K/V fetch), so everything is software-pipelined: the in-flight K/V blocks live in a per-lane
+// cp.async ring in shared memory (every lane copies and later re-reads only its own 16-byte slots, so
+// no barrier of any kind is needed - cp.async.wait_group orders a thread's own copies), ST-1 blocks
+// of 4*U keys are outstanding per warp at ~60 registers, and the position -> physical-row lookups
+// run one block further ahead.  Measured on the C3 decode (profiles/r1_selfattn_sweep*.txt): the
+// first version (register buffers, serial lookup -> load -> math, 16 warps/SM) averaged 81 us per
+// launch, register double-buffering 57 us, this ring with (U, ST, warps/CTA) = (2, 4, 4) 41 us;
+// deeper rings or larger CTAs lose more in occupancy than they gain in bytes in flight.
+template <typename T, int U, int ST>
+__global__ void __launch_bounds__(640) self_attention_kernel(const SelfParams p, int n_rows, int n_head) {
+  extern __shared__ __align__(16) uint8_t sa_smem[];
+  pdl_launch_dependents();
+  pdl_wait();
   if (p.skip_flag && *p.skip_flag) return;
-  const int w = blockIdx.x * kSaWarps + (threadIdx.x >> 5);
-  if (w >= n_pairs) return;
-  const int lane = threadIdx.x & 31;
+  const int lane = threadIdx.x & 31, wi = threadIdx.x >> 5;
   const int g = lane >> 3, c = lane & 7;
+  const int w = blockIdx.x * (blockDim.x >> 5) + wi;
+  if (w >= n_rows * n_head) return;
   const int row = w / n_head, h = w % n_head;
   const bool step = p.indir != nullptr;
   int kv_len, phys_fixed = 0;
@@ -400,20 +412,19 @@ __global__ void __launch_bounds__(kSaWarps * 32) self_attention_kernel(const Sel
     kv_len = row % p.n_init + 1;
     phys_fixed = (row / p.n_init) * p.group;
   }
-  const int pos_new = kv_len - 1;
+  const int pos_new = step ? kv_len - 1 : kv_len;       // prefill: every key is already in the cache
   const long long row_bytes = static_cast<long long>(p.d) * 2;
   const uint8_t* qrow = reinterpret_cast<const uint8_t*>(p.qkv) + static_cast<long long>(row) * 3 * row_bytes + h * 128;
-  const uint8_t* knew = qrow + row_bytes;
-  const uint8_t* vnew = qrow + 2 * row_bytes;
-  uint8_t* kc = reinterpret_cast<uint8_t*>(p.kcache);
-  uint8_t* vc = reinterpret_cast<uint8_t*>(p.vcache);
+  const uint8_t* knew = qrow + row_bytes + c * 16;
+  const uint8_t* vnew = qrow + 2 * row_bytes + c * 16;
+  uint8_t* kc = reinterpret_cast<uint8_t*>(p.kcache) + h * 128 + c * 16;
+  uint8_t* vc = reinterpret_cast<uint8_t*>(p.vcache) + h * 128 + c * 16;
   if (step && lane < 16) {
-    // append the new token's K/V (this head's 128 B each) to physical row `row`, position L-1
-    const long long off = (static_cast<long long>(row) * p.max_ctx + pos_new) * row_bytes + h * 128 + c * 16;
+    const long long off = (static_cast<long long>(row) * p.max_ctx + pos_new) * row_bytes;
     if (lane < 8)
-      *reinterpret_cast<uint4*>(kc + off) = *reinterpret_cast<const uint4*>(knew + c * 16);
+      *reinterpret_cast<uint4*>(kc + off) = *reinterpret_cast<const uint4*>(knew);
     else
-      *reinterpret_cast<uint4*>(vc + off) = *reinterpret_cast<const uint4*>(vnew + c * 16);
+      *reinterpret_cast<uint4*>(vc + off) = *reinterpret_cast<const uint4*>(vnew);
   }
   float q[8];
   {
@@ -431,60 +442,91 @@ __global__ void __launch_bounds__(kSaWarps * 32) self_attention_kernel(const Sel
 #pragma unroll
   for (int e = 0; e < 8; ++e) o[e] = 0.f;
 
-  constexpr int UNROLL = 4;
-  for (int base = 0; base < kv_len; base += 4 * UNROLL) {
-    uint4 kk[UNROLL], vv[UNROLL];
-    bool ok[UNROLL];
+  constexpr int KPB = 4 * U;                              // keys per block (= per ring stage)
+  // ring layout: [warp][stage][j][k|v][lane] x 16 B
+  uint8_t* ring = sa_smem + (static_cast<size_t>(wi) * ST * U * 2 * 32 + lane) * 16;
+  auto load_phys = [&](int (&ph)[U], int b) {
 #pragma unroll
-    for (int j = 0; j < UNROLL; ++j) {
-      const int key = base + j * 4 + g;
-      ok[j] = key < kv_len;
-      kk[j] = make_uint4(0, 0, 0, 0);
-      vv[j] = make_uint4(0, 0, 0, 0);
-      if (ok[j]) {
-        const uint8_t *ks, *vs;
-        if (step && key == pos_new) {       // not yet visible through the cache: read it from qkv
-          ks = knew;
-          vs = vnew;
-        } else {
-          const int phys = step ? __ldg(ind + key) : phys_fixed;
-          const long long off = (static_cast<long long>(phys) * p.max_ctx + key) * row_bytes + h * 128;
-          ks = kc + off;
-          vs = vc + off;
-        }
-        kk[j] = *reinterpret_cast<const uint4*>(ks + c * 16);
-        vv[j] = *reinterpret_cast<const uint4*>(vs + c * 16);
-      }
+    for (int j = 0; j < U; ++j) {
+      const int key = b + j * 4 + g;
+      ph[j] = (step && key < pos_new) ? __ldg(ind + key) : phys_fixed;
     }
+  };
+  auto issue = [&](int stage, const int (&ph)[U], int b) {
 #pragma unroll
-    for (int j = 0; j < UNROLL; ++j) {
-      const uint32_t wk[4] = {kk[j].x, kk[j].y, kk[j].z, kk[j].w};
-      float sdot = 0.f;
+    for (int j = 0; j < U; ++j) {
+      const int key = b + j * 4 + g;
+      const bool valid = key < kv_len;
+      const uint8_t *ks = knew, *vs = vnew;               // new token (or dummy address of a masked key)
+      if (key < pos_new) {
+        const long long off = (static_cast<long long>(ph[j]) * p.max_ctx + key) * row_bytes;
+        ks = kc + off;
+        vs = vc + off;
+      }
+      uint8_t* dst = ring + ((stage * U + j) * 2) * 512;
+      cp_async16_zfill(dst, ks, valid);
+      cp_async16_zfill(dst + 512, vs, valid);
+    }
+    cp_async_commit();
+  };
+  auto consume = [&](int stage, int b) {
+    float sd[U];
+    float mx = m;
+#pragma unroll
+    for (int j = 0; j < U; ++j) {
+      const uint4 kk = *reinterpret_cast<const uint4*>(ring + ((stage * U + j) * 2) * 512);
+      const uint32_t wk[4] = {kk.x, kk.y, kk.z, kk.w};
+      float acc = 0.f;
 #pragma unroll
       for (int e = 0; e < 4; ++e) {
         const float2 f = Cvt<T>::unpack2(wk[e]);
-        sdot = fmaf(q[2 * e], f.x, sdot);
-        sdot = fmaf(q[2 * e + 1], f.y, sdot);
+        acc = fmaf(q[2 * e], f.x, acc);
+        acc = fmaf(q[2 * e + 1], f.y, acc);
       }
-      sdot += __shfl_xor_sync(0xffffffffu, sdot, 1);
-      sdot += __shfl_xor_sync(0xffffffffu, sdot, 2);
-      sdot += __shfl_xor_sync(0xffffffffu, sdot, 4);
-      if (ok[j]) {                          // uniform within the 8-lane group
-        const float mn = fmaxf(m, sdot);
-        const float al = fast_exp2(m - mn);
-        const float pr = fast_exp2(sdot - mn);
-        m = mn;
-        l = l * al + pr;
-        const uint32_t wv[4] = {vv[j].x, vv[j].y, vv[j].z, vv[j].w};
+      acc += __shfl_xor_sync(0xffffffffu, acc, 1);
+      acc += __shfl_xor_sync(0xffffffffu, acc, 2);
+      acc += __shfl_xor_sync(0xffffffffu, acc, 4);
+      sd[j] = (b + j * 4 + g) < kv_len ? acc : -INFINITY;
+      mx = fmaxf(mx, sd[j]);
+    }
+    if (mx == -INFINITY) return;                          // this lane group has not seen a valid key yet
+    const float al = fast_exp2(m - mx);                   // m = -inf -> 0
+    m = mx;
+    l *= al;
 #pragma unroll
-        for (int e = 0; e < 4; ++e) {
-          const float2 f = Cvt<T>::unpack2(wv[e]);
-          o[2 * e] = o[2 * e] * al + pr * f.x;
-          o[2 * e + 1] = o[2 * e + 1] * al + pr * f.y;
-        }
+    for (int e = 0; e < 8; ++e) o[e] *= al;
+#pragma unroll
+    for (int j = 0; j < U; ++j) {
+      const float pr = fast_exp2(sd[j] - mx);             // masked key: exp2(-inf) = 0, and its V slot is zero-filled
+      l += pr;
+      const uint4 vv = *reinterpret_cast<const uint4*>(ring + ((stage * U + j) * 2 + 1) * 512);
+      const uint32_t wv[4] = {vv.x, vv.y, vv.z, vv.w};
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const float2 f = Cvt<T>::unpack2(wv[e]);
+        o[2 * e] = fmaf(pr, f.x, o[2 * e]);
+        o[2 * e + 1] = fmaf(pr, f.y, o[2 * e + 1]);
       }
     }
+  };
+
+  int ph[U];
+#pragma unroll
+  for (int st = 0; st < ST - 1; ++st) {
+    load_phys(ph, st * KPB);
+    issue(st, ph, st * KPB);
   }
+  load_phys(ph, (ST - 1) * KPB);
+  int cs = 0, is = ST - 1;                                 // consume / issue stage
+  for (int b = 0; b < kv_len; b += KPB) {
+    cp_async_wait<ST - 2>();                               // block b has landed
+    issue(is, ph, b + (ST - 1) * KPB);
+    load_phys(ph, b + ST * KPB);
+    consume(cs, b);
+    cs = cs + 1 == ST ? 0 : cs + 1;
+    is = is + 1 == ST ? 0 : is + 1;
+  }
+  cp_async_wait<0>();
   // merge the four key groups (lanes differing in bits 3 and 4)
 #pragma unroll
   for (int sh = 8; sh <= 16; sh <<= 1) {
@@ -510,6 +552,29 @@ __global__ void __launch_bounds__(kSaWarps * 32) self_attention_kernel(const Sel
     u.w = Cvt<T>::pack2(o[6] * inv, o[7] * inv);
     *reinterpret_cast<uint4*>(reinterpret_cast<uint8_t*>(p.out) + static_cast<long long>(row) * row_bytes + h * 128 + c * 16) = u;
   }
+}
+
+template <typename T, int U, int ST>
+static int launch_sa(const SelfParams& p, int n_rows, int n_head, int wpc, cudaStream_t s) {
+  auto kern = self_attention_kernel<T, U, ST>;
+  const int smem = wpc * ST * U * 1024;
+  static int attr_smem = 0;
+  if (smem > attr_smem) {
+    if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess) return 44;
+    attr_smem = smem;
+  }
+  const int n_pairs = n_rows * n_head;
+  return launch_pdl(kern, dim3((n_pairs + wpc - 1) / wpc), dim3(wpc * 32), smem, s, p, n_rows, n_head) == cudaSuccess ? 0 : 43;
+}
+
+template <typename T>
+static int dispatch_sa(const SelfParams& p, int n_rows, int n_head, int u, int st, int wpc, cudaStream_t s) {
+  if (u == 2 && st == 4) return launch_sa<T, 2, 4>(p, n_rows, n_head, wpc, s);
+  if (u == 2 && st == 3) return launch_sa<T, 2, 3>(p, n_rows, n_head, wpc, s);
+  if (u == 2 && st == 5) return launch_sa<T, 2, 5>(p, n_rows, n_head, wpc, s);
+  if (u == 1 && st == 6) return launch_sa<T, 1, 6>(p, n_rows, n_head, wpc, s);
+  if (u == 1 && st == 8) return launch_sa<T, 1, 8>(p, n_rows, n_head, wpc, s);
+  return 45;
 }
 
 // Prefill-mode append: copy k|v of qkv[(a, i)] into cache[(a*group, i)].  One warp per (row, k/v).
@@ -590,7 +655,7 @@ int launch_cross_attention(int dtype, const void* q, const void* k, const void* 
         return 40;                                                                                         \
       attr = true;                                                                                         \
     }                                                                                                      \
-    kern<<<grid, kDaThreads, smem, s>>>(p);                                                                \
+    if (launch_pdl(kern, grid, dim3(kDaThreads), smem, s, p) != cudaSuccess) return 41;                   \
   }
   if (dtype == DT_BF16) {
     if (stages_opt == 3) WB_XATTN(__nv_bfloat16, 3) else if (stages_opt == 6) WB_XATTN(__nv_bfloat16, 6) else WB_XATTN(__nv_bfloat16, 4)
@@ -618,8 +683,13 @@ int launch_self_attention(int dtype, const void* qkv, void* kcache, void* vcache
   p.max_ctx = max_ctx;
   p.n_init = n_init > 0 ? n_init : 1;
   p.group = group;
-  const int n_pairs = n_rows * n_head;
-  const int blocks = (n_pairs + kSaWarps - 1) / kSaWarps;
+  static int cfg_u = 0, cfg_st = 4, cfg_wpc = 4;
+  if (!cfg_u) {
+    cfg_u = 2;
+    const char* c = getenv("WB200_SA_CFG");         // tuning override: "U,ST,WPC" (keys/4 per block, ring depth, warps per CTA)
+    if (c) sscanf(c, "%d,%d,%d", &cfg_u, &cfg_st, &cfg_wpc);
+    if (cfg_wpc < 1 || cfg_wpc > 20) cfg_wpc = 4;
+  }
   if (dtype == DT_BF16) {
     if (!indir) {
       kv_append_kernel<__nv_bfloat16><<<(n_rows * 2 * 32 + 255) / 256, 256, 0, s>>>(
@@ -628,7 +698,8 @@ int launch_self_attention(int dtype, const void* qkv, void* kcache, void* vcache
       count_launch();
     }
     ProfileScope prof(PROF_SELF_ATTN, s);
-    self_attention_kernel<__nv_bfloat16><<<blocks, kSaWarps * 32, 0, s>>>(p, n_pairs, n_head);
+    const int rc = dispatch_sa<__nv_bfloat16>(p, n_rows, n_head, cfg_u, cfg_st, cfg_wpc, s);
+    if (rc) return rc;
   } else {
     if (!indir) {
       kv_append_kernel<__half><<<(n_rows * 2 * 32 + 255) / 256, 256, 0, s>>>(
@@ -637,7 +708,8 @@ int launch_self_attention(int dtype, const void* qkv, void* kcache, void* vcache
       count_launch();
     }
     ProfileScope prof(PROF_SELF_ATTN, s);
-    self_attention_kernel<__half><<<blocks, kSaWarps * 32, 0, s>>>(p, n_pairs, n_head);
+    const int rc = dispatch_sa<__half>(p, n_rows, n_head, cfg_u, cfg_st, cfg_wpc, s);
+    if (rc) return rc;
   }
   count_launch();
   return cudaGetLastError() == cudaSuccess ? 0 : 43;

@@ -25,6 +25,7 @@
 
 namespace wb {
 
+int g_pdl_on = -1;      // -1: read WB200_PDL on first use (default on); wb200_set_pdl() overrides
 int g_bm64_on = 1;      // wb200_set_option("bm64", 0/1): 64-row tiles for skinny problems
 int g_splitk_on = -1;   // -1: read WB200_SPLITK on first use; wb200_set_splitk() overrides
 
@@ -181,7 +182,7 @@ gemm_tcgen05_kernel(const GemmParams p, const __grid_constant__ CUtensorMap mapA
                     const __grid_constant__ CUtensorMap mapA1,
                     const __grid_constant__ CUtensorMap mapB) {
   using Cfg = GemmCfg<BN, BM, KS>;
-  if (p.skip_flag && *p.skip_flag) return;
+  pdl_launch_dependents();   // the next kernel may be scheduled as soon as every CTA of this one is resident
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
                                              ~static_cast<uintptr_t>(1023));
@@ -195,7 +196,6 @@ gemm_tcgen05_kernel(const GemmParams p, const __grid_constant__ CUtensorMap mapA
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   const int total_tiles = p.batch * p.m_tiles_per_batch * p.n_tiles;
-  const int total_items = total_tiles * p.splits;
   const int groups_per_tap = (p.k_blocks_per_tap + KS - 1) / KS;
   const int k_blocks = p.taps * groups_per_tap;          // pipeline stages per full K sweep
   __shared__ int s_ticket;
@@ -224,6 +224,10 @@ gemm_tcgen05_kernel(const GemmParams p, const __grid_constant__ CUtensorMap mapA
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr_smem;
+  // Everything above (barrier init, TMEM allocation, descriptor prefetch) touches no global data and
+  // overlaps the tail of the previous kernel; from here on its results are needed.
+  pdl_wait();
+  const int total_items = (p.skip_flag && *p.skip_flag) ? 0 : total_tiles * p.splits;
 
   if (warp == 0 && lane == 0) {
     // ===================== TMA producer =====================
@@ -429,9 +433,9 @@ static int launch_impl(const GemmParams& p, const CUtensorMap& a0, const CUtenso
   const int total = p.batch * p.m_tiles_per_batch * p.n_tiles * p.splits;
   const int grid = total < num_sms ? total : num_sms;
   ProfileScope prof(PROF_GEMM, s);
-  kern<<<grid, kGemmThreads, Cfg::kSmemBytes, s>>>(p, a0, a1, b);
+  const cudaError_t le = launch_pdl(kern, dim3(grid), dim3(kGemmThreads), Cfg::kSmemBytes, s, p, a0, a1, b);
   count_launch();
-  return cudaGetLastError() == cudaSuccess ? 0 : 11;
+  return (le == cudaSuccess && cudaGetLastError() == cudaSuccess) ? 0 : 11;
 }
 
 int launch_linear(const LinearArgs& a, cudaStream_t s) {

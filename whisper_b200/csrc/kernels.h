@@ -2,6 +2,8 @@
 // Nothing here is exported; the C-ABI lives in include/whisper_b200.h.
 #pragma once
 #include <cuda_runtime.h>
+#include <stdlib.h>
+#include <string.h>
 #include <stdint.h>
 
 namespace wb {
@@ -66,6 +68,31 @@ struct LinearArgs {
 int launch_linear(const LinearArgs& a, cudaStream_t s);
 extern int g_splitk_on;
 extern int g_bm64_on;
+extern int g_pdl_on;   // programmatic dependent launch for the decoder-layer kernels (wb200_set_pdl / WB200_PDL)
+
+// Launch with the programmatic-stream-serialization attribute (when enabled): inside a stream or a
+// captured graph the kernel may be scheduled while the previous kernel drains; the kernels that are
+// launched this way all call pdl_wait() before touching global memory.
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t s,
+                              Args&&... args) {
+  if (g_pdl_on < 0) {
+    const char* e = getenv("WB200_PDL");
+    g_pdl_on = (e && e[0] == '0') ? 0 : 1;
+  }
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = s;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = at;
+  cfg.numAttrs = g_pdl_on ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...);
+}
 
 // Row LayerNorm in fp32 (reference model.py:39-41): y = (x - mean) / sqrt(var + 1e-5) * g + b
 int launch_layernorm(int dtype, const void* x, long long ldx, void* y, long long ldy, const float* g,

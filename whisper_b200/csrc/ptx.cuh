@@ -196,6 +196,14 @@ __host__ __device__ constexpr uint32_t umma_idesc(uint32_t fmt, uint32_t M, uint
 // ----------------------------------------------------------------------------------------------
 // Ampere-style helpers used by the memory-bound decode-attention kernels
 // ----------------------------------------------------------------------------------------------
+// Programmatic dependent launch (PDL).  A kernel launched with the programmatic-stream-serialization
+// attribute may start while its predecessor is still running; pdl_wait() blocks until the predecessor
+// has completed and its writes are visible, pdl_launch_dependents() lets the successor start early.
+// Both are no-ops for a normally launched kernel.  Rule used throughout: every thread calls
+// pdl_wait() before its first access to global memory (and before any early return).
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
 __device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc) {
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(smem_dst)), "l"(gsrc)
                : "memory");

@@ -14,6 +14,8 @@ __global__ void __launch_bounds__(256) layernorm_kernel(const T* __restrict__ x,
                                                         const float* __restrict__ g,
                                                         const float* __restrict__ b, int rows, int d,
                                                         const int* skip_flag) {
+  pdl_launch_dependents();
+  pdl_wait();
   if (skip_flag && *skip_flag) return;
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
@@ -85,14 +87,15 @@ int launch_layernorm(int dtype, const void* x, long long ldx, void* y, long long
   const int threads = 256;
   const int blocks = (rows * 32 + threads - 1) / threads;
   ProfileScope prof(PROF_LAYERNORM, s);
+  cudaError_t le;
   if (dtype == DT_BF16)
-    layernorm_kernel<__nv_bfloat16, 8><<<blocks, threads, 0, s>>>(
-        static_cast<const __nv_bfloat16*>(x), ldx, static_cast<__nv_bfloat16*>(y), ldy, g, b, rows, d, skip_flag);
+    le = launch_pdl(layernorm_kernel<__nv_bfloat16, 8>, dim3(blocks), dim3(threads), 0, s,
+                    static_cast<const __nv_bfloat16*>(x), ldx, static_cast<__nv_bfloat16*>(y), ldy, g, b, rows, d, skip_flag);
   else
-    layernorm_kernel<__half, 8><<<blocks, threads, 0, s>>>(static_cast<const __half*>(x), ldx,
-                                                           static_cast<__half*>(y), ldy, g, b, rows, d, skip_flag);
+    le = launch_pdl(layernorm_kernel<__half, 8>, dim3(blocks), dim3(threads), 0, s, static_cast<const __half*>(x), ldx,
+                    static_cast<__half*>(y), ldy, g, b, rows, d, skip_flag);
   count_launch();
-  return cudaGetLastError() == cudaSuccess ? 0 : 21;
+  return (le == cudaSuccess && cudaGetLastError() == cudaSuccess) ? 0 : 21;
 }
 
 // 32x32 tile transpose through shared memory; reads coalesced along T, writes coalesced along C.
