@@ -311,8 +311,6 @@ gemm_tcgen05_kernel(const GemmParams p, const __grid_constant__ CUtensorMap mapA
     constexpr int kColsPerWarp = BN / 2;
     int acc = 0;
     uint32_t acc_phase = 0;
-    const T* bias = reinterpret_cast<const T*>(p.bias);
-    const T* resid = reinterpret_cast<const T*>(p.residual);
     for (int item = blockIdx.x; item < total_items; item += gridDim.x) {
       const int tile = item / p.splits, split = item % p.splits;
       const int m_tile = tile / p.n_tiles;
