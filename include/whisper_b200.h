@@ -179,6 +179,16 @@ int wb200_decoder_prefill(wb200_decoder* dec, const int32_t* initial_tokens, voi
 /* logit filters + GreedyDecoder.update / BeamSearchDecoder.update on the current logits
  * (decoding.py:699-703), including the beam kv-cache reorder (a parent-table update). */
 int wb200_decoder_select(wb200_decoder* dec, void* stream);
+/* GreedyDecoder with a temperature (decoding.py:283: Categorical(logits / temperature).sample(); n_group =
+ * best_of independent samples per audio, decoding.py:524-526).  temperature 0 (the default) is argmax.  The
+ * reference draws from torch's global generator, which no other implementation can replay; this library draws
+ * by Gumbel-max with a counter-based generator so that a (seed, row, step) triple fully determines the sample:
+ *     words  = Philox4x32-10(counter = (v >> 2, row, L, 0), key = (seed & 0xffffffff, seed >> 32))
+ *     u_v    = ((words[v & 3] >> 8) + 0.5) * 2^-24,   g_v = -log(-log(u_v))            (fp32)
+ *     token  = argmax_v( logit_v / temperature + g_v )   over the tokens the filters leave, ties to the lower id
+ * with L the number of tokens already in the row.  sum_logprobs accumulates the UN-tempered log-probability of
+ * the drawn token (decoding.py:285-287).  Only for greedy (non-beam) sessions; call before select / run. */
+int wb200_decoder_set_sampling(wb200_decoder* dec, float temperature, uint64_t seed);
 /* one TextDecoder step on the last token of every row with kv-cache append (decoding.py:687) */
 int wb200_decoder_step(wb200_decoder* dec, void* stream);
 /* up to max_steps x (step, select); stops early once the device-side completion flag is seen

@@ -93,6 +93,8 @@ class Options:
     suppress_blank: bool = True
     without_timestamps: bool = False
     max_initial_timestamp: Optional[float] = 1.0
+    best_of: Optional[int] = None       # independent samples per audio when temperature > 0 (decoding.py:524-526)
+    seed: int = 0                       # key of the counter-based sampler (sample_update)
 
 
 @dataclass
@@ -161,6 +163,68 @@ def greedy_update(tokens: List[List[int]], logits: torch.Tensor, sum_logprobs: t
     nxt = torch.where(last == eot, torch.full_like(nxt, eot), nxt)
     out = [t + [int(n)] for t, n in zip(tokens, nxt)]
     return out, all(t[-1] == eot for t in out)
+
+
+# ---- temperature sampling (decoding.py:283: Categorical(logits=logits / temperature).sample()) -------------
+# The reference draws from torch's global generator, which cannot be replayed elsewhere.  What
+# CAN be pinned is (1) the distribution - a Gumbel-max draw is an exact Categorical(softmax(logits / T)) sample -
+# and (2) a counter-based generator so that (seed, row, step) determines the draw on any implementation.
+# include/whisper_b200.h (wb200_decoder_set_sampling) states the same contract.
+_PHILOX_M0, _PHILOX_M1 = np.uint64(0xD2511F53), np.uint64(0xCD9E8D57)
+_PHILOX_W0, _PHILOX_W1 = 0x9E3779B9, 0xBB67AE85
+_MASK32 = np.uint64(0xFFFFFFFF)
+
+
+def philox4x32_10(counter: np.ndarray, key: Tuple[int, int]) -> np.ndarray:
+    """Philox4x32-10 (Salmon et al., SC'11; Random123 reference) on an array of counters [..., 4] uint32."""
+    c = np.asarray(counter, dtype=np.uint64).copy()
+    k0, k1 = int(key[0]) & 0xFFFFFFFF, int(key[1]) & 0xFFFFFFFF
+    for _ in range(10):
+        p0 = _PHILOX_M0 * c[..., 0]
+        p1 = _PHILOX_M1 * c[..., 2]
+        hi0, lo0 = p0 >> np.uint64(32), p0 & _MASK32
+        hi1, lo1 = p1 >> np.uint64(32), p1 & _MASK32
+        n0 = hi1 ^ c[..., 1] ^ np.uint64(k0)
+        n2 = hi0 ^ c[..., 3] ^ np.uint64(k1)
+        c = np.stack([n0, lo1, n2, lo0], axis=-1)
+        k0 = (k0 + _PHILOX_W0) & 0xFFFFFFFF
+        k1 = (k1 + _PHILOX_W1) & 0xFFFFFFFF
+    return c.astype(np.uint32)
+
+
+def gumbel_noise(seed: int, row: int, step: int, n_vocab: int) -> np.ndarray:
+    """g_v for v < n_vocab: counter (v >> 2, row, step, 0), key (seed & 0xffffffff, seed >> 32), word v & 3,
+    u = ((word >> 8) + 0.5) * 2^-24, g = -log(-log(u)) in fp32."""
+    n4 = (n_vocab + 3) // 4
+    ctr = np.zeros((n4, 4), dtype=np.uint64)
+    ctr[:, 0] = np.arange(n4, dtype=np.uint64)
+    ctr[:, 1] = row
+    ctr[:, 2] = step
+    words = philox4x32_10(ctr, (seed & 0xFFFFFFFF, (seed >> 32) & 0xFFFFFFFF)).reshape(-1)[:n_vocab]
+    u = ((words >> np.uint32(8)).astype(np.float32) + np.float32(0.5)) * np.float32(2.0 ** -24)
+    return -np.log(-np.log(u, dtype=np.float32), dtype=np.float32)
+
+
+def sample_update(tokens: List[List[int]], logits: torch.Tensor, sum_logprobs: torch.Tensor, eot: int,
+                  temperature: float, seed: int) -> Tuple[List[List[int]], bool, List[float]]:
+    """GreedyDecoder.update with temperature > 0 (decoding.py:277-293) under the Gumbel-max contract.
+    Also returns, per row, the gap between the best and second-best perturbed score (for margin-gated parity)."""
+    V = logits.shape[-1]
+    inv_t = np.float32(1.0 / np.float32(temperature))
+    nxt, gaps = [], []
+    for r, row in enumerate(logits.float().numpy()):
+        key = np.where(np.isneginf(row), -np.inf, row * inv_t + gumbel_noise(seed, r, len(tokens[r]), V)).astype(np.float32)
+        order = np.argsort(-key, kind="stable")            # ties -> lower id
+        nxt.append(int(order[0]))
+        gaps.append(float(key[order[0]] - key[order[1]]) if V > 1 else float("inf"))
+    nxt = torch.tensor(nxt)
+    logprobs = torch.log_softmax(logits.float(), dim=-1)   # un-tempered (decoding.py:285)
+    cur = logprobs[torch.arange(len(tokens)), nxt]
+    last = torch.tensor([t[-1] for t in tokens])
+    sum_logprobs += cur * (last != eot)
+    nxt = torch.where(last == eot, torch.full_like(nxt, eot), nxt)
+    out = [t + [int(n)] for t, n in zip(tokens, nxt)]
+    return out, all(t[-1] == eot for t in out), gaps
 
 
 class BeamState:
@@ -284,7 +348,7 @@ def decode(W: M.Weights, dims: Dict[str, int], mel_or_features: torch.Tensor, op
     import time as _time
     ids = token_ids(dims["n_vocab"])
     n_ctx = dims["n_text_ctx"]
-    G = opt.beam_size or 1
+    G = opt.beam_size or opt.best_of or 1                                    # decoding.py:524
     sample_len = opt.sample_len or n_ctx // 2
     init = initial_tokens(ids, opt, n_ctx, sample_len)
     sample_begin = len(init)
@@ -333,7 +397,11 @@ def decode(W: M.Weights, dims: Dict[str, int], mel_or_features: torch.Tensor, op
         top2 = logits.topk(2, dim=-1).values
         for r in range(R):
             margins[r].append(float(top2[r, 0] - top2[r, 1]))
-        if beam is None:
+        if beam is None and opt.temperature > 0:
+            tokens, completed, gaps = sample_update(tokens, logits, sum_lp, ids.eot, opt.temperature, opt.seed)
+            if record is not None:
+                record.setdefault("sample_gaps", []).append(gaps)
+        elif beam is None:
             tokens, completed = greedy_update(tokens, logits, sum_lp, ids.eot)
         else:
             tokens, src, completed = beam.update(tokens, logits, sum_lp)

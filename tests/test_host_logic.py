@@ -86,8 +86,13 @@ def test_option_validation_errors():
     for bad in (dict(beam_size=5, best_of=5), dict(best_of=3), dict(patience=1.0), dict(length_penalty=1.5)):
         with pytest.raises(ValueError):                        # decoding.py:572-585
             DecodingTask(m, DecodingOptions(language="en", **bad))
-    with pytest.raises(NotImplementedError):
-        DecodingTask(m, DecodingOptions(language="en", temperature=0.4))
+    with pytest.raises(ValueError):                            # sampling uses GreedyDecoder (decoding.py:548-552)
+        DecodingTask(m, DecodingOptions(language="en", temperature=0.4, beam_size=5))
+    with pytest.raises(ValueError):
+        DecodingTask(m, DecodingOptions(language="en", temperature=-0.1))
+    task = DecodingTask(m, DecodingOptions(language="en", temperature=0.4, best_of=3))
+    cfg = task.session_config(2)
+    assert cfg["n_group"] == 3 and cfg["beam_search"] == 0     # decoding.py:524-526
 
 
 def test_finalize_and_rank_match_oracle():
@@ -165,3 +170,46 @@ def test_window_splitting_rules():
     assert len(segs) == 1 and segs[0]["end"] == pytest.approx(6.0) and seek == 2000
     segs, seek = loop.split_window(0, 2000, 20.0, res([11, 12]))
     assert segs[0]["end"] == pytest.approx(20.0)
+
+
+def test_temperature_fallback_ladder():
+    """transcribe.py:184-224: walk the temperature ladder until the result passes the compression-ratio /
+    log-prob checks; beam options are dropped above temperature 0, best_of at 0; silence keeps a bad result."""
+    from whisper_b200.decoding import DecodingResult
+    from whisper_b200.transcribe import _WindowLoop
+
+    calls = []
+
+    class FakeModel:
+        def __init__(self, script):
+            self.script = script
+
+        def decode(self, segment, options):
+            calls.append(options)
+            cr, lp, ns = self.script[min(len(calls) - 1, len(self.script) - 1)]
+            return DecodingResult(audio_features=None, language="en", tokens=[1], temperature=options.temperature,
+                                  avg_logprob=lp, compression_ratio=cr, no_speech_prob=ns)
+
+    def make(script, **kw):
+        calls.clear()
+        loop = _WindowLoop.__new__(_WindowLoop)
+        loop.model = FakeModel(script)
+        loop.temperatures = [0.0, 0.2, 0.4]
+        loop.cr_threshold, loop.lp_threshold, loop.ns_threshold = 2.4, -1.0, 0.6
+        loop.decode_options = dict(language="en", beam_size=5, patience=1.0, best_of=3, **kw)
+        return loop
+
+    # first rung too repetitive, second has a low log-prob, third is fine
+    r = make([(3.0, -0.2, 0.0), (1.0, -1.5, 0.0), (1.0, -0.3, 0.0)]).decode_with_fallback(None)
+    assert r.temperature == 0.4 and len(calls) == 3
+    assert calls[0].beam_size == 5 and calls[0].best_of is None and calls[0].temperature == 0.0
+    assert calls[1].beam_size is None and calls[1].patience is None and calls[1].best_of == 3
+    # a good first rung stops the ladder
+    r = make([(1.0, -0.3, 0.0)]).decode_with_fallback(None)
+    assert r.temperature == 0.0 and len(calls) == 1
+    # low log-prob but probably silence: accepted as is (transcribe.py:216-222)
+    r = make([(1.0, -1.5, 0.9), (1.0, -0.1, 0.0)]).decode_with_fallback(None)
+    assert r.temperature == 0.0 and len(calls) == 1
+    # nothing passes: the last rung's result is returned
+    r = make([(3.0, -0.2, 0.0)]).decode_with_fallback(None)
+    assert r.temperature == 0.4 and len(calls) == 3

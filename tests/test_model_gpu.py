@@ -157,6 +157,124 @@ def test_selection_kernels_exact(name, case):
         sess.close()
 
 
+SAMPLING_CASES = [dict(temperature=0.7, best_of=3, seed=11), dict(temperature=1.0, seed=(1 << 40) + 5),
+                  dict(temperature=0.3, best_of=2, seed=3, without_timestamps=True)]
+
+
+@pytest.mark.parametrize("opts", SAMPLING_CASES)
+@pytest.mark.parametrize("name", ["test-en", "test-multi"])
+def test_sampling_kernel_matches_contract(name, opts):
+    """GreedyDecoder with a temperature (decoding.py:283): feed the oracle's fp32 logits to the device filter /
+    Gumbel-max kernel step by step.  The drawn tokens must equal the oracle's restatement of the RNG contract
+    (Philox4x32-10 counters, include/whisper_b200.h) wherever the oracle's best and second-best perturbed
+    scores are further apart than fp32 log round-off, and the accumulated UN-tempered log-probabilities agree."""
+    from oracle import decoding as OD
+    from whisper_b200.decoding import DecodingOptions, DecodingTask
+
+    meta, arrays, dims, W, mel, feats = oracle_features(name)
+    n_audio = 2
+    rec = {}
+    OD.decode(W, dims, feats[:n_audio], OD.Options(sample_len=12, **opts), record=rec)
+    model = gpu_model(name, torch.float16)
+    g_feats = model.embed_audio(gpu_mel(name))[:n_audio].contiguous()
+    task = DecodingTask(model, DecodingOptions(language="en", sample_len=12, **opts))
+    G = task.n_group
+    assert G == (opts.get("best_of") or 1)
+    sess = task.open_session(n_audio)
+    try:
+        sess.set_audio(g_feats)
+        sess.set_sampling(opts["temperature"], opts["seed"])
+        sess.prefill(np.tile(np.asarray(task.initial_tokens, dtype=np.int32), (n_audio, 1)))
+        checked = 0
+        for i in range(len(rec["raw_logits"])):
+            logits = rec["raw_logits"][i]
+            if i == 0:
+                sess.set_logits(logits[::G])
+            else:
+                sess.step()
+                sess.set_logits(logits)
+            sess.select()
+            if min(rec["sample_gaps"][i]) < 1e-4:      # a near-tie: fp32 log() round-off may flip it; stop comparing
+                break
+            L = int(sess.get("length").item())
+            toks = sess.get("tokens")[:, :L].cpu().numpy().tolist()
+            assert toks == rec["tokens_out"][i], f"step {i}: sampled tokens differ from the contract"
+            lp = sess.get("sum_logprobs").cpu()
+            assert torch.allclose(lp, rec["sum_logprobs_out"][i], atol=1e-4, rtol=1e-5), f"step {i}: sum_logprobs differ"
+            checked += 1
+        assert checked >= 3
+    finally:
+        sess.close()
+
+
+def test_sampling_distribution_on_device():
+    """Chi-square of the device sampler on a 5-token distribution: 1024 rows x 6 steps of injected logits."""
+    from whisper_b200.decoding import DecodingOptions, DecodingTask
+
+    model = gpu_model("test-en", torch.float16)
+    n_audio, G = 64, 16
+    task = DecodingTask(model, DecodingOptions(language="en", temperature=0.8, best_of=G, without_timestamps=True,
+                                               suppress_tokens="", suppress_blank=False, sample_len=8))
+    V = model.dims.n_vocab
+    live = [101, 2049, 2050, 7000, V - 1]
+    vals = torch.tensor([0.3, 1.7, -0.5, 2.2, 0.9])
+    p = torch.softmax(vals / 0.8, 0).numpy()
+    logits = torch.full((n_audio * G, V), float("-inf"))
+    logits[:, live] = vals
+    feats = model.embed_audio(gpu_mel("test-en"))[:1].expand(n_audio, -1, -1).contiguous()
+    sess = task.open_session(n_audio)
+    try:
+        sess.set_audio(feats)
+        sess.set_sampling(0.8, 2024)
+        sess.prefill(np.tile(np.asarray(task.initial_tokens, dtype=np.int32), (n_audio, 1)))
+        counts = np.zeros(len(live))
+        n = 0
+        for i in range(6):
+            if i == 0:
+                sess.set_logits(logits[::G])
+            else:
+                sess.step()
+                sess.set_logits(logits)
+            sess.select()
+            L = int(sess.get("length").item())
+            drawn = sess.get("tokens")[:, L - 1].cpu().numpy()
+            assert set(drawn.tolist()) <= set(live), "a filtered (-inf) token was drawn"
+            for k, t in enumerate(live):
+                counts[k] += int((drawn == t).sum())
+            n += len(drawn)
+        chi2 = float((((counts - n * p) ** 2) / (n * p)).sum())
+        assert chi2 < 18.5, (chi2, counts, n * p)          # 4 dof, p ~ 1e-3
+        lp = sess.get("sum_logprobs").cpu().numpy()
+        assert np.isfinite(lp).all() and (lp < 0).all()
+    finally:
+        sess.close()
+
+
+def test_decode_with_temperature_end_to_end():
+    """decode() with temperature > 0 / best_of (decoding.py:524-526, 283): repeatable for a fixed seed (also
+    through torch.manual_seed), with finite negative avg_logprob; the transcribe() ladder reaches the sampled rungs."""
+    import whisper_b200 as wb
+
+    model = gpu_model("test-en", torch.float16)
+    mel = gpu_mel("test-en")[:2]
+    o = dict(language="en", temperature=0.9, best_of=3, sample_len=16)
+    a = model.decode(mel, wb.DecodingOptions(seed=7, **o))
+    b = model.decode(mel, wb.DecodingOptions(seed=7, **o))
+    assert [r.tokens for r in a] == [r.tokens for r in b]
+    assert all(r.temperature == 0.9 and np.isfinite(r.avg_logprob) and r.avg_logprob < 0 for r in a)
+    torch.manual_seed(99)
+    d = model.decode(mel, wb.DecodingOptions(**o))
+    torch.manual_seed(99)
+    e = model.decode(mel, wb.DecodingOptions(**o))
+    assert [r.tokens for r in d] == [r.tokens for r in e]
+    greedy = model.decode(mel, wb.DecodingOptions(language="en", sample_len=16))
+    assert all(r.temperature == 0.0 for r in greedy)
+    # the fallback ladder of transcribe() reaches the sampling rungs on noise-like input without raising
+    audio = np.random.RandomState(0).randn(16000 * 3).astype(np.float32) * 0.1
+    out = model.transcribe(audio, temperature=(0.0, 0.4, 0.8), sample_len=8, compression_ratio_threshold=0.01)
+    assert "segments" in out
+
+
 def _first_risky_step(margins, tau):
     for i, m in enumerate(margins):
         if m < tau:

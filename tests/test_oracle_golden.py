@@ -113,3 +113,52 @@ def test_detect_language():
     toks, probs = OD.detect_language(W, dims, feats)
     assert toks.tolist() == meta["detect_language"]["tokens"]
     assert np.allclose(probs.max(dim=-1).values.numpy(), meta["detect_language"]["top_prob"], atol=1e-5)
+
+
+def test_philox_known_answers():
+    """Random123 known-answer vectors for Philox4x32-10 (kat_vectors of the reference implementation): pins the
+    generator the sampling contract (include/whisper_b200.h: wb200_decoder_set_sampling) is stated on."""
+    from oracle.decoding import philox4x32_10
+
+    kat = [((0, 0, 0, 0), (0, 0), (0x6627e8d5, 0xe169c58d, 0xbc57ac4c, 0x9b00dbd8)),
+           ((0xffffffff,) * 4, (0xffffffff, 0xffffffff), (0x408f276d, 0x41c83b0e, 0xa20bc7c6, 0x6d5451fd)),
+           ((0x243f6a88, 0x85a308d3, 0x13198a2e, 0x03707344), (0xa4093822, 0x299f31d0),
+            (0xd16cfe09, 0x94fdcceb, 0x5001e420, 0x24126ea1))]
+    for ctr, key, want in kat:
+        assert tuple(int(x) for x in philox4x32_10(np.array(ctr), key)) == want
+    batch = philox4x32_10(np.array([k[0] for k in kat[:1]] * 3), (0, 0))
+    assert batch.shape == (3, 4) and (batch == batch[0]).all()
+
+
+def test_gumbel_max_is_categorical():
+    """The Gumbel-max draw of the sampling contract is distributed as Categorical(softmax(logits / T))
+    (what decoding.py:283 samples) and never picks a filtered (-inf) token."""
+    import torch
+    from oracle.decoding import gumbel_noise, sample_update
+
+    logits = np.full(12, -np.inf, dtype=np.float32)
+    live = [1, 4, 5, 9, 11]
+    logits[live] = [0.3, 1.7, -0.5, 2.2, 0.9]
+    T = 0.8
+    p = np.exp(logits[live] / T)
+    p /= p.sum()
+    n = 4000
+    counts = np.zeros(12)
+    for step in range(n):
+        key = np.where(np.isneginf(logits), -np.inf, logits / np.float32(T) + gumbel_noise(77, 3, step, 12))
+        counts[int(np.argmax(key))] += 1
+    assert counts[[i for i in range(12) if i not in live]].sum() == 0
+    chi2 = float((((counts[live] - n * p) ** 2) / (n * p)).sum())
+    assert chi2 < 18.5, (chi2, counts[live], n * p)          # 4 dof, p ~ 1e-3
+    # noise differs across rows, steps and seeds, and is reproducible
+    assert not np.array_equal(gumbel_noise(1, 0, 0, 64), gumbel_noise(1, 1, 0, 64))
+    assert not np.array_equal(gumbel_noise(1, 0, 0, 64), gumbel_noise(1, 0, 1, 64))
+    assert not np.array_equal(gumbel_noise(1, 0, 0, 64), gumbel_noise(2, 0, 0, 64))
+    assert np.array_equal(gumbel_noise(1 << 40, 5, 9, 64), gumbel_noise(1 << 40, 5, 9, 64))
+    # sample_update: un-tempered log-probability accumulated, rows that ended keep emitting eot
+    lg = torch.from_numpy(np.stack([logits, logits]))
+    sums = torch.zeros(2)
+    toks, done, gaps = sample_update([[7, 8], [7, 0]], lg, sums, eot=0, temperature=T, seed=5)
+    assert toks[1][-1] == 0 and float(sums[1]) == 0.0 and toks[0][-1] in live and len(gaps) == 2
+    want = float(torch.log_softmax(lg[0], -1)[toks[0][-1]])
+    assert abs(float(sums[0]) - want) < 1e-6

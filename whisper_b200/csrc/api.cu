@@ -300,6 +300,11 @@ int wb200_decoder_set_audio(wb200_decoder* dec, const void* features, void* stre
 int wb200_decoder_prefill(wb200_decoder* dec, const int32_t* initial_tokens, void* stream) {
   return decoder_prefill(dec->d, initial_tokens, static_cast<cudaStream_t>(stream));
 }
+int wb200_decoder_set_sampling(wb200_decoder* dec, float temperature, uint64_t seed) {
+  if (!dec) return set_error(2, "wb200_decoder_set_sampling: null decoder");
+  return decoder_set_sampling(dec->d, temperature, seed);
+}
+
 int wb200_decoder_select(wb200_decoder* dec, void* stream) {
   return decoder_select(dec->d, static_cast<cudaStream_t>(stream));
 }

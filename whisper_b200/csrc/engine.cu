@@ -451,6 +451,20 @@ int decoder_step(Decoder* D, cudaStream_t s) {
   return 0;
 }
 
+int decoder_set_sampling(Decoder* D, float temperature, unsigned long long seed) {
+  if (!(temperature >= 0.f)) return set_error(243, "set_sampling: temperature must be >= 0");
+  if (temperature > 0.f && D->cfg.beam_search)
+    return set_error(244, "set_sampling: temperature > 0 needs a greedy session (decoding.py:548-552 builds a GreedyDecoder)");
+  D->temperature = temperature;
+  D->seed = seed;
+  if (D->pair_graph) {                 // the captured decode loop has the old parameters baked in
+    cudaGraphExecDestroy(D->pair_graph);
+    D->pair_graph = nullptr;
+    D->pair_graph_cur = -1;
+  }
+  return 0;
+}
+
 int decoder_select(Decoder* D, cudaStream_t s) {
   const Model* m = D->m;
   const wb200_decode_config& c = D->cfg;
@@ -474,6 +488,9 @@ int decoder_select(Decoder* D, cudaStream_t s) {
   f.suppress_blank = c.suppress_blank;
   f.ts_rules = c.timestamp_rules;
   f.K = c.beam_search ? G + 1 : 1;
+  f.inv_temp = (!c.beam_search && D->temperature > 0.f) ? 1.0f / D->temperature : 0.f;
+  f.seed_lo = static_cast<uint32_t>(D->seed & 0xffffffffull);
+  f.seed_hi = static_cast<uint32_t>(D->seed >> 32);
   f.top_val = D->top_val;
   f.top_idx = D->top_idx;
   WB_TRY(launch_filter_topk(f, R, s));

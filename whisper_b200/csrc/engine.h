@@ -89,6 +89,9 @@ struct Decoder {
   cudaGraphExec_t pair_graph = nullptr;
   int pair_graph_cur = -1;          // value of `cur` the graph was captured at
   int launches_per_pair = 0;        // kernels inside one replay (for wb200_launch_count)
+  // GreedyDecoder temperature sampling (wb200_decoder_set_sampling); 0 = argmax
+  float temperature = 0.f;
+  unsigned long long seed = 0;
 };
 
 size_t encoder_workspace_bytes(const Model* m, int B);
@@ -99,6 +102,7 @@ int decoder_set_audio(Decoder* D, const void* features, cudaStream_t s);
 int decoder_prefill(Decoder* D, const int32_t* init_tokens_host, cudaStream_t s);
 int decoder_step(Decoder* D, cudaStream_t s);
 int decoder_select(Decoder* D, cudaStream_t s);
+int decoder_set_sampling(Decoder* D, float temperature, unsigned long long seed);
 int decoder_append(Decoder* D, const int32_t* next_host, cudaStream_t s);
 int decoder_run(Decoder* D, int max_steps, int* steps_issued, cudaStream_t s);
 int decoder_state_ptr(Decoder* D, int what, void** ptr, size_t* bytes, cudaStream_t s);

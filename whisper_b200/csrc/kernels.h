@@ -135,6 +135,10 @@ struct FilterParams {
   int K;
   float* top_val;           // [R, K] log-probabilities, best first
   int* top_idx;             // [R, K]
+  // temperature sampling (K == 1 only): inv_temp = 1 / temperature, 0 = argmax.  The sample is the Gumbel-max
+  // argmax_v( logit_v * inv_temp + g_v ), g_v = -log(-log(u_v)), u_v from Philox4x32-10 (see select.cu).
+  float inv_temp;
+  uint32_t seed_lo, seed_hi;
 };
 struct GreedyParams {
   int* tokens;            // [R, max_ctx], appended in place

@@ -7,7 +7,9 @@
 //                        computed on the fly (the logits buffer is never rewritten), then the
 //                        log-softmax normaliser and the top-K (K = 1 greedy, beam+1 beam search)
 //                        by warp/CTA reductions.  Integer rules are exact; ties in the top-K go
-//                        to the lower token id.
+//                        to the lower token id.  With a temperature (GreedyDecoder, decoding.py:283:
+//                        Categorical(logits / T).sample()) the K = 1 selection becomes a Gumbel-max
+//                        draw with a counter-based generator, see gumbel_noise() for the contract.
 //   greedy_update_kernel / beam_update_kernel : one CTA.  Append the chosen tokens, update
 //                        sum_logprobs, EOT bookkeeping / finished-hypothesis store, beam parent
 //                        table (the kv-cache "reorder"), completion flag.
@@ -44,6 +46,37 @@ __device__ __forceinline__ void lse_merge(float& m, float& s, float m2, float s2
   }
 }
 
+
+// Philox4x32-10 (Salmon et al., "Parallel random numbers: as easy as 1, 2, 3", SC'11): counter-based, so the
+// noise of (row, step, token) needs no state and does not depend on launch geometry.
+__device__ __forceinline__ void philox4x32_10(uint32_t (&c)[4], uint32_t k0, uint32_t k1) {
+#pragma unroll
+  for (int round = 0; round < 10; ++round) {
+    const uint32_t hi0 = __umulhi(0xD2511F53u, c[0]), lo0 = 0xD2511F53u * c[0];
+    const uint32_t hi1 = __umulhi(0xCD9E8D57u, c[2]), lo1 = 0xCD9E8D57u * c[2];
+    const uint32_t n0 = hi1 ^ c[1] ^ k0, n2 = hi0 ^ c[3] ^ k1;
+    c[0] = n0;
+    c[1] = lo1;
+    c[2] = n2;
+    c[3] = lo0;
+    k0 += 0x9E3779B9u;
+    k1 += 0xBB67AE85u;
+  }
+}
+
+// RNG contract of the sampling path (restated by oracle/decoding.py: gumbel_noise):
+//   words  = Philox4x32-10(counter = (v >> 2, row, L, 0), key = (seed_lo, seed_hi)),  L = tokens in the row
+//   u      = ((words[v & 3] >> 8) + 0.5) * 2^-24            in (0, 1)
+//   g      = -log(-log(u))                                  fp32
+//   sample = argmax_v( logit_v / T + g_v ) over the tokens the filters leave, ties to the lower id,
+// which is an exact draw from Categorical(softmax(logits / T)) (decoding.py:283).
+__device__ __forceinline__ float gumbel_noise(uint32_t seed_lo, uint32_t seed_hi, int row, int L, int v) {
+  uint32_t c[4] = {static_cast<uint32_t>(v) >> 2, static_cast<uint32_t>(row), static_cast<uint32_t>(L), 0u};
+  philox4x32_10(c, seed_lo, seed_hi);
+  const uint32_t w = c[v & 3];
+  const float u = (static_cast<float>(w >> 8) + 0.5f) * 5.9604644775390625e-8f;
+  return -logf(-logf(u));
+}
 
 __global__ void __launch_bounds__(kSelThreads) filter_topk_kernel(const FilterParams p) {
   if (p.skip_flag && *p.skip_flag) return;
@@ -149,9 +182,11 @@ __global__ void __launch_bounds__(kSelThreads) filter_topk_kernel(const FilterPa
     mine.i[k] = 0x7fffffff;
   }
   const int K = p.K;
+  const bool sampling = p.inv_temp > 0.f && K == 1;
   for (int v = tid; v < p.V; v += kSelThreads) {
     float val = x[v];
     if (masked(v) || (drop_text && v < tb)) val = -INFINITY;
+    if (sampling && val != -INFINITY) val = fmaf(val, p.inv_temp, gumbel_noise(p.seed_lo, p.seed_hi, r, L, v));
     if (better(val, v, mine.v[K - 1], mine.i[K - 1])) {
       int k = K - 1;
       while (k > 0 && better(val, v, mine.v[k - 1], mine.i[k - 1])) {
@@ -210,7 +245,9 @@ __global__ void __launch_bounds__(kSelThreads) filter_topk_kernel(const FilterPa
       }
       if (have && head < K && ci == bi && cv == bv) ++head;
       if (lane == 0) {
-        p.top_val[static_cast<long long>(r) * K + k] = cv - lse;   // log-probability
+        // log-probability of the chosen token under the UN-tempered distribution (decoding.py:285-287)
+        const float chosen = sampling ? ((ci >= 0 && ci < p.V) ? x[ci] : -INFINITY) : cv;
+        p.top_val[static_cast<long long>(r) * K + k] = chosen - lse;
         p.top_idx[static_cast<long long>(r) * K + k] = ci;
       }
     }

@@ -51,6 +51,10 @@ class DecodingOptions:
     without_timestamps: bool = False
     max_initial_timestamp: Optional[float] = 1.0
     fp16: bool = True     # kept for signature compatibility; the compute type is the model's
+    # extension: seed of the counter-based sampler used when temperature > 0 (include/whisper_b200.h,
+    # wb200_decoder_set_sampling).  None draws one from torch's global generator, so torch.manual_seed()
+    # makes sampled decodes repeatable the way it does for the reference (decoding.py:283).
+    seed: Optional[int] = None
 
 
 @dataclass(frozen=True)
@@ -133,6 +137,13 @@ class DecoderSession:
         assert toks.shape == (self.cfg["n_audio"], self.cfg["n_init"])
         self._init_host = toks
         self._call("wb200_decoder_prefill", toks.ctypes.data_as(POINTER(c_int32)))
+
+    def set_sampling(self, temperature: float, seed: int):
+        """GreedyDecoder temperature sampling (decoding.py:283) with the library's counter-based generator."""
+        from ctypes import c_float, c_uint64
+        with torch.cuda.device(self.model.device):
+            check(lib().wb200_decoder_set_sampling(self._h, c_float(float(temperature)), c_uint64(int(seed) & (2 ** 64 - 1))),
+                  "wb200_decoder_set_sampling")
 
     def select(self):
         self._call("wb200_decoder_select")
@@ -280,9 +291,12 @@ class DecodingTask:
             raise ValueError("patience requires beam_size to be given")
         if options.length_penalty is not None and not (0 <= options.length_penalty <= 1):
             raise ValueError("length_penalty (alpha) should be a value between 0 and 1")
-        if options.temperature != 0:
-            raise NotImplementedError("temperature > 0 (Categorical sampling, decoding.py:283) is SURVEY.md 8f.4 "
-                                      "'next' work; this build decodes with temperature 0 only")
+        if options.temperature < 0:
+            raise ValueError("temperature must be >= 0")
+        if options.temperature > 0 and options.beam_size is not None:
+            # the reference silently prefers beam search when both are given (decoding.py:548-552) and the
+            # transcribe() ladder never combines them (transcribe.py:189-195); refuse the ambiguous request
+            raise ValueError("temperature > 0 samples with GreedyDecoder; drop beam_size (transcribe.py:189-195)")
         if options.beam_size is not None and options.beam_size > 16:
             raise ValueError("beam_size > 16 is not supported by the device beam kernel")
         return options
@@ -363,6 +377,11 @@ class DecodingTask:
         sess = self.open_session(n_audio)
         try:
             sess.set_audio(audio_features)
+            if self.options.temperature > 0:
+                seed = self.options.seed
+                if seed is None:
+                    seed = int(torch.randint(0, 2 ** 62, (1,)).item())
+                sess.set_sampling(self.options.temperature, seed)
             sess.prefill(init)                       # i == 0 forward + no_speech probabilities
             sess.select()                            # filters + first update
             if self.sample_len > 1:

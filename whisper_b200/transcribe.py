@@ -8,7 +8,6 @@ one device-resident decode.
 """
 from __future__ import annotations
 
-import warnings
 from typing import TYPE_CHECKING, List, Optional, Tuple, Union
 
 import numpy as np
@@ -191,9 +190,9 @@ def transcribe(
     (transcribe.py:38-126 documents every parameter).
 
     Differences from the reference, all explicit: the model always computes in its own 16-bit type
-    (`fp16=` is accepted and ignored); `temperature` entries above 0 are skipped with a warning because
-    the sampling path is not built yet, so the fallback ladder degenerates to its
-    first rung; `word_timestamps=True` raises (alignment path).
+    (`fp16=` is accepted and ignored); rungs of the `temperature` ladder above 0 sample with the library's
+    counter-based generator (seeded from torch's global generator, so `torch.manual_seed` makes a run
+    repeatable, but the draws are not the reference's); `word_timestamps=True` raises.
     """
     if word_timestamps:
         raise NotImplementedError(
@@ -202,10 +201,6 @@ def transcribe(
             "punctuation-merging / segment-clamping text heuristics of timing.py:245-388 are out of scope (SURVEY.md 2)")
     decode_options.pop("fp16", None)
     temps = [temperature] if isinstance(temperature, (int, float)) else list(temperature)
-    kept = [t for t in temps if t == 0]
-    if len(kept) != len(temps):
-        warnings.warn("whisper_b200: temperature > 0 (sampling fallback) is not built yet; using temperature 0 only")
-    temps = kept or [0.0]
 
     mel = log_mel_spectrogram(audio, model.dims.n_mels, padding=N_SAMPLES, device=model.device)   # transcribe.py:139
     content_frames = mel.shape[-1] - N_FRAMES
