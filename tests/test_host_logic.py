@@ -213,3 +213,116 @@ def test_temperature_fallback_ladder():
     # nothing passes: the last rung's result is returned
     r = make([(3.0, -0.2, 0.0)]).decode_with_fallback(None)
     assert r.temperature == 0.4 and len(calls) == 3
+
+
+def _fake_decode_fn(tb):
+    """A deterministic stand-in for the device decode: tokens / quality numbers are a pure function of the window's
+    content, the prompt and the temperature, with timestamps that move the seek position by different amounts."""
+    from whisper_b200.decoding import DecodingResult
+
+    def fake(segment, options):
+        h = int(abs(float(segment.double().sum())) * 1000) % 97
+        p = len(options.prompt or [])
+        t_end = 100 + (h * 13 + p) % 1300
+        tokens = [tb, 1000 + h, 1001 + (p % 7), tb + t_end // 2, tb + t_end // 2, 2000 + h, tb + t_end]
+        if h % 3 == 0:
+            tokens = tokens[:-1]                         # ends in text: seek goes to the last timestamp pair
+        bad = (h % 5 == 0) and options.temperature < 0.4
+        return DecodingResult(audio_features=None, language="en", tokens=tokens, temperature=options.temperature,
+                              avg_logprob=-1.5 if bad else -0.2, compression_ratio=1.0, no_speech_prob=0.1)
+
+    return fake
+
+
+def test_transcribe_batch_equals_per_file_transcribe(monkeypatch):
+    """transcribe_batch advances many files' window loops in lock-step; with a deterministic
+    decoder every file must get exactly what transcribe() gives it alone, requests must be batched across files,
+    and requests sharing a session must have prompts of one length."""
+    from oracle import audio as OA
+    import importlib
+
+    import whisper_b200.decoding as WD
+    from whisper_b200.tokenizer import get_tokenizer
+
+    WT = importlib.import_module("whisper_b200.transcribe")     # the package attribute of that name is the function
+
+    def cpu_mel(audio, n_mels=80, padding=0, device=None):
+        return torch.from_numpy(OA.log_mel_spectrogram(np.asarray(audio, dtype=np.float32), n_mels, padding).astype(np.float32))
+
+    monkeypatch.setattr(WT, "log_mel_spectrogram", cpu_mel)
+    tb = get_tokenizer(False).timestamp_begin
+    fake = _fake_decode_fn(tb)
+    model = fake_model("test-en")
+    model.decode = fake
+    rng = np.random.RandomState(5)
+    audios = [rng.randn(16000 * secs).astype(np.float32) * 0.1 for secs in (95, 31, 64, 140, 8)]
+    kw = dict(temperature=(0.0, 0.4), no_speech_threshold=0.6, logprob_threshold=-1.0)
+    alone = [WT.transcribe(model, a, **kw) for a in audios]
+    assert sum(len(r["segments"]) for r in alone) > 12
+
+    batches = []
+
+    def fake_requests(m, requests, max_batch=64):
+        tasks_len = {}
+        for seg, opt in requests:
+            tasks_len.setdefault((len(opt.prompt or []), opt.temperature), 0)
+            tasks_len[(len(opt.prompt or []), opt.temperature)] += 1
+        batches.append((len(requests), len(tasks_len)))
+        return [fake(seg, opt) for seg, opt in requests]
+
+    monkeypatch.setattr(WD, "decode_requests", fake_requests)
+    together = WT.transcribe_batch(model, audios, **kw)
+    for a, b in zip(alone, together):
+        assert a["text"] == b["text"] and a["language"] == b["language"]
+        assert [(s["seek"], s["start"], s["end"], s["tokens"], s["temperature"]) for s in a["segments"]] == \
+               [(s["seek"], s["start"], s["end"], s["tokens"], s["temperature"]) for s in b["segments"]]
+    rounds = together[0]["rounds"]
+    assert rounds == len(batches) and batches[0][0] == len(audios)
+    n_requests = sum(n for n, _ in batches)
+    assert rounds < n_requests                            # the files really shared rounds
+    assert transcribe_is_single_request_stream(WT, model, audios[1], kw, fake)
+
+
+def transcribe_is_single_request_stream(WT, model, audio, kw, fake):
+    """A one-file batch issues the same request sequence as transcribe()."""
+    seen = []
+    model.decode = lambda seg, opt: (seen.append(("single", len(opt.prompt or []), opt.temperature)), fake(seg, opt))[1]
+    WT.transcribe(model, audio, **kw)
+    single = [x[1:] for x in seen]
+    seen.clear()
+    import whisper_b200.decoding as WD
+    WD_decode = WD.decode_requests
+    try:
+        WD.decode_requests = lambda m, reqs, max_batch=64: [
+            (seen.append(("batch", len(o.prompt or []), o.temperature)), fake(s, o))[1] for s, o in reqs]
+        WT.transcribe_batch(model, [audio], **kw)
+    finally:
+        WD.decode_requests = WD_decode
+    return single == [x[1:] for x in seen]
+
+
+def test_decode_requests_groups_by_prompt_length(monkeypatch):
+    """decoding.decode_requests: requests with equal options and equally long prompts share one session (each row
+    prefilled with its own prompt); a different prompt length, temperature or beam size opens another."""
+    import whisper_b200.decoding as WD
+
+    model = fake_model("test-en")
+    runs = []
+
+    def fake_run(self, mel, initial_tokens=None):
+        runs.append((mel.shape[0], initial_tokens.copy(), self.options.temperature, self.options.beam_size))
+        return [WD.DecodingResult(audio_features=None, language="en", tokens=[int(initial_tokens[i, 1])])
+                for i in range(mel.shape[0])]
+
+    monkeypatch.setattr(WD.DecodingTask, "run", fake_run)
+    seg = torch.zeros(80, 3000)
+    O = WD.DecodingOptions
+    reqs = [(seg, O(language="en", prompt=[11, 12, 13])), (seg, O(language="en", prompt=[21, 22])),
+            (seg, O(language="en", prompt=[31, 32, 33])), (seg, O(language="en", prompt=[41, 42, 43], temperature=0.2)),
+            (seg, O(language="en", prompt=[51, 52, 53], beam_size=2)), (seg, O(language="en", prompt=[61, 62, 63]))]
+    out = WD.decode_requests(model, reqs, max_batch=2)
+    assert [r.tokens[0] for r in out] == [11, 21, 31, 41, 51, 61]          # request order kept, own prompt per row
+    sizes = sorted(n for n, _, _, _ in runs)
+    assert sizes == [1, 1, 1, 1, 2]                                         # {11,31} share (max_batch 2), 61 overflows
+    for n, init, _, _ in runs:
+        assert init.shape[0] == n and (init[:, 0] == init[0, 0]).all()      # <|startofprev|> first in every row

@@ -1,0 +1,69 @@
+"""GPU: the lock-step multi-file scheduler on the device path.
+
+Written after this round's GPU budget was spent: the scheduling logic is covered on CPU by
+tests/test_host_logic.py (deterministic fake decoder) and the per-row-prompt prefill it relies on is the same C-ABI
+call every other decode test uses, but these device tests have not run on hardware yet - hence non-strict xfail
+(they cannot fail the suite; an XPASS in the round-end log is the validation).
+"""
+import numpy as np
+import pytest
+import torch
+
+from helpers import fixture_inputs, load_model_fixture
+
+pytestmark = [pytest.mark.gpu, pytest.mark.xfail(strict=False, reason="first hardware run of transcribe_batch")]
+
+
+def _model(name="test-en"):
+    import whisper_b200 as wb
+
+    meta, _ = load_model_fixture(name)
+    dims, sd, _ = fixture_inputs(meta)
+    return wb.Whisper(wb.ModelDimensions(**dims), sd, device="cuda", dtype=torch.float16)
+
+
+def _audios():
+    rng = np.random.RandomState(21)
+    out = []
+    for secs in (41, 12, 75):
+        t = np.arange(16000 * secs) / 16000.0
+        x = 0.05 * rng.randn(len(t)) + 0.2 * np.sin(2 * np.pi * (200 + 30 * secs) * t) * (0.5 + 0.5 * np.sin(2 * np.pi * 3 * t))
+        out.append(x.astype(np.float32))
+    return out
+
+
+def test_transcribe_batch_matches_per_file():
+    """Greedy, temperature 0: every file gets the segments transcribe() gives it alone (each audio's decode is
+    independent of what shares its batch), and the batch needs no more rounds than the longest file has windows
+    (plus re-decodes)."""
+    import whisper_b200 as wb
+
+    model = _model()
+    audios = _audios()
+    kw = dict(temperature=0.0, sample_len=24, condition_on_previous_text=True, no_speech_threshold=None,
+              logprob_threshold=None, compression_ratio_threshold=None)
+    alone = [model.transcribe(a, **kw) for a in audios]
+    together = wb.transcribe_batch(model, audios, **kw)
+    assert len(together) == len(audios)
+    for a, b in zip(alone, together):
+        assert [s["tokens"] for s in a["segments"]] == [s["tokens"] for s in b["segments"]]
+        assert [s["seek"] for s in a["segments"]] == [s["seek"] for s in b["segments"]]
+        assert a["text"] == b["text"]
+    n_windows = [len({s["seek"] for s in r["segments"]}) for r in alone]
+    assert together[0]["rounds"] <= max(n_windows) + 2
+
+
+def test_decode_requests_per_row_prompts():
+    """decode_requests with different prompts of one length in ONE session == decode() one request at a time."""
+    import whisper_b200 as wb
+    from whisper_b200.decoding import decode_requests
+
+    model = _model()
+    mel = wb.log_mel_spectrogram(torch.from_numpy(_audios()[1]).cuda(), model.dims.n_mels, padding=480000)
+    seg = wb.pad_or_trim(mel, 3000)
+    prompts = [[1000, 1001, 1002], [2000, 2001, 2002], [3000, 3001, 3002]]
+    reqs = [(seg, wb.DecodingOptions(language="en", sample_len=12, prompt=p)) for p in prompts]
+    batched = decode_requests(model, reqs)
+    single = [wb.decode(model, seg, o) for _, o in reqs]
+    assert [r.tokens for r in batched] == [r.tokens for r in single]
+    assert len({tuple(r.tokens) for r in batched}) >= 1

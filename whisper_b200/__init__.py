@@ -19,7 +19,7 @@ from .audio import load_audio, log_mel_spectrogram, pad_or_trim
 from .decoding import DecodingOptions, DecodingResult, decode, detect_language
 from .model import ModelDimensions, Whisper
 from .synthetic import MODEL_DIMS, dims_dict, synthetic_state_dict
-from .transcribe import transcribe
+from .transcribe import transcribe, transcribe_batch
 
 __version__ = "0.1.0"
 

@@ -356,11 +356,21 @@ class DecodingTask:
         return DecoderSession(self.model, cfg, self.suppress, self.tokenizer.blank_tokens)
 
     @torch.no_grad()
-    def run(self, mel: torch.Tensor) -> List[DecodingResult]:
+    def run(self, mel: torch.Tensor, initial_tokens: Optional[np.ndarray] = None) -> List[DecodingResult]:
+        """DecodingTask.run (decoding.py:713-789).  `initial_tokens` (int [n_audio, n_init], optional) gives every
+        audio its OWN prompt of the common length n_init - what the lock-step multi-file scheduler
+        (transcribe.transcribe_batch) needs; the reference tiles one prompt over the batch (decoding.py:734)."""
         tokenizer = self.tokenizer
         n_audio = mel.shape[0]
         audio_features = self._get_audio_features(mel)
-        init = np.tile(np.asarray(self.initial_tokens, dtype=np.int32), (n_audio, 1))
+        if initial_tokens is None:
+            init = np.tile(np.asarray(self.initial_tokens, dtype=np.int32), (n_audio, 1))
+        else:
+            init = np.ascontiguousarray(initial_tokens, dtype=np.int32).copy()
+            if init.shape != (n_audio, len(self.initial_tokens)):
+                raise ValueError(f"initial_tokens must be [{n_audio}, {len(self.initial_tokens)}], got {init.shape}")
+            if not (init[:, self.sot_index] == tokenizer.sot).all():
+                raise ValueError("every row of initial_tokens needs <|startoftranscript|> at the task's sot_index")
 
         # language detection overwrites the language token (decoding.py:666-678)
         languages = [self.options.language] * n_audio
@@ -462,3 +472,28 @@ def decode(model: "Whisper", mel: torch.Tensor, options: DecodingOptions = Decod
         options = replace(options, **kwargs)
     result = DecodingTask(model, options).run(mel)
     return result[0] if single else result
+
+
+@torch.no_grad()
+def decode_requests(model: "Whisper", requests: Sequence[Tuple[torch.Tensor, DecodingOptions]],
+                    max_batch: int = 64) -> List[DecodingResult]:
+    """Decode many (segment, options) requests whose options may differ (different prompts, temperatures ...) in as
+    few device sessions as possible: requests that agree on everything except the CONTENT of equally long
+    prompts / prefixes share one batched session, each row prefilled with its own prompt.  Results come back in
+    request order.  This is the batching primitive of transcribe_batch; a single request is
+    exactly decode(model, segment, options)."""
+    tasks = [DecodingTask(model, opt) for _, opt in requests]
+    groups: Dict[tuple, List[int]] = {}
+    for i, (task, (_, opt)) in enumerate(zip(tasks, requests)):
+        key = (repr(replace(opt, prompt=None, prefix=None)), len(task.initial_tokens), task.sot_index,
+               task.sample_begin)
+        groups.setdefault(key, []).append(i)
+    out: List[Optional[DecodingResult]] = [None] * len(requests)
+    for idxs in groups.values():
+        for lo in range(0, len(idxs), max_batch):
+            chunk = idxs[lo: lo + max_batch]
+            mel = torch.stack([requests[i][0] for i in chunk])
+            init = np.asarray([tasks[i].initial_tokens for i in chunk], dtype=np.int32)
+            for i, r in zip(chunk, tasks[chunk[0]].run(mel, initial_tokens=init)):
+                out[i] = r
+    return out

@@ -8,7 +8,7 @@ one device-resident decode.
 """
 from __future__ import annotations
 
-from typing import TYPE_CHECKING, List, Optional, Tuple, Union
+from typing import TYPE_CHECKING, List, Optional, Sequence, Tuple, Union
 
 import numpy as np
 import torch
@@ -60,8 +60,10 @@ class _WindowLoop:
         else:
             self.initial_prompt_tokens = []
 
-    # temperature ladder (transcribe.py:184-224)
-    def decode_with_fallback(self, segment: torch.Tensor) -> DecodingResult:
+    # temperature ladder (transcribe.py:184-224), written as a generator: it YIELDS (segment, DecodingOptions)
+    # requests and is sent the DecodingResult, so one file can be driven by model.decode directly (run) or many
+    # files can be advanced in lock-step with their requests batched (transcribe_batch)
+    def fallback_steps(self, segment: torch.Tensor):
         result = None
         for t in self.temperatures:
             kwargs = {**self.decode_options}
@@ -70,7 +72,7 @@ class _WindowLoop:
                 kwargs.pop("patience", None)
             else:
                 kwargs.pop("best_of", None)
-            result = self.model.decode(segment, DecodingOptions(**kwargs, temperature=t))
+            result = yield segment, DecodingOptions(**kwargs, temperature=t)
             needs_fallback = False
             if self.cr_threshold is not None and result.compression_ratio > self.cr_threshold:
                 needs_fallback = True
@@ -82,6 +84,18 @@ class _WindowLoop:
             if not needs_fallback:
                 break
         return result
+
+    def drive(self, gen):
+        """Run a request generator to completion against self.model.decode; returns the generator's value."""
+        try:
+            req = next(gen)
+            while True:
+                req = gen.send(self.model.decode(req[0], req[1]))
+        except StopIteration as stop:
+            return stop.value
+
+    def decode_with_fallback(self, segment: torch.Tensor) -> DecodingResult:
+        return self.drive(self.fallback_steps(segment))
 
     def make_segment(self, seek, start, end, tokens: List[int], result: DecodingResult) -> dict:
         text_tokens = [t for t in tokens if t < self.tokenizer.eot]
@@ -123,7 +137,11 @@ class _WindowLoop:
         return segments, seek
 
     def run(self):
-        model = self.model
+        self.drive(self.steps())
+        return self
+
+    def steps(self):
+        """The window loop of transcribe.py:272-508 as a request generator (see fallback_steps)."""
         clip_idx = 0
         seek = self.clips[clip_idx][0]
         while clip_idx < len(self.clips):
@@ -144,7 +162,7 @@ class _WindowLoop:
                 self.decode_options["prompt"] = self.initial_prompt_tokens + remaining
             else:
                 self.decode_options["prompt"] = self.all_tokens[self.prompt_reset_since:]
-            result = self.decode_with_fallback(mel_segment)
+            result = yield from self.fallback_steps(mel_segment)
             if self.ns_threshold is not None:
                 should_skip = result.no_speech_prob > self.ns_threshold
                 if self.lp_threshold is not None and result.avg_logprob > self.lp_threshold:
@@ -164,7 +182,6 @@ class _WindowLoop:
             self.all_tokens.extend(t for s in segments for t in s["tokens"])
             if not self.condition or result.temperature > 0.5:
                 self.prompt_reset_since = len(self.all_tokens)
-        return self
 
 
 def transcribe(
@@ -194,16 +211,32 @@ def transcribe(
     counter-based generator (seeded from torch's global generator, so `torch.manual_seed` makes a run
     repeatable, but the draws are not the reference's); `word_timestamps=True` raises.
     """
+    loop, tokenizer, language = _prepare(model, audio, verbose=verbose, temperature=temperature,
+                                         compression_ratio_threshold=compression_ratio_threshold,
+                                         logprob_threshold=logprob_threshold, no_speech_threshold=no_speech_threshold,
+                                         condition_on_previous_text=condition_on_previous_text,
+                                         initial_prompt=initial_prompt, carry_initial_prompt=carry_initial_prompt,
+                                         word_timestamps=word_timestamps, clip_timestamps=clip_timestamps,
+                                         decode_options=decode_options)
+    loop.run()
+    return _result(loop, tokenizer, language)
+
+
+def _prepare(model, audio, *, verbose, temperature, compression_ratio_threshold, logprob_threshold, no_speech_threshold,
+             condition_on_previous_text, initial_prompt, carry_initial_prompt, word_timestamps, clip_timestamps,
+             decode_options):
+    """Everything transcribe() does before its window loop (transcribe.py:128-183): log-mel of the whole file,
+    language detection, tokenizer, loop state."""
     if word_timestamps:
         raise NotImplementedError(
             "word_timestamps=True is not wired into transcribe(): the tensor part of word timing is available as "
             "whisper_b200.timing.find_alignment (cross-attention export + median filter + DTW on the GPU), but the "
             "punctuation-merging / segment-clamping text heuristics of timing.py:245-388 are out of scope (SURVEY.md 2)")
+    decode_options = dict(decode_options)
     decode_options.pop("fp16", None)
     temps = [temperature] if isinstance(temperature, (int, float)) else list(temperature)
 
     mel = log_mel_spectrogram(audio, model.dims.n_mels, padding=N_SAMPLES, device=model.device)   # transcribe.py:139
-    content_frames = mel.shape[-1] - N_FRAMES
     if decode_options.get("language", None) is None:
         if not model.is_multilingual:
             decode_options["language"] = "en"
@@ -220,6 +253,64 @@ def transcribe(
                        logprob_threshold=logprob_threshold, no_speech_threshold=no_speech_threshold,
                        condition_on_previous_text=condition_on_previous_text, initial_prompt=initial_prompt,
                        carry_initial_prompt=carry_initial_prompt, clip_timestamps=clip_timestamps, verbose=verbose,
-                       decode_options=decode_options).run()
+                       decode_options=decode_options)
+    return loop, tokenizer, language
+
+
+def _result(loop: _WindowLoop, tokenizer, language: str) -> dict:
     return dict(text=tokenizer.decode(loop.all_tokens[len(loop.initial_prompt_tokens):]),
                 segments=loop.all_segments, language=language)
+
+
+def transcribe_batch(
+    model: "Whisper",
+    audios: Sequence[Union[str, np.ndarray, torch.Tensor]],
+    *,
+    max_batch: int = 64,
+    verbose: Optional[bool] = None,
+    temperature: Union[float, Tuple[float, ...]] = (0.0, 0.2, 0.4, 0.6, 0.8, 1.0),
+    compression_ratio_threshold: Optional[float] = 2.4,
+    logprob_threshold: Optional[float] = -1.0,
+    no_speech_threshold: Optional[float] = 0.6,
+    condition_on_previous_text: bool = True,
+    initial_prompt: Optional[str] = None,
+    carry_initial_prompt: bool = False,
+    clip_timestamps: Union[str, List[float]] = "0",
+    **decode_options,
+) -> List[dict]:
+    """transcribe() for MANY files at once.  One file's window loop is sequential by construction -
+    window n+1 starts at the last timestamp decoded in window n and is prompted with its text (transcribe.py:288-295,
+    369-377) - so a single long file keeps the GPU at one decoder row.  Here every file keeps its own loop state and
+    the loops advance in LOCK-STEP: each round gathers the next decode request of every unfinished file (a window,
+    or the next rung of that file's temperature ladder), decoding.decode_requests() batches the requests that can
+    share a session (same options, prompts of the same length - in steady state every prompt has the maximum
+    223 tokens), and each result is handed back to its file.  Per-file results are those of transcribe(); the order
+    of `audios` is kept.  The parameters are transcribe()'s and apply to every file."""
+    from .decoding import decode_requests
+
+    prepared = [_prepare(model, a, verbose=verbose, temperature=temperature,
+                         compression_ratio_threshold=compression_ratio_threshold, logprob_threshold=logprob_threshold,
+                         no_speech_threshold=no_speech_threshold, condition_on_previous_text=condition_on_previous_text,
+                         initial_prompt=initial_prompt, carry_initial_prompt=carry_initial_prompt, word_timestamps=False,
+                         clip_timestamps=clip_timestamps, decode_options=decode_options) for a in audios]
+    gens = [loop.steps() for loop, _, _ in prepared]
+    pending = {}
+    for i, g in enumerate(gens):
+        try:
+            pending[i] = next(g)
+        except StopIteration:
+            pass
+    rounds = 0
+    while pending:
+        order = sorted(pending)
+        results = decode_requests(model, [pending[i] for i in order], max_batch=max_batch)
+        rounds += 1
+        for i, r in zip(order, results):
+            try:
+                pending[i] = gens[i].send(r)
+            except StopIteration:
+                del pending[i]
+    out = [_result(loop, tok, lang) for loop, tok, lang in prepared]
+    for o in out:
+        o["rounds"] = rounds            # diagnostic: lock-step rounds the whole batch needed
+    return out
