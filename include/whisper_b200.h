@@ -67,6 +67,13 @@ int wb200_set_bm64(int enabled);
  * default (WB200_PDL=0 in the environment or this call turns it off).  Each of those kernels may be scheduled while
  * its predecessor drains and waits (griddepcontrol.wait) before it touches global memory. */
 int wb200_set_pdl(int enabled);
+/* Layout of the decoder's kv caches for sessions created AFTER the call (default 0, or WB200_KV_HEAD_MAJOR=1 in
+ * the environment).  0: cross-attention K/V [n_audio, 1500, 2d] and self-attention caches [rows, 448, d], i.e. one
+ * head's 128 bytes per position are strided by the model width.  1: head-major - cross K/V [n_audio, 2H, 1500, 64]
+ * (written that way by the K/V projection's epilogue), self caches [rows, H, 448, 64] - so every (audio, head) /
+ * (row, head) pair streams one contiguous block.  Results are identical bit for bit; only the HBM access pattern
+ * of the two decode-attention kernels changes.  (Built in round 1, not yet measured on hardware.) */
+int wb200_set_kv_head_major(int enabled);
 
 /* Same operator with split-K enabled for skinny problems (the 320-row decode-step GEMMs): `workspace`
  * holds fp32 partial slabs (up to 8 * M * N floats are used), `tickets` is an int32 array of n_tickets

@@ -107,6 +107,11 @@ int wb200_set_bm64(int enabled) {
   return 0;
 }
 
+int wb200_set_kv_head_major(int enabled) {
+  g_kv_head_major = enabled ? 1 : 0;
+  return 0;
+}
+
 int wb200_set_pdl(int enabled) {
   g_pdl_on = enabled ? 1 : 0;
   return 0;

@@ -270,6 +270,7 @@ struct CrossParams {
   int* counters;        // [n_audio * q_tiles * H], zero on entry, zero on exit
   const int* skip_flag; // optional device flag: non-zero -> kernel does nothing
   int n_q, q_tiles, T, d, splits, keys_per_split, kv_ld;
+  int head_major;       // k = one layer's [n_audio][2H][T][64] block (K heads, then V heads); v unused
 };
 
 template <typename T, int STAGES>
@@ -289,7 +290,13 @@ __global__ void __launch_bounds__(kDaThreads) cross_attention_kernel(const Cross
 
   const uint8_t* kbase = reinterpret_cast<const uint8_t*>(p.k) + (static_cast<long long>(audio) * p.T * p.kv_ld + h * 64) * 2;
   const uint8_t* vbase = reinterpret_cast<const uint8_t*>(p.v) + (static_cast<long long>(audio) * p.T * p.kv_ld + h * 64) * 2;
-  const long long row_bytes = static_cast<long long>(p.kv_ld) * 2;
+  long long row_bytes = static_cast<long long>(p.kv_ld) * 2;
+  if (p.head_major) {       // each (audio, head) streams one contiguous T x 128-byte block
+    const long long H = gridDim.y, hb = static_cast<long long>(p.T) * 128;
+    kbase = reinterpret_cast<const uint8_t*>(p.k) + (static_cast<long long>(audio) * 2 * H + h) * hb;
+    vbase = reinterpret_cast<const uint8_t*>(p.k) + (static_cast<long long>(audio) * 2 * H + H + h) * hb;
+    row_bytes = 128;
+  }
   auto src_of = [&](int key) {
     RowSrc s;
     s.k = kbase + key * row_bytes;
@@ -375,6 +382,7 @@ struct SelfParams {
   int d, max_ctx;
   int n_init;           // prefill mode: tokens per audio (query row = audio * n_init + i)
   int group;            // prefill mode: physical row of audio a is a * group
+  int head_major;       // caches are [phys_row][head][max_ctx][64] instead of [phys_row][max_ctx][d]
 };
 
 // One WARP per (row, head): with a single query there is nothing for a tensor-core tile to share, so
@@ -417,10 +425,14 @@ __global__ void __launch_bounds__(640) self_attention_kernel(const SelfParams p,
   const uint8_t* qrow = reinterpret_cast<const uint8_t*>(p.qkv) + static_cast<long long>(row) * 3 * row_bytes + h * 128;
   const uint8_t* knew = qrow + row_bytes + c * 16;
   const uint8_t* vnew = qrow + 2 * row_bytes + c * 16;
-  uint8_t* kc = reinterpret_cast<uint8_t*>(p.kcache) + h * 128 + c * 16;
-  uint8_t* vc = reinterpret_cast<uint8_t*>(p.vcache) + h * 128 + c * 16;
+  // byte offset of (physical row, position) for this head: row-major [row][pos][d] or head-major [row][head][pos][64]
+  const long long pos_bytes = p.head_major ? 128 : row_bytes;
+  const long long row_stride = static_cast<long long>(p.max_ctx) * row_bytes;      // bytes per physical row, either layout
+  const long long head_off = p.head_major ? static_cast<long long>(h) * p.max_ctx * 128 : static_cast<long long>(h) * 128;
+  uint8_t* kc = reinterpret_cast<uint8_t*>(p.kcache) + head_off + c * 16;
+  uint8_t* vc = reinterpret_cast<uint8_t*>(p.vcache) + head_off + c * 16;
   if (step && lane < 16) {
-    const long long off = (static_cast<long long>(row) * p.max_ctx + pos_new) * row_bytes;
+    const long long off = static_cast<long long>(row) * row_stride + pos_new * pos_bytes;
     if (lane < 8)
       *reinterpret_cast<uint4*>(kc + off) = *reinterpret_cast<const uint4*>(knew);
     else
@@ -459,7 +471,7 @@ __global__ void __launch_bounds__(640) self_attention_kernel(const SelfParams p,
       const bool valid = key < kv_len;
       const uint8_t *ks = knew, *vs = vnew;               // new token (or dummy address of a masked key)
       if (key < pos_new) {
-        const long long off = (static_cast<long long>(ph[j]) * p.max_ctx + key) * row_bytes;
+        const long long off = static_cast<long long>(ph[j]) * row_stride + key * pos_bytes;
         ks = kc + off;
         vs = vc + off;
       }
@@ -580,16 +592,19 @@ static int dispatch_sa(const SelfParams& p, int n_rows, int n_head, int u, int s
 // Prefill-mode append: copy k|v of qkv[(a, i)] into cache[(a*group, i)].  One warp per (row, k/v).
 template <typename T>
 __global__ void kv_append_kernel(const T* __restrict__ qkv, T* __restrict__ kcache, T* __restrict__ vcache,
-                                 int n_rows, int n_init, int group, int d, int max_ctx) {
+                                 int n_rows, int n_init, int group, int d, int max_ctx, int head_major) {
   const int w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
   if (w >= n_rows * 2) return;
   const int row = w >> 1, which = w & 1;
   const int a = row / n_init, i = row % n_init;
   const T* src = qkv + static_cast<long long>(row) * 3 * d + (1 + which) * d;
-  T* dst = (which ? vcache : kcache) + (static_cast<long long>(a) * group * max_ctx + i) * d;
-  for (int c = lane * 8; c < d; c += 256)
-    *reinterpret_cast<uint4*>(dst + c) = *reinterpret_cast<const uint4*>(src + c);
+  T* cache = (which ? vcache : kcache) + static_cast<long long>(a) * group * max_ctx * d;   // physical row a * group
+  for (int c = lane * 8; c < d; c += 256) {
+    T* dst = head_major ? cache + (static_cast<long long>(c >> 6) * max_ctx + i) * 64 + (c & 63)
+                        : cache + static_cast<long long>(i) * d + c;
+    *reinterpret_cast<uint4*>(dst) = *reinterpret_cast<const uint4*>(src + c);
+  }
 }
 
 // -------------------------------------------------------------------------------------------------
@@ -615,9 +630,10 @@ size_t cross_attention_partial_floats(int n_audio, int n_q, int n_head, int T) {
 
 int launch_cross_attention(int dtype, const void* q, const void* k, const void* v, void* out,
                            float* partial, int* counters, const int* skip_flag, int n_audio, int n_q,
-                           int T, int n_head, int kv_ld, cudaStream_t s) {
+                           int T, int n_head, int kv_ld, cudaStream_t s, int head_major) {
   if (n_audio <= 0 || n_q <= 0) return 0;
   CrossParams p;
+  p.head_major = head_major;
   p.q = q;
   p.k = k;
   p.v = v;
@@ -669,9 +685,10 @@ int launch_cross_attention(int dtype, const void* q, const void* k, const void* 
 
 int launch_self_attention(int dtype, const void* qkv, void* kcache, void* vcache, void* out,
                           const int* indir, const int* len_ptr, const int* skip_flag, int n_rows,
-                          int n_head, int max_ctx, int n_init, int group, cudaStream_t s) {
+                          int n_head, int max_ctx, int n_init, int group, cudaStream_t s, int head_major) {
   if (n_rows <= 0) return 0;
   SelfParams p;
+  p.head_major = head_major;
   p.qkv = qkv;
   p.kcache = kcache;
   p.vcache = vcache;
@@ -694,7 +711,7 @@ int launch_self_attention(int dtype, const void* qkv, void* kcache, void* vcache
     if (!indir) {
       kv_append_kernel<__nv_bfloat16><<<(n_rows * 2 * 32 + 255) / 256, 256, 0, s>>>(
           static_cast<const __nv_bfloat16*>(qkv), static_cast<__nv_bfloat16*>(kcache),
-          static_cast<__nv_bfloat16*>(vcache), n_rows, p.n_init, group, p.d, max_ctx);
+          static_cast<__nv_bfloat16*>(vcache), n_rows, p.n_init, group, p.d, max_ctx, head_major);
       count_launch();
     }
     ProfileScope prof(PROF_SELF_ATTN, s);
@@ -704,7 +721,7 @@ int launch_self_attention(int dtype, const void* qkv, void* kcache, void* vcache
     if (!indir) {
       kv_append_kernel<__half><<<(n_rows * 2 * 32 + 255) / 256, 256, 0, s>>>(
           static_cast<const __half*>(qkv), static_cast<__half*>(kcache), static_cast<__half*>(vcache),
-          n_rows, p.n_init, group, p.d, max_ctx);
+          n_rows, p.n_init, group, p.d, max_ctx, head_major);
       count_launch();
     }
     ProfileScope prof(PROF_SELF_ATTN, s);

@@ -116,7 +116,7 @@ struct Arena {
 
 static int linear(const Model* m, const void* A, long long lda, int M, const void* W, int N, int K, const void* bias,
                   const void* residual, void* C, long long ldc, int gelu, int out_f32, cudaStream_t s,
-                  const int* skip = nullptr, const Decoder* D = nullptr) {
+                  const int* skip = nullptr, const Decoder* D = nullptr, int head_major_T = 0) {
   LinearArgs a;
   a.dtype = m->dtype;
   a.batch = 1;
@@ -137,6 +137,7 @@ static int linear(const Model* m, const void* A, long long lda, int M, const voi
   a.gelu = gelu;
   a.out_f32 = out_f32;
   a.skip_flag = skip;
+  a.head_major_T = head_major_T;
   if (D) {
     a.splitk_ws = D->gemm_ws;
     a.splitk_ws_bytes = D->gemm_ws_bytes;
@@ -289,6 +290,11 @@ int decoder_create(const Model* m, const wb200_decode_config* c, void* ws, size_
   Decoder* D = new Decoder();
   D->m = m;
   D->cfg = *c;
+  if (g_kv_head_major < 0) {
+    const char* e = getenv("WB200_KV_HEAD_MAJOR");
+    g_kv_head_major = (e && e[0] && e[0] != '0') ? 1 : 0;
+  }
+  D->kv_head_major = g_kv_head_major != 0;
   D->cfg.suppress_ids = nullptr;
   D->cfg.blank_ids = nullptr;
   Arena ar{static_cast<uint8_t*>(ws), 0, ws_bytes};
@@ -336,7 +342,9 @@ int decoder_set_audio(Decoder* D, const void* features, cudaStream_t s) {
   for (int l = 0; l < m->dims.n_text_layer; ++l) {
     const void* const* L = m->dec_layer(l);
     void* kv = static_cast<uint8_t*>(D->cross_kv) + l * per_layer;
-    WB_TRY(linear(m, features, d, B * Ta, L[D_CKV_W], 2 * d, d, L[D_CKV_B], nullptr, kv, 2 * d, 0, 0, s));
+    // row-major: [B * Ta, 2d] (K | V per position); head-major: [B][2H][Ta][64] (K heads then V heads)
+    WB_TRY(linear(m, features, d, B * Ta, L[D_CKV_W], 2 * d, d, L[D_CKV_B], nullptr, kv, 2 * d, 0, 0, s, nullptr, nullptr,
+                  D->kv_head_major ? Ta : 0));
   }
   return 0;
 }
@@ -359,7 +367,7 @@ static int decoder_stack(Decoder* D, int rows, bool step, cudaStream_t s) {
     WB_TRY(launch_layernorm(dt, D->x, d, D->ln, d, (const float*)L[D_ATTN_LN_W], (const float*)L[D_ATTN_LN_B], rows, d, s, skip));
     WB_TRY(linear(m, D->ln, d, rows, L[D_QKV_W], 3 * d, d, L[D_QKV_B], nullptr, D->qkv, 3 * d, 0, 0, s, skip, D));
     WB_TRY(launch_self_attention(dt, D->qkv, kc, vc, D->att, step ? D->indir[D->cur] : nullptr, D->len_ptr, skip, rows, H,
-                                 ctx, D->cfg.n_init, G, s));
+                                 ctx, D->cfg.n_init, G, s, D->kv_head_major ? 1 : 0));
     WB_TRY(linear(m, D->att, d, rows, L[D_OUT_W], d, d, L[D_OUT_B], D->x, D->x, d, 0, 0, s, skip, D));
     WB_TRY(launch_layernorm(dt, D->x, d, D->ln, d, (const float*)L[D_CROSS_LN_W], (const float*)L[D_CROSS_LN_B], rows, d, s, skip));
     WB_TRY(linear(m, D->ln, d, rows, L[D_CQ_W], d, d, L[D_CQ_B], nullptr, D->q, d, 0, 0, s, skip, D));
@@ -369,12 +377,14 @@ static int decoder_stack(Decoder* D, int rows, bool step, cudaStream_t s) {
         if (D->align_heads[i] != l) continue;
         const int hh = D->align_heads[i + 1];
         float* dst = D->align_qk + (i / 2) * static_cast<size_t>(D->cfg.n_init) * Ta;
+        // K of audio 0, head hh: strided rows of the [Ta, 2d] block, or the contiguous [Ta, 64] block of that head
+        const uint8_t* k_head = D->kv_head_major ? ckv + static_cast<size_t>(hh) * Ta * 128 : ckv + static_cast<size_t>(hh) * 128;
         WB_TRY(launch_qk_export(dt, static_cast<const uint8_t*>(D->q) + static_cast<size_t>(hh) * 128, d,
-                                ckv + static_cast<size_t>(hh) * 128, 2 * d, dst, D->cfg.n_init, Ta, s));
+                                k_head, D->kv_head_major ? 64 : 2 * d, dst, D->cfg.n_init, Ta, s));
       }
     }
     WB_TRY(launch_cross_attention(dt, D->q, ckv, ckv + static_cast<size_t>(d) * 2, D->att, D->partial, D->counters, skip, B,
-                                  n_q, Ta, H, 2 * d, s));
+                                  n_q, Ta, H, 2 * d, s, D->kv_head_major ? 1 : 0));
     WB_TRY(linear(m, D->att, d, rows, L[D_COUT_W], d, d, L[D_COUT_B], D->x, D->x, d, 0, 0, s, skip, D));
     WB_TRY(launch_layernorm(dt, D->x, d, D->ln, d, (const float*)L[D_MLP_LN_W], (const float*)L[D_MLP_LN_B], rows, d, s, skip));
     WB_TRY(linear(m, D->ln, d, rows, L[D_FC1_W], 4 * d, d, L[D_FC1_B], nullptr, D->hid, 4 * d, 1, 0, s, skip, D));

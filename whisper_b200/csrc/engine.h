@@ -89,6 +89,7 @@ struct Decoder {
   cudaGraphExec_t pair_graph = nullptr;
   int pair_graph_cur = -1;          // value of `cur` the graph was captured at
   int launches_per_pair = 0;        // kernels inside one replay (for wb200_launch_count)
+  bool kv_head_major = false;       // kv caches stored per head ([.., head, position, 64]); fixed at create
   // GreedyDecoder temperature sampling (wb200_decoder_set_sampling); 0 = argmax
   float temperature = 0.f;
   unsigned long long seed = 0;

@@ -26,6 +26,7 @@
 namespace wb {
 
 int g_pdl_on = -1;      // -1: read WB200_PDL on first use (default on); wb200_set_pdl() overrides
+int g_kv_head_major = -1;   // -1: read WB200_KV_HEAD_MAJOR on first decoder_create (default off)
 int g_bm64_on = 1;      // wb200_set_option("bm64", 0/1): 64-row tiles for skinny problems
 int g_splitk_on = -1;   // -1: read WB200_SPLITK on first use; wb200_set_splitk() overrides
 
@@ -52,6 +53,7 @@ struct GemmParams {
   float* partial;
   long long partial_stride;   // floats per split slab
   int* tile_counters;
+  int hm_T;                   // > 0: head-major 16-bit output [rows / hm_T][N / 64][hm_T][64] (LinearArgs::head_major_T)
 };
 
 // KS = 64-wide K sub-blocks per pipeline stage.  The single MMA-issuing thread pays ~350 cycles of
@@ -158,6 +160,10 @@ __device__ __forceinline__ void epilogue_store(float (&v)[32], const GemmParams&
     }
   } else {
     T* out = reinterpret_cast<T*>(p.C) + grow * p.ldc + nb;
+    if (p.hm_T > 0) {          // [batch][head][t][64]: the 32 columns handled here lie inside one head
+      const long long bt = grow / p.hm_T, tt = grow % p.hm_T;
+      out = reinterpret_cast<T*>(p.C) + ((bt * (p.N >> 6) + (nb >> 6)) * p.hm_T + tt) * 64 + (nb & 63);
+    }
     if (full) {
 #pragma unroll
       for (int q = 0; q < 4; ++q) {
@@ -503,6 +509,11 @@ int launch_linear(const LinearArgs& a, cudaStream_t s) {
   p.partial = nullptr;
   p.partial_stride = rows * static_cast<long long>(a.N);
   p.tile_counters = a.splitk_counters;
+  p.hm_T = 0;
+  if (a.head_major_T > 0) {
+    if (a.out_f32 || a.N % 64 || a.batch != 1 || a.residual || a.rows_per_batch % a.head_major_T) return 14;
+    p.hm_T = a.head_major_T;
+  }
   {
     const int tiles = p.batch * p.m_tiles_per_batch * p.n_tiles;
     const int kblocks = p.taps * p.k_blocks_per_tap;
@@ -513,7 +524,7 @@ int launch_linear(const LinearArgs& a, cudaStream_t s) {
       const char* e = getenv("WB200_SPLITK");
       splitk_on = (e && e[0] && e[0] != '0') ? 1 : 0;
     }
-    if (splitk_on && ks_host == 1 && a.splitk_ws && a.splitk_counters && a.taps == 1 && tiles < 148 && kblocks >= 8 &&
+    if (splitk_on && !a.head_major_T && ks_host == 1 && a.splitk_ws && a.splitk_counters && a.taps == 1 && tiles < 148 && kblocks >= 8 &&
         tiles <= a.splitk_max_tiles) {
       int sp = (2 * 148 + tiles - 1) / tiles;          // aim at ~2 work items per SM
       if (sp > kblocks / 4) sp = kblocks / 4;          // keep >= 4 k-blocks (256 of K) per item

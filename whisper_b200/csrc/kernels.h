@@ -52,6 +52,10 @@ struct LinearArgs {
   const void* residual = nullptr;  // T[rows, ldr] or null (may alias C)
   long long ldr = 0;
   const float* pos = nullptr;      // fp32 [rows_per_batch, N] added per batch row, or null
+  // head-major output (16-bit, N % 64 == 0): element (row, n) of the [rows, N] result is stored at
+  // C[((row / hm_T) * (N / 64) + n / 64) * hm_T + row % hm_T][n % 64] - i.e. [batch][head][t][64] for rows = batch * hm_T.
+  // Used for the cross-attention K/V of the decoder when the head-major kv layout is on.  0 = row-major.
+  int head_major_T = 0;
   void* C = nullptr;
   long long ldc = 0;
   int gelu = 0;
@@ -68,6 +72,7 @@ struct LinearArgs {
 int launch_linear(const LinearArgs& a, cudaStream_t s);
 extern int g_splitk_on;
 extern int g_bm64_on;
+extern int g_kv_head_major;   // kv caches stored [.., head, position, 64] instead of [.., position, d] (wb200_set_kv_head_major)
 extern int g_pdl_on;   // programmatic dependent launch for the decoder-layer kernels (wb200_set_pdl / WB200_PDL)
 
 // Launch with the programmatic-stream-serialization attribute (when enabled): inside a stream or a
@@ -111,12 +116,12 @@ size_t cross_attention_partial_floats(int n_audio, int n_q, int n_head, int T);
 // q: [n_audio*n_q, d]; k/v: [n_audio, T, kv_ld] row stride kv_ld elements; out: [n_audio*n_q, d]
 int launch_cross_attention(int dtype, const void* q, const void* k, const void* v, void* out,
                            float* partial, int* counters, const int* skip_flag, int n_audio, int n_q,
-                           int T, int n_head, int kv_ld, cudaStream_t s);
+                           int T, int n_head, int kv_ld, cudaStream_t s, int head_major = 0);
 // step mode (indir != null): one new position per row, appended to the cache; prefill mode
 // (indir == null): n_init positions per audio, causal, cache rows a*group.
 int launch_self_attention(int dtype, const void* qkv, void* kcache, void* vcache, void* out,
                           const int* indir, const int* len_ptr, const int* skip_flag, int n_rows,
-                          int n_head, int max_ctx, int n_init, int group, cudaStream_t s);
+                          int n_head, int max_ctx, int n_init, int group, cudaStream_t s, int head_major = 0);
 
 // ---- token selection (select.cu)
 struct FilterParams {
