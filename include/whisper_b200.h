@@ -67,6 +67,11 @@ int wb200_set_bm64(int enabled);
  * default (WB200_PDL=0 in the environment or this call turns it off).  Each of those kernels may be scheduled while
  * its predecessor drains and waits (griddepcontrol.wait) before it touches global memory. */
 int wb200_set_pdl(int enabled);
+/* With programmatic dependent launch on, let the engine's GEMMs issue the WEIGHT half of their first pipeline
+ * stages before they wait for the previous kernel (model weights never change while the engine runs; activations
+ * still wait).  Default 0 (or WB200_GEMM_EARLY_B=1).  Affects only launches made by the engine - wb200_linear on
+ * caller tensors never assumes its weights are constant.  (Built in round 1, not yet measured on hardware.) */
+int wb200_set_gemm_early_weights(int enabled);
 /* Layout of the decoder's kv caches for sessions created AFTER the call (default 0, or WB200_KV_HEAD_MAJOR=1 in
  * the environment).  0: cross-attention K/V [n_audio, 1500, 2d] and self-attention caches [rows, 448, d], i.e. one
  * head's 128 bytes per position are strided by the model width.  1: head-major - cross K/V [n_audio, 2H, 1500, 64]

@@ -112,6 +112,11 @@ int wb200_set_kv_head_major(int enabled) {
   return 0;
 }
 
+int wb200_set_gemm_early_weights(int enabled) {
+  g_gemm_early_b = enabled ? 1 : 0;
+  return 0;
+}
+
 int wb200_set_pdl(int enabled) {
   g_pdl_on = enabled ? 1 : 0;
   return 0;

@@ -138,6 +138,7 @@ static int linear(const Model* m, const void* A, long long lda, int M, const voi
   a.out_f32 = out_f32;
   a.skip_flag = skip;
   a.head_major_T = head_major_T;
+  a.weights_constant = 1;            // W is a model tensor: never written while the engine runs
   if (D) {
     a.splitk_ws = D->gemm_ws;
     a.splitk_ws_bytes = D->gemm_ws_bytes;

@@ -27,6 +27,7 @@ namespace wb {
 
 int g_pdl_on = -1;      // -1: read WB200_PDL on first use (default on); wb200_set_pdl() overrides
 int g_kv_head_major = -1;   // -1: read WB200_KV_HEAD_MAJOR on first decoder_create (default off)
+int g_gemm_early_b = -1;    // -1: read WB200_GEMM_EARLY_B on first use (default off): weight tiles before the PDL wait
 int g_bm64_on = 1;      // wb200_set_option("bm64", 0/1): 64-row tiles for skinny problems
 int g_splitk_on = -1;   // -1: read WB200_SPLITK on first use; wb200_set_splitk() overrides
 
@@ -53,6 +54,7 @@ struct GemmParams {
   float* partial;
   long long partial_stride;   // floats per split slab
   int* tile_counters;
+  int early_b;                // producer issues the first weight tiles BEFORE griddepcontrol.wait (g_gemm_early_b)
   int hm_T;                   // > 0: head-major 16-bit output [rows / hm_T][N / 64][hm_T][64] (LinearArgs::head_major_T)
 };
 
@@ -232,36 +234,72 @@ gemm_tcgen05_kernel(const GemmParams p, const __grid_constant__ CUtensorMap mapA
   const uint32_t tmem_base = *tmem_ptr_smem;
   // Everything above (barrier init, TMEM allocation, descriptor prefetch) touches no global data and
   // overlaps the tail of the previous kernel; from here on its results are needed.
+  //
+  // Optional (p.early_b): the WEIGHT half of the first pipeline stages does not depend on the previous kernel
+  // either - weights are constant for the whole decode - so the producer arms those stages and issues their B
+  // loads before the dependency wait; only the activation (A) loads wait.  For the latency-bound 320-row GEMMs
+  // this takes the first-byte latency of the weight stream off the critical path.
+  int pre = 0;
+  if (p.early_b && warp == 0 && lane == 0 && static_cast<int>(blockIdx.x) < total_tiles * p.splits) {
+    const int item = blockIdx.x;
+    const int tile = item / p.splits, split = item % p.splits;
+    const int n0 = (tile % p.n_tiles) * BN;
+    const int kb_lo = split * p.k_per_split, kb_hi = min(k_blocks, kb_lo + p.k_per_split);
+    for (int tap = 0; tap < p.taps && pre < Cfg::kStages; ++tap)
+      for (int kg = 0; kg < groups_per_tap && pre < Cfg::kStages; ++kg) {
+        const int kidx = tap * groups_per_tap + kg;
+        if (kidx < kb_lo || kidx >= kb_hi) continue;
+        uint8_t* sb = tiles + pre * Cfg::kStageBytes + Cfg::kABytes;
+        mbar_expect_tx(&full_bar[pre], Cfg::kStageBytes);       // A bytes of this stage arrive after the wait
+#pragma unroll
+        for (int sub = 0; sub < KS; ++sub)
+          tma_load_2d(sb + sub * Cfg::kBSub, &mapB, &full_bar[pre], tap * p.K_tap + (kg * KS + sub) * kBK, n0);
+        ++pre;
+      }
+  }
   pdl_wait();
-  const int total_items = (p.skip_flag && *p.skip_flag) ? 0 : total_tiles * p.splits;
+  const bool skip = p.skip_flag && *p.skip_flag;
+  const int total_items = skip ? 0 : total_tiles * p.splits;
 
   if (warp == 0 && lane == 0) {
     // ===================== TMA producer =====================
     int stage = 0;
     uint32_t phase = 0;
-    for (int item = blockIdx.x; item < total_items; item += gridDim.x) {
+    int issued = 0;                  // k-groups handed to the pipeline so far (the first `pre` were armed early)
+    bool stop = false;
+    // a skipped launch still has to retire its early loads: walk the first item's first `pre` groups A-side only
+    const int producer_items = (skip && pre > 0) ? static_cast<int>(blockIdx.x) + 1 : total_items;
+    for (int item = blockIdx.x; item < producer_items && !stop; item += gridDim.x) {
       const int tile = item / p.splits, split = item % p.splits;
       const int m_tile = tile / p.n_tiles;
       const int n0 = (tile % p.n_tiles) * BN;
       const int b = m_tile / p.m_tiles_per_batch;
       const int t0 = (m_tile % p.m_tiles_per_batch) * BM;
       const int kb_lo = split * p.k_per_split, kb_hi = min(k_blocks, kb_lo + p.k_per_split);
-      for (int tap = 0; tap < p.taps; ++tap) {
+      for (int tap = 0; tap < p.taps && !stop; ++tap) {
         const CUtensorMap* ma = p.a_map_sel[tap] ? &mapA1 : &mapA0;
         const int row0 = t0 + p.a_row_off[tap];
         for (int kg = 0; kg < groups_per_tap; ++kg) {
           const int kidx = tap * groups_per_tap + kg;
           if (kidx < kb_lo || kidx >= kb_hi) continue;
-          mbar_wait(&empty_bar[stage], phase ^ 1);
+          const bool early = issued < pre;             // armed and B-loaded before the dependency wait
+          if (skip && !early) {
+            stop = true;
+            break;
+          }
           uint8_t* sa = tiles + stage * Cfg::kStageBytes;
           uint8_t* sb = sa + Cfg::kABytes;
-          mbar_expect_tx(&full_bar[stage], Cfg::kStageBytes);
+          if (!early) {
+            mbar_wait(&empty_bar[stage], phase ^ 1);
+            mbar_expect_tx(&full_bar[stage], Cfg::kStageBytes);
+          }
 #pragma unroll
           for (int sub = 0; sub < KS; ++sub) {     // sub-blocks past K are zero-filled by TMA
             const int kb = kg * KS + sub;
             tma_load_3d(sa + sub * Cfg::kASub, ma, &full_bar[stage], kb * kBK, row0, b);
-            tma_load_2d(sb + sub * Cfg::kBSub, &mapB, &full_bar[stage], tap * p.K_tap + kb * kBK, n0);
+            if (!early) tma_load_2d(sb + sub * Cfg::kBSub, &mapB, &full_bar[stage], tap * p.K_tap + kb * kBK, n0);
           }
+          ++issued;
           if (++stage == Cfg::kStages) {
             stage = 0;
             phase ^= 1;
@@ -269,6 +307,8 @@ gemm_tcgen05_kernel(const GemmParams p, const __grid_constant__ CUtensorMap mapA
         }
       }
     }
+    if (skip)                          // nobody consumes these stages; just let the bulk copies land before exit
+      for (int st = 0; st < pre; ++st) mbar_wait(&full_bar[st], 0);
   } else if (warp == 1 && lane == 0) {
     // ===================== MMA issuer =====================
     constexpr uint32_t idesc = umma_idesc(Cvt<T>::kUmmaFmt, BM, BN, 0, 0);
@@ -509,6 +549,11 @@ int launch_linear(const LinearArgs& a, cudaStream_t s) {
   p.partial = nullptr;
   p.partial_stride = rows * static_cast<long long>(a.N);
   p.tile_counters = a.splitk_counters;
+  if (g_gemm_early_b < 0) {
+    const char* e = getenv("WB200_GEMM_EARLY_B");
+    g_gemm_early_b = (e && e[0] && e[0] != '0') ? 1 : 0;
+  }
+  p.early_b = (g_gemm_early_b && g_pdl_on != 0 && a.weights_constant) ? 1 : 0;
   p.hm_T = 0;
   if (a.head_major_T > 0) {
     if (a.out_f32 || a.N % 64 || a.batch != 1 || a.residual || a.rows_per_batch % a.head_major_T) return 14;

@@ -56,6 +56,10 @@ struct LinearArgs {
   // C[((row / hm_T) * (N / 64) + n / 64) * hm_T + row % hm_T][n % 64] - i.e. [batch][head][t][64] for rows = batch * hm_T.
   // Used for the cross-attention K/V of the decoder when the head-major kv layout is on.  0 = row-major.
   int head_major_T = 0;
+  // W is constant while the stream runs (model weights): lets the kernel fetch weight tiles before it waits for
+  // the previous kernel under programmatic dependent launch.  Leave 0 when W is produced by earlier work in the
+  // same stream (e.g. wb200_linear on caller tensors).
+  int weights_constant = 0;
   void* C = nullptr;
   long long ldc = 0;
   int gelu = 0;
@@ -73,6 +77,7 @@ int launch_linear(const LinearArgs& a, cudaStream_t s);
 extern int g_splitk_on;
 extern int g_bm64_on;
 extern int g_kv_head_major;   // kv caches stored [.., head, position, 64] instead of [.., position, d] (wb200_set_kv_head_major)
+extern int g_gemm_early_b;   // GEMM: issue the first weight tiles before griddepcontrol.wait (wb200_set_gemm_early_weights)
 extern int g_pdl_on;   // programmatic dependent launch for the decoder-layer kernels (wb200_set_pdl / WB200_PDL)
 
 // Launch with the programmatic-stream-serialization attribute (when enabled): inside a stream or a

@@ -98,6 +98,23 @@ class _Encoder:
     forward = __call__
 
 
+class _Decoder:
+    """Callable stand-in for `model.decoder` (reference TextDecoder.forward, model.py:227-249): the un-cached
+    forward `decoder(tokens, audio_features) -> logits`.  The incremental path with a kv-cache lives inside the
+    device session (csrc/engine.cu), so a non-empty `kv_cache` dict - the reference's hook protocol - is refused."""
+
+    def __init__(self, model: "Whisper"):
+        self._m = model
+
+    def __call__(self, x: torch.Tensor, xa: torch.Tensor, kv_cache: Optional[dict] = None) -> torch.Tensor:
+        if kv_cache:
+            raise NotImplementedError("the kv-cache is resident inside the decoder session; use model.decode() / "
+                                      "whisper_b200.decoding.DecoderSession for incremental decoding")
+        return self._m.logits(x, xa)
+
+    forward = __call__
+
+
 class Whisper:
     def __init__(self, dims: ModelDimensions, state_dict: Optional[dict] = None, device="cuda",
                  dtype: torch.dtype = torch.float16):
@@ -111,6 +128,7 @@ class Whisper:
         self._workspace = None
         self._sessions = {}
         self.encoder = _Encoder(self)
+        self.decoder = _Decoder(self)
         # default alignment heads: the last half of the decoder layers (model.py:268-276)
         heads = torch.zeros(dims.n_text_layer, dims.n_text_head, dtype=torch.bool)
         heads[dims.n_text_layer // 2:] = True
