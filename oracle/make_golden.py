@@ -16,6 +16,11 @@ Fixtures:
   alignment_<name>.npz     find_alignment tensor part: alignment matrix, DTW path, token probabilities
   model_<name>.npz/.json   encoder features (sub-sampled), prefill logits probes, and decode()
                            results (tokens, avg_logprob, no_speech_prob) for several DecodingOptions
+  transcribe_<name>.json   whisper.transcribe() runs (transcribe.py:38-514) recorded as: every model.decode() call
+                           the reference made (prompt, temperature, beam / best_of, a fingerprint of the window) with
+                           its DecodingResult, every tokenizer.decode() text, and the final segments - enough to
+                           replay the window loop (seek advance, prompt conditioning, temperature fallback,
+                           no-speech skip, segment splitting) without a model
 """
 from __future__ import annotations
 
@@ -222,6 +227,75 @@ def gen_alignment(name: str, seed: int, regime: str):
                         token_probs=probs.numpy().astype(np.float32), seed=np.array(seed))
 
 
+TRANSCRIBE_CASES = {
+    # name -> (seconds of audio, audio kind, transcribe kwargs); thresholds are placed inside the range the
+    # synthetic model produces (avg_logprob -0.7 .. -0.35, compression ratio 1.1 .. 1.8, no_speech_prob ~ 0) so that
+    # some windows pass, some fall back to a sampled rung and some are skipped as silence
+    "ladder_conditioned": (83, "speechlike", dict(sample_len=40, logprob_threshold=-0.45)),
+    "ladder_compression": (70, "speechlike", dict(sample_len=40, compression_ratio_threshold=1.6,
+                                                  temperature=(0.0, 0.6, 1.0))),
+    "greedy_unconditioned": (64, "noise", dict(temperature=0.0, condition_on_previous_text=False, sample_len=32)),
+    "beam_clips": (95, "speechlike", dict(temperature=(0.0, 0.4), beam_size=3, best_of=2, sample_len=28,
+                                          clip_timestamps=[4.0, 41.5, 50.0], logprob_threshold=-0.43)),
+    "silence_skip": (76, "noise", dict(temperature=(0.0, 0.4), no_speech_threshold=-1.0, logprob_threshold=-0.62,
+                                       sample_len=32)),
+    "no_thresholds": (47, "noise", dict(temperature=0.0, sample_len=36, no_speech_threshold=None,
+                                        logprob_threshold=None, compression_ratio_threshold=None)),
+}
+
+
+def gen_transcribe(name: str, seed: int, regime: str):
+    """Run the reference's transcribe() on synthetic weights / audio and record what its window loop did."""
+    import importlib
+
+    ref_tr = importlib.import_module("whisper.transcribe")     # the package attribute of that name is the function
+
+    model, dims = build_reference_model(name, seed, regime)
+    out = {"model": name, "seed": seed, "regime": regime, "cases": {}}
+    for case, (secs, kind, kw) in TRANSCRIBE_CASES.items():
+        audio = synthetic.synthetic_audio(1, 16000 * secs, seed=900 + secs, kind=kind)[0]
+        calls, texts = [], {}
+        orig_decode = model.decode
+
+        def rec_decode(segment, options, _calls=calls, _orig=orig_decode):
+            r = _orig(segment, options)
+            _calls.append(dict(
+                prompt=list(options.prompt or []), temperature=float(options.temperature),
+                beam_size=options.beam_size, best_of=options.best_of, patience=options.patience,
+                sample_len=options.sample_len,
+                window_sum=float(segment.double().sum()), window_abs=float(segment.double().abs().sum()),
+                tokens=list(r.tokens), avg_logprob=float(r.avg_logprob), no_speech_prob=float(r.no_speech_prob),
+                compression_ratio=float(r.compression_ratio), result_temperature=float(r.temperature)))
+            return r
+
+        tok = get_tokenizer(model.is_multilingual, num_languages=model.num_languages, language="en", task="transcribe")
+        orig_tok_decode = tok.decode
+
+        def rec_tok_decode(token_ids, *a, _texts=texts, _orig=orig_tok_decode, **k):
+            t = _orig(token_ids, *a, **k)
+            _texts[",".join(str(int(x)) for x in token_ids)] = t
+            return t
+
+        tok.decode = rec_tok_decode              # get_tokenizer is lru_cached: transcribe() gets this same object
+        model.decode = rec_decode
+        torch.manual_seed(1234)
+        try:
+            result = ref_tr.transcribe(model, audio, verbose=None, fp16=False, language="en", **kw)
+        finally:
+            model.decode = orig_decode
+            tok.decode = orig_tok_decode
+        segs = [dict(id=sg["id"], seek=sg["seek"], start=sg["start"], end=sg["end"], text=sg["text"],
+                     tokens=list(sg["tokens"]), temperature=sg["temperature"], avg_logprob=sg["avg_logprob"],
+                     compression_ratio=sg["compression_ratio"], no_speech_prob=sg["no_speech_prob"])
+                for sg in result["segments"]]
+        out["cases"][case] = dict(seconds=secs, audio_kind=kind, audio_seed=900 + secs, kwargs=kw, calls=calls,
+                                  texts=texts, segments=segs, text=result["text"], language=result["language"])
+        print(f"transcribe {name}/{case}: {len(calls)} decode calls, {len(segs)} segments, "
+              f"temperatures {sorted({c['temperature'] for c in calls})}")
+    with open(os.path.join(GOLD, f"transcribe_{name}.json"), "w") as f:
+        json.dump(out, f)
+
+
 def main():
     torch.set_num_threads(os.cpu_count() or 1)
     gen_static()
@@ -231,6 +305,7 @@ def main():
     gen_model("test-multi", seed=12, audio_kind="noise", full_length=True, regime="diverse")
     gen_model("tiny.en", seed=13, audio_kind="speechlike", full_length=False, regime="confident")
     gen_alignment("test-en", seed=11, regime="confident")
+    gen_transcribe("test-multi", seed=12, regime="diverse")
     print("golden fixtures written to", GOLD)
 
 

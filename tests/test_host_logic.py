@@ -326,3 +326,66 @@ def test_decode_requests_groups_by_prompt_length(monkeypatch):
     assert sizes == [1, 1, 1, 1, 2]                                         # {11,31} share (max_batch 2), 61 overflows
     for n, init, _, _ in runs:
         assert init.shape[0] == n and (init[:, 0] == init[0, 0]).all()      # <|startofprev|> first in every row
+
+
+def _replay_transcribe_case(case, monkeypatch):
+    """Drive OUR window loop with the decode results the REFERENCE's transcribe() run recorded (tests/golden/
+    transcribe_*.json, made by oracle/make_golden.py: gen_transcribe).  Every request our loop issues must be the one
+    the reference issued at that point - same prompt tokens, temperature, beam / best_of switching, same window of
+    the spectrogram - and the final segments must be the reference's."""
+    import importlib
+
+    from oracle import audio as OA
+    from whisper_b200 import synthetic
+    from whisper_b200.decoding import DecodingResult
+    from whisper_b200.tokenizer import get_tokenizer
+
+    WT = importlib.import_module("whisper_b200.transcribe")
+    with open(os.path.join(GOLD, "transcribe_test-multi.json")) as f:
+        gold = json.load(f)
+    c = gold["cases"][case]
+    audio = synthetic.synthetic_audio(1, 16000 * c["seconds"], seed=c["audio_seed"], kind=c["audio_kind"])[0]
+
+    def cpu_mel(a, n_mels=80, padding=0, device=None):
+        return torch.from_numpy(OA.log_mel_spectrogram(np.asarray(a, dtype=np.float32), n_mels, padding).astype(np.float32))
+
+    monkeypatch.setattr(WT, "log_mel_spectrogram", cpu_mel)
+    model = fake_model(gold["model"])
+    tok = get_tokenizer(model.is_multilingual, num_languages=model.num_languages, language="en", task="transcribe")
+    texts = c["texts"]
+    monkeypatch.setattr(tok, "decode", lambda ids, **kw: texts[",".join(str(int(t)) for t in ids)])
+    calls = iter(c["calls"])
+    n_seen = [0]
+
+    def decode(segment, options):
+        want = next(calls)
+        n_seen[0] += 1
+        assert list(options.prompt or []) == want["prompt"], f"call {n_seen[0]}: prompt differs"
+        assert options.temperature == pytest.approx(want["temperature"])
+        assert (options.beam_size, options.best_of, options.patience) == (want["beam_size"], want["best_of"], want["patience"])
+        assert options.sample_len == want["sample_len"]
+        assert float(segment.double().abs().sum()) == pytest.approx(want["window_abs"], rel=2e-4), \
+            f"call {n_seen[0]}: a different window of the spectrogram was decoded"
+        return DecodingResult(audio_features=None, language="en", tokens=want["tokens"], text="",
+                              avg_logprob=want["avg_logprob"], no_speech_prob=want["no_speech_prob"],
+                              temperature=want["result_temperature"], compression_ratio=want["compression_ratio"])
+
+    model.decode = decode
+    kw = dict(c["kwargs"])
+    if isinstance(kw.get("temperature"), list):
+        kw["temperature"] = tuple(kw["temperature"])
+    out = WT.transcribe(model, audio, language="en", **kw)
+    assert n_seen[0] == len(c["calls"]), "our loop issued fewer decode requests than the reference"
+    assert out["language"] == c["language"] and out["text"] == c["text"]
+    assert len(out["segments"]) == len(c["segments"])
+    for ours, ref in zip(out["segments"], c["segments"]):
+        assert (ours["id"], ours["seek"], ours["tokens"], ours["text"]) == (ref["id"], ref["seek"], ref["tokens"], ref["text"])
+        assert ours["start"] == pytest.approx(ref["start"], abs=1e-6) and ours["end"] == pytest.approx(ref["end"], abs=1e-6)
+        for k in ("temperature", "avg_logprob", "compression_ratio", "no_speech_prob"):
+            assert ours[k] == pytest.approx(ref[k])
+
+
+@pytest.mark.parametrize("case", ["ladder_conditioned", "ladder_compression", "greedy_unconditioned", "beam_clips",
+                                  "silence_skip", "no_thresholds"])
+def test_transcribe_window_loop_replays_reference(case, monkeypatch):
+    _replay_transcribe_case(case, monkeypatch)
