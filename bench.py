@@ -334,8 +334,6 @@ def main():
     ms_e2e, _ = timed(step_e2e, e2e_steps)
 
     if rank != 0:
-        if world > 1:
-            dist.destroy_process_group()
         return
     audio_s = world * B * CHUNK_S
     value = audio_s * args.steps / (ms / 1000.0)
@@ -399,8 +397,6 @@ def main():
                        f"beam-{G} iterations, extrapolated to {DECODE_STEPS} (enc {s['t_enc']:.2f}s, prefill "
                        f"{s['t_prefill']:.2f}s, {s['t_step']:.3f}s/iter; {s['wall']:.1f}s of CPU work)")}
     print(json.dumps(line))
-    if world > 1:
-        dist.destroy_process_group()
 
 
 if __name__ == "__main__":

@@ -8,11 +8,10 @@
 // are the same activation matrix shifted by one row; the zero padding comes from TMA's
 // out-of-bounds fill, the stride-2 of conv2 from a tensor map with a doubled row stride.
 //
-// Structure (persistent, one CTA per SM, 256 threads):
-//   warp 0   : TMA producer (one elected thread) - A tile 128x64, W tile BNx64, 128B swizzle
-//   (384 threads: warps 0-3 control, warps 4-11 epilogue)
-//   warp 1   : tcgen05.mma issuer (one thread)   - UMMA 128 x BN x 16, accumulators in TMEM
-//   warp 2   : TMEM allocator / deallocator
+// Structure (persistent, one CTA per SM, 384 threads = 4 control warps + 8 epilogue warps):
+//   warp 0    : TMA producer (one elected thread) - A tile BMx64, W tile BNx64 (x KS sub-blocks), 128B swizzle
+//   warp 1    : tcgen05.mma issuer (one thread)   - UMMA BM x BN x 16, accumulators in TMEM
+//   warp 2    : TMEM allocator / deallocator
 //   warps 4-11: epilogue - tcgen05.ld -> bias / GELU / positional add / residual -> global
 // Pipelines: smem ring (full/empty mbarriers) between TMA and MMA; two TMEM accumulator
 // stages (tmem_full/tmem_empty) between MMA and epilogue so tile i+1's main loop overlaps
