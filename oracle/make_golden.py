@@ -16,6 +16,7 @@ Fixtures:
   alignment_<name>.npz     find_alignment tensor part: alignment matrix, DTW path, token probabilities
   model_<name>.npz/.json   encoder features (sub-sampled), prefill logits probes, and decode()
                            results (tokens, avg_logprob, no_speech_prob) for several DecodingOptions
+  state_dict_keys.json     names and shapes of the reference Whisper.state_dict() per architecture
   transcribe_<name>.json   whisper.transcribe() runs (transcribe.py:38-514) recorded as: every model.decode() call
                            the reference made (prompt, temperature, beam / best_of, a fingerprint of the window) with
                            its DecodingResult, every tokenizer.decode() text, and the final segments - enough to
@@ -296,6 +297,25 @@ def gen_transcribe(name: str, seed: int, regime: str):
         json.dump(out, f)
 
 
+def gen_state_dict_keys():
+    """Names and shapes of the reference model's state dict (what a released checkpoint holds, __init__.py:147-156)
+    for every architecture, built on the meta device so that large-v3 costs nothing."""
+    out = {}
+    for name in ("tiny.en", "tiny", "small", "large-v3", "large-v3-turbo", "test-en", "test-multi"):
+        dims = synthetic.dims_dict(name)
+        to_sparse = torch.Tensor.to_sparse           # the alignment-head buffer (non-persistent) has no meta kernel
+        torch.Tensor.to_sparse = lambda self, *a, **k: self
+        try:
+            with torch.device("meta"):
+                model = Whisper(ModelDimensions(**dims))
+        finally:
+            torch.Tensor.to_sparse = to_sparse
+        out[name] = {k: list(v.shape) for k, v in model.state_dict().items()}
+    with open(os.path.join(GOLD, "state_dict_keys.json"), "w") as f:
+        json.dump(out, f)
+    print("state dict keys:", {k: len(v) for k, v in out.items()})
+
+
 def main():
     torch.set_num_threads(os.cpu_count() or 1)
     gen_static()
@@ -306,6 +326,7 @@ def main():
     gen_model("tiny.en", seed=13, audio_kind="speechlike", full_length=False, regime="confident")
     gen_alignment("test-en", seed=11, regime="confident")
     gen_transcribe("test-multi", seed=12, regime="diverse")
+    gen_state_dict_keys()
     print("golden fixtures written to", GOLD)
 
 

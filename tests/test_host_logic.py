@@ -389,3 +389,50 @@ def _replay_transcribe_case(case, monkeypatch):
                                   "silence_skip", "no_thresholds"])
 def test_transcribe_window_loop_replays_reference(case, monkeypatch):
     _replay_transcribe_case(case, monkeypatch)
+
+
+def test_checkpoint_keys_and_weight_packing():
+    """Checkpoint ingest (reference __init__.py:147-156 -> model.load_state_dict): the tensors a released checkpoint
+    holds - names and shapes of the REFERENCE's Whisper.state_dict(), tests/golden/state_dict_keys.json - are exactly
+    the ones whisper_b200 expects, pack_weights() consumes every one of them, and the packed slots have the layout
+    include/whisper_b200.h documents (tap-major conv weights, fused q|k|v with a zero key bias, fp32 LayerNorms)."""
+    from whisper_b200 import synthetic
+    from whisper_b200.model import ModelDimensions, pack_weights
+
+    with open(os.path.join(GOLD, "state_dict_keys.json")) as f:
+        ref_keys = json.load(f)
+    for name, shapes in ref_keys.items():
+        spec = {n: list(s) for n, s, _ in synthetic.state_dict_spec(synthetic.dims_dict(name))}
+        assert spec == shapes, f"{name}: state dict layout differs from the reference"
+
+    class Tracking(dict):
+        def __init__(self, *a):
+            super().__init__(*a)
+            self.read = set()
+
+        def __getitem__(self, k):
+            self.read.add(k)
+            return super().__getitem__(k)
+
+    for name in ("test-en", "test-multi", "tiny.en"):
+        dd = synthetic.dims_dict(name)
+        dims = ModelDimensions(**dd)
+        sd = Tracking(synthetic.synthetic_state_dict(dd, seed=3))
+        packed = pack_weights(sd, dims, "cpu", torch.float16)
+        assert sd.read == set(ref_keys[name]), f"{name}: unread checkpoint tensors {set(ref_keys[name]) - sd.read}"
+        assert len(packed) == 12 + 12 * dims.n_audio_layer + 20 * dims.n_text_layer
+        d = dims.n_audio_state
+        w1 = torch.from_numpy(sd["encoder.conv1.weight"])                     # [out, in, 3] -> [out, 3 * in] tap-major
+        assert torch.equal(packed[0], w1.permute(0, 2, 1).reshape(d, -1).half())
+        assert packed[4].dtype == torch.float32 and packed[4].shape == (dims.n_audio_ctx, d)       # sinusoids stay fp32
+        enc0 = packed[12:24]
+        q, k, v = (torch.from_numpy(sd[f"encoder.blocks.0.attn.{n}.weight"]).half() for n in ("query", "key", "value"))
+        assert torch.equal(enc0[2], torch.cat([q, k, v], 0)) and enc0[0].dtype == torch.float32
+        bias = enc0[3]
+        assert torch.equal(bias[:d], torch.from_numpy(sd["encoder.blocks.0.attn.query.bias"]).half())
+        assert float(bias[d: 2 * d].abs().max()) == 0.0                       # key has no bias (model.py:88)
+        dec0 = packed[12 + 12 * dims.n_audio_layer: 12 + 12 * dims.n_audio_layer + 20]
+        kv = torch.cat([torch.from_numpy(sd[f"decoder.blocks.0.cross_attn.{n}.weight"]).half() for n in ("key", "value")], 0)
+        assert torch.equal(dec0[10], kv) and dec0[10].shape == (2 * dims.n_text_state, dims.n_text_state)
+        assert packed[7].dtype == torch.float16 and packed[8].dtype == torch.float32               # tied embedding, both types
+        assert torch.equal(packed[8], torch.from_numpy(sd["decoder.token_embedding.weight"]).float())
