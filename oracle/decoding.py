@@ -104,6 +104,8 @@ class Result:
     no_speech_prob: float = float("nan")
     sum_logprob: float = float("nan")
     audio_features: Optional[torch.Tensor] = None
+    language: Optional[str] = None
+    top_language_prob: float = float("nan")
     # diagnostics for margin-gated comparisons
     step_margins: List[float] = field(default_factory=list)
 
@@ -363,6 +365,17 @@ def decode(W: M.Weights, dims: Dict[str, int], mel_or_features: torch.Tensor, op
     B = feats.shape[0]
     R = B * G
     tokens: List[List[int]] = [list(init) for _ in range(R)]
+    languages: List[Optional[str]] = [opt.language] * B
+    top_lang_prob = [float("nan")] * B
+    if opt.language is None or opt.task == "lang_id":                         # decoding.py:666-678
+        lang_tokens, lang_probs = detect_language(W, dims, feats)
+        languages = [ids.language_codes[int(t) - ids.sot - 1] for t in lang_tokens]
+        top_lang_prob = lang_probs.max(dim=-1).values.tolist()
+        if opt.language is None:
+            for r in range(R):
+                tokens[r][sot_index + 1] = int(lang_tokens[r // G])            # write the language token
+    if opt.task == "lang_id":                                                 # decoding.py:722-727
+        return [Result(language=languages[a], top_language_prob=top_lang_prob[a], audio_features=feats[a]) for a in range(B)]
     xa = feats.repeat_interleave(G, dim=0) if G > 1 else feats
     cache = M.KVCache(dims["n_text_layer"])
     sum_lp = torch.zeros(R)
@@ -430,7 +443,7 @@ def decode(W: M.Weights, dims: Dict[str, int], mel_or_features: torch.Tensor, op
         lp = cand_lp[a][pick[a]]
         out.append(Result(tokens=toks, avg_logprob=lp / (len(toks) + 1), sum_logprob=lp,
                           no_speech_prob=no_speech[a * G], audio_features=feats[a],
-                          step_margins=margins[a * G]))
+                          step_margins=margins[a * G], language=languages[a], top_language_prob=top_lang_prob[a]))
     if record is not None:
         record["all_margins"] = margins
         record["beam_min_gap"] = beam.min_gap if beam is not None else None

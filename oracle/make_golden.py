@@ -16,6 +16,7 @@ Fixtures:
   alignment_<name>.npz     find_alignment tensor part: alignment matrix, DTW path, token probabilities
   model_<name>.npz/.json   encoder features (sub-sampled), prefill logits probes, and decode()
                            results (tokens, avg_logprob, no_speech_prob) for several DecodingOptions
+  decode_extra_<name>.json decode() with task="translate", other language tokens, language=None and task="lang_id"
   state_dict_keys.json     names and shapes of the reference Whisper.state_dict() per architecture
   transcribe_<name>.json   whisper.transcribe() runs (transcribe.py:38-514) recorded as: every model.decode() call
                            the reference made (prompt, temperature, beam / best_of, a fingerprint of the window) with
@@ -297,6 +298,43 @@ def gen_transcribe(name: str, seed: int, regime: str):
         json.dump(out, f)
 
 
+EXTRA_DECODE_CASES = {
+    # name -> (DecodingOptions kwargs incl. language / task, n_audio); results are per audio
+    "translate": (dict(language="en", task="translate", sample_len=32), 2),
+    "translate_de_beam": (dict(language="de", task="translate", beam_size=3, sample_len=24), 1),
+    "auto_language": (dict(language=None, sample_len=24), 2),
+    "auto_language_beam": (dict(language=None, beam_size=2, sample_len=20), 2),
+    "lang_id": (dict(language=None, task="lang_id"), 2),
+    "french_prompt": (dict(language="fr", sample_len=20, prompt=[900 + 11 * i for i in range(9)]), 1),
+}
+
+
+def gen_decode_extra(name: str, seed: int, audio_kind: str, regime: str):
+    """decode() with the task / language options the main fixture leaves at their defaults: translate, another
+    language token, language=None (detect_language inside decode, decoding.py:666-678) and task="lang_id"."""
+    model, dims = build_reference_model(name, seed, regime)
+    audio = synthetic.synthetic_audio(2, 480000, seed=4321, kind=audio_kind)
+    with torch.no_grad():
+        mel = torch.stack([log_mel_spectrogram(torch.from_numpy(a), n_mels=dims["n_mels"]) for a in audio])
+    out = {"name": name, "seed": seed, "audio_seed": 4321, "audio_kind": audio_kind, "regime": regime, "cases": {}}
+    for cname, (opts, n_audio) in EXTRA_DECODE_CASES.items():
+        options = DecodingOptions(fp16=False, temperature=0.0, **opts)
+        with torch.no_grad():
+            if opts.get("beam_size"):          # the reference cannot batch beam search (decoding.py:734,740)
+                results = [model.decode(mel[a], options) for a in range(n_audio)]
+            else:
+                results = model.decode(mel[:n_audio], options)
+        out["cases"][cname] = {"options": opts, "n_audio": n_audio, "results": [
+            dict(tokens=list(map(int, r.tokens)), language=r.language,
+                 avg_logprob=None if np.isnan(r.avg_logprob) else float(r.avg_logprob),
+                 no_speech_prob=None if np.isnan(r.no_speech_prob) else float(r.no_speech_prob),
+                 top_language_prob=None if r.language_probs is None else float(max(r.language_probs.values())))
+            for r in results]}
+        print(f"  {name}/{cname}: languages {[r.language for r in results]}, {[len(r.tokens) for r in results]} tokens")
+    with open(os.path.join(GOLD, f"decode_extra_{name}.json"), "w") as f:
+        json.dump(out, f)
+
+
 def gen_state_dict_keys():
     """Names and shapes of the reference model's state dict (what a released checkpoint holds, __init__.py:147-156)
     for every architecture, built on the meta device so that large-v3 costs nothing."""
@@ -327,6 +365,7 @@ def main():
     gen_alignment("test-en", seed=11, regime="confident")
     gen_transcribe("test-multi", seed=12, regime="diverse")
     gen_state_dict_keys()
+    gen_decode_extra("test-multi", seed=12, audio_kind="noise", regime="diverse")
     print("golden fixtures written to", GOLD)
 
 

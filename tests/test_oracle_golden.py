@@ -2,6 +2,7 @@
 (oracle/make_golden.py).  This is what pins the oracle: every stage of the hot path, on the same
 synthetic inputs, must reproduce the reference's outputs - token ids exactly, floating-point
 values to the stated tolerances."""
+import json
 import os
 
 import numpy as np
@@ -104,6 +105,29 @@ def test_decode_matches_reference(name, case):
         assert r.tokens == g["tokens"]
         assert abs(r.avg_logprob - g["avg_logprob"]) < 1e-5
         assert abs(r.no_speech_prob - g["no_speech_prob"]) <= 1e-5 * max(g["no_speech_prob"], 1e-30) + 1e-12
+
+
+@pytest.mark.parametrize("case", ["translate", "translate_de_beam", "auto_language", "auto_language_beam", "lang_id",
+                                  "french_prompt"])
+def test_decode_task_and_language_options(case):
+    """decode() with task="translate", other language tokens, language=None (detect_language inside decode,
+    decoding.py:666-678) and task="lang_id" (:722-727) against the reference's results."""
+    from oracle import decoding as OD
+
+    with open(os.path.join(GOLD, "decode_extra_test-multi.json")) as f:
+        gold = json.load(f)
+    meta, arrays, dims, W, mel, feats = oracle_features("test-multi")
+    c = gold["cases"][case]
+    res = OD.decode(W, dims, feats[: c["n_audio"]], OD.Options(**c["options"]))
+    assert len(res) == len(c["results"])
+    for r, g in zip(res, c["results"]):
+        assert r.language == g["language"]
+        assert r.tokens == g["tokens"]
+        if g["avg_logprob"] is not None:
+            assert abs(r.avg_logprob - g["avg_logprob"]) < 1e-5
+            assert abs(r.no_speech_prob - g["no_speech_prob"]) <= 1e-5 * max(g["no_speech_prob"], 1e-30) + 1e-12
+        if g["top_language_prob"] is not None:
+            assert abs(r.top_language_prob - g["top_language_prob"]) < 1e-5
 
 
 def test_detect_language():
