@@ -31,7 +31,12 @@ import torch
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-METRIC = "RTFx (audio-s/wall-s) large-v3 beam=5"
+METRIC = "RTFx (audio-s/wall-s) large-v3 beam=5"       # BASELINE.json's metric (the default workload)
+
+
+def metric_name(args):
+    """BASELINE.json's metric string for the default workload; other --model / --beam values are labelled as such."""
+    return METRIC if (args.model, args.beam) == ("large-v3", 5) else f"RTFx (audio-s/wall-s) {args.model} beam={args.beam}"
 CHUNK_S = 30.0
 N_SAMPLES = 480000
 DECODE_STEPS = 224
@@ -208,7 +213,7 @@ def run_reference_arm(args, rank):
               f"iterations of {DECODE_STEPS}, extrapolated linearly (enc {vals[-1]['t_enc']:.2f}s, prefill "
               f"{vals[-1]['t_prefill']:.2f}s, {vals[-1]['t_step']:.3f}s/iter); fp32, torch CPU threads={threads}")
     print(json.dumps({
-        "impl": "reference", "metric": METRIC, "value": v, "unit": "x realtime", "n_gpus": args.gpus,
+        "impl": "reference", "metric": metric_name(args), "value": v, "unit": "x realtime", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1000.0 * wall / max(1, args.steps),
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": f"{args.model} beam={args.beam} batch={args.batch} synthetic 30 s @16 kHz, "
@@ -354,7 +359,7 @@ def main():
     d2h = R * (len(tok.sot_sequence) + args.decode_steps) * 4 + R * 4 + B * 4 + 4 + \
         (B * G * ctx * 4 + 3 * B * G * 4 if G > 1 else 0)
     line = {
-        "metric": METRIC, "value": value, "unit": "x realtime", "n_gpus": world, "steps": args.steps,
+        "metric": metric_name(args), "value": value, "unit": "x realtime", "n_gpus": world, "steps": args.steps,
         "warmup": max(3, args.warmup), "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": args.dtype, "data": "synthetic",
         "config": {
