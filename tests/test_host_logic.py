@@ -436,3 +436,108 @@ def test_checkpoint_keys_and_weight_packing():
         assert torch.equal(dec0[10], kv) and dec0[10].shape == (2 * dims.n_text_state, dims.n_text_state)
         assert packed[7].dtype == torch.float16 and packed[8].dtype == torch.float32               # tied embedding, both types
         assert torch.equal(packed[8], torch.from_numpy(sd["decoder.token_embedding.weight"]).float())
+
+
+class _FakeSession:
+    """Stands in for decoding.DecoderSession: 'decodes' each audio to tokens that are a pure function of its
+    features and prompt, stops after a per-session number of steps, and keeps beam-style finished stores."""
+    log = []
+
+    def __init__(self, task, n_audio):
+        self.task, self.n_audio, self.G = task, n_audio, task.n_group
+        self.temperature, self.seed = 0.0, None
+
+    def set_audio(self, feats):
+        self.key = [int(abs(float(f.sum())) * 10) % 50 for f in feats]
+
+    def set_sampling(self, temperature, seed):
+        self.temperature, self.seed = temperature, seed
+
+    def prefill(self, init):
+        self.init = np.asarray(init)
+
+    def select(self):
+        pass
+
+    def run(self, max_steps):
+        self.steps = 3 + (self.n_audio % 4)             # sessions of different size stop at different lengths
+        _FakeSession.log.append((self.n_audio, self.seed))
+        return self.steps
+
+    def get(self, what):
+        eot = self.task.tokenizer.eot
+        n_init = self.init.shape[1]
+        L = n_init + self.steps
+        R = self.n_audio * self.G
+        if what == "length":
+            return torch.tensor([L])
+        if what == "tokens":
+            t = np.full((R, 448), eot, dtype=np.int32)
+            for a in range(self.n_audio):
+                for j in range(self.G):
+                    t[a * self.G + j, :n_init] = self.init[a]
+                    body = [1000 + self.key[a], 2000 + j, 3000 + int(self.init[a, -1]) % 7]
+                    t[a * self.G + j, n_init: n_init + 3] = body
+            return torch.from_numpy(t)
+        if what == "sum_logprobs":
+            return torch.tensor([-(1.0 + 0.1 * j + 0.01 * self.key[a]) for a in range(self.n_audio) for j in range(self.G)])
+        if what == "no_speech":
+            return torch.tensor([0.01 * self.key[a] for a in range(self.n_audio)])
+        mc = max(1, round((self.task.options.beam_size or 1) * (self.task.options.patience or 1.0)))
+        if what == "fin_tokens":
+            t = np.full((self.n_audio, mc, 448), eot, dtype=np.int32)
+            for a in range(self.n_audio):
+                t[a, 0, : n_init + 2] = list(self.init[a]) + [1500 + self.key[a], eot]
+            return torch.from_numpy(t)
+        if what == "fin_len":
+            return torch.from_numpy(np.tile(np.array([n_init + 2] + [0] * (mc - 1), dtype=np.int32), (self.n_audio, 1)))
+        if what == "fin_score":
+            return torch.from_numpy(np.tile(np.array([-0.5] + [0.0] * (mc - 1), dtype=np.float32), (self.n_audio, 1)))
+        if what == "fin_count":
+            return torch.ones(self.n_audio, dtype=torch.int32)
+        raise KeyError(what)
+
+    def close(self):
+        pass
+
+
+@pytest.mark.parametrize("opts", [dict(), dict(beam_size=3), dict(temperature=0.5, best_of=2, seed=9)])
+def test_decoding_task_run_and_concurrent_sessions(opts, monkeypatch):
+    """DecodingTask.run's host logic around the device session - result assembly, ranking, and the split of one
+    batch into several concurrent sessions (model.decode_streams) - with a fake session: the concurrent path must
+    return exactly what the single session returns, audio by audio."""
+    import contextlib
+
+    import whisper_b200.decoding as WD
+
+    class DummyStream:
+        def wait_stream(self, other):
+            pass
+
+    monkeypatch.setattr(torch.cuda, "current_stream", lambda dev=None: DummyStream())
+    monkeypatch.setattr(torch.cuda, "Stream", lambda device=None: DummyStream())
+    monkeypatch.setattr(torch.cuda, "stream", lambda st: contextlib.nullcontext())
+    monkeypatch.setattr(torch.cuda, "device", lambda dev: contextlib.nullcontext())
+    monkeypatch.setattr(WD.DecodingTask, "open_session", lambda self, n: _FakeSession(self, n))
+    model = fake_model("test-en")
+    feats = torch.arange(7 * 4 * 3, dtype=torch.float32).reshape(7, 4, 3) * 0.37
+    monkeypatch.setattr(WD.DecodingTask, "_get_audio_features", lambda self, mel: mel)
+    prompts = np.asarray([[50257, 50362 + (a % 3)] for a in range(7)], dtype=np.int32)
+
+    def run(streams):
+        model.decode_streams = streams
+        _FakeSession.log = []
+        task = WD.DecodingTask(model, WD.DecodingOptions(language="en", without_timestamps=True, **opts))
+        init = np.tile(np.asarray(task.initial_tokens, dtype=np.int32), (7, 1))
+        init[:, -1] = prompts[:, 1]
+        res = task.run(feats, initial_tokens=init)
+        return [(r.tokens, round(r.avg_logprob, 6), round(r.no_speech_prob, 6), r.temperature) for r in res], list(_FakeSession.log)
+
+    single, log1 = run(1)
+    assert len(single) == 7 and log1[0][0] == 7
+    for streams in (2, 3, 7, 16):
+        multi, logn = run(streams)
+        assert multi == single, f"{streams} sessions changed the results"
+        assert sum(n for n, _ in logn) == 7 and len(logn) == min(streams, 7)
+        if opts.get("temperature"):
+            assert len({sd for _, sd in logn}) == len(logn)        # every session samples with its own key

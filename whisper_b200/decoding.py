@@ -384,28 +384,16 @@ class DecodingTask:
             return [DecodingResult(audio_features=f, language=l, language_probs=p)
                     for f, l, p in zip(audio_features, languages, language_probs)]
 
-        sess = self.open_session(n_audio)
-        try:
-            sess.set_audio(audio_features)
-            if self.options.temperature > 0:
-                seed = self.options.seed
-                if seed is None:
-                    seed = int(torch.randint(0, 2 ** 62, (1,)).item())
-                sess.set_sampling(self.options.temperature, seed)
-            sess.prefill(init)                       # i == 0 forward + no_speech probabilities
-            sess.select()                            # filters + first update
-            if self.sample_len > 1:
-                sess.run(self.sample_len - 1)        # i = 1 .. sample_len-1, stops on completion
-            length = int(sess.get("length").item())
-            tokens = sess.get("tokens")[:, :length].cpu().numpy()
-            sum_logprobs = sess.get("sum_logprobs").cpu().numpy()
-            no_speech = sess.get("no_speech").cpu().tolist() if tokenizer.no_speech is not None else [np.nan] * n_audio
-            finished = None
-            if self.options.beam_size is not None:
-                finished = (sess.get("fin_tokens").cpu().numpy(), sess.get("fin_len").cpu().numpy(),
-                            sess.get("fin_score").cpu().numpy(), sess.get("fin_count").cpu().numpy())
-        finally:
-            sess.close()
+        seed = None
+        if self.options.temperature > 0:
+            seed = self.options.seed
+            if seed is None:
+                seed = int(torch.randint(0, 2 ** 62, (1,)).item())
+        n_streams = max(1, min(int(getattr(self.model, "decode_streams", 1) or 1), n_audio))
+        if n_streams == 1:
+            tokens, sum_logprobs, no_speech, finished = self._run_session(audio_features, init, seed)
+        else:
+            tokens, sum_logprobs, no_speech, finished = self._run_concurrent(audio_features, init, seed, n_streams)
 
         G = self.n_group
         tokens = tokens.reshape(n_audio, G, -1)
@@ -424,6 +412,85 @@ class DecodingTask:
         return [DecodingResult(audio_features=f, language=l, tokens=t, text=x, avg_logprob=a, no_speech_prob=n,
                                temperature=self.options.temperature, compression_ratio=compression_ratio(x))
                 for x, l, t, f, a, n in zip(*fields)]
+
+    def _run_session(self, audio_features: torch.Tensor, init: np.ndarray, seed: Optional[int]):
+        """One device-resident decode of `init.shape[0]` audios on the current stream: (tokens [R, L], sum_logprobs [R],
+        no_speech [n_audio], finished-hypothesis store or None)."""
+        n_audio = init.shape[0]
+        sess = self.open_session(n_audio)
+        try:
+            sess.set_audio(audio_features)
+            if seed is not None:
+                sess.set_sampling(self.options.temperature, seed)
+            sess.prefill(init)                       # i == 0 forward + no_speech probabilities
+            sess.select()                            # filters + first update
+            if self.sample_len > 1:
+                sess.run(self.sample_len - 1)        # i = 1 .. sample_len-1, stops on completion
+            length = int(sess.get("length").item())
+            tokens = sess.get("tokens")[:, :length].cpu().numpy()
+            sum_logprobs = sess.get("sum_logprobs").cpu().numpy()
+            no_speech = (sess.get("no_speech").cpu().tolist() if self.tokenizer.no_speech is not None
+                         else [np.nan] * n_audio)
+            finished = None
+            if self.options.beam_size is not None:
+                finished = (sess.get("fin_tokens").cpu().numpy(), sess.get("fin_len").cpu().numpy(),
+                            sess.get("fin_score").cpu().numpy(), sess.get("fin_count").cpu().numpy())
+        finally:
+            sess.close()
+        return tokens, sum_logprobs, no_speech, finished
+
+    def _run_concurrent(self, audio_features: torch.Tensor, init: np.ndarray, seed: Optional[int], n_streams: int):
+        """The same decode as `n_streams` independent sessions over contiguous slices of the batch, each driven by its
+        own host thread on its own CUDA stream (`model.decode_streams`, default 1 = off).  A decoder step alternates
+        latency-bound phases (six skinny GEMMs and three LayerNorms per layer that leave most SMs and all of HBM idle)
+        with bandwidth-bound phases (the two attention kernels); with several sessions in flight one session's
+        attention streams K/V while another's GEMMs wait on their pipelines.  Audios are independent, so the results
+        are those of the single session up to fp reduction order (the cross-attention key split depends on the batch).
+        Staged in round 1, not yet measured on hardware."""
+        import threading
+
+        dev = self.model.device
+        main = torch.cuda.current_stream(dev)
+        bounds = np.linspace(0, init.shape[0], n_streams + 1).astype(int)
+        slices = [(int(bounds[i]), int(bounds[i + 1])) for i in range(n_streams) if bounds[i + 1] > bounds[i]]
+        streams = [torch.cuda.Stream(device=dev) for _ in slices]
+        results = [None] * len(slices)
+        errors = [None] * len(slices)
+
+        def work(i):
+            lo, hi = slices[i]
+            try:
+                with torch.cuda.device(dev), torch.cuda.stream(streams[i]):
+                    sub_seed = None if seed is None else (seed + i * 0x9E3779B97F4A7C15) % (1 << 64)
+                    results[i] = self._run_session(audio_features[lo:hi].contiguous(), init[lo:hi], sub_seed)
+            except BaseException as e:      # re-raised on the caller's thread
+                errors[i] = e
+
+        for st in streams:
+            st.wait_stream(main)             # the features were produced on the caller's stream
+        threads = [threading.Thread(target=work, args=(i,), daemon=True) for i in range(len(slices))]
+        for t in threads:
+            t.start()
+        for t in threads:
+            t.join()
+        for st in streams:
+            main.wait_stream(st)
+        for e in errors:
+            if e is not None:
+                raise e
+        eot = self.tokenizer.eot
+        length = max(r[0].shape[1] for r in results)
+
+        def pad(tok):                        # sessions may stop at different lengths; everything past the end is EOT
+            return np.pad(tok, ((0, 0), (0, length - tok.shape[1])), constant_values=eot)
+
+        tokens = np.concatenate([pad(r[0]) for r in results], 0)
+        sum_logprobs = np.concatenate([r[1] for r in results], 0)
+        no_speech = [x for r in results for x in r[2]]
+        finished = None
+        if results[0][3] is not None:
+            finished = tuple(np.concatenate([r[3][k] for r in results], 0) for k in range(4))
+        return tokens, sum_logprobs, no_speech, finished
 
     def _finalize(self, tokens: np.ndarray, sum_logprobs: np.ndarray, finished):
         """GreedyDecoder.finalize (decoding.py:295-298) / BeamSearchDecoder.finalize (:384-404)."""

@@ -129,6 +129,9 @@ class Whisper:
         self._sessions = {}
         self.encoder = _Encoder(self)
         self.decoder = _Decoder(self)
+        # number of concurrent decoder sessions a batched decode() is split into (decoding.DecodingTask._run_concurrent);
+        # 1 = one session for the whole batch
+        self.decode_streams = 1
         # default alignment heads: the last half of the decoder layers (model.py:268-276)
         heads = torch.zeros(dims.n_text_layer, dims.n_text_head, dtype=torch.bool)
         heads[dims.n_text_layer // 2:] = True
