@@ -317,6 +317,8 @@ def main():
     # (the timed steps above replay it from CUDA graphs, where per-launch events cannot be interleaved).
     import ctypes
 
+    # per-launch event timing keeps its records in process-wide state: the profiled steps always run as one session
+    model.decode_streams = 1
     lib.wb200_profile_enable(1)
     ms_prof, _ = timed(step_resident, 1)
     prof_ms, prof_n = ctypes.c_double(0), ctypes.c_int64(0)
@@ -338,6 +340,7 @@ def main():
             lib.wb200_profile_enable(0)
             breakdown[name] = {"ms": t_k.value, "launches": int(n_k.value), "step_ms": ms_k}
 
+    model.decode_streams = max(1, args.decode_streams)
     e2e_steps = max(1, min(args.steps, 3))
     step_e2e()
     ms_e2e, _ = timed(step_e2e, e2e_steps)
