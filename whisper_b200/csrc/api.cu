@@ -12,6 +12,7 @@
 
 namespace wb {
 unsigned long long g_launch_count = 0;
+thread_local unsigned long long t_launch_count = 0;
 int g_profile_kernel = 0;
 static std::vector<cudaEvent_t> g_prof_events;   // begin/end pairs
 static size_t g_prof_used = 0;
@@ -43,7 +44,7 @@ extern "C" {
 
 const char* wb200_version(void) { return "whisper_b200 0.1 (sm_100a)"; }
 const char* wb200_last_error(void) { return g_err; }
-uint64_t wb200_launch_count(void) { return g_launch_count; }
+uint64_t wb200_launch_count(void) { return __atomic_load_n(&g_launch_count, __ATOMIC_RELAXED); }
 
 int wb200_profile_enable(int kernel_id) {
   g_profile_kernel = kernel_id;

@@ -639,15 +639,17 @@ int decoder_run(Decoder* D, int max_steps, int* steps_issued, cudaStream_t s) {
     cudaGraph_t graph = nullptr;
     if (cudaStreamBeginCapture(g, cudaStreamCaptureModeThreadLocal) != cudaSuccess)
       return set_error(281, "decoder: stream capture failed to start");
-    const unsigned long long launches0 = g_launch_count;
+    const unsigned long long launches0 = t_launch_count;
     int r = 0;
     for (int k = 0; k < 2 && !r; ++k) {
       r = decoder_step(D, g);
       if (!r) r = decoder_select(D, g);
     }
     cudaError_t ce = cudaStreamEndCapture(g, &graph);
-    D->launches_per_pair = static_cast<int>(g_launch_count - launches0);
-    g_launch_count = launches0;                    // capture records launches, it does not run them
+    D->launches_per_pair = static_cast<int>(t_launch_count - launches0);
+    // capture records launches, it does not run them: take this thread's recordings back out of the global count
+    __atomic_fetch_sub(&g_launch_count, t_launch_count - launches0, __ATOMIC_RELAXED);
+    t_launch_count = launches0;
     D->host_len = len0;
     D->cur = cur0;
     if (r || ce != cudaSuccess || !graph) return set_error(282, "decoder: graph capture failed (%d, %s)", r, cudaGetErrorString(ce));

@@ -12,7 +12,14 @@ enum { DT_BF16 = 0, DT_F16 = 1 };
 
 // kernels launched by this library since load (reported by bench.py as gpu_launches)
 extern unsigned long long g_launch_count;
-inline void count_launch(int n = 1) { g_launch_count += static_cast<unsigned long long>(n); }
+// Launch accounting (wb200_launch_count).  The process-wide counter is updated atomically because several host
+// threads may drive decoder sessions at once (model.decode_streams); the thread-local one lets a stream capture
+// subtract exactly the launches IT recorded (a capture records kernels, it does not run them).
+extern thread_local unsigned long long t_launch_count;
+inline void count_launch(int n = 1) {
+  __atomic_fetch_add(&g_launch_count, static_cast<unsigned long long>(n), __ATOMIC_RELAXED);
+  t_launch_count += static_cast<unsigned long long>(n);
+}
 
 // Optional per-kernel timing for bench.py's roofline: when profiling is enabled for a kernel id,
 // every launch of that kernel is bracketed by CUDA events on its own stream (api.cu owns the pool).
