@@ -239,6 +239,7 @@ class BeamState:
         assert self.max_candidates > 0
         self.finished: Optional[List[Dict[tuple, float]]] = None
         self.min_gap = float("inf")     # diagnostics: smallest score gap that could reorder candidates
+        self.step_gaps: List[float] = []   # the same, per update() call (margin-gated step-wise parity)
 
     def update(self, tokens: List[List[int]], logits: torch.Tensor, sum_logprobs: torch.Tensor):
         G = self.beam
@@ -250,6 +251,8 @@ class BeamState:
         new_tokens: List[List[int]] = []
         sources: List[int] = []
         newly: List[Dict[tuple, float]] = []
+        gap_before = self.min_gap
+        self.min_gap = float("inf")
         for a in range(n_audio):
             score: Dict[tuple, float] = {}
             origin: Dict[tuple, int] = {}
@@ -286,6 +289,8 @@ class BeamState:
                     break
                 prev[seq] = new[seq]
         completed = all(len(s) >= self.max_candidates for s in self.finished)
+        self.step_gaps.append(self.min_gap)
+        self.min_gap = min(self.min_gap, gap_before)
         return new_tokens, sources, completed
 
     def finalize(self, tokens: List[List[List[int]]], sum_logprobs: torch.Tensor):
@@ -340,6 +345,30 @@ def suppress_list(ids: TokenIds, opt: Options) -> Tuple[int, ...]:
         sup.extend(ids.non_speech)
     sup.extend([ids.transcribe, ids.translate, ids.sot, ids.sot_prev, ids.sot_lm, ids.no_speech])
     return tuple(sorted(set(sup)))
+
+
+def apply_filters(logits: torch.Tensor, tokens: List[List[int]], ids: TokenIds, opt: Options, sample_begin: int,
+                  sup: Sequence[int], mits: Optional[int]) -> None:
+    """The LogitFilter chain in the order DecodingTask builds it (decoding.py:554-570), in place."""
+    if opt.suppress_blank:
+        suppress_blank(logits, tokens, ids, sample_begin)
+    if sup:
+        suppress_tokens(logits, sup)
+    if not opt.without_timestamps:
+        timestamp_rules(logits, tokens, ids, sample_begin, mits)
+
+
+def filter_context(dims: Dict[str, int], opt: Options):
+    """(ids, initial tokens, sample_begin, suppress list, max_initial_timestamp_index) of a task - what
+    apply_filters needs (decoding.py:521-570)."""
+    ids = token_ids(dims["n_vocab"])
+    n_ctx = dims["n_text_ctx"]
+    init = initial_tokens(ids, opt, n_ctx, opt.sample_len or n_ctx // 2)
+    sup = suppress_list(ids, opt) if opt.suppress_tokens else ()
+    mits = None
+    if not opt.without_timestamps and opt.max_initial_timestamp:
+        mits = round(opt.max_initial_timestamp / (30.0 / dims["n_audio_ctx"]))
+    return ids, init, len(init), sup, mits
 
 
 def decode(W: M.Weights, dims: Dict[str, int], mel_or_features: torch.Tensor, opt: Options = Options(),
@@ -398,12 +427,7 @@ def decode(W: M.Weights, dims: Dict[str, int], mel_or_features: torch.Tensor, op
         if record is not None:
             record.setdefault("raw_logits", []).append(logits.clone())
             record.setdefault("tokens_in", []).append([list(t) for t in tokens])
-        if opt.suppress_blank:
-            suppress_blank(logits, tokens, ids, sample_begin)
-        if sup:
-            suppress_tokens(logits, sup)
-        if not opt.without_timestamps:
-            timestamp_rules(logits, tokens, ids, sample_begin, mits)
+        apply_filters(logits, tokens, ids, opt, sample_begin, sup, mits)
         if record is not None:
             record.setdefault("filtered_logits", []).append(logits.clone())
             record.setdefault("sum_logprobs_in", []).append(sum_lp.clone())
@@ -447,6 +471,7 @@ def decode(W: M.Weights, dims: Dict[str, int], mel_or_features: torch.Tensor, op
     if record is not None:
         record["all_margins"] = margins
         record["beam_min_gap"] = beam.min_gap if beam is not None else None
+        record["beam_step_gaps"] = list(beam.step_gaps) if beam is not None else None
     return out
 
 

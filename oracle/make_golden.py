@@ -70,11 +70,21 @@ FULL_LENGTH_CASE = ("greedy_full", dict(), 1)   # default sample_len = 224
 SYNTH = {
     "confident": dict(),
     "diverse": dict(row_sigma=0.0, eot_scale=2.5, timestamp_scale=1.3),
+    # "peaked" = even heavier-tailed token-embedding norms: beam candidates are separated by far more than 16-bit
+    # activation noise (checked with the 16-bit emulation of oracle/model.py: the fp16-rounded trajectory of
+    # beam5 equals the fp32 one for every step), so FREE-RUNNING beam search can be asserted step by step on the GPU
+    "peaked": dict(row_sigma=1.0),
+}
+PEAKED_CASES = {
+    "beam5": (dict(sample_len=24, beam_size=5), 2),
+    "beam5_patience2": (dict(sample_len=24, beam_size=5, patience=2.0), 1),
+    "beam3_lenpen": (dict(sample_len=24, beam_size=3, length_penalty=0.6), 1),
+    "greedy": (dict(sample_len=24), 2),
 }
 
 
 def build_reference_model(name: str, seed: int, regime: str):
-    dims = synthetic.dims_dict(name)
+    dims = synthetic.dims_dict({"test-peak": "test-en"}.get(name, name))
     sd = synthetic.synthetic_state_dict(dims, seed=seed, **SYNTH[regime])
     model = Whisper(ModelDimensions(**dims))
     missing = model.load_state_dict({k: torch.from_numpy(v) for k, v in sd.items()}, strict=True)
@@ -149,7 +159,7 @@ def decode_case(model, mel, opts, n_audio):
                  no_speech_prob=float(r.no_speech_prob)) for r in results]
 
 
-def gen_model(name: str, seed: int, audio_kind: str, full_length: bool, regime: str):
+def gen_model(name: str, seed: int, audio_kind: str, full_length: bool, regime: str, cases=None):
     t0 = time.time()
     model, dims = build_reference_model(name, seed, regime)
     audio = synthetic.synthetic_audio(2, 480000, seed=4321, kind=audio_kind)
@@ -170,7 +180,7 @@ def gen_model(name: str, seed: int, audio_kind: str, full_length: bool, regime: 
     }
     meta = {"name": name, "seed": seed, "audio_seed": 4321, "audio_kind": audio_kind, "dims": dims,
             "regime": regime, "synth_kwargs": SYNTH[regime], "decode": {}}
-    cases = dict(DECODE_CASES)
+    cases = dict(DECODE_CASES if cases is None else cases)
     if full_length:
         cases[FULL_LENGTH_CASE[0]] = (FULL_LENGTH_CASE[1], FULL_LENGTH_CASE[2])
     for cname, (opts, n_audio) in cases.items():
@@ -356,12 +366,16 @@ def gen_state_dict_keys():
 
 def main():
     torch.set_num_threads(os.cpu_count() or 1)
+    if sys.argv[1:] == ["test-peak"]:        # only the round-2 fixture (the others are unchanged since round 1)
+        gen_model("test-peak", seed=21, audio_kind="speechlike", full_length=False, regime="peaked", cases=PEAKED_CASES)
+        return
     gen_static()
     gen_timing()
     gen_mel()
     gen_model("test-en", seed=11, audio_kind="speechlike", full_length=True, regime="confident")
     gen_model("test-multi", seed=12, audio_kind="noise", full_length=True, regime="diverse")
     gen_model("tiny.en", seed=13, audio_kind="speechlike", full_length=False, regime="confident")
+    gen_model("test-peak", seed=21, audio_kind="speechlike", full_length=False, regime="peaked", cases=PEAKED_CASES)
     gen_alignment("test-en", seed=11, regime="confident")
     gen_transcribe("test-multi", seed=12, regime="diverse")
     gen_state_dict_keys()

@@ -14,6 +14,16 @@ import torch
 
 Weights = Dict[str, torch.Tensor]
 
+# Optional emulation of the reference's 16-bit execution (fp16 on CUDA: every module output is rounded to the
+# activation type, matmuls accumulate in fp32, LayerNorm / softmax run in fp32 - model.py:39-50, 124, 247):
+# when set, every op output below is rounded to this dtype.  Used to size parity tolerances and decision-margin
+# gates, and to pick well-conditioned fixtures; None = pure fp32 (the oracle proper).
+ACT_DTYPE: Optional[torch.dtype] = None
+
+
+def _r(x: torch.Tensor) -> torch.Tensor:
+    return x if ACT_DTYPE is None else x.to(ACT_DTYPE).float()
+
 
 def to_weights(state_dict: Dict[str, np.ndarray]) -> Weights:
     return {k: torch.from_numpy(np.ascontiguousarray(v)).float() for k, v in state_dict.items()}
@@ -23,19 +33,19 @@ def layer_norm(x: torch.Tensor, w: torch.Tensor, b: torch.Tensor) -> torch.Tenso
     """model.py:39-41: fp32 LayerNorm over the last dim, eps = nn.LayerNorm default 1e-5."""
     mu = x.mean(-1, keepdim=True)
     var = ((x - mu) ** 2).mean(-1, keepdim=True)
-    return (x - mu) / torch.sqrt(var + 1e-5) * w + b
+    return _r((x - mu) / torch.sqrt(var + 1e-5) * w + b)
 
 
 def gelu(x: torch.Tensor) -> torch.Tensor:
     """Exact (erf) GELU: F.gelu / nn.GELU defaults used at model.py:156,193-194."""
-    return 0.5 * x * (1.0 + torch.erf(x * (1.0 / math.sqrt(2.0))))
+    return _r(0.5 * x * (1.0 + torch.erf(x * (1.0 / math.sqrt(2.0)))))
 
 
 def linear(x: torch.Tensor, W: Weights, prefix: str) -> torch.Tensor:
     """model.py:44-50; `key` projections have no bias (model.py:88)."""
     y = x @ W[prefix + ".weight"].T
     b = W.get(prefix + ".bias")
-    return y if b is None else y + b
+    return _r(y if b is None else y + b)
 
 
 def conv1d_k3(x: torch.Tensor, w: torch.Tensor, b: torch.Tensor, stride: int) -> torch.Tensor:
@@ -48,7 +58,7 @@ def conv1d_k3(x: torch.Tensor, w: torch.Tensor, b: torch.Tensor, stride: int) ->
     for k in range(3):
         seg = xp[:, :, k: k + stride * (T_out - 1) + 1: stride]       # (B, C_in, T_out)
         y = y + torch.einsum("oc,bct->bot", w[:, :, k], seg)
-    return y + b[None, :, None]
+    return _r(y + b[None, :, None])
 
 
 def attention(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, n_head: int,
@@ -69,7 +79,7 @@ def attention(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, n_head: int,
         kpos = torch.arange(Tk)[None, :]
         qk = qk.masked_fill(kpos > qpos, float("-inf"))
     w = torch.softmax(qk.float(), dim=-1)
-    out = (w @ vh).permute(0, 2, 1, 3).reshape(B, Tq, D)
+    out = _r((w @ vh).permute(0, 2, 1, 3).reshape(B, Tq, D))
     return out, qk
 
 
@@ -82,7 +92,7 @@ def encoder_forward(W: Weights, dims: Dict[str, int], mel: torch.Tensor,
     x = gelu(conv1d_k3(x, W["encoder.conv2.weight"], W["encoder.conv2.bias"], 2))
     x = x.permute(0, 2, 1)
     assert x.shape[1:] == W["encoder.positional_embedding"].shape, "incorrect audio shape"  # model.py:197
-    x = x + W["encoder.positional_embedding"]
+    x = _r(x + W["encoder.positional_embedding"])
     if collect is not None:
         collect["stem"] = x
     H = dims["n_audio_head"]
@@ -91,9 +101,9 @@ def encoder_forward(W: Weights, dims: Dict[str, int], mel: torch.Tensor,
         h = layer_norm(x, W[p + ".attn_ln.weight"], W[p + ".attn_ln.bias"])
         a, _ = attention(linear(h, W, p + ".attn.query"), linear(h, W, p + ".attn.key"),
                          linear(h, W, p + ".attn.value"), H, causal=False)
-        x = x + linear(a, W, p + ".attn.out")
+        x = _r(x + linear(a, W, p + ".attn.out"))
         h = layer_norm(x, W[p + ".mlp_ln.weight"], W[p + ".mlp_ln.bias"])
-        x = x + linear(gelu(linear(h, W, p + ".mlp.0")), W, p + ".mlp.2")
+        x = _r(x + linear(gelu(linear(h, W, p + ".mlp.0")), W, p + ".mlp.2"))
         if collect is not None:
             collect[f"block{i}"] = x
     return layer_norm(x, W["encoder.ln_post.weight"], W["encoder.ln_post.bias"])
@@ -128,8 +138,8 @@ def decoder_forward(W: Weights, dims: Dict[str, int], tokens: torch.Tensor, xa: 
     """TextDecoder.forward, model.py:227-249.  tokens: (R, n) int64, xa: (B_or_R, 1500, d);
     returns fp32 logits (R, n, V).  With a cache, `tokens` are the new positions only."""
     offset = cache.length if cache is not None else 0                                  # model.py:234
-    x = W["decoder.token_embedding.weight"][tokens] + \
-        W["decoder.positional_embedding"][offset: offset + tokens.shape[-1]]           # model.py:235-238
+    x = _r(W["decoder.token_embedding.weight"][tokens] +
+           W["decoder.positional_embedding"][offset: offset + tokens.shape[-1]])        # model.py:235-238
     H = dims["n_text_head"]
     for i in range(dims["n_text_layer"]):
         p = f"decoder.blocks.{i}"
@@ -141,7 +151,7 @@ def decoder_forward(W: Weights, dims: Dict[str, int], tokens: torch.Tensor, xa: 
                 v_new = torch.cat([cache.self_v[i], v_new], dim=1)
             cache.self_k[i], cache.self_v[i] = k_new, v_new
         a, _ = attention(linear(h, W, p + ".attn.query"), k_new, v_new, H, causal=True)  # model.py:124-127
-        x = x + linear(a, W, p + ".attn.out")
+        x = _r(x + linear(a, W, p + ".attn.out"))
         h = layer_norm(x, W[p + ".cross_attn_ln.weight"], W[p + ".cross_attn_ln.bias"])
         if cache is not None and cache.cross_k[i] is not None:                          # model.py:106-109
             ck, cv = cache.cross_k[i], cache.cross_v[i]
@@ -152,8 +162,8 @@ def decoder_forward(W: Weights, dims: Dict[str, int], tokens: torch.Tensor, xa: 
         a, qk = attention(linear(h, W, p + ".cross_attn.query"), ck, cv, H, causal=False)
         if collect_qk is not None:
             collect_qk.append(qk)
-        x = x + linear(a, W, p + ".cross_attn.out")
+        x = _r(x + linear(a, W, p + ".cross_attn.out"))
         h = layer_norm(x, W[p + ".mlp_ln.weight"], W[p + ".mlp_ln.bias"])
-        x = x + linear(gelu(linear(h, W, p + ".mlp.0")), W, p + ".mlp.2")
+        x = _r(x + linear(gelu(linear(h, W, p + ".mlp.0")), W, p + ".mlp.2"))
     x = layer_norm(x, W["decoder.ln.weight"], W["decoder.ln.bias"])
     return (x @ W["decoder.token_embedding.weight"].T).float()                         # model.py:245-247

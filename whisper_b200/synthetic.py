@@ -53,9 +53,12 @@ def round_to_16bit_common(x: np.ndarray) -> np.ndarray:
     """Round fp32 to an 8-bit significand (bf16, round-to-nearest-even) and flush |x| < 2^-14 to 0,
     so the value is exact in both bf16 and fp16."""
     x = np.ascontiguousarray(x, dtype=np.float32)
-    u = x.view(np.uint32).astype(np.uint64)
-    u = (u + 0x7FFF + ((u >> 16) & 1)) & 0xFFFF0000
-    y = u.astype(np.uint32).view(np.float32).copy()
+    u = x.view(np.uint32).copy()                 # finite inputs only: the +0x7FFF cannot carry out of 32 bits
+    lsb = (u >> np.uint32(16)) & np.uint32(1)
+    u += np.uint32(0x7FFF)
+    u += lsb
+    u &= np.uint32(0xFFFF0000)
+    y = u.view(np.float32)
     y[np.abs(y) < 2.0 ** -14] = 0.0
     np.clip(y, -60000.0, 60000.0, out=y)
     return y
