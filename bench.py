@@ -54,9 +54,6 @@ def parse():
     ap.add_argument("--dtype", default="bf16", choices=["bf16", "fp16"])
     ap.add_argument("--decode-steps", type=int, default=DECODE_STEPS)
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--decode-streams", type=int, default=1,
-                    help="split each rank's batch into this many concurrent decoder sessions (model.decode_streams); "
-                         "1 = one session, the configuration every number in profiles/ was measured with")
     ap.add_argument("--breakdown", action="store_true",
                     help="after the timed region, run one extra plain-launch step per kernel class with per-launch "
                          "CUDA events and report each class's total device time (diagnostic, not part of `value`)")
@@ -256,7 +253,6 @@ def main():
     sd = synthetic.synthetic_state_dict(dims, seed=0) if rank == 0 else None
     sd_dev = parallel.broadcast_state_dict(sd, spec, dev)
     model = wb.Whisper(wb.ModelDimensions(**dims), sd_dev, device=dev, dtype=dtype)
-    model.decode_streams = max(1, args.decode_streams)
     del sd, sd_dev
     torch.cuda.empty_cache()
 
@@ -317,8 +313,6 @@ def main():
     # (the timed steps above replay it from CUDA graphs, where per-launch events cannot be interleaved).
     import ctypes
 
-    # per-launch event timing keeps its records in process-wide state: the profiled steps always run as one session
-    model.decode_streams = 1
     lib.wb200_profile_enable(1)
     ms_prof, _ = timed(step_resident, 1)
     prof_ms, prof_n = ctypes.c_double(0), ctypes.c_int64(0)
@@ -340,7 +334,6 @@ def main():
             lib.wb200_profile_enable(0)
             breakdown[name] = {"ms": t_k.value, "launches": int(n_k.value), "step_ms": ms_k}
 
-    model.decode_streams = max(1, args.decode_streams)
     e2e_steps = max(1, min(args.steps, 3))
     step_e2e()
     ms_e2e, _ = timed(step_e2e, e2e_steps)
@@ -376,7 +369,6 @@ def main():
             "parallelism": f"dp{world} (replicated weights, segments sharded, no per-step collective)",
             "l2": "per-step working set (cross-K/V 15.7 GB + self-K/V) far exceeds the 126 MB L2; no flush needed",
             "tokens_per_segment": int(np.mean(n_tokens)),
-            "decode_streams": max(1, args.decode_streams),
         },
         "clocks": clocks,
         "e2e": {"value": e2e_value, "unit": "x realtime", "h2d_bytes_per_step": B * N_SAMPLES * 4,

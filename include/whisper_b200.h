@@ -44,6 +44,7 @@ uint64_t wb200_launch_count(void);
 #define WB200_KERNEL_LAYERNORM 5
 #define WB200_KERNEL_SELECT 6
 #define WB200_KERNEL_LOG_MEL 7
+#define WB200_KERNEL_DECODER_LAYER 8   /* fused decoder-layer GEMM chain (LayerNorm folded in), csrc/dec_layer.cu */
 int wb200_profile_enable(int kernel_id);
 int wb200_profile_read(double* total_ms, int64_t* launches);
 
@@ -67,17 +68,18 @@ int wb200_set_bm64(int enabled);
  * default (WB200_PDL=0 in the environment or this call turns it off).  Each of those kernels may be scheduled while
  * its predecessor drains and waits (griddepcontrol.wait) before it touches global memory. */
 int wb200_set_pdl(int enabled);
-/* With programmatic dependent launch on, let the engine's GEMMs issue the WEIGHT half of their first pipeline
- * stages before they wait for the previous kernel (model weights never change while the engine runs; activations
- * still wait).  Default 0 (or WB200_GEMM_EARLY_B=1).  Affects only launches made by the engine - wb200_linear on
- * caller tensors never assumes its weights are constant.  (Built in round 1, not yet measured on hardware.) */
-int wb200_set_gemm_early_weights(int enabled);
+/* Fused decoder-layer kernel for the autoregressive step (ResidualAttentionBlock, whisper/model.py:142-171, as driven
+ * per token by decoding.py:680-710): the six Linears and three LayerNorms of a layer run as three persistent launches
+ * (QKV | out-proj + cross-query | cross-out + MLP + next layer's QKV) around the two attention kernels, LayerNorm folded
+ * into the consuming Linear.  On by default for sessions created AFTER the call (WB200_FUSED_LAYER=0 in the environment
+ * or this call turns it off; the unfused kernels then run, as they always do for the prefill). */
+int wb200_set_fused_decoder_layer(int enabled);
 /* Layout of the decoder's kv caches for sessions created AFTER the call (default 0, or WB200_KV_HEAD_MAJOR=1 in
  * the environment).  0: cross-attention K/V [n_audio, 1500, 2d] and self-attention caches [rows, 448, d], i.e. one
  * head's 128 bytes per position are strided by the model width.  1: head-major - cross K/V [n_audio, 2H, 1500, 64]
  * (written that way by the K/V projection's epilogue), self caches [rows, H, 448, 64] - so every (audio, head) /
  * (row, head) pair streams one contiguous block.  Results are identical bit for bit; only the HBM access pattern
- * of the two decode-attention kernels changes.  (Built in round 1, not yet measured on hardware.) */
+ * of the two decode-attention kernels changes (measured on B200: +1 %, profiles/r2_ab_switches.txt). */
 int wb200_set_kv_head_major(int enabled);
 
 /* Same operator with split-K enabled for skinny problems (the 320-row decode-step GEMMs): `workspace`
@@ -134,9 +136,13 @@ int wb200_log_mel(const float* audio, int n_audio, int64_t n_samples, int n_mels
  *   per encoder layer (12): attn_ln.w F, attn_ln.b F, qkv.w T[3d,d] (query|key|value), qkv.b T[3d]
  *                (key part zero: model.py:88), out.w T, out.b T, mlp_ln.w F, mlp_ln.b F,
  *                fc1.w T[4d,d], fc1.b T, fc2.w T[d,4d], fc2.b T
- *   per decoder layer (20): attn_ln.w/b F, qkv.w T, qkv.b T, out.w T, out.b T, cross_ln.w/b F,
+ *   per decoder layer (29): attn_ln.w/b F, qkv.w T, qkv.b T, out.w T, out.b T, cross_ln.w/b F,
  *                cq.w T[d,d], cq.b T, ckv.w T[2d,d] (key|value), ckv.b T[2d] (key part zero),
- *                cout.w T, cout.b T, mlp_ln.w/b F, fc1.w T, fc1.b T, fc2.w T, fc2.b T
+ *                cout.w T, cout.b T, mlp_ln.w/b F, fc1.w T, fc1.b T, fc2.w T, fc2.b T,
+ *                then the LayerNorm-folded forms used by the fused decoder-layer kernel, for each of
+ *                (attn_ln -> qkv), (cross_ln -> cq), (mlp_ln -> fc1):  wf T = W * gamma (per input column),
+ *                c1 F[out] = row sums of wf (as stored in T), c2 F[out] = W beta + bias:
+ *                qkv.wf, qkv.c1, qkv.c2, cq.wf, cq.c1, cq.c2, fc1.wf, fc1.c1, fc1.c2
  * The handle stores the pointers only; the caller keeps the tensors alive until destroy.
  * Replaces the nn.Module state of whisper/model.py:252-276 (and the per-call weight casts of
  * model.py:44-59). */

@@ -96,7 +96,9 @@ def gen_static():
     os.makedirs(GOLD, exist_ok=True)
     np.savez_compressed(os.path.join(GOLD, "mel_filters.npz"),
                         mel_80=mel_filters("cpu", 80).numpy(), mel_128=mel_filters("cpu", 128).numpy())
-    table = {"languages": list(LANGUAGES.keys())}
+    from whisper.tokenizer import TO_LANGUAGE_CODE
+
+    table = {"languages": list(LANGUAGES.keys()), "language_names": dict(TO_LANGUAGE_CODE)}   # tokenizer.py:10-128
     for key, multilingual, nl in (("gpt2", False, 99), ("multilingual", True, 99)):
         tok = get_tokenizer(multilingual, num_languages=nl, language="en", task="transcribe")
         table[key] = {"non_speech_tokens": list(tok.non_speech_tokens), "blank": tok.encode(" ")}

@@ -1,0 +1,89 @@
+"""GPU: the fused decoder-layer kernel (csrc/dec_layer.cu: LayerNorm folded into the Linears, six Linears of a layer
+in three persistent launches with grid-wide phase barriers) against the unfused round-1 kernels and the fp32 oracle.
+
+The two device paths compute the same reference math (whisper/model.py:142-171) with different roundings - the fused
+path never rounds LN(x) to 16 bits but rounds W (.) gamma once - so they agree to 16-bit activation noise, not bit for
+bit; both must sit inside the oracle tolerance of tests/test_model_gpu.py."""
+import numpy as np
+import pytest
+import torch
+
+from helpers import fixture_inputs, load_model_fixture, oracle_features
+
+pytestmark = pytest.mark.gpu
+
+LOGIT_TOL = {torch.float16: 2.5e-3, torch.bfloat16: 2.5e-2}
+
+
+def _set_fused(on: bool):
+    from whisper_b200 import _lib
+
+    assert _lib.lib().wb200_set_fused_decoder_layer(int(on)) == 0
+
+
+def _teacher_forced_logits(model, g_feats, rec, n_audio, opts):
+    from oracle import parity
+
+    task, sess = parity.open_session(model, opts, n_audio, g_feats)
+    G = task.n_group
+    out = []
+    try:
+        for i in range(len(rec["raw_logits"])):
+            if i > 0:
+                sess.step()
+            out.append(sess.get_logits(n_audio if i == 0 else n_audio * G).float().cpu())
+            ref = rec["raw_logits"][i]
+            sess.set_logits(ref[::G] if i == 0 else ref)
+            sess.select()
+    finally:
+        sess.close()
+    return out
+
+
+@pytest.mark.parametrize("dtype", [torch.float16, torch.bfloat16])
+@pytest.mark.parametrize("name,opts", [("test-en", dict(beam_size=5, sample_len=16)), ("test-multi", dict(sample_len=16)),
+                                       ("tiny.en", dict(beam_size=3, sample_len=12))])
+def test_fused_layer_matches_unfused_and_oracle(name, opts, dtype):
+    import whisper_b200 as wb
+    from oracle import parity
+
+    meta, arrays, dims, W, mel, feats = oracle_features(name)
+    rec = parity.oracle_record(W, dims, feats, opts, 2)
+    _, sd, audio = fixture_inputs(meta)
+    model = wb.Whisper(wb.ModelDimensions(**dims), sd, device="cuda", dtype=dtype)
+    g_mel = torch.stack([wb.log_mel_spectrogram(torch.from_numpy(a).cuda(), dims["n_mels"]) for a in audio])
+    g_feats = model.embed_audio(g_mel)
+    try:
+        _set_fused(False)
+        plain = _teacher_forced_logits(model, g_feats, rec, 2, opts)
+        _set_fused(True)
+        fused = _teacher_forced_logits(model, g_feats, rec, 2, opts)
+    finally:
+        _set_fused(True)
+    worst_pair, worst_ora = 0.0, 0.0
+    for i, (a, b) in enumerate(zip(plain, fused)):
+        assert bool(torch.isfinite(b).all()), f"step {i}: non-finite logits from the fused path"
+        ref = rec["raw_logits"][i]
+        ref = ref[::(opts.get("beam_size") or 1)] if i == 0 else ref
+        scale = float(ref.abs().max())
+        worst_pair = max(worst_pair, float((a - b).abs().max()) / scale)
+        worst_ora = max(worst_ora, float((b - ref).abs().max()) / scale)
+    print(f"{name} {dtype}: fused vs unfused {worst_pair:.5f}, fused vs oracle {worst_ora:.5f} (of max |logit|), {len(fused)} steps")
+    assert worst_ora < LOGIT_TOL[dtype]
+    assert worst_pair < LOGIT_TOL[dtype]
+
+
+def test_fused_layer_is_deterministic():
+    """Grid barriers, LN partial merges and the column split must not make results depend on scheduling."""
+    import whisper_b200 as wb
+
+    meta, _ = load_model_fixture("test-en")
+    dims, sd, audio = fixture_inputs(meta)
+    model = wb.Whisper(wb.ModelDimensions(**dims), sd, device="cuda", dtype=torch.float16)
+    mel = torch.stack([wb.log_mel_spectrogram(torch.from_numpy(a).cuda(), dims["n_mels"]) for a in audio])
+    opt = wb.DecodingOptions(language="en", beam_size=5, sample_len=32)
+    a = model.decode(mel, opt)
+    for _ in range(3):
+        b = model.decode(mel, opt)
+        assert [r.tokens for r in a] == [r.tokens for r in b]
+        assert [r.avg_logprob for r in a] == [r.avg_logprob for r in b]

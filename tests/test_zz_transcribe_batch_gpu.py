@@ -67,25 +67,3 @@ def test_decode_requests_per_row_prompts():
     single = [wb.decode(model, seg, o) for _, o in reqs]
     assert [r.tokens for r in batched] == [r.tokens for r in single]
     assert len({tuple(r.tokens) for r in batched}) >= 1
-
-
-def test_concurrent_decoder_sessions_match_single_session():
-    """model.decode_streams = 2: the batch is decoded by two sessions on two host threads / CUDA streams; every audio
-    must get the tokens the single session gives it."""
-    import whisper_b200 as wb
-
-    model = _model()
-    meta, _ = load_model_fixture("test-en")
-    dims, sd, audio = fixture_inputs(meta)
-    mel = torch.stack([wb.log_mel_spectrogram(torch.from_numpy(a).cuda(), dims["n_mels"]) for a in audio])
-    mel = torch.cat([mel, mel.flip(0)], 0)                      # 4 audios
-    for opts in (dict(beam_size=5, sample_len=24), dict(sample_len=24)):
-        model.decode_streams = 1
-        one = model.decode(mel, wb.DecodingOptions(language="en", **opts))
-        model.decode_streams = 2
-        try:
-            two = model.decode(mel, wb.DecodingOptions(language="en", **opts))
-        finally:
-            model.decode_streams = 1
-        assert [r.tokens for r in one] == [r.tokens for r in two]
-        assert np.allclose([r.avg_logprob for r in one], [r.avg_logprob for r in two], atol=1e-3)

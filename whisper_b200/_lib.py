@@ -22,11 +22,19 @@ class WhisperB200Error(RuntimeError):
     pass
 
 
+EXPORTS_PATH = os.path.join(_HERE, "lib", "exports.txt")
+
+
 def header_symbols() -> List[str]:
-    """Every function name declared in include/whisper_b200.h (used by the ABI export test)."""
-    text = open(HEADER_PATH).read()
-    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
-    return sorted(set(re.findall(r"\b(wb200_[a-z0-9_]+)\s*\(", text)))
+    """Every function name declared in include/whisper_b200.h (used by the ABI export test).  A copy of the package
+    without the repository's include/ directory falls back to lib/exports.txt, the list build.py writes next to the
+    shared library from that same header."""
+    if os.path.exists(HEADER_PATH):
+        text = open(HEADER_PATH).read()
+        text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+        return sorted(set(re.findall(r"\b(wb200_[a-z0-9_]+)\s*\(", text)))
+    with open(EXPORTS_PATH) as f:
+        return sorted(set(f.read().split()))
 
 
 def lib() -> ctypes.CDLL:

@@ -82,6 +82,13 @@ def build_library(force: bool = False, verbose: bool = False) -> str:
         if r.returncode != 0:
             sys.stderr.write(r.stdout + r.stderr)
             raise RuntimeError("link of libwhisper_b200.so failed")
+    # the export list the ctypes binder falls back to when the package is used without the repository's include/
+    import re
+    hdr = open(os.path.join(os.path.dirname(ROOT), "include", "whisper_b200.h")).read()
+    hdr = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)
+    names = sorted(set(re.findall(r"\b(wb200_[a-z0-9_]+)\s*\(", hdr)))
+    with open(os.path.join(LIBDIR, "exports.txt"), "w") as f:
+        f.write("\n".join(names) + "\n")
     return LIBPATH
 
 

@@ -113,8 +113,8 @@ int wb200_set_kv_head_major(int enabled) {
   return 0;
 }
 
-int wb200_set_gemm_early_weights(int enabled) {
-  g_gemm_early_b = enabled ? 1 : 0;
+int wb200_set_fused_decoder_layer(int enabled) {
+  g_fused_layer = enabled ? 1 : 0;
   return 0;
 }
 

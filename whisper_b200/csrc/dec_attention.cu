@@ -570,11 +570,8 @@ template <typename T, int U, int ST>
 static int launch_sa(const SelfParams& p, int n_rows, int n_head, int wpc, cudaStream_t s) {
   auto kern = self_attention_kernel<T, U, ST>;
   const int smem = wpc * ST * U * 1024;
-  static int attr_smem = 0;
-  if (smem > attr_smem) {
-    if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess) return 44;
-    attr_smem = smem;
-  }
+  static SmemOptIn optin;
+  if (!optin.ensure(kern, smem)) return 44;
   const int n_pairs = n_rows * n_head;
   return launch_pdl(kern, dim3((n_pairs + wpc - 1) / wpc), dim3(wpc * 32), smem, s, p, n_rows, n_head) == cudaSuccess ? 0 : 43;
 }
@@ -665,12 +662,8 @@ int launch_cross_attention(int dtype, const void* q, const void* k, const void* 
 #define WB_XATTN(TT, ST)                                                                                   \
   {                                                                                                        \
     auto kern = cross_attention_kernel<TT, ST>;                                                            \
-    static bool attr = false;                                                                              \
-    if (!attr) {                                                                                           \
-      if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess)    \
-        return 40;                                                                                         \
-      attr = true;                                                                                         \
-    }                                                                                                      \
+    static SmemOptIn optin;                                                                                \
+    if (!optin.ensure(kern, smem)) return 40;                                                              \
     if (launch_pdl(kern, grid, dim3(kDaThreads), smem, s, p) != cudaSuccess) return 41;                   \
   }
   if (dtype == DT_BF16) {

@@ -1,0 +1,463 @@
+// Fused decoder-layer GEMM chain for the autoregressive step (reference whisper/model.py:142-171,
+// ResidualAttentionBlock.forward, as driven once per generated token by decoding.py:680-710).
+//
+// One step of one layer is 3 LayerNorms and 6 Linears over R = n_audio x beams rows (320 at the headline
+// configuration): ~46 MB of weights against 0.8 MB of activations.  Launched one by one (round 1) every Linear
+// paid a launch, a prologue (barrier init, TMEM allocation, descriptor fetch), a cold pipeline and a tail: ~10-18 us
+// each for 0.5-2 us worth of HBM traffic, plus ~6 us per LayerNorm.  Here a run of consecutive Linears is ONE
+// persistent kernel (one CTA per SM) that walks through them as PHASES separated by a grid-wide barrier
+// (1.3 us measured on B200, tools/microbench.cu):
+//
+//   * LayerNorm never runs as a pass of its own.  For y = LN(x) W^T + b the kernel multiplies the RAW residual rows by
+//     W' = W (.) gamma (folded once at load time) and finishes in the epilogue:
+//         y[r, n] = rstd_r * (acc[r, n] - mean_r * c1[n]) + c2[n],   c1 = sum_k W'[n, k],  c2 = W beta + b
+//     The row statistics come from the PRODUCER of x: the epilogue that writes the residual stream also writes, per
+//     row and per column slice, a (count, mean, M2) partial, and the consumer merges the ~30 partials of a row with
+//     Chan's formula - no re-read of the activations, no extra launch, fp32 throughout like nn.LayerNorm
+//     (model.py:39-41).
+//   * Work split of a phase: the R rows are cut into 64-row blocks (UMMA M = 64); the CTAs assigned to a row block
+//     split the N output features evenly in units of 16 columns, so every CTA streams its own weight slab exactly
+//     once plus one 64-row activation block: bytes per CTA = 2K (64 + N / ctas_per_block), the minimum over tile
+//     shapes for 148 CTAs, and all SMs pull weights concurrently.
+//   * Roles per CTA (384 threads): warp 0 = TMA producer (activation block + weight slab through one smem ring that
+//     lives across phases), warp 1 = tcgen05.mma issuer (accumulator 64 x <=192 fp32 in TMEM, two buffers), warp 2 =
+//     TMEM allocator, warp 3 = grid-barrier poller, warps 4-11 = epilogue (tcgen05.ld -> LN fold / bias / erf-GELU /
+//     residual add / LN partials -> global).
+//
+// Phases of a decoder layer (engine.cu strings them together; the two attention kernels stay separate launches):
+//     [QKV] | self-attention | [out-proj + residual, cross-query] | cross-attention |
+//     [cross-out + residual, fc1 + GELU, fc2 + residual, QKV of the NEXT layer]
+#include <stdio.h>
+#include <stdlib.h>
+
+#include "dec_layer.h"
+#include "kernels.h"
+#include "ptx.cuh"
+#include "tmap.cuh"
+
+namespace wb {
+
+int g_fused_layer = -1;   // -1: read WB200_FUSED_LAYER on first use; wb200_set_fused_decoder_layer() overrides
+
+constexpr int kDLThreads = 384;
+constexpr int kDLASub = 64 * 128;                    // 64 rows x 64 x 16-bit
+constexpr int kDLBSub = kDLMaxUnits * kDLUnit * 128;   // weight rows x 64 x 16-bit
+constexpr int kDLTmemCols = 512;                     // two accumulator buffers of 256 columns
+
+template <int KS, int STAGES>
+struct DLCfg {
+  static constexpr int kStageBytes = KS * (kDLASub + kDLBSub);
+  static constexpr int kTileBytes = STAGES * kStageBytes;
+  // tail: barriers (full, empty, tmem_full[2], tmem_empty[2], ready[kDLMaxPhases]) + tmem pointer + LN scratch
+  static constexpr int kTailBytes = 8 * (2 * STAGES + 4 + kDLMaxPhases) + 16 + 2 * 64 * 16 + 64;
+  static constexpr int kSmemBytes = kTileBytes + kTailBytes + 1024;
+};
+
+// bounded waits: a protocol bug must end in a trap (an error the host sees), never in a hung GPU
+__device__ __forceinline__ void dl_mbar_wait(uint64_t* bar, uint32_t parity) {
+  for (long long i = 0; i < (1ll << 28); ++i)
+    if (mbar_try_wait(bar, parity)) return;
+  __trap();
+}
+
+__device__ __forceinline__ void fence_proxy_async_global() { asm volatile("fence.proxy.async.global;" ::: "memory"); }
+
+// (count, mean, M2) merge of two disjoint samples (Chan et al.)
+__device__ __forceinline__ void chan_merge(float& n, float& mean, float& m2, float nb, float meanb, float m2b) {
+  if (nb == 0.f) return;
+  const float nt = n + nb;
+  const float delta = meanb - mean;
+  const float f = nb / nt;
+  mean = fmaf(delta, f, mean);
+  m2 = m2 + m2b + delta * delta * n * f;
+  n = nt;
+}
+
+template <typename T, int KS, int STAGES>
+__global__ void __launch_bounds__(kDLThreads, 1)
+dec_layer_kernel(const DLParams P, const __grid_constant__ DLMaps M) {
+  using Cfg = DLCfg<KS, STAGES>;
+  pdl_launch_dependents();
+  extern __shared__ uint8_t dl_smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(dl_smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
+  uint8_t* tiles = smem;
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + Cfg::kTileBytes);
+  uint64_t* empty_bar = full_bar + STAGES;
+  uint64_t* tmem_full = empty_bar + STAGES;
+  uint64_t* tmem_empty = tmem_full + 2;
+  uint64_t* ready_bar = tmem_empty + 2;
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(ready_bar + kDLMaxPhases);
+  float4* s_stats = reinterpret_cast<float4*>(tmem_ptr_smem + 4);      // [2][64] (count, mean, M2, -)
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int grid = gridDim.x;
+  const int cta = blockIdx.x;
+
+  if (warp == 0 && lane == 0) {
+    for (int p = 0; p < P.n_phases; ++p) {
+      tma_prefetch_desc(&M.a[p]);
+      tma_prefetch_desc(&M.b_main[p]);
+      tma_prefetch_desc(&M.b_unit[p]);
+    }
+  }
+  if (warp == 1 && lane == 0) {
+    for (int i = 0; i < STAGES; ++i) {
+      mbar_init(&full_bar[i], 1);
+      mbar_init(&empty_bar[i], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&tmem_full[i], 1);
+      mbar_init(&tmem_empty[i], 256);
+    }
+    for (int i = 0; i < kDLMaxPhases; ++i) mbar_init(&ready_bar[i], 1);
+    mbar_fence_init();
+  }
+  if (warp == 2) {
+    tmem_alloc(tmem_ptr_smem, kDLTmemCols);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr_smem;
+  pdl_wait();       // everything above overlaps the tail of the previous kernel
+  const bool skip = P.skip_flag && *P.skip_flag;
+  const int n_phases = skip ? 0 : P.n_phases;
+
+  // this CTA's share of a phase: row block m, columns [u0, u0 + nu) in units of 16
+  const int m_blk = cta % P.m_tiles;
+  const int slot = cta / P.m_tiles;
+  const int n_slots = (grid - m_blk + P.m_tiles - 1) / P.m_tiles;
+  auto share = [&](int p, int& u0, int& nu) {
+    const int total = P.ph[p].N / kDLUnit;
+    u0 = static_cast<int>(static_cast<long long>(slot) * total / n_slots);
+    nu = static_cast<int>(static_cast<long long>(slot + 1) * total / n_slots) - u0;
+  };
+
+  if (warp == 0 && lane == 0) {
+    // ===================== TMA producer =====================
+    int stage = 0;
+    uint32_t par = 0;
+    for (int p = 0; p < n_phases; ++p) {
+      int u0, nu;
+      share(p, u0, nu);
+      if (p > 0) {
+        dl_mbar_wait(&ready_bar[p], 0);      // the previous phase's outputs are complete grid-wide
+        fence_proxy_async_global();          // generic-proxy writes of other CTAs -> this thread's async-proxy (TMA) reads
+      }
+      if (nu == 0) continue;
+      const DLPhase& ph = P.ph[p];
+      const int kblocks = (ph.K + 63) / 64;
+      const int groups = (kblocks + KS - 1) / KS;
+      const uint32_t bytes = static_cast<uint32_t>(KS) * (kDLASub + nu * kDLUnit * 128);
+      const int box_units = ph.units_box;
+      for (int g = 0; g < groups; ++g) {
+        dl_mbar_wait(&empty_bar[stage], par ^ 1);
+        mbar_expect_tx(&full_bar[stage], bytes);
+        uint8_t* sa = tiles + stage * Cfg::kStageBytes;
+        uint8_t* sb = sa + KS * kDLASub;
+#pragma unroll
+        for (int sub = 0; sub < KS; ++sub) {       // sub-blocks past K are zero-filled by TMA (full byte count)
+          const int kc = (g * KS + sub) * 64;
+          tma_load_2d(sa + sub * kDLASub, &M.a[p], &full_bar[stage], kc, m_blk * 64);
+          tma_load_2d(sb + sub * kDLBSub, &M.b_main[p], &full_bar[stage], kc, u0 * kDLUnit);
+          for (int e = box_units; e < nu; ++e)
+            tma_load_2d(sb + sub * kDLBSub + e * kDLUnit * 128, &M.b_unit[p], &full_bar[stage], kc, (u0 + e) * kDLUnit);
+        }
+        if (++stage == STAGES) {
+          stage = 0;
+          par ^= 1;
+        }
+      }
+    }
+  } else if (warp == 1 && lane == 0) {
+    // ===================== MMA issuer =====================
+    int stage = 0;
+    uint32_t par = 0;
+    int acc = 0;
+    uint32_t acc_par = 0;
+    for (int p = 0; p < n_phases; ++p) {
+      int u0, nu;
+      share(p, u0, nu);
+      if (nu == 0) continue;
+      const DLPhase& ph = P.ph[p];
+      const int kblocks = (ph.K + 63) / 64;
+      const int groups = (kblocks + KS - 1) / KS;
+      const uint32_t idesc = umma_idesc(Cvt<T>::kUmmaFmt, 64, static_cast<uint32_t>(nu * kDLUnit), 0, 0);
+      dl_mbar_wait(&tmem_empty[acc], acc_par ^ 1);
+      tc_fence_after();
+      const uint32_t d_tmem = tmem_base + acc * 256;
+      for (int g = 0; g < groups; ++g) {
+        dl_mbar_wait(&full_bar[stage], par);
+        tc_fence_after();
+        const uint32_t sa = smem_u32(tiles + stage * Cfg::kStageBytes);
+        const uint32_t sb = sa + KS * kDLASub;
+#pragma unroll
+        for (int sub = 0; sub < KS; ++sub) {
+          const uint64_t adesc = umma_desc_sw128(sa + sub * kDLASub, 16, 1024);
+          const uint64_t bdesc = umma_desc_sw128(sb + sub * kDLBSub, 16, 1024);
+#pragma unroll
+          for (int k = 0; k < 4; ++k)
+            umma_f16(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (g != 0) || (sub != 0) || (k != 0));
+        }
+        umma_commit(&empty_bar[stage]);
+        if (++stage == STAGES) {
+          stage = 0;
+          par ^= 1;
+        }
+      }
+      umma_commit(&tmem_full[acc]);
+      acc ^= 1;
+      if (acc == 0) acc_par ^= 1;
+    }
+  } else if (warp == 3 && lane == 0) {
+    // ===================== grid-barrier poller =====================
+    for (int p = 1; p < n_phases; ++p) {
+      const unsigned int target = static_cast<unsigned int>(p) * static_cast<unsigned int>(grid);
+      long long spins = 0;
+      while (true) {
+        unsigned int v;
+        asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(P.sync) : "memory");
+        if (v >= target) break;
+        if (++spins > (1ll << 27)) __trap();
+      }
+      mbar_arrive(&ready_bar[p]);
+    }
+  } else if (warp >= 4) {
+    // ===================== epilogue =====================
+    // UMMA M = 64: accumulator row i sits in lane (i % 16) of TMEM quadrant i / 16, so lanes 16-31 of every warp idle.
+    const int ct = threadIdx.x - 128;
+    const int quad = warp & 3;
+    const int half = (warp - 4) >> 2;
+    const int trow = quad * 16 + lane;                // row inside the 64-row block
+    const long long grow = static_cast<long long>(m_blk) * 64 + trow;
+    const bool row_ok = lane < 16 && grow < P.R;
+    int acc = 0;
+    uint32_t acc_par = 0;
+    for (int p = 0; p < n_phases; ++p) {
+      int u0, nu;
+      share(p, u0, nu);
+      const DLPhase& ph = P.ph[p];
+      if (p > 0) dl_mbar_wait(&ready_bar[p], 0);
+      // ---- LayerNorm statistics of this row from the partials its producer left (model.py:39-41, eps 1e-5)
+      float mean = 0.f, rstd = 0.f;
+      if ((ph.flags & DL_FOLD) && row_ok) {
+        const int slots = (p == 0 && P.ln_slots_in > 0) ? P.ln_slots_in : n_slots;
+        float n = 0.f, m2 = 0.f;
+        for (int s0 = 0; s0 < slots; s0 += 8) {
+          float4 part[8];
+#pragma unroll
+          for (int j = 0; j < 8; ++j)
+            part[j] = (s0 + j < slots) ? __ldcg(P.ln_part + static_cast<long long>(s0 + j) * P.ln_ld + grow)
+                                       : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) chan_merge(n, mean, m2, part[j].x, part[j].y, part[j].z);
+        }
+        rstd = rsqrtf(m2 / n + 1e-5f);
+      }
+      float sn = 0.f, smean = 0.f, sm2 = 0.f;          // LN partial of the values this thread writes
+      if (nu > 0) {
+        dl_mbar_wait(&tmem_full[acc], acc_par);
+        tc_fence_after();
+        const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + acc * 256;
+        for (int e = half; e < nu; e += 2) {
+          uint32_t r[16];
+          tmem_ld16(taddr + e * kDLUnit, r);
+          tmem_ld_wait();
+          if (row_ok) {
+            const int nb = (u0 + e) * kDLUnit;
+            float v[16];
+#pragma unroll
+            for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(r[j]);
+            if (ph.flags & DL_FOLD) {
+#pragma unroll
+              for (int q = 0; q < 4; ++q) {
+                const float4 a = __ldg(reinterpret_cast<const float4*>(ph.c1 + nb) + q);
+                const float4 b = __ldg(reinterpret_cast<const float4*>(ph.c2 + nb) + q);
+                v[q * 4 + 0] = fmaf(rstd, v[q * 4 + 0] - mean * a.x, b.x);
+                v[q * 4 + 1] = fmaf(rstd, v[q * 4 + 1] - mean * a.y, b.y);
+                v[q * 4 + 2] = fmaf(rstd, v[q * 4 + 2] - mean * a.z, b.z);
+                v[q * 4 + 3] = fmaf(rstd, v[q * 4 + 3] - mean * a.w, b.w);
+              }
+            } else {
+              const T* bias = reinterpret_cast<const T*>(ph.bias) + nb;
+#pragma unroll
+              for (int q = 0; q < 2; ++q) {
+                const uint4 u = __ldg(reinterpret_cast<const uint4*>(bias) + q);
+                const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                  const float2 f = Cvt<T>::unpack2(w[i]);
+                  v[q * 8 + i * 2] += f.x;
+                  v[q * 8 + i * 2 + 1] += f.y;
+                }
+              }
+            }
+            if (ph.flags & DL_GELU) {
+#pragma unroll
+              for (int j = 0; j < 16; ++j) v[j] = gelu_erf(round_to<T>(v[j]));
+            }
+            T* out = reinterpret_cast<T*>(ph.out) + grow * ph.ldo + nb;
+            if (ph.flags & DL_RESID) {
+#pragma unroll
+              for (int q = 0; q < 2; ++q) {
+                const uint4 u = __ldcg(reinterpret_cast<const uint4*>(out) + q);
+                const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                  const float2 f = Cvt<T>::unpack2(w[i]);
+                  v[q * 8 + i * 2] = round_to<T>(v[q * 8 + i * 2]) + f.x;
+                  v[q * 8 + i * 2 + 1] = round_to<T>(v[q * 8 + i * 2 + 1]) + f.y;
+                }
+              }
+            }
+            uint32_t pk[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) pk[i] = Cvt<T>::pack2(v[2 * i], v[2 * i + 1]);
+            *reinterpret_cast<uint4*>(out) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+            *(reinterpret_cast<uint4*>(out) + 1) = make_uint4(pk[4], pk[5], pk[6], pk[7]);
+            if (ph.flags & DL_STATS) {
+              // statistics of the STORED (16-bit rounded) values: what the next LayerNorm would read
+              float w16[16], cs = 0.f;
+#pragma unroll
+              for (int i = 0; i < 8; ++i) {
+                const float2 f = Cvt<T>::unpack2(pk[i]);
+                w16[2 * i] = f.x;
+                w16[2 * i + 1] = f.y;
+                cs += f.x + f.y;
+              }
+              const float cm = cs * (1.0f / 16.0f);
+              float c2 = 0.f;
+#pragma unroll
+              for (int i = 0; i < 16; ++i) {
+                const float t = w16[i] - cm;
+                c2 = fmaf(t, t, c2);
+              }
+              chan_merge(sn, smean, sm2, 16.f, cm, c2);
+            }
+          }
+        }
+        tc_fence_before();
+        mbar_arrive(&tmem_empty[acc]);
+        acc ^= 1;
+        if (acc == 0) acc_par ^= 1;
+      }
+      if (ph.flags & DL_STATS) {
+        if (lane < 16) s_stats[half * 64 + trow] = make_float4(sn, smean, sm2, 0.f);
+        asm volatile("bar.sync 1, 256;" ::: "memory");
+        if (ct < 64) {
+          const float4 a = s_stats[ct], b = s_stats[64 + ct];
+          float n = a.x, mu = a.y, m2 = a.z;
+          chan_merge(n, mu, m2, b.x, b.y, b.z);
+          __stcg(P.ln_part + static_cast<long long>(slot) * P.ln_ld + m_blk * 64 + ct, make_float4(n, mu, m2, 0.f));
+        }
+      }
+      if (p + 1 < n_phases) {
+        // publish this CTA's outputs: every writer orders its stores against later async-proxy (TMA) readers, the CTA
+        // barrier collects them, one thread releases them at gpu scope and arrives on the grid counter
+        fence_proxy_async_global();
+        asm volatile("bar.sync 1, 256;" ::: "memory");
+        if (ct == 0) {
+          __threadfence();
+          asm volatile("red.release.gpu.global.add.u32 [%0], %1;" ::"l"(P.sync), "r"(1u) : "memory");
+        }
+      }
+    }
+    // the last CTA out re-arms the counters for the next launch (which cannot touch them before this grid is complete)
+    if (ct == 0 && n_phases > 1) {
+      const unsigned int prev = atomicAdd(P.sync + 1, 1u);
+      if (prev == static_cast<unsigned int>(grid) - 1) {
+        P.sync[0] = 0;
+        P.sync[1] = 0;
+        __threadfence();
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) tmem_dealloc(tmem_base, kDLTmemCols);
+}
+
+// -------------------------------------------------------------------------------------------------
+// host side
+// -------------------------------------------------------------------------------------------------
+int dl_grid_size() { return sm_count(); }
+
+bool dl_supported(int R, int d, int grid) {
+  if (R <= 0 || d % 64 != 0 || grid <= 0) return false;
+  const int m_tiles = (R + 63) / 64;
+  if (m_tiles > grid) return false;
+  const int min_slots = grid / m_tiles;                       // fewest CTAs a row block gets
+  const int widest = 4 * d / kDLUnit;                          // fc1
+  return (widest + min_slots - 1) / min_slots <= kDLMaxUnits;
+}
+
+int dl_fill_phase(DLLaunch& L, int idx, int dtype, int R, int grid, const void* A, long long lda, const void* W, int N, int K,
+                  const void* bias, const float* c1, const float* c2, int flags, void* out, long long ldo) {
+  if (idx >= kDLMaxPhases || N % kDLUnit || K % 8) return 1;
+  DLPhase& ph = L.p.ph[idx];
+  ph.N = N;
+  ph.K = K;
+  ph.flags = flags;
+  ph.bias = bias;
+  ph.c1 = c1;
+  ph.c2 = c2;
+  ph.out = out;
+  ph.ldo = ldo;
+  const int m_tiles = (R + 63) / 64;
+  const int max_slots = (grid + m_tiles - 1) / m_tiles;
+  int box = (N / kDLUnit) / max_slots;                          // every CTA owns at least this many units
+  if (box < 1) box = 1;
+  ph.units_box = box;
+  {
+    uint64_t dims[2] = {static_cast<uint64_t>(K), static_cast<uint64_t>(R)};
+    uint64_t strides[1] = {static_cast<uint64_t>(lda * 2)};
+    uint32_t bx[2] = {64, 64};
+    if (make_tmap_16bit(&L.maps.a[idx], dtype, A, 2, dims, strides, bx)) return 2;
+  }
+  {
+    uint64_t dims[2] = {static_cast<uint64_t>(K), static_cast<uint64_t>(N)};
+    uint64_t strides[1] = {static_cast<uint64_t>(K) * 2};
+    uint32_t bx[2] = {64, static_cast<uint32_t>(box * kDLUnit)};
+    if (make_tmap_16bit(&L.maps.b_main[idx], dtype, W, 2, dims, strides, bx)) return 3;
+    uint32_t bu[2] = {64, kDLUnit};
+    if (make_tmap_16bit(&L.maps.b_unit[idx], dtype, W, 2, dims, strides, bu)) return 4;
+  }
+  return 0;
+}
+
+void dl_init_launch(DLLaunch& L, int dtype, int R, int grid, float4* ln_part, int ln_ld, unsigned int* sync,
+                    const int* skip_flag, int ln_slots_in) {
+  L.dtype = dtype;
+  L.grid = grid;
+  L.p.n_phases = 0;
+  L.p.R = R;
+  L.p.m_tiles = (R + 63) / 64;
+  L.p.ln_slots_in = ln_slots_in;
+  L.p.ln_part = ln_part;
+  L.p.ln_ld = ln_ld;
+  L.p.sync = sync;
+  L.p.skip_flag = skip_flag;
+}
+
+template <typename T>
+static int dl_launch_t(const DLLaunch& L, cudaStream_t s) {
+  constexpr int KS = 2, STAGES = 3;
+  using Cfg = DLCfg<KS, STAGES>;
+  auto kern = dec_layer_kernel<T, KS, STAGES>;
+  static SmemOptIn optin;
+  if (!optin.ensure(kern, Cfg::kSmemBytes)) return 60;
+  ProfileScope prof(PROF_DEC_LAYER, s);
+  const cudaError_t le = launch_pdl(kern, dim3(L.grid), dim3(kDLThreads), Cfg::kSmemBytes, s, L.p, L.maps);
+  count_launch();
+  return (le == cudaSuccess && cudaGetLastError() == cudaSuccess) ? 0 : 61;
+}
+
+int dl_launch(const DLLaunch& L, cudaStream_t s) {
+  if (L.p.n_phases <= 0) return 0;
+  return L.dtype == DT_BF16 ? dl_launch_t<__nv_bfloat16>(L, s) : dl_launch_t<__half>(L, s);
+}
+
+}  // namespace wb

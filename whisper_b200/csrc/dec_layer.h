@@ -1,0 +1,63 @@
+// Launch description of the fused decoder-layer kernel (dec_layer.cu); built once per decoder session by engine.cu.
+#pragma once
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace wb {
+
+constexpr int kDLMaxPhases = 4;
+constexpr int kDLUnit = 16;        // output columns per work unit (one tcgen05.ld .x16, one 16-row weight box)
+constexpr int kDLMaxUnits = 12;    // widest per-CTA tile: 192 columns
+
+enum { DL_FOLD = 1, DL_GELU = 2, DL_RESID = 4, DL_STATS = 8 };
+
+// One Linear of the chain.  DL_FOLD: the input is LayerNorm(x) - W holds W (.) gamma, c1 / c2 the fold vectors, the row
+// statistics come from the LN partials left by the producer of x.  DL_RESID: out is the residual stream,
+// out = round(acc + bias) + out (model.py:165-170).  DL_STATS: also leave LN partials of the rows written.
+struct DLPhase {
+  int N, K;
+  int flags;
+  int units_box;          // rows of the main weight box / 16 (every CTA owns at least this many units)
+  const void* bias;       // T[N]   (phases without DL_FOLD)
+  const float* c1;        // fp32 [N] (DL_FOLD)
+  const float* c2;
+  void* out;              // T [R, ldo]
+  long long ldo;
+};
+
+struct DLParams {
+  int n_phases;
+  int R, m_tiles;
+  int ln_slots_in;        // > 0: LN partial slots left for the FIRST phase by an earlier kernel with another split (1 after embed)
+  float4* ln_part;        // [slot][ln_ld] (count, mean, M2, -) partial statistics of the residual stream
+  int ln_ld;
+  unsigned int* sync;     // [0] grid-barrier counter, [1] exit counter; zero between launches
+  const int* skip_flag;
+  DLPhase ph[kDLMaxPhases];
+};
+
+struct alignas(64) DLMaps {
+  CUtensorMap a[kDLMaxPhases];        // activations [R, K], box 64 x 64
+  CUtensorMap b_main[kDLMaxPhases];   // weights [N, K], box 64 x 16 * units_box
+  CUtensorMap b_unit[kDLMaxPhases];   // weights [N, K], box 64 x 16
+};
+
+struct DLLaunch {
+  int dtype = 0;
+  int grid = 0;
+  DLParams p;
+  DLMaps maps;
+};
+
+extern int g_fused_layer;
+int dl_grid_size();
+bool dl_supported(int R, int d, int grid);
+void dl_init_launch(DLLaunch& L, int dtype, int R, int grid, float4* ln_part, int ln_ld, unsigned int* sync,
+                    const int* skip_flag, int ln_slots_in);
+// appends nothing by itself: fills phase `idx` (caller sets p.n_phases)
+int dl_fill_phase(DLLaunch& L, int idx, int dtype, int R, int grid, const void* A, long long lda, const void* W, int N, int K,
+                  const void* bias, const float* c1, const float* c2, int flags, void* out, long long ldo);
+int dl_launch(const DLLaunch& L, cudaStream_t s);
+
+}  // namespace wb

@@ -303,22 +303,14 @@ int launch_enc_attention(int dtype, const void* qkv, void* out, int B, int T, in
   if (make_tmap_16bit(&map, dtype, qkv, 3, dims, strides, box)) return 31;
   dim3 grid((T + 255) / 256, n_head, B);
   ProfileScope prof(PROF_ENC_ATTN, s);
-  static bool attr[2] = {false, false};
+  static SmemOptIn optin[2];
   if (dtype == DT_BF16) {
     auto kern = enc_attention_kernel<__nv_bfloat16>;
-    if (!attr[0]) {
-      if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kAttSmem) != cudaSuccess)
-        return 32;
-      attr[0] = true;
-    }
+    if (!optin[0].ensure(kern, kAttSmem)) return 32;
     kern<<<grid, kAttThreads, kAttSmem, s>>>(map, static_cast<__nv_bfloat16*>(out), T, n_head, d);
   } else {
     auto kern = enc_attention_kernel<__half>;
-    if (!attr[1]) {
-      if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kAttSmem) != cudaSuccess)
-        return 32;
-      attr[1] = true;
-    }
+    if (!optin[1].ensure(kern, kAttSmem)) return 32;
     kern<<<grid, kAttThreads, kAttSmem, s>>>(map, static_cast<__half*>(out), T, n_head, d);
   }
   count_launch();

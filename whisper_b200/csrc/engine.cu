@@ -20,10 +20,12 @@ int set_error(int code, const char* fmt, ...);
 // small kernels: embedding gather, row gather, state initialisation
 // -------------------------------------------------------------------------------------------------
 // x[row] = T(token_embedding[tok] + positional_embedding[pos])   (reference model.py:235-239)
+// ln_part (optional): also leave the row's LayerNorm statistics (count, mean, M2 of the STORED values) as partial
+// slot 0 for the fused decoder-layer kernel, which never runs LayerNorm as a pass of its own (dec_layer.cu).
 template <typename T>
-__global__ void embed_kernel(const int* __restrict__ tokens, int max_ctx, const int* __restrict__ len_ptr,
-                             int n_init, int group, const float* __restrict__ emb, const float* __restrict__ pos,
-                             T* __restrict__ x, int d, const int* skip_flag) {
+__global__ void __launch_bounds__(128) embed_kernel(const int* __restrict__ tokens, int max_ctx, const int* __restrict__ len_ptr,
+                                                    int n_init, int group, const float* __restrict__ emb, const float* __restrict__ pos,
+                                                    T* __restrict__ x, int d, const int* skip_flag, float4* ln_part) {
   if (skip_flag && *skip_flag) return;
   const int row = blockIdx.x;
   int tok, p;
@@ -38,11 +40,43 @@ __global__ void embed_kernel(const int* __restrict__ tokens, int max_ctx, const 
   const float* e = emb + static_cast<long long>(tok) * d;
   const float* pp = pos + static_cast<long long>(p) * d;
   T* xr = x + static_cast<long long>(row) * d;
-  for (int c = threadIdx.x * 2; c < d; c += blockDim.x * 2) {
-    const float2 a = *reinterpret_cast<const float2*>(e + c);
-    const float2 b = *reinterpret_cast<const float2*>(pp + c);
-    *reinterpret_cast<uint32_t*>(xr + c) = Cvt<T>::pack2(a.x + b.x, a.y + b.y);
+  float2 kept[8];           // d <= 2048: at most 8 pairs per thread
+  float sum = 0.f;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int c = threadIdx.x * 2 + i * 256;
+    kept[i] = make_float2(0.f, 0.f);
+    if (c < d) {
+      const float2 a = *reinterpret_cast<const float2*>(e + c);
+      const float2 b = *reinterpret_cast<const float2*>(pp + c);
+      const uint32_t pk = Cvt<T>::pack2(a.x + b.x, a.y + b.y);
+      *reinterpret_cast<uint32_t*>(xr + c) = pk;
+      kept[i] = Cvt<T>::unpack2(pk);
+      sum += kept[i].x + kept[i].y;
+    }
   }
+  if (!ln_part) return;
+  __shared__ float red[4];
+  __shared__ float s_mean;
+  sum = warp_sum(sum);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = sum;
+  __syncthreads();
+  if (threadIdx.x == 0) s_mean = (red[0] + red[1] + red[2] + red[3]) / static_cast<float>(d);
+  __syncthreads();
+  const float mean = s_mean;
+  float m2 = 0.f;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    if (threadIdx.x * 2 + i * 256 < d) {
+      const float t0 = kept[i].x - mean, t1 = kept[i].y - mean;
+      m2 += t0 * t0 + t1 * t1;
+    }
+  }
+  m2 = warp_sum(m2);
+  __syncthreads();
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = m2;
+  __syncthreads();
+  if (threadIdx.x == 0) ln_part[row] = make_float4(static_cast<float>(d), mean, red[0] + red[1] + red[2] + red[3], 0.f);
 }
 
 // dst[i] = src[idx(i)] for the two prefill positions whose logits are needed (decoding.py:692,696)
@@ -60,7 +94,7 @@ __global__ void gather_prefill_rows_kernel(const T* __restrict__ x, T* __restric
 __global__ void decoder_init_state_kernel(int* tokens0, int* tokens1, int* indir0, int* indir1, int max_ctx, int R,
                                           int group, int n_init, const int* __restrict__ init_tokens /*[n_audio,n_init]*/,
                                           float* sum_lp, int* len_ptr, int* done, int* cur, int* fin_count, int* fin_len,
-                                          int n_audio, int max_cand, int* counters, int n_counters) {
+                                          int n_audio, int max_cand, int* counters, int n_counters, unsigned int* dl_sync) {
   const int tid = blockIdx.x * blockDim.x + threadIdx.x;
   const int stride = gridDim.x * blockDim.x;
   for (long long i = tid; i < static_cast<long long>(R) * max_ctx; i += stride) {
@@ -83,6 +117,8 @@ __global__ void decoder_init_state_kernel(int* tokens0, int* tokens1, int* indir
     *cur = 0;
     cur[8] = 0;      // beam tickets (scalars + 24, + 25)
     cur[9] = 0;
+    dl_sync[0] = 0;  // grid-barrier / exit counters of the fused decoder-layer kernel
+    dl_sync[1] = 0;
   }
 }
 
@@ -138,7 +174,6 @@ static int linear(const Model* m, const void* A, long long lda, int M, const voi
   a.out_f32 = out_f32;
   a.skip_flag = skip;
   a.head_major_T = head_major_T;
-  a.weights_constant = 1;            // W is a model tensor: never written while the engine runs
   if (D) {
     a.splitk_ws = D->gemm_ws;
     a.splitk_ws_bytes = D->gemm_ws_bytes;
@@ -273,12 +308,70 @@ static void dec_carve(const Model* m, const wb200_decode_config& c, Arena& ar, D
   o->blank_mask = static_cast<uint32_t*>(ar.take(ldv / 8 + 64));
   o->init_tokens = static_cast<int*>(ar.take(P * 4 + 64));
   o->scalars = static_cast<int*>(ar.take(256));
+  // fused decoder-layer kernel: LN partial statistics [slots <= SMs][rows padded to 64] and its two counters
+  o->ln_ld = static_cast<int>((R + 63) / 64 * 64);
+  o->ln_part = static_cast<float4*>(ar.take(static_cast<size_t>(256) * o->ln_ld * sizeof(float4)));
+  o->dl_sync = static_cast<unsigned int*>(ar.take(256));
 }
 
 size_t decoder_workspace_bytes(const Model* m, const wb200_decode_config* c) {
   Arena ar{nullptr, 0, 0};
   dec_carve(m, *c, ar, nullptr);
   return ar.off + 512;
+}
+
+// Launch plans of the fused decoder-layer kernel for the step path (R = n_audio * n_group new positions per step):
+//   head[l] = {QKV}                                   (used for layer 0 only; other layers get it from the previous tail)
+//   mid[l]  = {out-proj + residual, cross-query}
+//   tail[l] = {cross-out + residual, fc1 + GELU, fc2 + residual, QKV of layer l + 1}
+static int build_fused_plan(Decoder* D) {
+  const Model* m = D->m;
+  D->fused = false;
+  if (g_fused_layer < 0) {
+    const char* e = getenv("WB200_FUSED_LAYER");
+    g_fused_layer = (e && e[0] == '0') ? 0 : 1;
+  }
+  const int R = D->cfg.n_audio * D->cfg.n_group, d = m->dims.n_text_state, dt = m->dtype;
+  const int grid = dl_grid_size();
+  if (!g_fused_layer || D->cfg.all_logits || !dl_supported(R, d, grid)) return 0;
+  const int NL = m->dims.n_text_layer;
+  D->dl_head.assign(NL, DLLaunch());
+  D->dl_mid.assign(NL, DLLaunch());
+  D->dl_tail.assign(NL, DLLaunch());
+  const int* skip = D->done_ptr;
+  for (int l = 0; l < NL; ++l) {
+    const void* const* L = m->dec_layer(l);
+    auto qkv_phase = [&](DLLaunch& X, int idx, const void* const* LL) {
+      return dl_fill_phase(X, idx, dt, R, grid, D->x, d, LL[D_QKV_WF], 3 * d, d, nullptr, (const float*)LL[D_QKV_C1],
+                           (const float*)LL[D_QKV_C2], DL_FOLD, D->qkv, 3LL * d);
+    };
+    DLLaunch& H = D->dl_head[l];
+    dl_init_launch(H, dt, R, grid, D->ln_part, D->ln_ld, D->dl_sync, skip, l == 0 ? 1 : 0);
+    if (int r = qkv_phase(H, 0, L)) return 10 + r;
+    H.p.n_phases = 1;
+    DLLaunch& Mi = D->dl_mid[l];
+    dl_init_launch(Mi, dt, R, grid, D->ln_part, D->ln_ld, D->dl_sync, skip, 0);
+    if (int r = dl_fill_phase(Mi, 0, dt, R, grid, D->att, d, L[D_OUT_W], d, d, L[D_OUT_B], nullptr, nullptr,
+                              DL_RESID | DL_STATS, D->x, d)) return 20 + r;
+    if (int r = dl_fill_phase(Mi, 1, dt, R, grid, D->x, d, L[D_CQ_WF], d, d, nullptr, (const float*)L[D_CQ_C1],
+                              (const float*)L[D_CQ_C2], DL_FOLD, D->q, d)) return 30 + r;
+    Mi.p.n_phases = 2;
+    DLLaunch& Ta = D->dl_tail[l];
+    dl_init_launch(Ta, dt, R, grid, D->ln_part, D->ln_ld, D->dl_sync, skip, 0);
+    if (int r = dl_fill_phase(Ta, 0, dt, R, grid, D->att, d, L[D_COUT_W], d, d, L[D_COUT_B], nullptr, nullptr,
+                              DL_RESID | DL_STATS, D->x, d)) return 40 + r;
+    if (int r = dl_fill_phase(Ta, 1, dt, R, grid, D->x, d, L[D_FC1_WF], 4 * d, d, nullptr, (const float*)L[D_FC1_C1],
+                              (const float*)L[D_FC1_C2], DL_FOLD | DL_GELU, D->hid, 4LL * d)) return 50 + r;
+    if (int r = dl_fill_phase(Ta, 2, dt, R, grid, D->hid, 4LL * d, L[D_FC2_W], d, 4 * d, L[D_FC2_B], nullptr, nullptr,
+                              DL_RESID | DL_STATS, D->x, d)) return 60 + r;
+    Ta.p.n_phases = 3;
+    if (l + 1 < NL) {
+      if (int r = qkv_phase(Ta, 3, m->dec_layer(l + 1))) return 70 + r;
+      Ta.p.n_phases = 4;
+    }
+  }
+  D->fused = true;
+  return 0;
 }
 
 int decoder_create(const Model* m, const wb200_decode_config* c, void* ws, size_t ws_bytes, Decoder** out,
@@ -327,8 +420,17 @@ int decoder_create(const Model* m, const wb200_decode_config* c, void* ws, size_
   if (cudaMemcpyAsync(D->suppress_mask, sup.data(), words * 4, cudaMemcpyHostToDevice, s) != cudaSuccess ||
       cudaMemcpyAsync(D->blank_mask, blank.data(), words * 4, cudaMemcpyHostToDevice, s) != cudaSuccess ||
       cudaStreamSynchronize(s) != cudaSuccess) {
+    cudaFreeHost(D->pinned);
     delete D;
     return set_error(215, "decoder: mask upload failed");
+  }
+  {
+    int r = build_fused_plan(D);
+    if (r) {
+      cudaFreeHost(D->pinned);
+      delete D;
+      return set_error(217, "decoder: fused decoder-layer plan failed (%d)", r);
+    }
   }
   *out = D;
   return 0;
@@ -360,6 +462,22 @@ static int decoder_stack(Decoder* D, int rows, bool step, cudaStream_t s) {
   const size_t cross_per_layer = static_cast<size_t>(B) * Ta * 2 * d * 2;
   const size_t self_per_layer = static_cast<size_t>(R) * ctx * d * 2;
   const int n_q = step ? G : D->cfg.n_init;
+  if (step && D->fused) {
+    // fused GEMM chains (dec_layer.cu) around the two attention kernels: 4 launches per layer instead of 11
+    for (int l = 0; l < m->dims.n_text_layer; ++l) {
+      void* kc = static_cast<uint8_t*>(D->self_k) + l * self_per_layer;
+      void* vc = static_cast<uint8_t*>(D->self_v) + l * self_per_layer;
+      const uint8_t* ckv = static_cast<const uint8_t*>(D->cross_kv) + l * cross_per_layer;
+      if (l == 0) WB_TRY(dl_launch(D->dl_head[0], s));
+      WB_TRY(launch_self_attention(dt, D->qkv, kc, vc, D->att, D->indir[D->cur], D->len_ptr, skip, rows, H, ctx,
+                                   D->cfg.n_init, G, s, D->kv_head_major ? 1 : 0));
+      WB_TRY(dl_launch(D->dl_mid[l], s));
+      WB_TRY(launch_cross_attention(dt, D->q, ckv, ckv + static_cast<size_t>(d) * 2, D->att, D->partial, D->counters, skip, B,
+                                    n_q, Ta, H, 2 * d, s, D->kv_head_major ? 1 : 0));
+      WB_TRY(dl_launch(D->dl_tail[l], s));
+    }
+    return 0;
+  }
   for (int l = 0; l < m->dims.n_text_layer; ++l) {
     const void* const* L = m->dec_layer(l);
     void* kc = static_cast<uint8_t*>(D->self_k) + l * self_per_layer;
@@ -399,7 +517,8 @@ static void launch_embed(Decoder* D, int rows, bool step, cudaStream_t s) {
   const Model* m = D->m;
   embed_kernel<T><<<rows, 128, 0, s>>>(D->tokens[D->cur], m->dims.n_text_ctx, step ? D->len_ptr : nullptr, D->cfg.n_init,
                                        D->cfg.n_group, (const float*)m->t[G_TOK_EMB32], (const float*)m->t[G_DEC_POS],
-                                       static_cast<T*>(D->x), m->dims.n_text_state, step ? D->done_ptr : nullptr);
+                                       static_cast<T*>(D->x), m->dims.n_text_state, step ? D->done_ptr : nullptr,
+                                       (step && D->fused) ? D->ln_part : nullptr);
   count_launch();
 }
 
@@ -413,7 +532,8 @@ int decoder_prefill(Decoder* D, const int32_t* init_tokens_host, cudaStream_t s)
   D->cur = 0;
   decoder_init_state_kernel<<<256, 256, 0, s>>>(D->tokens[0], D->tokens[1], D->indir[0], D->indir[1], ctx, R, G, c.n_init,
                                                 D->init_tokens, D->sum_lp, D->len_ptr, D->done_ptr, D->cur_ptr, D->fin_count, D->fin_len,
-                                                B, c.max_candidates > 0 ? c.max_candidates : 1, D->counters, D->n_counters + 256);
+                                                B, c.max_candidates > 0 ? c.max_candidates : 1, D->counters, D->n_counters + 256,
+                                                D->dl_sync);
   count_launch();
   if (dt == DT_BF16) launch_embed<__nv_bfloat16>(D, P, false, s); else launch_embed<__half>(D, P, false, s);
   WB_TRY(decoder_stack(D, P, false, s));

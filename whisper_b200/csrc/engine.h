@@ -6,6 +6,7 @@
 #include <vector>
 
 #include "../../include/whisper_b200.h"
+#include "dec_layer.h"
 
 namespace wb {
 
@@ -21,7 +22,10 @@ enum EncSlot {
 enum DecSlot {
   D_ATTN_LN_W, D_ATTN_LN_B, D_QKV_W, D_QKV_B, D_OUT_W, D_OUT_B, D_CROSS_LN_W, D_CROSS_LN_B,
   D_CQ_W, D_CQ_B, D_CKV_W, D_CKV_B, D_COUT_W, D_COUT_B, D_MLP_LN_W, D_MLP_LN_B,
-  D_FC1_W, D_FC1_B, D_FC2_W, D_FC2_B, D_COUNT
+  D_FC1_W, D_FC1_B, D_FC2_W, D_FC2_B,
+  // LayerNorm folded into the consuming Linear for the fused decoder-layer kernel (dec_layer.cu):
+  // *_WF = W (.) gamma in the 16-bit type, *_C1 = fp32 row sums of WF, *_C2 = fp32 W beta + bias
+  D_QKV_WF, D_QKV_C1, D_QKV_C2, D_CQ_WF, D_CQ_C1, D_CQ_C2, D_FC1_WF, D_FC1_C1, D_FC1_C2, D_COUNT
 };
 
 struct Dims {
@@ -90,6 +94,13 @@ struct Decoder {
   int pair_graph_cur = -1;          // value of `cur` the graph was captured at
   int launches_per_pair = 0;        // kernels inside one replay (for wb200_launch_count)
   bool kv_head_major = false;       // kv caches stored per head ([.., head, position, 64]); fixed at create
+  // fused decoder-layer GEMM chain of the step path (dec_layer.cu): per layer [QKV] (layer 0 only; later layers get
+  // theirs from the previous layer's tail), [out-proj, cross-query], [cross-out, fc1, fc2, next layer's QKV]
+  bool fused = false;
+  std::vector<DLLaunch> dl_head, dl_mid, dl_tail;
+  float4* ln_part = nullptr;        // LN partial statistics of the residual stream
+  int ln_ld = 0;
+  unsigned int* dl_sync = nullptr;  // grid-barrier / exit counters of the fused kernel
   // GreedyDecoder temperature sampling (wb200_decoder_set_sampling); 0 = argmax
   float temperature = 0.f;
   unsigned long long seed = 0;

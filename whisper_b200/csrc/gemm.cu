@@ -26,7 +26,6 @@ namespace wb {
 
 int g_pdl_on = -1;      // -1: read WB200_PDL on first use (default on); wb200_set_pdl() overrides
 int g_kv_head_major = -1;   // -1: read WB200_KV_HEAD_MAJOR on first decoder_create (default off)
-int g_gemm_early_b = -1;    // -1: read WB200_GEMM_EARLY_B on first use (default off): weight tiles before the PDL wait
 int g_bm64_on = 1;      // wb200_set_option("bm64", 0/1): 64-row tiles for skinny problems
 int g_splitk_on = -1;   // -1: read WB200_SPLITK on first use; wb200_set_splitk() overrides
 
@@ -53,7 +52,6 @@ struct GemmParams {
   float* partial;
   long long partial_stride;   // floats per split slab
   int* tile_counters;
-  int early_b;                // producer issues the first weight tiles BEFORE griddepcontrol.wait (g_gemm_early_b)
   int hm_T;                   // > 0: head-major 16-bit output [rows / hm_T][N / 64][hm_T][64] (LinearArgs::head_major_T)
 };
 
@@ -71,26 +69,6 @@ struct GemmCfg {
   static constexpr int kTmemCols = (2 * BN < 32) ? 32 : 2 * BN;  // BN in {64,128,256} -> pow2
   static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align*/ + 256 /*barriers*/;
 };
-
-// Exact (erf) GELU of nn.GELU() / F.gelu (reference model.py:156,193-194).  erf is evaluated with the
-// Abramowitz-Stegun 7.1.26 rational form (|error| <= 1.5e-7, below fp32 round-off of 1 + erf and far below
-// the 16-bit rounding applied to the result); the negative side uses erfc directly so the tail does not
-// cancel.  ~16 instructions (one MUFU.RCP, one MUFU.EX2) against ~40 for erff: the fc1 epilogue of the
-// encoder MLP was instruction-bound on this (profiles/r1_summary.md).
-__device__ __forceinline__ float gelu_erf(float x) {
-  // w = |x| * sqrt(log2(e) / 2): then exp(-x^2 / 2) = 2^(-w^2) and p * |x| / sqrt(2) = p' * w
-  const float w = fabsf(x) * 0.84932180028801904272f;
-  float t;
-  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(t) : "f"(fmaf(0.27274054f, w, 1.0f)));   // 0.3275911 / sqrt(log2 e)
-  float poly = fmaf(1.061405429f, t, -1.453152027f);
-  poly = fmaf(poly, t, 1.421413741f);
-  poly = fmaf(poly, t, -0.284496736f);
-  poly = fmaf(poly, t, 0.254829592f);
-  const float erfc_z = poly * t * fast_exp2(-w * w);          // erfc(|x| / sqrt 2)
-  // x >= 0: 0.5 x (2 - erfc) ; x < 0: 0.5 x erfc
-  const float phi2 = x >= 0.f ? 2.0f - erfc_z : erfc_z;
-  return 0.5f * x * phi2;
-}
 
 // bias / GELU / positional add / residual, then the store of 32 consecutive columns of one row
 template <typename T, bool OUT_F32>
@@ -233,29 +211,6 @@ gemm_tcgen05_kernel(const GemmParams p, const __grid_constant__ CUtensorMap mapA
   const uint32_t tmem_base = *tmem_ptr_smem;
   // Everything above (barrier init, TMEM allocation, descriptor prefetch) touches no global data and
   // overlaps the tail of the previous kernel; from here on its results are needed.
-  //
-  // Optional (p.early_b): the WEIGHT half of the first pipeline stages does not depend on the previous kernel
-  // either - weights are constant for the whole decode - so the producer arms those stages and issues their B
-  // loads before the dependency wait; only the activation (A) loads wait.  For the latency-bound 320-row GEMMs
-  // this takes the first-byte latency of the weight stream off the critical path.
-  int pre = 0;
-  if (p.early_b && warp == 0 && lane == 0 && static_cast<int>(blockIdx.x) < total_tiles * p.splits) {
-    const int item = blockIdx.x;
-    const int tile = item / p.splits, split = item % p.splits;
-    const int n0 = (tile % p.n_tiles) * BN;
-    const int kb_lo = split * p.k_per_split, kb_hi = min(k_blocks, kb_lo + p.k_per_split);
-    for (int tap = 0; tap < p.taps && pre < Cfg::kStages; ++tap)
-      for (int kg = 0; kg < groups_per_tap && pre < Cfg::kStages; ++kg) {
-        const int kidx = tap * groups_per_tap + kg;
-        if (kidx < kb_lo || kidx >= kb_hi) continue;
-        uint8_t* sb = tiles + pre * Cfg::kStageBytes + Cfg::kABytes;
-        mbar_expect_tx(&full_bar[pre], Cfg::kStageBytes);       // A bytes of this stage arrive after the wait
-#pragma unroll
-        for (int sub = 0; sub < KS; ++sub)
-          tma_load_2d(sb + sub * Cfg::kBSub, &mapB, &full_bar[pre], tap * p.K_tap + (kg * KS + sub) * kBK, n0);
-        ++pre;
-      }
-  }
   pdl_wait();
   const bool skip = p.skip_flag && *p.skip_flag;
   const int total_items = skip ? 0 : total_tiles * p.splits;
@@ -264,41 +219,29 @@ gemm_tcgen05_kernel(const GemmParams p, const __grid_constant__ CUtensorMap mapA
     // ===================== TMA producer =====================
     int stage = 0;
     uint32_t phase = 0;
-    int issued = 0;                  // k-groups handed to the pipeline so far (the first `pre` were armed early)
-    bool stop = false;
-    // a skipped launch still has to retire its early loads: walk the first item's first `pre` groups A-side only
-    const int producer_items = (skip && pre > 0) ? static_cast<int>(blockIdx.x) + 1 : total_items;
-    for (int item = blockIdx.x; item < producer_items && !stop; item += gridDim.x) {
+    for (int item = blockIdx.x; item < total_items; item += gridDim.x) {
       const int tile = item / p.splits, split = item % p.splits;
       const int m_tile = tile / p.n_tiles;
       const int n0 = (tile % p.n_tiles) * BN;
       const int b = m_tile / p.m_tiles_per_batch;
       const int t0 = (m_tile % p.m_tiles_per_batch) * BM;
       const int kb_lo = split * p.k_per_split, kb_hi = min(k_blocks, kb_lo + p.k_per_split);
-      for (int tap = 0; tap < p.taps && !stop; ++tap) {
+      for (int tap = 0; tap < p.taps; ++tap) {
         const CUtensorMap* ma = p.a_map_sel[tap] ? &mapA1 : &mapA0;
         const int row0 = t0 + p.a_row_off[tap];
         for (int kg = 0; kg < groups_per_tap; ++kg) {
           const int kidx = tap * groups_per_tap + kg;
           if (kidx < kb_lo || kidx >= kb_hi) continue;
-          const bool early = issued < pre;             // armed and B-loaded before the dependency wait
-          if (skip && !early) {
-            stop = true;
-            break;
-          }
           uint8_t* sa = tiles + stage * Cfg::kStageBytes;
           uint8_t* sb = sa + Cfg::kABytes;
-          if (!early) {
-            mbar_wait(&empty_bar[stage], phase ^ 1);
-            mbar_expect_tx(&full_bar[stage], Cfg::kStageBytes);
-          }
+          mbar_wait(&empty_bar[stage], phase ^ 1);
+          mbar_expect_tx(&full_bar[stage], Cfg::kStageBytes);
 #pragma unroll
           for (int sub = 0; sub < KS; ++sub) {     // sub-blocks past K are zero-filled by TMA
             const int kb = kg * KS + sub;
             tma_load_3d(sa + sub * Cfg::kASub, ma, &full_bar[stage], kb * kBK, row0, b);
-            if (!early) tma_load_2d(sb + sub * Cfg::kBSub, &mapB, &full_bar[stage], tap * p.K_tap + kb * kBK, n0);
+            tma_load_2d(sb + sub * Cfg::kBSub, &mapB, &full_bar[stage], tap * p.K_tap + kb * kBK, n0);
           }
-          ++issued;
           if (++stage == Cfg::kStages) {
             stage = 0;
             phase ^= 1;
@@ -306,8 +249,6 @@ gemm_tcgen05_kernel(const GemmParams p, const __grid_constant__ CUtensorMap mapA
         }
       }
     }
-    if (skip)                          // nobody consumes these stages; just let the bulk copies land before exit
-      for (int st = 0; st < pre; ++st) mbar_wait(&full_bar[st], 0);
   } else if (warp == 1 && lane == 0) {
     // ===================== MMA issuer =====================
     constexpr uint32_t idesc = umma_idesc(Cvt<T>::kUmmaFmt, BM, BN, 0, 0);
@@ -459,20 +400,10 @@ template <typename T, int BN, bool OUT_F32, int BM = kBM, int KS = 1>
 static int launch_impl(const GemmParams& p, const CUtensorMap& a0, const CUtensorMap& a1,
                        const CUtensorMap& b, cudaStream_t s) {
   using Cfg = GemmCfg<BN, BM, KS>;
-  static bool attr_set = false;
+  static SmemOptIn optin;
   auto kern = gemm_tcgen05_kernel<T, BN, OUT_F32, BM, KS>;
-  if (!attr_set) {
-    cudaError_t e =
-        cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes);
-    if (e != cudaSuccess) return 10;
-    attr_set = true;
-  }
-  static int num_sms = 0;
-  if (!num_sms) {
-    int dev = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev);
-  }
+  if (!optin.ensure(kern, Cfg::kSmemBytes)) return 10;
+  const int num_sms = sm_count();
   const int total = p.batch * p.m_tiles_per_batch * p.n_tiles * p.splits;
   const int grid = total < num_sms ? total : num_sms;
   ProfileScope prof(PROF_GEMM, s);
@@ -548,11 +479,6 @@ int launch_linear(const LinearArgs& a, cudaStream_t s) {
   p.partial = nullptr;
   p.partial_stride = rows * static_cast<long long>(a.N);
   p.tile_counters = a.splitk_counters;
-  if (g_gemm_early_b < 0) {
-    const char* e = getenv("WB200_GEMM_EARLY_B");
-    g_gemm_early_b = (e && e[0] && e[0] != '0') ? 1 : 0;
-  }
-  p.early_b = (g_gemm_early_b && g_pdl_on != 0 && a.weights_constant) ? 1 : 0;
   p.hm_T = 0;
   if (a.head_major_T > 0) {
     if (a.out_f32 || a.N % 64 || a.batch != 1 || a.residual || a.rows_per_batch % a.head_major_T) return 14;

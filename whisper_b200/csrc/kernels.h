@@ -13,7 +13,7 @@ enum { DT_BF16 = 0, DT_F16 = 1 };
 // kernels launched by this library since load (reported by bench.py as gpu_launches)
 extern unsigned long long g_launch_count;
 // Launch accounting (wb200_launch_count).  The process-wide counter is updated atomically because several host
-// threads may drive decoder sessions at once (model.decode_streams); the thread-local one lets a stream capture
+// threads may drive decoder sessions at once; the thread-local one lets a stream capture
 // subtract exactly the launches IT recorded (a capture records kernels, it does not run them).
 extern thread_local unsigned long long t_launch_count;
 inline void count_launch(int n = 1) {
@@ -24,7 +24,7 @@ inline void count_launch(int n = 1) {
 // Optional per-kernel timing for bench.py's roofline: when profiling is enabled for a kernel id,
 // every launch of that kernel is bracketed by CUDA events on its own stream (api.cu owns the pool).
 enum { PROF_NONE = 0, PROF_CROSS_ATTN = 1, PROF_SELF_ATTN = 2, PROF_GEMM = 3, PROF_ENC_ATTN = 4,
-       PROF_LAYERNORM = 5, PROF_SELECT = 6, PROF_MEL = 7 };
+       PROF_LAYERNORM = 5, PROF_SELECT = 6, PROF_MEL = 7, PROF_DEC_LAYER = 8 };
 extern int g_profile_kernel;
 void profile_mark(cudaStream_t s, bool begin);
 struct ProfileScope {
@@ -63,10 +63,6 @@ struct LinearArgs {
   // C[((row / hm_T) * (N / 64) + n / 64) * hm_T + row % hm_T][n % 64] - i.e. [batch][head][t][64] for rows = batch * hm_T.
   // Used for the cross-attention K/V of the decoder when the head-major kv layout is on.  0 = row-major.
   int head_major_T = 0;
-  // W is constant while the stream runs (model weights): lets the kernel fetch weight tiles before it waits for
-  // the previous kernel under programmatic dependent launch.  Leave 0 when W is produced by earlier work in the
-  // same stream (e.g. wb200_linear on caller tensors).
-  int weights_constant = 0;
   void* C = nullptr;
   long long ldc = 0;
   int gelu = 0;
@@ -84,8 +80,34 @@ int launch_linear(const LinearArgs& a, cudaStream_t s);
 extern int g_splitk_on;
 extern int g_bm64_on;
 extern int g_kv_head_major;   // kv caches stored [.., head, position, 64] instead of [.., position, d] (wb200_set_kv_head_major)
-extern int g_gemm_early_b;   // GEMM: issue the first weight tiles before griddepcontrol.wait (wb200_set_gemm_early_weights)
 extern int g_pdl_on;   // programmatic dependent launch for the decoder-layer kernels (wb200_set_pdl / WB200_PDL)
+
+// Per-DEVICE caches of launch state.  cudaFuncSetAttribute(MaxDynamicSharedMemorySize) applies to the current device
+// only and SM counts differ between devices, so "done once" flags are indexed by the device ordinal: a second model
+// on cuda:1 in the same process makes its own opt-ins.  Races between host threads write identical values.
+constexpr int kMaxDevices = 64;
+inline int device_ordinal() {
+  int d = 0;
+  cudaGetDevice(&d);
+  return (d >= 0 && d < kMaxDevices) ? d : 0;
+}
+struct SmemOptIn {
+  int bytes[kMaxDevices] = {};
+  template <typename K>
+  bool ensure(K kern, int want) {      // false on failure
+    const int d = device_ordinal();
+    if (bytes[d] >= want) return true;
+    if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, want) != cudaSuccess) return false;
+    bytes[d] = want;
+    return true;
+  }
+};
+inline int sm_count() {
+  static int n[kMaxDevices] = {};
+  const int d = device_ordinal();
+  if (!n[d]) cudaDeviceGetAttribute(&n[d], cudaDevAttrMultiProcessorCount, d);
+  return n[d];
+}
 
 // Launch with the programmatic-stream-serialization attribute (when enabled): inside a stream or a
 // captured graph the kernel may be scheduled while the previous kernel drains; the kernels that are

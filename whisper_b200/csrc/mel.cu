@@ -263,11 +263,8 @@ int launch_log_mel(const float* audio, int n_audio, long long n_samples, int n_m
   const size_t smem = (kSpan + 16 + kNFFT) * 4 + (25 * 9 + 1 + 25 + 1 + 8 * 9 * 25) * 8 + (8 * 208) * 4 +
                       static_cast<size_t>(n_mels) * 33 * 4 + 128;
   auto kern = log_mel_kernel<128>;
-  static bool attr = false;
-  if (!attr) {
-    if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024) != cudaSuccess) return 63;
-    attr = true;
-  }
+  static SmemOptIn optin;
+  if (!optin.ensure(kern, 96 * 1024)) return 63;
   dim3 grid((n_frames + kFramesPerCta - 1) / kFramesPerCta, n_audio);
   ProfileScope prof(PROF_MEL, s);
   kern<<<grid, kMelThreads, smem, s>>>(audio, n_samples, n_frames, n_mels, sp, out, gmax, per_row_max);

@@ -171,6 +171,18 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
       : "memory");
 }
 
+// 32 lanes x 16 consecutive fp32 columns
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32"
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]),
+        "=r"(r[7]), "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]),
+        "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr)
+      : "memory");
+}
+
 // Shared-memory matrix descriptor (sm_100 UMMA), 128-byte swizzle.
 //   K-major tile  : rows of 128 B (64 x 16-bit), 8-row groups 1024 B apart (SBO), LBO unused (=1).
 //   MN-major tile : 64 MN-elements (128 B) contiguous, k rows 128 B apart, 8-k groups SBO apart,
@@ -294,6 +306,26 @@ __device__ __forceinline__ float fast_exp2(float x) {
   float y;
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
   return y;
+}
+
+// Exact (erf) GELU of nn.GELU() / F.gelu (reference model.py:156,193-194).  erf is evaluated with the
+// Abramowitz-Stegun 7.1.26 rational form (|error| <= 1.5e-7, below fp32 round-off of 1 + erf and far below
+// the 16-bit rounding applied to the result); the negative side uses erfc directly so the tail does not
+// cancel.  ~16 instructions (one MUFU.RCP, one MUFU.EX2) against ~40 for erff: the fc1 epilogue of the
+// encoder MLP was instruction-bound on this (profiles/r1_summary.md).
+__device__ __forceinline__ float gelu_erf(float x) {
+  // w = |x| * sqrt(log2(e) / 2): then exp(-x^2 / 2) = 2^(-w^2) and p * |x| / sqrt(2) = p' * w
+  const float w = fabsf(x) * 0.84932180028801904272f;
+  float t;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(t) : "f"(fmaf(0.27274054f, w, 1.0f)));   // 0.3275911 / sqrt(log2 e)
+  float poly = fmaf(1.061405429f, t, -1.453152027f);
+  poly = fmaf(poly, t, 1.421413741f);
+  poly = fmaf(poly, t, -0.284496736f);
+  poly = fmaf(poly, t, 0.254829592f);
+  const float erfc_z = poly * t * fast_exp2(-w * w);          // erfc(|x| / sqrt 2)
+  // x >= 0: 0.5 x (2 - erfc) ; x < 0: 0.5 x erfc
+  const float phi2 = x >= 0.f ? 2.0f - erfc_z : erfc_z;
+  return 0.5f * x * phi2;
 }
 
 __device__ __forceinline__ float warp_max(float v) {

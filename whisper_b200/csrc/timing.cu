@@ -146,12 +146,8 @@ int launch_dtw(const float* x, int N, int M, int* path, int* path_len, void* wor
   if (N <= 0 || M <= 0) return 74;
   const size_t smem = 3 * static_cast<size_t>(N + 1) * sizeof(float);
   if (smem > 200 * 1024) return 75;
-  static bool attr = false;
-  if (!attr) {
-    if (cudaFuncSetAttribute(dtw_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024) != cudaSuccess)
-      return 76;
-    attr = true;
-  }
+  static SmemOptIn optin;
+  if (!optin.ensure(dtw_kernel, 200 * 1024)) return 76;
   unsigned char* trace = reinterpret_cast<unsigned char*>(workspace);
   dtw_kernel<<<1, kDtwThreads, smem, s>>>(x, N, M, trace, tie_mode);
   dtw_backtrace_kernel<<<1, 32, 0, s>>>(trace, N, M, path, path_len);

@@ -100,6 +100,8 @@ class DecoderSession:
         c.suppress_ids = ctypes.cast(self._sup, POINTER(c_int32))
         c.blank_ids = ctypes.cast(self._blank, POINTER(c_int32))
         self._c = c
+        self._cache_key = None
+        self._dirty = False          # sampling / alignment settings a reuse has to clear
         self.R = cfg["n_audio"] * cfg["n_group"]
         self.K = cfg["n_group"] + 1 if cfg["beam_search"] else 1
         self.ctx = model.dims.n_text_ctx
@@ -111,15 +113,23 @@ class DecoderSession:
                                              ctypes.byref(h), stream_ptr()), "wb200_decoder_create")
         self._h = h
 
-    def close(self):
+    def destroy(self):
         if self._h:
             lib().wb200_decoder_destroy(self._h)
             self._h = c_void_p(0)
         self.workspace = None
 
+    def close(self):
+        """Give the session back.  Sessions opened through DecodingTask.open_session are parked on the model and reused by
+        the next decode() with the same shape and filters (kv arenas, tensor maps and the instantiated CUDA graph of the
+        decode loop survive; wb200_decoder_prefill resets all per-decode state), others are destroyed."""
+        if self._h and self._cache_key is not None and self.model._park_session(self):
+            return
+        self.destroy()
+
     def __del__(self):
         try:
-            self.close()
+            self.destroy()
         except Exception:
             pass
 
@@ -141,6 +151,7 @@ class DecoderSession:
     def set_sampling(self, temperature: float, seed: int):
         """GreedyDecoder temperature sampling (decoding.py:283) with the library's counter-based generator."""
         from ctypes import c_float, c_uint64
+        self._dirty = True
         with torch.cuda.device(self.model.device):
             check(lib().wb200_decoder_set_sampling(self._h, c_float(float(temperature)), c_uint64(int(seed) & (2 ** 64 - 1))),
                   "wb200_decoder_set_sampling")
@@ -161,6 +172,7 @@ class DecoderSession:
         ((layer, head) pairs) for audio 0; returns the fp32 tensor [n_heads, n_init, n_audio_ctx]
         that will receive them (reference timing.py:185-197)."""
         n = len(heads)
+        self._dirty = True
         flat = np.ascontiguousarray(np.asarray(heads, dtype=np.int32).reshape(-1))
         self._align_heads = flat
         self._align_qk = torch.empty((n, self.cfg["n_init"], self.model.dims.n_audio_ctx), device=self.model.device,
@@ -169,6 +181,14 @@ class DecoderSession:
             check(lib().wb200_decoder_set_alignment(self._h, flat.ctypes.data_as(POINTER(c_int32)), c_int(n),
                                                     ptr(self._align_qk)), "wb200_decoder_set_alignment")
         return self._align_qk
+
+    def reset_for_reuse(self):
+        if self._dirty:
+            from ctypes import c_float, c_uint64
+            with torch.cuda.device(self.model.device):
+                check(lib().wb200_decoder_set_sampling(self._h, c_float(0.0), c_uint64(0)), "wb200_decoder_set_sampling")
+                check(lib().wb200_decoder_set_alignment(self._h, None, c_int(0), None), "wb200_decoder_set_alignment")
+            self._dirty = False
 
     def force_tokens(self, next_tokens: Sequence[int]):
         arr = np.ascontiguousarray(next_tokens, dtype=np.int32)
@@ -293,10 +313,6 @@ class DecodingTask:
             raise ValueError("length_penalty (alpha) should be a value between 0 and 1")
         if options.temperature < 0:
             raise ValueError("temperature must be >= 0")
-        if options.temperature > 0 and options.beam_size is not None:
-            # the reference silently prefers beam search when both are given (decoding.py:548-552) and the
-            # transcribe() ladder never combines them (transcribe.py:189-195); refuse the ambiguous request
-            raise ValueError("temperature > 0 samples with GreedyDecoder; drop beam_size (transcribe.py:189-195)")
         if options.beam_size is not None and options.beam_size > 16:
             raise ValueError("beam_size > 16 is not supported by the device beam kernel")
         return options
@@ -353,7 +369,12 @@ class DecodingTask:
         cfg = self.session_config(n_audio)
         if cfg["beam_search"] and cfg["max_candidates"] <= 0:
             raise AssertionError(f"Invalid beam size ({self.options.beam_size}) or patience ({self.options.patience})")
-        return DecoderSession(self.model, cfg, self.suppress, self.tokenizer.blank_tokens)
+        key = (tuple(sorted(cfg.items())), tuple(self.suppress), tuple(self.tokenizer.blank_tokens))
+        sess = self.model._take_session(key)
+        if sess is None:
+            sess = DecoderSession(self.model, cfg, self.suppress, self.tokenizer.blank_tokens)
+            sess._cache_key = key
+        return sess
 
     @torch.no_grad()
     def run(self, mel: torch.Tensor, initial_tokens: Optional[np.ndarray] = None) -> List[DecodingResult]:
@@ -385,15 +406,11 @@ class DecodingTask:
                     for f, l, p in zip(audio_features, languages, language_probs)]
 
         seed = None
-        if self.options.temperature > 0:
+        if self.options.temperature > 0 and self.options.beam_size is None:   # beam search ignores the temperature (decoding.py:548-552)
             seed = self.options.seed
             if seed is None:
                 seed = int(torch.randint(0, 2 ** 62, (1,)).item())
-        n_streams = max(1, min(int(getattr(self.model, "decode_streams", 1) or 1), n_audio))
-        if n_streams == 1:
-            tokens, sum_logprobs, no_speech, finished = self._run_session(audio_features, init, seed)
-        else:
-            tokens, sum_logprobs, no_speech, finished = self._run_concurrent(audio_features, init, seed, n_streams)
+        tokens, sum_logprobs, no_speech, finished = self._run_session(audio_features, init, seed)
 
         G = self.n_group
         tokens = tokens.reshape(n_audio, G, -1)
@@ -437,59 +454,6 @@ class DecodingTask:
                             sess.get("fin_score").cpu().numpy(), sess.get("fin_count").cpu().numpy())
         finally:
             sess.close()
-        return tokens, sum_logprobs, no_speech, finished
-
-    def _run_concurrent(self, audio_features: torch.Tensor, init: np.ndarray, seed: Optional[int], n_streams: int):
-        """The same decode as `n_streams` independent sessions over contiguous slices of the batch, each driven by its
-        own host thread on its own CUDA stream (`model.decode_streams`, default 1 = off).  A decoder step alternates
-        latency-bound phases (six skinny GEMMs and three LayerNorms per layer that leave most SMs and all of HBM idle)
-        with bandwidth-bound phases (the two attention kernels); with several sessions in flight one session's
-        attention streams K/V while another's GEMMs wait on their pipelines.  Audios are independent, so the results
-        are those of the single session up to fp reduction order (the cross-attention key split depends on the batch).
-        Staged in round 1, not yet measured on hardware."""
-        import threading
-
-        dev = self.model.device
-        main = torch.cuda.current_stream(dev)
-        bounds = np.linspace(0, init.shape[0], n_streams + 1).astype(int)
-        slices = [(int(bounds[i]), int(bounds[i + 1])) for i in range(n_streams) if bounds[i + 1] > bounds[i]]
-        streams = [torch.cuda.Stream(device=dev) for _ in slices]
-        results = [None] * len(slices)
-        errors = [None] * len(slices)
-
-        def work(i):
-            lo, hi = slices[i]
-            try:
-                with torch.cuda.device(dev), torch.cuda.stream(streams[i]):
-                    sub_seed = None if seed is None else (seed + i * 0x9E3779B97F4A7C15) % (1 << 64)
-                    results[i] = self._run_session(audio_features[lo:hi].contiguous(), init[lo:hi], sub_seed)
-            except BaseException as e:      # re-raised on the caller's thread
-                errors[i] = e
-
-        for st in streams:
-            st.wait_stream(main)             # the features were produced on the caller's stream
-        threads = [threading.Thread(target=work, args=(i,), daemon=True) for i in range(len(slices))]
-        for t in threads:
-            t.start()
-        for t in threads:
-            t.join()
-        for st in streams:
-            main.wait_stream(st)
-        for e in errors:
-            if e is not None:
-                raise e
-        eot = self.tokenizer.eot
-        length = max(r[0].shape[1] for r in results)
-
-        def pad(tok):                        # sessions may stop at different lengths; everything past the end is EOT
-            return np.pad(tok, ((0, 0), (0, length - tok.shape[1])), constant_values=eot)
-
-        tokens = np.concatenate([pad(r[0]) for r in results], 0)
-        sum_logprobs = np.concatenate([r[1] for r in results], 0)
-        no_speech = [x for r in results for x in r[2]]
-        finished = None
-        if results[0][3] is not None:
-            finished = tuple(np.concatenate([r[3][k] for r in results], 0) for k in range(4))
         return tokens, sum_logprobs, no_speech, finished
 
     def _finalize(self, tokens: np.ndarray, sum_logprobs: np.ndarray, finished):

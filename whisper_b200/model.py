@@ -73,16 +73,31 @@ def pack_weights(sd: Dict[str, "np.ndarray | torch.Tensor"], dims: ModelDimensio
     def ln(prefix):
         return [_t(sd, prefix + ".weight", device, F32), _t(sd, prefix + ".bias", device, F32)]
 
+    def folded(w, b, ln_prefix):
+        """LayerNorm folded into the Linear that consumes it (csrc/dec_layer.cu): with y = LN(x) W^T + b,
+        LN(x) = (x - mean) * rstd * gamma + beta, the kernel multiplies RAW rows by wf = W * gamma and finishes with
+        y = rstd * (x wf^T - mean * c1) + c2.  c1 sums wf AS STORED in the 16-bit type so that the mean term cancels
+        exactly what the tensor cores accumulate."""
+        g, beta = _t(sd, ln_prefix + ".weight", device, F32), _t(sd, ln_prefix + ".bias", device, F32)
+        wf = (w.to(F32) * g[None, :]).to(T).contiguous()
+        c1 = wf.to(F32).sum(dim=1).contiguous()
+        c2 = (w.to(F32) @ beta + b.to(F32)).contiguous()
+        return [wf, c1, c2]
+
     for i in range(dims.n_audio_layer):
         p = f"encoder.blocks.{i}"
         out += ln(p + ".attn_ln") + list(fused(p + ".attn", ("query", "key", "value"), (True, False, True)))
         out += lin(p + ".attn.out") + ln(p + ".mlp_ln") + lin(p + ".mlp.0") + lin(p + ".mlp.2")
     for i in range(dims.n_text_layer):
         p = f"decoder.blocks.{i}"
-        out += ln(p + ".attn_ln") + list(fused(p + ".attn", ("query", "key", "value"), (True, False, True)))
-        out += lin(p + ".attn.out") + ln(p + ".cross_attn_ln") + lin(p + ".cross_attn.query")
+        qkv_w, qkv_b = fused(p + ".attn", ("query", "key", "value"), (True, False, True))
+        cq, fc1 = lin(p + ".cross_attn.query"), lin(p + ".mlp.0")
+        out += ln(p + ".attn_ln") + [qkv_w, qkv_b]
+        out += lin(p + ".attn.out") + ln(p + ".cross_attn_ln") + cq
         out += list(fused(p + ".cross_attn", ("key", "value"), (False, True)))
-        out += lin(p + ".cross_attn.out") + ln(p + ".mlp_ln") + lin(p + ".mlp.0") + lin(p + ".mlp.2")
+        out += lin(p + ".cross_attn.out") + ln(p + ".mlp_ln") + fc1 + lin(p + ".mlp.2")
+        out += folded(qkv_w, qkv_b, p + ".attn_ln") + folded(cq[0], cq[1], p + ".cross_attn_ln")
+        out += folded(fc1[0], fc1[1], p + ".mlp_ln")
     return out
 
 
@@ -126,12 +141,12 @@ class Whisper:
         self._handle = c_void_p(0)
         self._tensors = []
         self._workspace = None
+        # decoder sessions parked between decode() calls, most recently used last (decoding.DecoderSession.close)
         self._sessions = {}
+        self.session_cache_entries = 4            # 0 disables the reuse
+        self.session_cache_bytes = 64 << 30
         self.encoder = _Encoder(self)
         self.decoder = _Decoder(self)
-        # number of concurrent decoder sessions a batched decode() is split into (decoding.DecodingTask._run_concurrent);
-        # 1 = one session for the whole batch
-        self.decode_streams = 1
         # default alignment heads: the last half of the decoder layers (model.py:268-276)
         heads = torch.zeros(dims.n_text_layer, dims.n_text_head, dtype=torch.bool)
         heads[dims.n_text_layer // 2:] = True
@@ -147,6 +162,7 @@ class Whisper:
             if n != len(self._tensors):
                 raise WhisperB200Error(f"weight packing produced {len(self._tensors)} tensors, library expects {n}")
             arr = (c_void_p * n)(*[t.data_ptr() for t in self._tensors])
+            self.clear_sessions()
             if self._handle:
                 lib().wb200_model_destroy(self._handle)
             h = c_void_p(0)
@@ -173,10 +189,34 @@ class Whisper:
     def eval(self):
         return self
 
+    # ---- decoder-session reuse: every decode() of the same shape otherwise re-creates the kv arenas, 96 launch plans
+    # with ~1000 tensor maps and re-captures / instantiates the CUDA graph of the decode loop (transcribe() calls
+    # decode() once per 30-second window, reference transcribe.py:272-508)
+    def _take_session(self, key):
+        sess = self._sessions.pop(key, None)
+        if sess is not None:
+            sess.reset_for_reuse()
+        return sess
+
+    def _park_session(self, sess) -> bool:
+        if self.session_cache_entries <= 0 or sess._cache_key in self._sessions:
+            return False
+        self._sessions[sess._cache_key] = sess
+        def total():
+            return sum(s.workspace.numel() for s in self._sessions.values())
+        while len(self._sessions) > self.session_cache_entries or (len(self._sessions) > 1 and total() > self.session_cache_bytes):
+            oldest = next(iter(self._sessions))
+            self._sessions.pop(oldest).destroy()
+        return sess._cache_key in self._sessions
+
+    def clear_sessions(self):
+        for s in list(self._sessions.values()):
+            s.destroy()
+        self._sessions = {}
+
     def __del__(self):
         try:
-            for dec, _ in self._sessions.values():
-                lib().wb200_decoder_destroy(dec)
+            self.clear_sessions()
             if self._handle:
                 lib().wb200_model_destroy(self._handle)
         except Exception:

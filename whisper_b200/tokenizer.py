@@ -33,6 +33,8 @@ def _id_table() -> dict:
 
 
 LANGUAGE_CODES: Tuple[str, ...] = tuple(_id_table()["languages"])
+# language name / alias -> code (reference tokenizer.py:114-128, TO_LANGUAGE_CODE): data table dumped by oracle/make_golden.py
+TO_LANGUAGE_CODE: Dict[str, str] = dict(_id_table().get("language_names", {}))
 
 
 def _find_rank_file(name: str) -> Optional[str]:
@@ -242,7 +244,10 @@ def get_tokenizer(multilingual: bool, *, num_languages: int = 99, language: Opti
     if language is not None:
         language = language.lower()
         if language not in LANGUAGE_CODES:
-            raise ValueError(f"Unsupported language: {language}")
+            if language in TO_LANGUAGE_CODE:                    # tokenizer.py:376-378: "english", "castilian", ...
+                language = TO_LANGUAGE_CODE[language]
+            else:
+                raise ValueError(f"Unsupported language: {language}")
     if multilingual:
         name = "multilingual"
         language = language or "en"
