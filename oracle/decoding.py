@@ -159,8 +159,8 @@ def greedy_update(tokens: List[List[int]], logits: torch.Tensor, sum_logprobs: t
     """GreedyDecoder.update with temperature 0 (decoding.py:277-293)."""
     nxt = logits.argmax(dim=-1)
     logprobs = torch.log_softmax(logits.float(), dim=-1)
-    cur = logprobs[torch.arange(len(tokens)), nxt]
-    last = torch.tensor([t[-1] for t in tokens])
+    cur = logprobs[torch.arange(len(tokens), device=logits.device), nxt]
+    last = torch.tensor([t[-1] for t in tokens], device=logits.device)
     sum_logprobs += cur * (last != eot)
     nxt = torch.where(last == eot, torch.full_like(nxt, eot), nxt)
     out = [t + [int(n)] for t, n in zip(tokens, nxt)]
@@ -297,7 +297,7 @@ class BeamState:
         """decoding.py:384-404; tokens indexed [audio][beam]."""
         for a, seqs in enumerate(self.finished):
             if len(seqs) < self.beam:
-                for j in list(np.argsort(sum_logprobs[a].numpy()))[::-1]:
+                for j in list(np.argsort(sum_logprobs[a].cpu().numpy()))[::-1]:
                     seqs[tuple(tokens[a][j] + [self.eot])] = float(sum_logprobs[a][j])
                     if len(seqs) >= self.beam:
                         break
@@ -384,7 +384,7 @@ def decode(W: M.Weights, dims: Dict[str, int], mel_or_features: torch.Tensor, op
     init = initial_tokens(ids, opt, n_ctx, sample_len)
     sample_begin = len(init)
     sot_index = init.index(ids.sot)
-    x = mel_or_features.float()
+    x = mel_or_features if mel_or_features.is_cuda else mel_or_features.float()     # CUDA: keep the caller's 16-bit type
     if x.dim() == 2:
         x = x[None]
     if tuple(x.shape[-2:]) == (dims["n_audio_ctx"], dims["n_audio_state"]):   # decoding.py:648-653
@@ -407,7 +407,7 @@ def decode(W: M.Weights, dims: Dict[str, int], mel_or_features: torch.Tensor, op
         return [Result(language=languages[a], top_language_prob=top_lang_prob[a], audio_features=feats[a]) for a in range(B)]
     xa = feats.repeat_interleave(G, dim=0) if G > 1 else feats
     cache = M.KVCache(dims["n_text_layer"])
-    sum_lp = torch.zeros(R)
+    sum_lp = torch.zeros(R, device=feats.device)
     no_speech = [float("nan")] * R
     beam = BeamState(G, ids.eot, opt.patience) if opt.beam_size is not None else None
     sup = suppress_list(ids, opt) if opt.suppress_tokens else ()
@@ -418,7 +418,7 @@ def decode(W: M.Weights, dims: Dict[str, int], mel_or_features: torch.Tensor, op
     steps = sample_len if max_steps is None else min(sample_len, max_steps)
     for i in range(steps):                                                   # decoding.py:686
         _t0 = _time.perf_counter()
-        new = torch.tensor([t[cache.length:] for t in tokens])               # decoding.py:159-161
+        new = torch.tensor([t[cache.length:] for t in tokens], device=feats.device)   # decoding.py:159-161
         logits_all = M.decoder_forward(W, dims, new, xa, cache)
         if i == 0:                                                           # decoding.py:689-693
             probs = torch.softmax(logits_all[:, sot_index].float(), dim=-1)
@@ -431,9 +431,10 @@ def decode(W: M.Weights, dims: Dict[str, int], mel_or_features: torch.Tensor, op
         if record is not None:
             record.setdefault("filtered_logits", []).append(logits.clone())
             record.setdefault("sum_logprobs_in", []).append(sum_lp.clone())
-        top2 = logits.topk(2, dim=-1).values
-        for r in range(R):
-            margins[r].append(float(top2[r, 0] - top2[r, 1]))
+        if record is not None:                 # decision margins: diagnostics for the margin-gated parity tests only
+            top2 = logits.topk(2, dim=-1).values.cpu()
+            for r in range(R):
+                margins[r].append(float(top2[r, 0] - top2[r, 1]))
         if beam is None and opt.temperature > 0:
             tokens, completed, gaps = sample_update(tokens, logits, sum_lp, ids.eot, opt.temperature, opt.seed)
             if record is not None:
@@ -453,7 +454,7 @@ def decode(W: M.Weights, dims: Dict[str, int], mel_or_features: torch.Tensor, op
         if completed or len(tokens[0]) > n_ctx:                              # decoding.py:705
             break
     grouped = [[tokens[a * G + j] for j in range(G)] for a in range(B)]
-    lp_grouped = sum_lp.reshape(B, G)
+    lp_grouped = sum_lp.reshape(B, G).cpu()
     if beam is None:
         cands = [[t + [ids.eot] for t in grp] for grp in grouped]            # decoding.py:295-298
         cand_lp = lp_grouped.tolist()

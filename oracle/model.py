@@ -25,15 +25,19 @@ def _r(x: torch.Tensor) -> torch.Tensor:
     return x if ACT_DTYPE is None else x.to(ACT_DTYPE).float()
 
 
-def to_weights(state_dict: Dict[str, np.ndarray]) -> Weights:
-    return {k: torch.from_numpy(np.ascontiguousarray(v)).float() for k, v in state_dict.items()}
+def to_weights(state_dict: Dict[str, np.ndarray], device=None) -> Weights:
+    """fp32 tensors, like the reference model after load_model() (parameters stay fp32 on any device; Linear / Conv1d
+    cast them to the activation type per call, model.py:44-59)."""
+    out = {k: torch.from_numpy(np.ascontiguousarray(v)).float() for k, v in state_dict.items()}
+    return out if device is None else {k: v.to(device) for k, v in out.items()}
 
 
 def layer_norm(x: torch.Tensor, w: torch.Tensor, b: torch.Tensor) -> torch.Tensor:
     """model.py:39-41: fp32 LayerNorm over the last dim, eps = nn.LayerNorm default 1e-5."""
-    mu = x.mean(-1, keepdim=True)
-    var = ((x - mu) ** 2).mean(-1, keepdim=True)
-    return _r((x - mu) / torch.sqrt(var + 1e-5) * w + b)
+    xf = x.float()                                                      # super().forward(x.float()).type(x.dtype)
+    mu = xf.mean(-1, keepdim=True)
+    var = ((xf - mu) ** 2).mean(-1, keepdim=True)
+    return _r((xf - mu) / torch.sqrt(var + 1e-5) * w + b).to(x.dtype)
 
 
 def gelu(x: torch.Tensor) -> torch.Tensor:
@@ -43,9 +47,9 @@ def gelu(x: torch.Tensor) -> torch.Tensor:
 
 def linear(x: torch.Tensor, W: Weights, prefix: str) -> torch.Tensor:
     """model.py:44-50; `key` projections have no bias (model.py:88)."""
-    y = x @ W[prefix + ".weight"].T
+    y = x @ W[prefix + ".weight"].to(x.dtype).T                         # self.weight.to(x.dtype), model.py:46-49
     b = W.get(prefix + ".bias")
-    return _r(y if b is None else y + b)
+    return _r(y if b is None else y + b.to(x.dtype))
 
 
 def conv1d_k3(x: torch.Tensor, w: torch.Tensor, b: torch.Tensor, stride: int) -> torch.Tensor:
@@ -54,7 +58,8 @@ def conv1d_k3(x: torch.Tensor, w: torch.Tensor, b: torch.Tensor, stride: int) ->
     B, C, T = x.shape
     xp = torch.nn.functional.pad(x, (1, 1))
     T_out = (T + 2 - 3) // stride + 1
-    y = torch.zeros(B, w.shape[0], T_out)
+    w, b = w.to(x.dtype), b.to(x.dtype)                                 # model.py:56-59
+    y = torch.zeros(B, w.shape[0], T_out, dtype=x.dtype, device=x.device)
     for k in range(3):
         seg = xp[:, :, k: k + stride * (T_out - 1) + 1: stride]       # (B, C_in, T_out)
         y = y + torch.einsum("oc,bct->bot", w[:, :, k], seg)
@@ -75,10 +80,10 @@ def attention(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, n_head: int,
     if causal:
         # queries are the LAST Tq positions of the key sequence (kv-cache decoding)
         Tk = kh.shape[2]
-        qpos = torch.arange(Tk - Tq, Tk)[:, None]
-        kpos = torch.arange(Tk)[None, :]
+        qpos = torch.arange(Tk - Tq, Tk, device=q.device)[:, None]
+        kpos = torch.arange(Tk, device=q.device)[None, :]
         qk = qk.masked_fill(kpos > qpos, float("-inf"))
-    w = torch.softmax(qk.float(), dim=-1)
+    w = torch.softmax(qk.float(), dim=-1).to(q.dtype)                   # model.py:136
     out = _r((w @ vh).permute(0, 2, 1, 3).reshape(B, Tq, D))
     return out, qk
 
@@ -92,7 +97,7 @@ def encoder_forward(W: Weights, dims: Dict[str, int], mel: torch.Tensor,
     x = gelu(conv1d_k3(x, W["encoder.conv2.weight"], W["encoder.conv2.bias"], 2))
     x = x.permute(0, 2, 1)
     assert x.shape[1:] == W["encoder.positional_embedding"].shape, "incorrect audio shape"  # model.py:197
-    x = _r(x + W["encoder.positional_embedding"])
+    x = _r(x + W["encoder.positional_embedding"]).to(x.dtype)
     if collect is not None:
         collect["stem"] = x
     H = dims["n_audio_head"]
@@ -140,6 +145,7 @@ def decoder_forward(W: Weights, dims: Dict[str, int], tokens: torch.Tensor, xa: 
     offset = cache.length if cache is not None else 0                                  # model.py:234
     x = _r(W["decoder.token_embedding.weight"][tokens] +
            W["decoder.positional_embedding"][offset: offset + tokens.shape[-1]])        # model.py:235-238
+    x = x.to(xa.dtype)                                                                 # model.py:239
     H = dims["n_text_head"]
     for i in range(dims["n_text_layer"]):
         p = f"decoder.blocks.{i}"
@@ -166,4 +172,4 @@ def decoder_forward(W: Weights, dims: Dict[str, int], tokens: torch.Tensor, xa: 
         h = layer_norm(x, W[p + ".mlp_ln.weight"], W[p + ".mlp_ln.bias"])
         x = _r(x + linear(gelu(linear(h, W, p + ".mlp.0")), W, p + ".mlp.2"))
     x = layer_norm(x, W["decoder.ln.weight"], W["decoder.ln.bias"])
-    return (x @ W["decoder.token_embedding.weight"].T).float()                         # model.py:245-247
+    return (x @ W["decoder.token_embedding.weight"].to(x.dtype).T).float()             # model.py:245-247

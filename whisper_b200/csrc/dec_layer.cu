@@ -19,10 +19,16 @@
 //     split the N output features evenly in units of 16 columns, so every CTA streams its own weight slab exactly
 //     once plus one 64-row activation block: bytes per CTA = 2K (64 + N / ctas_per_block), the minimum over tile
 //     shapes for 148 CTAs, and all SMs pull weights concurrently.
-//   * Roles per CTA (384 threads): warp 0 = TMA producer (activation block + weight slab through one smem ring that
-//     lives across phases), warp 1 = tcgen05.mma issuer (accumulator 64 x <=192 fp32 in TMEM, two buffers), warp 2 =
-//     TMEM allocator, warp 3 = grid-barrier poller, warps 4-11 = epilogue (tcgen05.ld -> LN fold / bias / erf-GELU /
-//     residual add / LN partials -> global).
+//   * Roles per CTA (416 threads): warps 0, 2, 3 = TMA producers, ONE PER RING STAGE (activation block + weight slab
+//     through a 3 x 64 KB smem ring that lives across phases), warp 1 = tcgen05.mma issuer (accumulator 64 x <=192 fp32
+//     in TMEM, two buffers), warp 2 also allocates TMEM, warps 4-11 = epilogue (tcgen05.ld -> LN fold / bias / erf-GELU /
+//     residual add / LN partials -> global), warp 12 = grid-barrier poller.
+//     Why a producer per stage: measured on B200 (tools/microbench_tma.cu, profiles/r2_microbench_tma.txt) one thread
+//     that waits on an mbarrier, re-arms it and issues a TMA tile sustains one such round every ~500 clk whatever the
+//     box size (8 KB boxes: 16 B/clk/SM, 32 KB boxes: 62 B/clk/SM) while every further back-to-back TMA costs ~60 clk,
+//     and N issuing threads scale N-fold (4 threads x 8 KB: 62 B/clk/SM; L2 delivers 17-20 TB/s chip-wide).  So each
+//     ring stage has its own issuing thread, weight slabs travel as ONE box of up to 192 rows, and a stage carries as many
+//     64-wide K sub-blocks as fit in 64 KB (4 for the 1280-wide projections, 2 for QKV / fc1).
 //
 // Phases of a decoder layer (engine.cu strings them together; the two attention kernels stay separate launches):
 //     [QKV] | self-attention | [out-proj + residual, cross-query] | cross-attention |
@@ -39,14 +45,23 @@ namespace wb {
 
 int g_fused_layer = -1;   // -1: read WB200_FUSED_LAYER on first use; wb200_set_fused_decoder_layer() overrides
 
-constexpr int kDLThreads = 384;
+constexpr int kDLThreads = 416;                      // 13 warps
 constexpr int kDLASub = 64 * 128;                    // 64 rows x 64 x 16-bit
-constexpr int kDLBSub = kDLMaxUnits * kDLUnit * 128;   // weight rows x 64 x 16-bit
+constexpr int kDLUnitBytes = kDLUnit * 128;          // 16 weight rows x 64 x 16-bit
+constexpr int kDLSlotBytes = 64 * 1024;              // one ring stage
+constexpr int kDLMaxKS = 4;
 constexpr int kDLTmemCols = 512;                     // two accumulator buffers of 256 columns
+static_assert(2 * (kDLASub + kDLMaxUnits * kDLUnitBytes) <= kDLSlotBytes, "a stage must hold two K sub-blocks of the widest tile");
 
-template <int KS, int STAGES>
+// 64-wide K sub-blocks per ring stage for a tile of nu units
+__device__ __forceinline__ int dl_ks(int nu) {
+  const int k = kDLSlotBytes / (kDLASub + nu * kDLUnitBytes);
+  return k > kDLMaxKS ? kDLMaxKS : k;
+}
+
+template <int STAGES>
 struct DLCfg {
-  static constexpr int kStageBytes = KS * (kDLASub + kDLBSub);
+  static constexpr int kStageBytes = kDLSlotBytes;
   static constexpr int kTileBytes = STAGES * kStageBytes;
   // tail: barriers (full, empty, tmem_full[2], tmem_empty[2], ready[kDLMaxPhases]) + tmem pointer + LN scratch
   static constexpr int kTailBytes = 8 * (2 * STAGES + 4 + kDLMaxPhases) + 16 + 2 * 64 * 16 + 64;
@@ -55,7 +70,7 @@ struct DLCfg {
 
 // bounded waits: a protocol bug must end in a trap (an error the host sees), never in a hung GPU
 __device__ __forceinline__ void dl_mbar_wait(uint64_t* bar, uint32_t parity) {
-  for (long long i = 0; i < (1ll << 28); ++i)
+  for (int i = 0; i < (1 << 22); ++i)
     if (mbar_try_wait(bar, parity)) return;
   __trap();
 }
@@ -73,10 +88,11 @@ __device__ __forceinline__ void chan_merge(float& n, float& mean, float& m2, flo
   n = nt;
 }
 
-template <typename T, int KS, int STAGES>
+template <typename T, int STAGES>
 __global__ void __launch_bounds__(kDLThreads, 1)
 dec_layer_kernel(const DLParams P, const __grid_constant__ DLMaps M) {
-  using Cfg = DLCfg<KS, STAGES>;
+  using Cfg = DLCfg<STAGES>;
+  static_assert(STAGES == 3, "one producer warp per stage: warps 0, 2, 3");
   pdl_launch_dependents();
   extern __shared__ uint8_t dl_smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(dl_smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
@@ -135,10 +151,10 @@ dec_layer_kernel(const DLParams P, const __grid_constant__ DLMaps M) {
     nu = static_cast<int>(static_cast<long long>(slot + 1) * total / n_slots) - u0;
   };
 
-  if (warp == 0 && lane == 0) {
-    // ===================== TMA producer =====================
-    int stage = 0;
-    uint32_t par = 0;
+  const int prod = warp == 0 ? 0 : (warp == 2 ? 1 : (warp == 3 ? 2 : -1));
+  if (prod >= 0 && lane == 0) {
+    // ===================== TMA producers: producer j owns ring stage j =====================
+    int q = 0;                                 // running stage number across phases (the ring never drains)
     for (int p = 0; p < n_phases; ++p) {
       int u0, nu;
       share(p, u0, nu);
@@ -148,33 +164,30 @@ dec_layer_kernel(const DLParams P, const __grid_constant__ DLMaps M) {
       }
       if (nu == 0) continue;
       const DLPhase& ph = P.ph[p];
+      const int ks = dl_ks(nu);
       const int kblocks = (ph.K + 63) / 64;
-      const int groups = (kblocks + KS - 1) / KS;
-      const uint32_t bytes = static_cast<uint32_t>(KS) * (kDLASub + nu * kDLUnit * 128);
+      const int groups = (kblocks + ks - 1) / ks;
+      const int bsub = nu * kDLUnitBytes;
+      const uint32_t bytes = static_cast<uint32_t>(ks) * (kDLASub + bsub);
       const int box_units = ph.units_box;
-      for (int g = 0; g < groups; ++g) {
-        dl_mbar_wait(&empty_bar[stage], par ^ 1);
-        mbar_expect_tx(&full_bar[stage], bytes);
-        uint8_t* sa = tiles + stage * Cfg::kStageBytes;
-        uint8_t* sb = sa + KS * kDLASub;
-#pragma unroll
-        for (int sub = 0; sub < KS; ++sub) {       // sub-blocks past K are zero-filled by TMA (full byte count)
-          const int kc = (g * KS + sub) * 64;
-          tma_load_2d(sa + sub * kDLASub, &M.a[p], &full_bar[stage], kc, m_blk * 64);
-          tma_load_2d(sb + sub * kDLBSub, &M.b_main[p], &full_bar[stage], kc, u0 * kDLUnit);
+      for (int g = 0; g < groups; ++g, ++q) {
+        if (q % STAGES != prod) continue;
+        dl_mbar_wait(&empty_bar[prod], ((q / STAGES) & 1) ^ 1);
+        mbar_expect_tx(&full_bar[prod], bytes);
+        uint8_t* sa = tiles + prod * Cfg::kStageBytes;
+        uint8_t* sb = sa + ks * kDLASub;
+        for (int sub = 0; sub < ks; ++sub) {       // sub-blocks past K are zero-filled by TMA (full byte count)
+          const int kc = (g * ks + sub) * 64;
+          tma_load_2d(sa + sub * kDLASub, &M.a[p], &full_bar[prod], kc, m_blk * 64);
+          tma_load_2d(sb + sub * bsub, &M.b_main[p], &full_bar[prod], kc, u0 * kDLUnit);
           for (int e = box_units; e < nu; ++e)
-            tma_load_2d(sb + sub * kDLBSub + e * kDLUnit * 128, &M.b_unit[p], &full_bar[stage], kc, (u0 + e) * kDLUnit);
-        }
-        if (++stage == STAGES) {
-          stage = 0;
-          par ^= 1;
+            tma_load_2d(sb + sub * bsub + e * kDLUnitBytes, &M.b_unit[p], &full_bar[prod], kc, (u0 + e) * kDLUnit);
         }
       }
     }
   } else if (warp == 1 && lane == 0) {
     // ===================== MMA issuer =====================
-    int stage = 0;
-    uint32_t par = 0;
+    int q = 0;
     int acc = 0;
     uint32_t acc_par = 0;
     for (int p = 0; p < n_phases; ++p) {
@@ -182,36 +195,34 @@ dec_layer_kernel(const DLParams P, const __grid_constant__ DLMaps M) {
       share(p, u0, nu);
       if (nu == 0) continue;
       const DLPhase& ph = P.ph[p];
+      const int ks = dl_ks(nu);
       const int kblocks = (ph.K + 63) / 64;
-      const int groups = (kblocks + KS - 1) / KS;
+      const int groups = (kblocks + ks - 1) / ks;
+      const int bsub = nu * kDLUnitBytes;
       const uint32_t idesc = umma_idesc(Cvt<T>::kUmmaFmt, 64, static_cast<uint32_t>(nu * kDLUnit), 0, 0);
       dl_mbar_wait(&tmem_empty[acc], acc_par ^ 1);
       tc_fence_after();
       const uint32_t d_tmem = tmem_base + acc * 256;
-      for (int g = 0; g < groups; ++g) {
-        dl_mbar_wait(&full_bar[stage], par);
+      for (int g = 0; g < groups; ++g, ++q) {
+        const int stage = q % STAGES;
+        dl_mbar_wait(&full_bar[stage], (q / STAGES) & 1);
         tc_fence_after();
         const uint32_t sa = smem_u32(tiles + stage * Cfg::kStageBytes);
-        const uint32_t sb = sa + KS * kDLASub;
-#pragma unroll
-        for (int sub = 0; sub < KS; ++sub) {
+        const uint32_t sb = sa + ks * kDLASub;
+        for (int sub = 0; sub < ks; ++sub) {
           const uint64_t adesc = umma_desc_sw128(sa + sub * kDLASub, 16, 1024);
-          const uint64_t bdesc = umma_desc_sw128(sb + sub * kDLBSub, 16, 1024);
+          const uint64_t bdesc = umma_desc_sw128(sb + sub * bsub, 16, 1024);
 #pragma unroll
           for (int k = 0; k < 4; ++k)
             umma_f16(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (g != 0) || (sub != 0) || (k != 0));
         }
         umma_commit(&empty_bar[stage]);
-        if (++stage == STAGES) {
-          stage = 0;
-          par ^= 1;
-        }
       }
       umma_commit(&tmem_full[acc]);
       acc ^= 1;
       if (acc == 0) acc_par ^= 1;
     }
-  } else if (warp == 3 && lane == 0) {
+  } else if (warp == 12 && lane == 0) {
     // ===================== grid-barrier poller =====================
     for (int p = 1; p < n_phases; ++p) {
       const unsigned int target = static_cast<unsigned int>(p) * static_cast<unsigned int>(grid);
@@ -220,11 +231,11 @@ dec_layer_kernel(const DLParams P, const __grid_constant__ DLMaps M) {
         unsigned int v;
         asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(P.sync) : "memory");
         if (v >= target) break;
-        if (++spins > (1ll << 27)) __trap();
+        if (++spins > (1ll << 23)) __trap();
       }
       mbar_arrive(&ready_bar[p]);
     }
-  } else if (warp >= 4) {
+  } else if (warp >= 4 && warp < 12) {
     // ===================== epilogue =====================
     // UMMA M = 64: accumulator row i sits in lane (i % 16) of TMEM quadrant i / 16, so lanes 16-31 of every warp idle.
     const int ct = threadIdx.x - 128;
@@ -444,9 +455,9 @@ void dl_init_launch(DLLaunch& L, int dtype, int R, int grid, float4* ln_part, in
 
 template <typename T>
 static int dl_launch_t(const DLLaunch& L, cudaStream_t s) {
-  constexpr int KS = 2, STAGES = 3;
-  using Cfg = DLCfg<KS, STAGES>;
-  auto kern = dec_layer_kernel<T, KS, STAGES>;
+  constexpr int STAGES = 3;
+  using Cfg = DLCfg<STAGES>;
+  auto kern = dec_layer_kernel<T, STAGES>;
   static SmemOptIn optin;
   if (!optin.ensure(kern, Cfg::kSmemBytes)) return 60;
   ProfileScope prof(PROF_DEC_LAYER, s);

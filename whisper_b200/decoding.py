@@ -351,7 +351,15 @@ class DecodingTask:
         """decoding.py:644-664: accept pre-encoded features."""
         if tuple(mel.shape[-2:]) == (self.model.dims.n_audio_ctx, self.model.dims.n_audio_state):
             return mel.to(device=self.model.device, dtype=self.model.dtype).contiguous()
-        return self.model.encoder(mel)
+        timing = getattr(self.model, "timing", None)
+        if timing is None:
+            return self.model.encoder(mel)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        out = self.model.encoder(mel)
+        e1.record()
+        timing.setdefault("marks", []).extend([("encoder", e0), ("encoder_end", e1)])
+        return out
 
     def session_config(self, n_audio: int) -> dict:
         tk, o = self.tokenizer, self.options
@@ -432,17 +440,33 @@ class DecodingTask:
 
     def _run_session(self, audio_features: torch.Tensor, init: np.ndarray, seed: Optional[int]):
         """One device-resident decode of `init.shape[0]` audios on the current stream: (tokens [R, L], sum_logprobs [R],
-        no_speech [n_audio], finished-hypothesis store or None)."""
+        no_speech [n_audio], finished-hypothesis store or None).  If `model.timing` is a dict, CUDA events around the
+        cross-K/V build, the prefill and the decode loop are appended to it (bench.py's per-phase rooflines)."""
         n_audio = init.shape[0]
         sess = self.open_session(n_audio)
+        timing = getattr(self.model, "timing", None)
+
+        def mark(name):
+            if timing is not None:
+                ev = torch.cuda.Event(enable_timing=True)
+                ev.record()
+                timing.setdefault("marks", []).append((name, ev))
+
         try:
+            mark("cross_kv")
             sess.set_audio(audio_features)
             if seed is not None:
                 sess.set_sampling(self.options.temperature, seed)
+            mark("prefill")
             sess.prefill(init)                       # i == 0 forward + no_speech probabilities
             sess.select()                            # filters + first update
+            mark("decode_loop")
+            steps = 1
             if self.sample_len > 1:
-                sess.run(self.sample_len - 1)        # i = 1 .. sample_len-1, stops on completion
+                steps += sess.run(self.sample_len - 1)        # i = 1 .. sample_len-1, stops on completion
+            mark("end")
+            if timing is not None:
+                timing.setdefault("loop_steps", []).append(steps - 1)
             length = int(sess.get("length").item())
             tokens = sess.get("tokens")[:, :length].cpu().numpy()
             sum_logprobs = sess.get("sum_logprobs").cpu().numpy()

@@ -143,6 +143,7 @@ class Whisper:
         self._workspace = None
         # decoder sessions parked between decode() calls, most recently used last (decoding.DecoderSession.close)
         self._sessions = {}
+        self.timing = None                        # dict: decode() appends CUDA events per phase (bench.py)
         self.session_cache_entries = 4            # 0 disables the reuse
         self.session_cache_bytes = 64 << 30
         self.encoder = _Encoder(self)
