@@ -74,13 +74,19 @@ int wb200_set_pdl(int enabled);
  * into the consuming Linear.  On by default for sessions created AFTER the call (WB200_FUSED_LAYER=0 in the environment
  * or this call turns it off; the unfused kernels then run, as they always do for the prefill). */
 int wb200_set_fused_decoder_layer(int enabled);
-/* Layout of the decoder's kv caches for sessions created AFTER the call (default 0, or WB200_KV_HEAD_MAJOR=1 in
- * the environment).  0: cross-attention K/V [n_audio, 1500, 2d] and self-attention caches [rows, 448, d], i.e. one
- * head's 128 bytes per position are strided by the model width.  1: head-major - cross K/V [n_audio, 2H, 1500, 64]
- * (written that way by the K/V projection's epilogue), self caches [rows, H, 448, 64] - so every (audio, head) /
- * (row, head) pair streams one contiguous block.  Results are identical bit for bit; only the HBM access pattern
- * of the two decode-attention kernels changes (measured on B200: +1 %, profiles/r2_ab_switches.txt). */
+/* Layout of the decoder's kv caches for sessions created AFTER the call (default 1, or WB200_KV_HEAD_MAJOR=0 in
+ * the environment).  1: head-major - cross-attention K/V [n_audio, 2H, 1500, 64] (written that way by the K/V
+ * projection's epilogue), self-attention caches [rows, H, 448, 64] - so every (audio, head) / (row, head) pair streams
+ * one contiguous block, which is also what the TMA cross-attention kernel needs.  0: cross K/V [n_audio, 1500, 2d] and
+ * self caches [rows, 448, d], one head's 128 bytes per position strided by the model width.  With the cp.async
+ * attention kernels the two layouts give bit-identical results (measured on B200: head-major +1 %,
+ * profiles/r2_ab_switches.txt). */
 int wb200_set_kv_head_major(int enabled);
+/* Decoder-step cross attention (whisper/model.py:101-109 + SDPA, one query per beam against the audio's 1500 cached
+ * keys): 1 (default, WB200_XATTN_TMA=0 to disable) = persistent kernel, one CTA per SM, K/V tiles streamed by TMA
+ * through an mbarrier ring that stays full across (audio, head) work items; needs the head-major layout.  0 = the
+ * cp.async kernel (always used for the prefill).  Takes effect at the next launch. */
+int wb200_set_cross_attention_tma(int enabled);
 
 /* Same operator with split-K enabled for skinny problems (the 320-row decode-step GEMMs): `workspace`
  * holds fp32 partial slabs (up to 8 * M * N floats are used), `tickets` is an int32 array of n_tickets

@@ -25,6 +25,7 @@
 
 #include "kernels.h"
 #include "ptx.cuh"
+#include "tmap.cuh"
 
 namespace wb {
 
@@ -365,6 +366,229 @@ __global__ void __launch_bounds__(kDaThreads) cross_attention_kernel(const Cross
     u.z = Cvt<T>::pack2(o[4] * inv, o[5] * inv);
     u.w = Cvt<T>::pack2(o[6] * inv, o[7] * inv);
     *reinterpret_cast<uint4*>(orow) = u;
+  }
+}
+
+// =================================================================================================
+// cross attention, step mode, TMA-fed and persistent (head-major K/V only)
+// =================================================================================================
+// The cp.async kernel above plateaus at ~5.2 TB/s whatever its ring depth or key split (profiles/r1_xattn_sweep.txt)
+// while a read-only stream reaches 7.3 TB/s on the same part (tools/microbench.cu): each of its 2560 short-lived
+// CTAs pays its own pipeline fill, query load, 4-warp merge and drain for only 192 KB of K/V.  Here ONE CTA per SM
+// stays resident and walks through its share of the (audio, head, key-split) items with the memory pipeline kept full
+// ACROSS items: a dedicated producer warp streams 128-key K and V tiles (one 16 KB TMA box each, 128-byte swizzle = the
+// layout ldmatrix wants) and the next item's query tile through mbarrier rings, eight consumer warps (16 keys of every
+// tile each) run the same mma.sync online-softmax tile code as above, merge once per item and hand their partial to the
+// same last-arriver combine.
+constexpr int kX2Consumers = 8;
+constexpr int kX2Threads = (kX2Consumers + 1) * 32;
+constexpr int kX2TileKeys = 128;
+constexpr int kX2Stages = 4;
+constexpr int kX2TileBytes = kX2TileKeys * 128;                  // one K (or V) tile
+constexpr int kX2StageBytes = 2 * kX2TileBytes;
+constexpr int kX2QBytes = 16 * 128;                              // 16 query rows x 64 dims
+constexpr int kX2RedFloats = kX2Consumers * 32 * 40;
+constexpr int kX2SmemBytes = kX2Stages * kX2StageBytes + 2 * kX2QBytes + kX2RedFloats * 4 + 256 + 1024;
+
+struct Cross2Params {
+  void* out;            // [n_audio * n_q, d]
+  float* partial;       // [n_audio * H, splits, 16, 66]
+  int* counters;        // [n_audio * H], zero on entry, zero on exit
+  const int* skip_flag;
+  int n_q, n_head, T, d, splits, tiles_per_split, total_tiles, total_items;
+};
+
+__device__ __forceinline__ void x2_wait(uint64_t* bar, uint32_t parity) {
+  for (int i = 0; i < (1 << 22); ++i)
+    if (mbar_try_wait(bar, parity)) return;
+  __trap();                                                      // protocol bug: fail loudly instead of hanging the GPU
+}
+
+template <typename T>
+__global__ void __launch_bounds__(kX2Threads, 1)
+cross_attention_tma_kernel(const Cross2Params p, const __grid_constant__ CUtensorMap mapQ,
+                           const __grid_constant__ CUtensorMap mapKV) {
+  pdl_launch_dependents();
+  extern __shared__ uint8_t x2_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(x2_raw) + 1023) & ~static_cast<uintptr_t>(1023));
+  uint8_t* ring = smem;
+  uint8_t* sQ = ring + kX2Stages * kX2StageBytes;
+  float* red = reinterpret_cast<float*>(sQ + 2 * kX2QBytes);
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(red + kX2RedFloats);
+  uint64_t* empty_bar = full_bar + kX2Stages;
+  uint64_t* qfull_bar = empty_bar + kX2Stages;
+  uint64_t* qempty_bar = qfull_bar + 2;
+  int* s_last = reinterpret_cast<int*>(qempty_bar + 2);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < kX2Stages; ++i) {
+      mbar_init(&full_bar[i], 1);
+      mbar_init(&empty_bar[i], kX2Consumers);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&qfull_bar[i], 1);
+      mbar_init(&qempty_bar[i], kX2Consumers);
+    }
+    mbar_fence_init();
+    tma_prefetch_desc(&mapQ);
+    tma_prefetch_desc(&mapKV);
+  }
+  __syncthreads();
+  pdl_wait();
+  if (p.skip_flag && *p.skip_flag) return;
+  const int H = p.n_head;
+
+  if (warp == kX2Consumers) {
+    // ===================== producer =====================
+    if (lane == 0) {
+      int q = 0, iq = 0;
+      for (int item = blockIdx.x; item < p.total_items; item += gridDim.x, ++iq) {
+        const int split = item % p.splits, ah = item / p.splits;
+        const int head = ah % H, audio = ah / H;
+        const int qs = iq & 1;
+        x2_wait(&qempty_bar[qs], ((iq >> 1) & 1) ^ 1);
+        mbar_expect_tx(&qfull_bar[qs], kX2QBytes);
+        tma_load_2d(sQ + qs * kX2QBytes, &mapQ, &qfull_bar[qs], head * 64, audio * p.n_q);
+        const int t0 = split * p.tiles_per_split;
+        const int nt = min(p.tiles_per_split, p.total_tiles - t0);
+        for (int t = 0; t < nt; ++t, ++q) {
+          const int st = q % kX2Stages;
+          x2_wait(&empty_bar[st], ((q / kX2Stages) & 1) ^ 1);
+          mbar_expect_tx(&full_bar[st], kX2StageBytes);
+          uint8_t* dst = ring + st * kX2StageBytes;
+          tma_load_3d(dst, &mapKV, &full_bar[st], 0, (t0 + t) * kX2TileKeys, audio * 2 * H + head);
+          tma_load_3d(dst + kX2TileBytes, &mapKV, &full_bar[st], 0, (t0 + t) * kX2TileKeys, audio * 2 * H + H + head);
+        }
+      }
+    }
+    return;
+  }
+  // ===================== consumers =====================
+  int q = 0, iq = 0;
+  for (int item = blockIdx.x; item < p.total_items; item += gridDim.x, ++iq) {
+    const int split = item % p.splits, ah = item / p.splits;
+    const int head = ah % H, audio = ah / H;
+    const int qs = iq & 1;
+    uint32_t qa[4][4];
+    x2_wait(&qfull_bar[qs], (iq >> 1) & 1);
+    {
+      const uint8_t* sq = sQ + qs * kX2QBytes;
+      const int row = lane & 15;
+#pragma unroll
+      for (int ks = 0; ks < 4; ++ks) {
+        const int chunk = ks * 2 + (lane >> 4);
+        ldmatrix_x4(qa[ks], sq + row * 128 + ((chunk ^ (row & 7)) << 4));
+      }
+    }
+    __syncwarp();
+    if (lane == 0) mbar_arrive(&qempty_bar[qs]);
+    WarpAcc acc;
+    acc_init(acc);
+    const int t0 = split * p.tiles_per_split;
+    const int nt = min(p.tiles_per_split, p.total_tiles - t0);
+    for (int t = 0; t < nt; ++t, ++q) {
+      const int st = q % kX2Stages;
+      x2_wait(&full_bar[st], (q / kX2Stages) & 1);
+      const uint8_t* sK = ring + st * kX2StageBytes;
+      const int key0 = (t0 + t) * kX2TileKeys + warp * 16;
+      warp_tile<T>(sK, sK + kX2TileBytes, warp * 16, qa, p.T - key0, acc);
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&empty_bar[st]);
+    }
+    // ---- merge the eight warps' (m, l, O) into warp 0
+#pragma unroll
+    for (int r = 0; r < 2; ++r) {
+      acc.l[r] += __shfl_xor_sync(0xffffffffu, acc.l[r], 1);
+      acc.l[r] += __shfl_xor_sync(0xffffffffu, acc.l[r], 2);
+    }
+    {
+      float* mine = red + (warp * 32 + lane) * 40;
+#pragma unroll
+      for (int i = 0; i < 8; ++i)
+        *reinterpret_cast<float4*>(mine + i * 4) = make_float4(acc.o[i][0], acc.o[i][1], acc.o[i][2], acc.o[i][3]);
+      *reinterpret_cast<float4*>(mine + 32) = make_float4(acc.m[0], acc.m[1], acc.l[0], acc.l[1]);
+    }
+    asm volatile("bar.sync 1, 256;" ::: "memory");
+    const long long tile_id = ah;
+    const int g = lane >> 2, t4 = lane & 3;
+    if (warp == 0) {
+      float m0 = -INFINITY, m1 = -INFINITY;
+#pragma unroll
+      for (int w = 0; w < kX2Consumers; ++w) {
+        m0 = fmaxf(m0, red[(w * 32 + lane) * 40 + 32]);
+        m1 = fmaxf(m1, red[(w * 32 + lane) * 40 + 33]);
+      }
+      float l0 = 0.f, l1 = 0.f, o[8][4];
+#pragma unroll
+      for (int i = 0; i < 8; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) o[i][j] = 0.f;
+#pragma unroll
+      for (int w = 0; w < kX2Consumers; ++w) {
+        const float* src = red + (w * 32 + lane) * 40;
+        const float4 ml = *reinterpret_cast<const float4*>(src + 32);
+        const float f0 = ml.x == -INFINITY ? 0.f : fast_exp2(ml.x - m0);
+        const float f1 = ml.y == -INFINITY ? 0.f : fast_exp2(ml.y - m1);
+        l0 += ml.z * f0;
+        l1 += ml.w * f1;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const float4 v = *reinterpret_cast<const float4*>(src + i * 4);
+          o[i][0] += v.x * f0;
+          o[i][1] += v.y * f0;
+          o[i][2] += v.z * f1;
+          o[i][3] += v.w * f1;
+        }
+      }
+      float* part = p.partial + (tile_id * p.splits + split) * (16 * 66);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        *reinterpret_cast<float2*>(part + g * 66 + i * 8 + 2 * t4) = make_float2(o[i][0], o[i][1]);
+        *reinterpret_cast<float2*>(part + (g + 8) * 66 + i * 8 + 2 * t4) = make_float2(o[i][2], o[i][3]);
+      }
+      if (t4 == 0) {
+        *reinterpret_cast<float2*>(part + g * 66 + 64) = make_float2(m0, l0);
+        *reinterpret_cast<float2*>(part + (g + 8) * 66 + 64) = make_float2(m1, l1);
+      }
+      __threadfence();
+      __syncwarp();
+      if (lane == 0) {
+        const int prev = atomicAdd(&p.counters[tile_id], 1);
+        const int last = (prev == p.splits - 1);
+        if (last) p.counters[tile_id] = 0;          // ready for the next launch
+        *s_last = last;
+      }
+    }
+    asm volatile("bar.sync 1, 256;" ::: "memory");
+    if (*s_last && warp < 4) {
+      __threadfence();
+      // ---- combine the splits: 128 threads = 16 rows x 8 column groups of 8
+      const int row = threadIdx.x >> 3, cg = threadIdx.x & 7;
+      if (row < p.n_q) {
+        const float* base = p.partial + tile_id * p.splits * (16 * 66) + row * 66;
+        float m = -INFINITY;
+        for (int sp = 0; sp < p.splits; ++sp) m = fmaxf(m, __ldcg(base + sp * 16 * 66 + 64));
+        float l = 0.f, o[8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) o[e] = 0.f;
+        for (int sp = 0; sp < p.splits; ++sp) {
+          const float* ps = base + sp * 16 * 66;
+          const float ms = __ldcg(ps + 64);
+          const float f = ms == -INFINITY ? 0.f : fast_exp2(ms - m);
+          l += __ldcg(ps + 65) * f;
+#pragma unroll
+          for (int e = 0; e < 8; ++e) o[e] += __ldcg(ps + cg * 8 + e) * f;
+        }
+        const float inv = 1.0f / l;
+        T* orow = reinterpret_cast<T*>(p.out) + (static_cast<long long>(audio) * p.n_q + row) * p.d + head * 64 + cg * 8;
+        uint4 u;
+        u.x = Cvt<T>::pack2(o[0] * inv, o[1] * inv);
+        u.y = Cvt<T>::pack2(o[2] * inv, o[3] * inv);
+        u.z = Cvt<T>::pack2(o[4] * inv, o[5] * inv);
+        u.w = Cvt<T>::pack2(o[6] * inv, o[7] * inv);
+        *reinterpret_cast<uint4*>(orow) = u;
+      }
+    }
   }
 }
 
@@ -723,6 +947,78 @@ int launch_self_attention(int dtype, const void* qkv, void* kcache, void* vcache
   }
   count_launch();
   return cudaGetLastError() == cudaSuccess ? 0 : 43;
+}
+
+// Step-mode cross attention through the TMA kernel: q [n_audio * n_q, d] (n_q <= 16), kv = ONE layer's head-major block
+// [n_audio][2H][T][64].  Returns -1 when the shape is not covered (the caller falls back to the cp.async kernel).
+int launch_cross_attention_tma(int dtype, const void* q, const void* kv, void* out, float* partial, int* counters,
+                               const int* skip_flag, int n_audio, int n_q, int T, int n_head, cudaStream_t s) {
+  if (n_q > 16 || n_audio <= 0 || T < kX2TileKeys) return -1;
+  const int d = n_head * 64;
+  Cross2Params p;
+  p.out = out;
+  p.partial = partial;
+  p.counters = counters;
+  p.skip_flag = skip_flag;
+  p.n_q = n_q;
+  p.n_head = n_head;
+  p.T = T;
+  p.d = d;
+  p.total_tiles = (T + kX2TileKeys - 1) / kX2TileKeys;
+  const int sms = sm_count();
+  const int pairs = n_audio * n_head;
+  // key splits: the count (1..4, at least 2 tiles each) that balances items over the persistent CTAs best
+  int best = 1;
+  double best_eff = 0.0;
+  for (int sp = 1; sp <= 4; ++sp) {
+    const int tps = (p.total_tiles + sp - 1) / sp;
+    if (sp > 1 && (tps < 2 || (sp - 1) * tps >= p.total_tiles)) continue;
+    const long long items = static_cast<long long>(pairs) * sp;
+    const long long rounds = (items + sms - 1) / sms;
+    const double eff = static_cast<double>(items) / static_cast<double>(rounds * sms) - 0.01 * sp;
+    if (eff > best_eff) {
+      best_eff = eff;
+      best = sp;
+    }
+  }
+  static int splits_opt = -1;
+  if (splits_opt < 0) {
+    const char* e = getenv("WB200_XATTN_SPLITS");
+    splits_opt = (e && atoi(e) >= 1 && atoi(e) <= 8) ? atoi(e) : 0;
+  }
+  if (splits_opt && (splits_opt - 1) * ((p.total_tiles + splits_opt - 1) / splits_opt) < p.total_tiles) best = splits_opt;
+  p.splits = best;
+  p.tiles_per_split = (p.total_tiles + best - 1) / best;
+  p.total_items = pairs * best;
+  CUtensorMap mapQ, mapKV;
+  {
+    uint64_t dims[2] = {static_cast<uint64_t>(d), static_cast<uint64_t>(n_audio) * n_q};
+    uint64_t strides[1] = {static_cast<uint64_t>(d) * 2};
+    uint32_t box[2] = {64, 16};
+    if (make_tmap_16bit(&mapQ, dtype, q, 2, dims, strides, box)) return 46;
+  }
+  {
+    uint64_t dims[3] = {64, static_cast<uint64_t>(T), static_cast<uint64_t>(n_audio) * 2 * n_head};
+    uint64_t strides[2] = {128, static_cast<uint64_t>(T) * 128};
+    uint32_t box[3] = {64, kX2TileKeys, 1};
+    if (make_tmap_16bit(&mapKV, dtype, kv, 3, dims, strides, box)) return 47;
+  }
+  const int grid = p.total_items < sms ? p.total_items : sms;
+  ProfileScope prof(PROF_CROSS_ATTN, s);
+  cudaError_t le;
+  if (dtype == DT_BF16) {
+    static SmemOptIn optin;
+    auto kern = cross_attention_tma_kernel<__nv_bfloat16>;
+    if (!optin.ensure(kern, kX2SmemBytes)) return 48;
+    le = launch_pdl(kern, dim3(grid), dim3(kX2Threads), kX2SmemBytes, s, p, mapQ, mapKV);
+  } else {
+    static SmemOptIn optin;
+    auto kern = cross_attention_tma_kernel<__half>;
+    if (!optin.ensure(kern, kX2SmemBytes)) return 48;
+    le = launch_pdl(kern, dim3(grid), dim3(kX2Threads), kX2SmemBytes, s, p, mapQ, mapKV);
+  }
+  count_launch();
+  return (le == cudaSuccess && cudaGetLastError() == cudaSuccess) ? 0 : 49;
 }
 
 }  // namespace wb

@@ -140,6 +140,9 @@ dec_layer_kernel(const DLParams P, const __grid_constant__ DLMaps M) {
   pdl_wait();       // everything above overlaps the tail of the previous kernel
   const bool skip = P.skip_flag && *P.skip_flag;
   const int n_phases = skip ? 0 : P.n_phases;
+  auto stamp = [&](int p, int slot_id) {
+    if (P.trace) P.trace[(static_cast<long long>(cta) * kDLMaxPhases + p) * 8 + slot_id] = clock64();
+  };
 
   // this CTA's share of a phase: row block m, columns [u0, u0 + nu) in units of 16
   const int m_blk = cta % P.m_tiles;
@@ -162,6 +165,7 @@ dec_layer_kernel(const DLParams P, const __grid_constant__ DLMaps M) {
         dl_mbar_wait(&ready_bar[p], 0);      // the previous phase's outputs are complete grid-wide
         fence_proxy_async_global();          // generic-proxy writes of other CTAs -> this thread's async-proxy (TMA) reads
       }
+      if (prod == 0) stamp(p, 0);
       if (nu == 0) continue;
       const DLPhase& ph = P.ph[p];
       const int ks = dl_ks(nu);
@@ -206,6 +210,7 @@ dec_layer_kernel(const DLParams P, const __grid_constant__ DLMaps M) {
       for (int g = 0; g < groups; ++g, ++q) {
         const int stage = q % STAGES;
         dl_mbar_wait(&full_bar[stage], (q / STAGES) & 1);
+        if (g == 0) stamp(p, 1);
         tc_fence_after();
         const uint32_t sa = smem_u32(tiles + stage * Cfg::kStageBytes);
         const uint32_t sb = sa + ks * kDLASub;
@@ -219,6 +224,7 @@ dec_layer_kernel(const DLParams P, const __grid_constant__ DLMaps M) {
         umma_commit(&empty_bar[stage]);
       }
       umma_commit(&tmem_full[acc]);
+      stamp(p, 2);
       acc ^= 1;
       if (acc == 0) acc_par ^= 1;
     }
@@ -234,6 +240,7 @@ dec_layer_kernel(const DLParams P, const __grid_constant__ DLMaps M) {
         if (++spins > (1ll << 23)) __trap();
       }
       mbar_arrive(&ready_bar[p]);
+      stamp(p - 1, 6);
     }
   } else if (warp >= 4 && warp < 12) {
     // ===================== epilogue =====================
@@ -267,9 +274,11 @@ dec_layer_kernel(const DLParams P, const __grid_constant__ DLMaps M) {
         }
         rstd = rsqrtf(m2 / n + 1e-5f);
       }
+      if (ct == 0) stamp(p, 7);
       float sn = 0.f, smean = 0.f, sm2 = 0.f;          // LN partial of the values this thread writes
       if (nu > 0) {
         dl_mbar_wait(&tmem_full[acc], acc_par);
+        if (ct == 0) stamp(p, 3);
         tc_fence_after();
         const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + acc * 256;
         for (int e = half; e < nu; e += 2) {
@@ -354,6 +363,7 @@ dec_layer_kernel(const DLParams P, const __grid_constant__ DLMaps M) {
         acc ^= 1;
         if (acc == 0) acc_par ^= 1;
       }
+      if (ct == 0) stamp(p, 4);
       if (ph.flags & DL_STATS) {
         if (lane < 16) s_stats[half * 64 + trow] = make_float4(sn, smean, sm2, 0.f);
         asm volatile("bar.sync 1, 256;" ::: "memory");
@@ -372,6 +382,7 @@ dec_layer_kernel(const DLParams P, const __grid_constant__ DLMaps M) {
         if (ct == 0) {
           __threadfence();
           asm volatile("red.release.gpu.global.add.u32 [%0], %1;" ::"l"(P.sync), "r"(1u) : "memory");
+          stamp(p, 5);
         }
       }
     }
@@ -451,6 +462,7 @@ void dl_init_launch(DLLaunch& L, int dtype, int R, int grid, float4* ln_part, in
   L.p.ln_ld = ln_ld;
   L.p.sync = sync;
   L.p.skip_flag = skip_flag;
+  L.p.trace = nullptr;
 }
 
 template <typename T>

@@ -34,6 +34,10 @@ struct DLParams {
   int ln_ld;
   unsigned int* sync;     // [0] grid-barrier counter, [1] exit counter; zero between launches
   const int* skip_flag;
+  // optional trace (tools/bench_dec_layer.cu): [cta][phase][8] SM-clock stamps - 0 producer start, 1 first stage landed,
+  // 2 last MMA committed, 3 accumulator seen by the epilogue, 4 stores done, 5 arrived on the grid barrier,
+  // 6 next phase released (poller), 7 LN statistics gathered
+  unsigned long long* trace;
   DLPhase ph[kDLMaxPhases];
 };
 

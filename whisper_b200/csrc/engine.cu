@@ -386,7 +386,11 @@ int decoder_create(const Model* m, const wb200_decode_config* c, void* ws, size_
   D->cfg = *c;
   if (g_kv_head_major < 0) {
     const char* e = getenv("WB200_KV_HEAD_MAJOR");
-    g_kv_head_major = (e && e[0] && e[0] != '0') ? 1 : 0;
+    g_kv_head_major = (e && e[0] == '0') ? 0 : 1;        // default: head-major (contiguous (audio, head) streams, TMA-able)
+  }
+  if (g_xattn_tma < 0) {
+    const char* e = getenv("WB200_XATTN_TMA");
+    g_xattn_tma = (e && e[0] == '0') ? 0 : 1;
   }
   D->kv_head_major = g_kv_head_major != 0;
   D->cfg.suppress_ids = nullptr;
@@ -452,6 +456,20 @@ int decoder_set_audio(Decoder* D, const void* features, cudaStream_t s) {
   return 0;
 }
 
+// decoder cross-attention of one layer: the persistent TMA kernel for the step (head-major K/V, <= 16 queries per
+// audio), the cp.async kernel for the prefill and every other shape
+static int cross_attention(Decoder* D, const uint8_t* ckv, bool step, int n_q, cudaStream_t s) {
+  const Model* m = D->m;
+  const int d = m->dims.n_text_state, H = m->dims.n_text_head, Ta = m->dims.n_audio_ctx, B = D->cfg.n_audio;
+  const int* skip = step ? D->done_ptr : nullptr;
+  if (step && D->kv_head_major && g_xattn_tma) {
+    const int r = launch_cross_attention_tma(m->dtype, D->q, ckv, D->att, D->partial, D->counters, skip, B, n_q, Ta, H, s);
+    if (r >= 0) return r;
+  }
+  return launch_cross_attention(m->dtype, D->q, ckv, ckv + static_cast<size_t>(d) * 2, D->att, D->partial, D->counters, skip, B,
+                                n_q, Ta, H, 2 * d, s, D->kv_head_major ? 1 : 0);
+}
+
 // the transformer stack for `rows` new positions; step mode when `step` is true
 static int decoder_stack(Decoder* D, int rows, bool step, cudaStream_t s) {
   const Model* m = D->m;
@@ -472,8 +490,7 @@ static int decoder_stack(Decoder* D, int rows, bool step, cudaStream_t s) {
       WB_TRY(launch_self_attention(dt, D->qkv, kc, vc, D->att, D->indir[D->cur], D->len_ptr, skip, rows, H, ctx,
                                    D->cfg.n_init, G, s, D->kv_head_major ? 1 : 0));
       WB_TRY(dl_launch(D->dl_mid[l], s));
-      WB_TRY(launch_cross_attention(dt, D->q, ckv, ckv + static_cast<size_t>(d) * 2, D->att, D->partial, D->counters, skip, B,
-                                    n_q, Ta, H, 2 * d, s, D->kv_head_major ? 1 : 0));
+      WB_TRY(cross_attention(D, ckv, true, n_q, s));
       WB_TRY(dl_launch(D->dl_tail[l], s));
     }
     return 0;
@@ -502,8 +519,7 @@ static int decoder_stack(Decoder* D, int rows, bool step, cudaStream_t s) {
                                 k_head, D->kv_head_major ? 64 : 2 * d, dst, D->cfg.n_init, Ta, s));
       }
     }
-    WB_TRY(launch_cross_attention(dt, D->q, ckv, ckv + static_cast<size_t>(d) * 2, D->att, D->partial, D->counters, skip, B,
-                                  n_q, Ta, H, 2 * d, s, D->kv_head_major ? 1 : 0));
+    WB_TRY(cross_attention(D, ckv, step, n_q, s));
     WB_TRY(linear(m, D->att, d, rows, L[D_COUT_W], d, d, L[D_COUT_B], D->x, D->x, d, 0, 0, s, skip, D));
     WB_TRY(launch_layernorm(dt, D->x, d, D->ln, d, (const float*)L[D_MLP_LN_W], (const float*)L[D_MLP_LN_B], rows, d, s, skip));
     WB_TRY(linear(m, D->ln, d, rows, L[D_FC1_W], 4 * d, d, L[D_FC1_B], nullptr, D->hid, 4 * d, 1, 0, s, skip, D));

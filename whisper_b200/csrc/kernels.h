@@ -79,6 +79,7 @@ struct LinearArgs {
 int launch_linear(const LinearArgs& a, cudaStream_t s);
 extern int g_splitk_on;
 extern int g_bm64_on;
+extern int g_xattn_tma;       // step-mode cross attention through the persistent TMA kernel (wb200_set_cross_attention_tma)
 extern int g_kv_head_major;   // kv caches stored [.., head, position, 64] instead of [.., position, d] (wb200_set_kv_head_major)
 extern int g_pdl_on;   // programmatic dependent launch for the decoder-layer kernels (wb200_set_pdl / WB200_PDL)
 
@@ -151,6 +152,10 @@ size_t cross_attention_partial_floats(int n_audio, int n_q, int n_head, int T);
 int launch_cross_attention(int dtype, const void* q, const void* k, const void* v, void* out,
                            float* partial, int* counters, const int* skip_flag, int n_audio, int n_q,
                            int T, int n_head, int kv_ld, cudaStream_t s, int head_major = 0);
+// Step-mode cross attention fed by TMA from ONE layer's head-major K/V block [n_audio][2H][T][64] (n_q <= 16);
+// -1: shape not covered, use launch_cross_attention.
+int launch_cross_attention_tma(int dtype, const void* q, const void* kv, void* out, float* partial, int* counters,
+                               const int* skip_flag, int n_audio, int n_q, int T, int n_head, cudaStream_t s);
 // step mode (indir != null): one new position per row, appended to the cache; prefill mode
 // (indir == null): n_init positions per audio, causal, cache rows a*group.
 int launch_self_attention(int dtype, const void* qkv, void* kcache, void* vcache, void* out,
