@@ -254,6 +254,14 @@ int64_t wb200_decoder_logits_ld(const wb200_decoder* dec);
 int wb200_decoder_get_state(wb200_decoder* dec, int what, void* dst, size_t bytes, void* stream);
 int wb200_decoder_set_state(wb200_decoder* dec, int what, const void* src, size_t bytes, void* stream);
 
+/* softmax over the token range [first, first + n) of each of `rows` fp32 logit rows (row stride ld), everything outside
+ * the range counting as masked.  Replaces the mask / argmax / softmax of detect_language (whisper/decoding.py:60-66,
+ * range = the language tokens) and the softmax + gather of find_alignment (whisper/timing.py:198-201, range = [0, eot)).
+ * Optional outputs (null to skip): probs [rows, n]; argmax [rows] token ids (ties to the lower id); gather_probs [rows] =
+ * probability of gather_tokens[row]. */
+int wb200_range_softmax(const float* logits, int64_t ld, int first, int n, int rows, float* probs, int32_t* argmax,
+                        const int32_t* gather_tokens, float* gather_probs, void* stream);
+
 /* ---------------------------------------------------------------------------------------------
  * word timing
  * ------------------------------------------------------------------------------------------- */

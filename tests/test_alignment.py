@@ -106,3 +106,45 @@ def test_gpu_logits_method_matches_prefill_session():
         sess.close()
     full = model.logits(torch.tensor([list(task.initial_tokens)]), feats)[0]
     assert torch.equal(full[-1], last)
+
+
+def test_word_spans_match_the_reference_formula():
+    """timing.word_spans against the reference's own arithmetic (whisper/timing.py:227-241, restated here as the checker:
+    word_boundaries = pad(cumsum(len(word_tokens[:-1]))), jumps = pad(diff(text_indices), 1) != 0,
+    jump_times = time_indices[jumps] / 50, start / end = jump_times[boundaries[:-1] / [1:]]) on random monotone paths."""
+    from whisper_b200.timing import word_spans
+
+    rng = np.random.default_rng(5)
+    for trial in range(50):
+        n_tok = int(rng.integers(2, 40))
+        # a monotone DTW path over n_tok + 1 text positions (the last is <|endoftext|>) and ~3 frames per token
+        steps = []
+        t = f = 0
+        path_t, path_f = [0], [0]
+        while t < n_tok:
+            move = rng.integers(0, 3)
+            if move == 0:
+                t += 1
+                f += 1
+            elif move == 1:
+                t += 1
+            else:
+                f += 1
+            path_t.append(t)
+            path_f.append(f)
+        text_indices, time_indices = np.array(path_t), np.array(path_f)
+        cuts = sorted(set(rng.integers(1, n_tok, size=int(rng.integers(0, 6))).tolist())) if n_tok > 1 else []
+        bounds = [0] + cuts + [n_tok]
+        word_tokens = [list(range(a, b)) for a, b in zip(bounds, bounds[1:])] + [[99999]]
+        words = [f"w{i}" for i in range(len(word_tokens))]
+        probs = rng.random(n_tok)
+        got = word_spans(words, word_tokens, text_indices, time_indices, probs)
+        word_boundaries = np.pad(np.cumsum([len(t) for t in word_tokens[:-1]]), (1, 0))
+        jumps = np.pad(np.diff(text_indices), (1, 0), constant_values=1).astype(bool)
+        jump_times = time_indices[jumps] / 50.0
+        start, end = jump_times[word_boundaries[:-1]], jump_times[word_boundaries[1:]]
+        want_p = [np.mean(probs[i:j]) for i, j in zip(word_boundaries[:-1], word_boundaries[1:])]
+        assert len(got) == len(word_tokens) - 1
+        for k, w in enumerate(got):
+            assert (w.word, w.tokens) == (words[k], word_tokens[k])
+            assert w.start == start[k] and w.end == end[k] and abs(w.probability - want_p[k]) < 1e-12

@@ -385,6 +385,13 @@ int wb200_decoder_set_state(wb200_decoder* dec, int what, const void* src, size_
   return 0;
 }
 
+int wb200_range_softmax(const float* logits, int64_t ld, int first, int n, int rows, float* probs, int32_t* argmax,
+                        const int32_t* gather_tokens, float* gather_probs, void* stream) {
+  if (first < 0 || n <= 0 || rows < 0 || ld < first + n) return set_error(160, "wb200_range_softmax: bad range [%d, %d) of %lld", first, first + n, (long long)ld);
+  int r = launch_range_softmax(logits, ld, first, n, rows, probs, argmax, gather_tokens, gather_probs, static_cast<cudaStream_t>(stream));
+  return r ? set_error(r, "wb200_range_softmax: failed (%d)", r) : 0;
+}
+
 int wb200_median_filter(const float* x, float* y, int64_t rows, int T, int width, void* stream) {
   int r = launch_median_filter(x, y, rows, T, width, static_cast<cudaStream_t>(stream));
   return r ? set_error(r, "wb200_median_filter: failed (%d) rows=%lld T=%d width=%d", r, (long long)rows, T, width) : 0;

@@ -53,9 +53,9 @@ constexpr int kDLMaxKS = 4;
 constexpr int kDLTmemCols = 512;                     // two accumulator buffers of 256 columns
 static_assert(2 * (kDLASub + kDLMaxUnits * kDLUnitBytes) <= kDLSlotBytes, "a stage must hold two K sub-blocks of the widest tile");
 
-// 64-wide K sub-blocks per ring stage for a tile of nu units
-__device__ __forceinline__ int dl_ks(int nu) {
-  const int k = kDLSlotBytes / (kDLASub + nu * kDLUnitBytes);
+// 64-wide K sub-blocks per ring stage for a weight box of `box` units (the same for every CTA of a phase)
+__device__ __forceinline__ int dl_ks(int box) {
+  const int k = kDLSlotBytes / (kDLASub + box * kDLUnitBytes);
   return k > kDLMaxKS ? kDLMaxKS : k;
 }
 
@@ -63,8 +63,9 @@ template <int STAGES>
 struct DLCfg {
   static constexpr int kStageBytes = kDLSlotBytes;
   static constexpr int kTileBytes = STAGES * kStageBytes;
-  // tail: barriers (full, empty, tmem_full[2], tmem_empty[2], ready[kDLMaxPhases]) + tmem pointer + LN scratch
-  static constexpr int kTailBytes = 8 * (2 * STAGES + 4 + kDLMaxPhases) + 16 + 2 * 64 * 16 + 64;
+  // tail: barriers (full, empty, tmem_full[2], tmem_empty[2], ready[kDLMaxPhases]) + tmem pointer + LN scratch +
+  // the epilogue's per-column vectors (c1 | c2 or bias) of this CTA's columns
+  static constexpr int kTailBytes = 8 * (2 * STAGES + 4 + kDLMaxPhases) + 16 + 2 * 64 * 16 + 2 * kDLMaxUnits * kDLUnit * 4 + 64;
   static constexpr int kSmemBytes = kTileBytes + kTailBytes + 1024;
 };
 
@@ -104,6 +105,7 @@ dec_layer_kernel(const DLParams P, const __grid_constant__ DLMaps M) {
   uint64_t* ready_bar = tmem_empty + 2;
   uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(ready_bar + kDLMaxPhases);
   float4* s_stats = reinterpret_cast<float4*>(tmem_ptr_smem + 4);      // [2][64] (count, mean, M2, -)
+  float* s_vec = reinterpret_cast<float*>(s_stats + 128);              // [2][kDLMaxUnits * 16]: c1 | c2, or bias
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -113,8 +115,7 @@ dec_layer_kernel(const DLParams P, const __grid_constant__ DLMaps M) {
   if (warp == 0 && lane == 0) {
     for (int p = 0; p < P.n_phases; ++p) {
       tma_prefetch_desc(&M.a[p]);
-      tma_prefetch_desc(&M.b_main[p]);
-      tma_prefetch_desc(&M.b_unit[p]);
+      tma_prefetch_desc(&M.b[p]);
     }
   }
   if (warp == 1 && lane == 0) {
@@ -161,32 +162,36 @@ dec_layer_kernel(const DLParams P, const __grid_constant__ DLMaps M) {
     for (int p = 0; p < n_phases; ++p) {
       int u0, nu;
       share(p, u0, nu);
-      if (p > 0) {
-        dl_mbar_wait(&ready_bar[p], 0);      // the previous phase's outputs are complete grid-wide
-        fence_proxy_async_global();          // generic-proxy writes of other CTAs -> this thread's async-proxy (TMA) reads
-      }
-      if (prod == 0) stamp(p, 0);
       if (nu == 0) continue;
       const DLPhase& ph = P.ph[p];
-      const int ks = dl_ks(nu);
+      // ONE weight box per K sub-block, as tall as the widest share of the phase (the TMA unit costs ~120 clk per request
+      // whatever its size: a second 2 KB box for the odd unit cost as much as 8 KB of payload); rows past this CTA's own
+      // share are loaded and ignored, rows past N are zero-filled
+      const int box = ph.units_box;
+      const int ks = dl_ks(box);
       const int kblocks = (ph.K + 63) / 64;
       const int groups = (kblocks + ks - 1) / ks;
-      const int bsub = nu * kDLUnitBytes;
+      const int bsub = box * kDLUnitBytes;
       const uint32_t bytes = static_cast<uint32_t>(ks) * (kDLASub + bsub);
-      const int box_units = ph.units_box;
+      bool released = (p == 0);
       for (int g = 0; g < groups; ++g, ++q) {
         if (q % STAGES != prod) continue;
         dl_mbar_wait(&empty_bar[prod], ((q / STAGES) & 1) ^ 1);
         mbar_expect_tx(&full_bar[prod], bytes);
         uint8_t* sa = tiles + prod * Cfg::kStageBytes;
         uint8_t* sb = sa + ks * kDLASub;
-        for (int sub = 0; sub < ks; ++sub) {       // sub-blocks past K are zero-filled by TMA (full byte count)
-          const int kc = (g * ks + sub) * 64;
-          tma_load_2d(sa + sub * kDLASub, &M.a[p], &full_bar[prod], kc, m_blk * 64);
-          tma_load_2d(sb + sub * bsub, &M.b_main[p], &full_bar[prod], kc, u0 * kDLUnit);
-          for (int e = box_units; e < nu; ++e)
-            tma_load_2d(sb + sub * bsub + e * kDLUnitBytes, &M.b_unit[p], &full_bar[prod], kc, (u0 + e) * kDLUnit);
+        // weights first: they are constants, so the first stage of a phase streams them in while the grid barrier of the
+        // previous phase is still closing; the activation rows follow once that phase is complete grid-wide
+        for (int sub = 0; sub < ks; ++sub)         // sub-blocks past K are zero-filled by TMA (full byte count)
+          tma_load_2d(sb + sub * bsub, &M.b[p], &full_bar[prod], (g * ks + sub) * 64, u0 * kDLUnit);
+        if (!released) {
+          dl_mbar_wait(&ready_bar[p], 0);
+          fence_proxy_async_global();              // generic-proxy writes of other CTAs -> this thread's async-proxy (TMA) reads
+          released = true;
         }
+        if (prod == 0 && g == 0) stamp(p, 0);
+        for (int sub = 0; sub < ks; ++sub)
+          tma_load_2d(sa + sub * kDLASub, &M.a[p], &full_bar[prod], (g * ks + sub) * 64, m_blk * 64);
       }
     }
   } else if (warp == 1 && lane == 0) {
@@ -199,10 +204,10 @@ dec_layer_kernel(const DLParams P, const __grid_constant__ DLMaps M) {
       share(p, u0, nu);
       if (nu == 0) continue;
       const DLPhase& ph = P.ph[p];
-      const int ks = dl_ks(nu);
+      const int ks = dl_ks(ph.units_box);
       const int kblocks = (ph.K + 63) / 64;
       const int groups = (kblocks + ks - 1) / ks;
-      const int bsub = nu * kDLUnitBytes;
+      const int bsub = ph.units_box * kDLUnitBytes;
       const uint32_t idesc = umma_idesc(Cvt<T>::kUmmaFmt, 64, static_cast<uint32_t>(nu * kDLUnit), 0, 0);
       dl_mbar_wait(&tmem_empty[acc], acc_par ^ 1);
       tc_fence_after();
@@ -257,79 +262,97 @@ dec_layer_kernel(const DLParams P, const __grid_constant__ DLMaps M) {
       int u0, nu;
       share(p, u0, nu);
       const DLPhase& ph = P.ph[p];
+      const bool fold = (ph.flags & DL_FOLD) != 0;
+      // ---- per-column vectors of this CTA's columns into shared memory while the main loop runs: c1 | c2 (LN fold) or
+      //      the bias; constants of the model, so no need to wait for the previous phase
+      for (int i = ct; i < nu * kDLUnit; i += 256) {
+        const int n = u0 * kDLUnit + i;
+        if (fold) {
+          s_vec[i] = __ldg(ph.c1 + n);
+          s_vec[kDLMaxUnits * kDLUnit + i] = __ldg(ph.c2 + n);
+        } else {
+          s_vec[i] = Cvt<T>::to_f(__ldg(reinterpret_cast<const T*>(ph.bias) + n));
+        }
+      }
       if (p > 0) dl_mbar_wait(&ready_bar[p], 0);
       // ---- LayerNorm statistics of this row from the partials its producer left (model.py:39-41, eps 1e-5)
       float mean = 0.f, rstd = 0.f;
-      if ((ph.flags & DL_FOLD) && row_ok) {
+      if (fold && row_ok) {
         const int slots = (p == 0 && P.ln_slots_in > 0) ? P.ln_slots_in : n_slots;
         float n = 0.f, m2 = 0.f;
-        for (int s0 = 0; s0 < slots; s0 += 8) {
-          float4 part[8];
+        for (int s0 = 0; s0 < slots; s0 += 16) {
+          float4 part[16];
 #pragma unroll
-          for (int j = 0; j < 8; ++j)
+          for (int j = 0; j < 16; ++j)
             part[j] = (s0 + j < slots) ? __ldcg(P.ln_part + static_cast<long long>(s0 + j) * P.ln_ld + grow)
                                        : make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
-          for (int j = 0; j < 8; ++j) chan_merge(n, mean, m2, part[j].x, part[j].y, part[j].z);
+          for (int j = 0; j < 16; ++j) chan_merge(n, mean, m2, part[j].x, part[j].y, part[j].z);
         }
         rstd = rsqrtf(m2 / n + 1e-5f);
       }
+      // ---- residual rows of the first two chunks of this thread, fetched before the accumulator is ready
+      uint4 xo[2][2];
+      if ((ph.flags & DL_RESID) && row_ok) {
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {
+          const int e = half + 2 * j;
+          if (e < nu) {
+            const uint4* src = reinterpret_cast<const uint4*>(reinterpret_cast<const T*>(ph.out) + grow * ph.ldo + (u0 + e) * kDLUnit);
+            xo[j][0] = __ldcg(src);
+            xo[j][1] = __ldcg(src + 1);
+          }
+        }
+      }
       if (ct == 0) stamp(p, 7);
+      asm volatile("bar.sync 1, 256;" ::: "memory");   // s_vec is complete
       float sn = 0.f, smean = 0.f, sm2 = 0.f;          // LN partial of the values this thread writes
       if (nu > 0) {
         dl_mbar_wait(&tmem_full[acc], acc_par);
         if (ct == 0) stamp(p, 3);
         tc_fence_after();
         const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + acc * 256;
-        for (int e = half; e < nu; e += 2) {
+        for (int e = half, j = 0; e < nu; e += 2, ++j) {
           uint32_t r[16];
           tmem_ld16(taddr + e * kDLUnit, r);
           tmem_ld_wait();
           if (row_ok) {
             const int nb = (u0 + e) * kDLUnit;
+            const float* v0 = s_vec + e * kDLUnit;
             float v[16];
 #pragma unroll
-            for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(r[j]);
-            if (ph.flags & DL_FOLD) {
+            for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
+            if (fold) {
+              const float* v1 = v0 + kDLMaxUnits * kDLUnit;
 #pragma unroll
-              for (int q = 0; q < 4; ++q) {
-                const float4 a = __ldg(reinterpret_cast<const float4*>(ph.c1 + nb) + q);
-                const float4 b = __ldg(reinterpret_cast<const float4*>(ph.c2 + nb) + q);
-                v[q * 4 + 0] = fmaf(rstd, v[q * 4 + 0] - mean * a.x, b.x);
-                v[q * 4 + 1] = fmaf(rstd, v[q * 4 + 1] - mean * a.y, b.y);
-                v[q * 4 + 2] = fmaf(rstd, v[q * 4 + 2] - mean * a.z, b.z);
-                v[q * 4 + 3] = fmaf(rstd, v[q * 4 + 3] - mean * a.w, b.w);
-              }
+              for (int i = 0; i < 16; ++i) v[i] = fmaf(rstd, v[i] - mean * v0[i], v1[i]);
             } else {
-              const T* bias = reinterpret_cast<const T*>(ph.bias) + nb;
 #pragma unroll
-              for (int q = 0; q < 2; ++q) {
-                const uint4 u = __ldg(reinterpret_cast<const uint4*>(bias) + q);
-                const uint32_t w[4] = {u.x, u.y, u.z, u.w};
-#pragma unroll
-                for (int i = 0; i < 4; ++i) {
-                  const float2 f = Cvt<T>::unpack2(w[i]);
-                  v[q * 8 + i * 2] += f.x;
-                  v[q * 8 + i * 2 + 1] += f.y;
-                }
-              }
+              for (int i = 0; i < 16; ++i) v[i] += v0[i];
             }
             if (ph.flags & DL_GELU) {
 #pragma unroll
-              for (int j = 0; j < 16; ++j) v[j] = gelu_erf(round_to<T>(v[j]));
+              for (int i = 0; i < 16; ++i) v[i] = gelu_erf(round_to<T>(v[i]));
             }
             T* out = reinterpret_cast<T*>(ph.out) + grow * ph.ldo + nb;
             if (ph.flags & DL_RESID) {
+              uint4 u0v, u1v;
+              if (j == 0) {
+                u0v = xo[0][0];
+                u1v = xo[0][1];
+              } else if (j == 1) {
+                u0v = xo[1][0];
+                u1v = xo[1][1];
+              } else {
+                u0v = __ldcg(reinterpret_cast<const uint4*>(out));
+                u1v = __ldcg(reinterpret_cast<const uint4*>(out) + 1);
+              }
+              const uint32_t w[8] = {u0v.x, u0v.y, u0v.z, u0v.w, u1v.x, u1v.y, u1v.z, u1v.w};
 #pragma unroll
-              for (int q = 0; q < 2; ++q) {
-                const uint4 u = __ldcg(reinterpret_cast<const uint4*>(out) + q);
-                const uint32_t w[4] = {u.x, u.y, u.z, u.w};
-#pragma unroll
-                for (int i = 0; i < 4; ++i) {
-                  const float2 f = Cvt<T>::unpack2(w[i]);
-                  v[q * 8 + i * 2] = round_to<T>(v[q * 8 + i * 2]) + f.x;
-                  v[q * 8 + i * 2 + 1] = round_to<T>(v[q * 8 + i * 2 + 1]) + f.y;
-                }
+              for (int i = 0; i < 8; ++i) {
+                const float2 f = Cvt<T>::unpack2(w[i]);
+                v[2 * i] = round_to<T>(v[2 * i]) + f.x;
+                v[2 * i + 1] = round_to<T>(v[2 * i + 1]) + f.y;
               }
             }
             uint32_t pk[8];
@@ -375,12 +398,11 @@ dec_layer_kernel(const DLParams P, const __grid_constant__ DLMaps M) {
         }
       }
       if (p + 1 < n_phases) {
-        // publish this CTA's outputs: every writer orders its stores against later async-proxy (TMA) readers, the CTA
-        // barrier collects them, one thread releases them at gpu scope and arrives on the grid counter
-        fence_proxy_async_global();
+        // publish this CTA's outputs: the CTA barrier orders every epilogue thread's stores before thread 0, whose
+        // gpu-scope release (cumulative) publishes them with the arrival; the consumers' producer threads add the
+        // generic -> async proxy fence on their side before any TMA read
         asm volatile("bar.sync 1, 256;" ::: "memory");
         if (ct == 0) {
-          __threadfence();
           asm volatile("red.release.gpu.global.add.u32 [%0], %1;" ::"l"(P.sync), "r"(1u) : "memory");
           stamp(p, 5);
         }
@@ -429,9 +451,10 @@ int dl_fill_phase(DLLaunch& L, int idx, int dtype, int R, int grid, const void* 
   ph.out = out;
   ph.ldo = ldo;
   const int m_tiles = (R + 63) / 64;
-  const int max_slots = (grid + m_tiles - 1) / m_tiles;
-  int box = (N / kDLUnit) / max_slots;                          // every CTA owns at least this many units
+  const int min_slots = grid / m_tiles;                         // fewest CTAs a row block gets
+  int box = ((N / kDLUnit) + min_slots - 1) / min_slots;        // widest share: the weight box every CTA loads
   if (box < 1) box = 1;
+  if (box > kDLMaxUnits) return 5;
   ph.units_box = box;
   {
     uint64_t dims[2] = {static_cast<uint64_t>(K), static_cast<uint64_t>(R)};
@@ -443,9 +466,7 @@ int dl_fill_phase(DLLaunch& L, int idx, int dtype, int R, int grid, const void* 
     uint64_t dims[2] = {static_cast<uint64_t>(K), static_cast<uint64_t>(N)};
     uint64_t strides[1] = {static_cast<uint64_t>(K) * 2};
     uint32_t bx[2] = {64, static_cast<uint32_t>(box * kDLUnit)};
-    if (make_tmap_16bit(&L.maps.b_main[idx], dtype, W, 2, dims, strides, bx)) return 3;
-    uint32_t bu[2] = {64, kDLUnit};
-    if (make_tmap_16bit(&L.maps.b_unit[idx], dtype, W, 2, dims, strides, bu)) return 4;
+    if (make_tmap_16bit(&L.maps.b[idx], dtype, W, 2, dims, strides, bx)) return 3;
   }
   return 0;
 }

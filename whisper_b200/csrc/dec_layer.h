@@ -18,7 +18,7 @@ enum { DL_FOLD = 1, DL_GELU = 2, DL_RESID = 4, DL_STATS = 8 };
 struct DLPhase {
   int N, K;
   int flags;
-  int units_box;          // rows of the main weight box / 16 (every CTA owns at least this many units)
+  int units_box;          // rows of the weight box / 16 = the widest per-CTA share of the phase
   const void* bias;       // T[N]   (phases without DL_FOLD)
   const float* c1;        // fp32 [N] (DL_FOLD)
   const float* c2;
@@ -43,8 +43,7 @@ struct DLParams {
 
 struct alignas(64) DLMaps {
   CUtensorMap a[kDLMaxPhases];        // activations [R, K], box 64 x 64
-  CUtensorMap b_main[kDLMaxPhases];   // weights [N, K], box 64 x 16 * units_box
-  CUtensorMap b_unit[kDLMaxPhases];   // weights [N, K], box 64 x 16
+  CUtensorMap b[kDLMaxPhases];        // weights [N, K], box 64 x 16 * units_box
 };
 
 struct DLLaunch {

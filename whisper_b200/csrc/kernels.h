@@ -219,6 +219,8 @@ struct BeamParams {
 int launch_filter_topk(const FilterParams& p, int R, cudaStream_t s);
 int launch_no_speech(const float* logits, long long ld, int V, int no_speech, float* out, int rows,
                      int row_stride, int row_offset, cudaStream_t s);
+int launch_range_softmax(const float* logits, long long ld, int first, int n, int rows, float* probs, int* argmax,
+                         const int* gather_tok, float* gather_out, cudaStream_t s);
 int launch_greedy_update(const GreedyParams& p, cudaStream_t s);
 int launch_beam_update(const BeamParams& p, cudaStream_t s);
 

@@ -483,6 +483,74 @@ int launch_no_speech(const float* logits, long long ld, int V, int no_speech, fl
   count_launch();
   return cudaGetLastError() == cudaSuccess ? 0 : 52;
 }
+// softmax over the token range [first, first + n) of every row (everything outside is treated as masked: the
+// `logits[:, mask] = -inf` of decoding.py:60-62, the `[:, :eot]` slice of timing.py:198-201).  One CTA per row;
+// writes any of: the n probabilities, the arg-max token id, the probability of one given token per row.
+__global__ void __launch_bounds__(256) range_softmax_kernel(const float* __restrict__ logits, long long ld, int first, int n,
+                                                            float* __restrict__ probs, int* __restrict__ argmax,
+                                                            const int* __restrict__ gather_tok, float* __restrict__ gather_out) {
+  __shared__ float s_val[8];
+  __shared__ int s_idx[8];
+  const float* row = logits + static_cast<long long>(blockIdx.x) * ld + first;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  float mx = -INFINITY;
+  int mi = 0x7fffffff;
+  for (int i = tid; i < n; i += 256) {
+    const float v = row[i];
+    if (v > mx) {          // strided scan in increasing i: the first maximum of this thread
+      mx = v;
+      mi = i;
+    }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const float ov = __shfl_xor_sync(0xffffffffu, mx, o);
+    const int oi = __shfl_xor_sync(0xffffffffu, mi, o);
+    if (ov > mx || (ov == mx && oi < mi)) {      // ties -> lower id, like torch.argmax
+      mx = ov;
+      mi = oi;
+    }
+  }
+  if (lane == 0) {
+    s_val[warp] = mx;
+    s_idx[warp] = mi;
+  }
+  __syncthreads();
+  mx = s_val[0];
+  mi = s_idx[0];
+  for (int w = 1; w < 8; ++w)
+    if (s_val[w] > mx || (s_val[w] == mx && s_idx[w] < mi)) {
+      mx = s_val[w];
+      mi = s_idx[w];
+    }
+  __syncthreads();
+  float sum = 0.f;
+  for (int i = tid; i < n; i += 256) sum += expf(row[i] - mx);
+  sum = warp_sum(sum);
+  if (lane == 0) s_val[warp] = sum;
+  __syncthreads();
+  sum = 0.f;
+  for (int w = 0; w < 8; ++w) sum += s_val[w];
+  const float inv = 1.0f / sum;
+  if (probs)
+    for (int i = tid; i < n; i += 256) probs[static_cast<long long>(blockIdx.x) * n + i] = expf(row[i] - mx) * inv;
+  if (tid == 0) {
+    if (argmax) argmax[blockIdx.x] = first + mi;
+    if (gather_tok && gather_out) {
+      const int t = gather_tok[blockIdx.x] - first;
+      gather_out[blockIdx.x] = (t >= 0 && t < n) ? expf(row[t] - mx) * inv : 0.f;
+    }
+  }
+}
+
+int launch_range_softmax(const float* logits, long long ld, int first, int n, int rows, float* probs, int* argmax,
+                         const int* gather_tok, float* gather_out, cudaStream_t s) {
+  if (rows <= 0 || n <= 0) return 0;
+  range_softmax_kernel<<<rows, 256, 0, s>>>(logits, ld, first, n, probs, argmax, gather_tok, gather_out);
+  count_launch();
+  return cudaGetLastError() == cudaSuccess ? 0 : 56;
+}
+
 int launch_greedy_update(const GreedyParams& p, cudaStream_t s) {
   greedy_update_kernel<<<1, 1024, 0, s>>>(p);
   count_launch();

@@ -256,17 +256,24 @@ def detect_language(model: "Whisper", mel: torch.Tensor, tokenizer: Tokenizer = 
     try:
         sess.set_audio(feats)
         sess.prefill(np.full((n_audio, 1), tokenizer.sot, dtype=np.int32))     # decoding.py:56-57
-        logits = sess.get_logits(n_audio).clone()
+        logits = sess.get_logits(n_audio)      # a view of [n_audio, ld] rows
     finally:
         sess.close()
-    mask = torch.ones(logits.shape[-1], dtype=torch.bool, device=logits.device)
-    mask[list(tokenizer.all_language_tokens)] = False
-    logits[:, mask] = -np.inf                                                 # decoding.py:60-62
-    language_tokens = logits.argmax(dim=-1)
-    language_token_probs = logits.softmax(dim=-1).cpu()
+    # mask everything but the language tokens, argmax, softmax (decoding.py:60-66) in one kernel: the language ids are
+    # the contiguous range right after <|startoftranscript|> (tokenizer.py:340-355)
+    lang_ids = list(tokenizer.all_language_tokens)
+    first, n_lang = lang_ids[0], len(lang_ids)
+    assert lang_ids == list(range(first, first + n_lang))
+    probs = torch.empty((n_audio, n_lang), device=logits.device, dtype=torch.float32)
+    language_tokens = torch.empty((n_audio,), device=logits.device, dtype=torch.int32)
+    with torch.cuda.device(model.device):
+        check(lib().wb200_range_softmax(ptr(logits), ctypes.c_int64(logits.stride(0)), c_int(first), c_int(n_lang),
+                                        c_int(n_audio), ptr(probs), ptr(language_tokens), None, None, stream_ptr()),
+              "wb200_range_softmax")
+    language_tokens = language_tokens.long()
+    language_token_probs = probs.cpu()
     language_probs = [
-        {c: language_token_probs[i, j].item()
-         for j, c in zip(tokenizer.all_language_tokens, tokenizer.all_language_codes)}
+        {c: language_token_probs[i, j].item() for j, c in enumerate(tokenizer.all_language_codes)}
         for i in range(n_audio)]
     if single:
         language_tokens = language_tokens[0]

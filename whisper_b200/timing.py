@@ -60,6 +60,7 @@ def dtw(x: torch.Tensor, cpu_tie_break: bool = False) -> np.ndarray:
 # alignment into per-segment word lists (merge_punctuations / add_word_timestamps, timing.py:245-388)
 # are host-side text post-processing that SURVEY.md section 2 leaves out of scope; they are not rebuilt.
 # ------------------------------------------------------------------------------------------------
+import ctypes
 from dataclasses import dataclass as _dataclass
 from typing import TYPE_CHECKING as _TC, List as _List
 
@@ -111,23 +112,42 @@ def find_alignment(model: "Whisper", tokenizer: "Tokenizer", text_tokens: _List[
         audio_features = model.embed_audio(mel)
     heads = model.alignment_heads.indices().T.tolist()                     # (layer, head) pairs, timing.py:207
     logits, qk = model.logits(torch.tensor([tokens]), audio_features, alignment_heads=heads)
-    logits = logits[0]
-    sampled_logits = logits[len(tokenizer.sot_sequence):, : tokenizer.eot]   # timing.py:198-201
-    token_probs = sampled_logits.softmax(dim=-1)
-    text_token_probs = token_probs[np.arange(len(text_tokens)), text_tokens].tolist()
+    # probability of every text token under the softmax over the text vocabulary [0, eot) (timing.py:198-203)
+    n_sot = len(tokenizer.sot_sequence)
+    rows = logits[0, n_sot: n_sot + len(text_tokens)]
+    assert rows.stride(1) == 1
+    tok_dev = torch.tensor(text_tokens, device=rows.device, dtype=torch.int32)
+    tok_prob = torch.empty((len(text_tokens),), device=rows.device, dtype=torch.float32)
+    with torch.cuda.device(rows.device):
+        check(lib().wb200_range_softmax(ptr(rows), ctypes.c_int64(rows.stride(0)), c_int(0), c_int(tokenizer.eot),
+                                        c_int(len(text_tokens)), None, None, ptr(tok_dev), ptr(tok_prob), stream_ptr()),
+              "wb200_range_softmax")
+    text_token_probs = tok_prob.cpu().numpy()
 
     matrix = alignment_matrix(qk, num_frames // 2, qk_scale, medfilt_width, negate=True)   # already -matrix
-    matrix = matrix[len(tokenizer.sot_sequence): -1].contiguous()          # timing.py:215
+    matrix = matrix[n_sot: -1].contiguous()                                # timing.py:215
     text_indices, time_indices = dtw(matrix)                               # timing.py:216
 
     words, word_tokens = tokenizer.split_to_word_tokens(text_tokens + [tokenizer.eot])
     if len(word_tokens) <= 1:
-        return []                                                          # timing.py:219-225
-    word_boundaries = np.pad(np.cumsum([len(t) for t in word_tokens[:-1]]), (1, 0))
-    jumps = np.pad(np.diff(text_indices), (1, 0), constant_values=1).astype(bool)
-    jump_times = time_indices[jumps] / TOKENS_PER_SECOND
-    start_times = jump_times[word_boundaries[:-1]]
-    end_times = jump_times[word_boundaries[1:]]
-    word_probabilities = [np.mean(text_token_probs[i:j]) for i, j in zip(word_boundaries[:-1], word_boundaries[1:])]
-    return [WordTiming(w, t, s, e, p) for w, t, s, e, p in zip(words, word_tokens, start_times, end_times,
-                                                               word_probabilities)]
+        return []                                                          # only <|endoftext|>: timing.py:219-225
+    return word_spans(words, word_tokens, text_indices, time_indices, text_token_probs)
+
+
+def word_spans(words, word_tokens, text_indices, time_indices, token_probs) -> _List[WordTiming]:
+    """Start / end time and mean token probability of every word from a DTW path (timing.py:227-241).
+
+    Word k owns the token positions [first_tok[k], first_tok[k + 1]); the monotone path reaches token position t for the
+    first time at some path index, i.e. at frame time_indices[that index].  A word starts when the path reaches its first
+    token and ends when it reaches the next word's first token; the trailing <|endoftext|> "word" only closes the last
+    real one and is not returned."""
+    first_tok = np.concatenate([[0], np.cumsum([len(t) for t in word_tokens[:-1]])]).astype(np.int64)
+    text_indices = np.asarray(text_indices)
+    advanced = np.concatenate([[True], text_indices[1:] != text_indices[:-1]])
+    reach_time = np.asarray(time_indices)[advanced] / TOKENS_PER_SECOND
+    timings = []
+    for k in range(len(word_tokens) - 1):
+        lo, hi = int(first_tok[k]), int(first_tok[k + 1])
+        timings.append(WordTiming(words[k], word_tokens[k], reach_time[lo], reach_time[hi],
+                                  float(np.mean(token_probs[lo:hi]))))
+    return timings
