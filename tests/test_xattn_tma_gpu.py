@@ -56,6 +56,6 @@ def test_tma_cross_attention_matches_cp_async(name, opts, dtype):
     for i, (a, b) in enumerate(zip(old, new)):
         assert bool(torch.isfinite(b).all()), f"step {i}: non-finite logits"
         worst = max(worst, float((a - b).abs().max() / a.abs().max()))
-    tol = 1e-3 if dtype == torch.float16 else 8e-3
+    tol = 2e-3 if dtype == torch.float16 else 1.6e-2        # P is rounded to 16 bits per 16-key slice in either kernel
     print(f"{name} {dtype}: TMA vs cp.async cross attention, worst |dlogit| / max|logit| = {worst:.6f} over {len(new)} steps")
     assert worst < tol

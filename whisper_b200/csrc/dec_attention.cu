@@ -375,20 +375,25 @@ __global__ void __launch_bounds__(kDaThreads) cross_attention_kernel(const Cross
 // The cp.async kernel above plateaus at ~5.2 TB/s whatever its ring depth or key split (profiles/r1_xattn_sweep.txt)
 // while a read-only stream reaches 7.3 TB/s on the same part (tools/microbench.cu): each of its 2560 short-lived
 // CTAs pays its own pipeline fill, query load, 4-warp merge and drain for only 192 KB of K/V.  Here ONE CTA per SM
-// stays resident and walks through its share of the (audio, head, key-split) items with the memory pipeline kept full
-// ACROSS items: a dedicated producer warp streams 128-key K and V tiles (one 16 KB TMA box each, 128-byte swizzle = the
-// layout ldmatrix wants) and the next item's query tile through mbarrier rings, eight consumer warps (16 keys of every
-// tile each) run the same mma.sync online-softmax tile code as above, merge once per item and hand their partial to the
-// same last-arriver combine.
+// stays resident and walks through its share of the (audio, head[, key-split]) items with the memory pipeline kept full
+// ACROSS items, three decoupled roles talking through mbarriers only:
+//   producer warp : streams 128-key K and V tiles (one 16 KB TMA box each, 128-byte swizzle = the layout ldmatrix
+//                   wants) and the next item's 16-row query tile, never waiting for anything but free ring slots
+//   8 consumer warps : 16 keys of every tile each, the same mma.sync online-softmax tile code as above; at the end
+//                   of an item they drop their (m, l, O) fragments into one of two exchange buffers and move on
+//   epilogue warp : merges the eight fragments, normalises and stores the output (or, with key splits, writes the
+//                   partial and runs the last-arriver combine) while the consumers are already in the next item.
+// (A first version that let consumer warp 0 do the merge, fence and ticket while the other seven waited at a CTA barrier
+// ran at 171 us against the cp.async kernel's 94: nothing else on the SM overlapped that tail.)
 constexpr int kX2Consumers = 8;
-constexpr int kX2Threads = (kX2Consumers + 1) * 32;
+constexpr int kX2Threads = (kX2Consumers + 2) * 32;
 constexpr int kX2TileKeys = 128;
 constexpr int kX2Stages = 4;
 constexpr int kX2TileBytes = kX2TileKeys * 128;                  // one K (or V) tile
 constexpr int kX2StageBytes = 2 * kX2TileBytes;
 constexpr int kX2QBytes = 16 * 128;                              // 16 query rows x 64 dims
-constexpr int kX2RedFloats = kX2Consumers * 32 * 40;
-constexpr int kX2SmemBytes = kX2Stages * kX2StageBytes + 2 * kX2QBytes + kX2RedFloats * 4 + 256 + 1024;
+constexpr int kX2RedFloats = kX2Consumers * 32 * 36;             // per buffer: 8 warps x 32 lanes x (32 O + m0 m1 l0 l1)
+constexpr int kX2SmemBytes = kX2Stages * kX2StageBytes + 2 * kX2QBytes + 2 * kX2RedFloats * 4 + 256 + 1024;
 
 struct Cross2Params {
   void* out;            // [n_audio * n_q, d]
@@ -413,12 +418,13 @@ cross_attention_tma_kernel(const Cross2Params p, const __grid_constant__ CUtenso
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(x2_raw) + 1023) & ~static_cast<uintptr_t>(1023));
   uint8_t* ring = smem;
   uint8_t* sQ = ring + kX2Stages * kX2StageBytes;
-  float* red = reinterpret_cast<float*>(sQ + 2 * kX2QBytes);
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(red + kX2RedFloats);
+  float* red = reinterpret_cast<float*>(sQ + 2 * kX2QBytes);     // [2][kX2RedFloats]
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(red + 2 * kX2RedFloats);
   uint64_t* empty_bar = full_bar + kX2Stages;
   uint64_t* qfull_bar = empty_bar + kX2Stages;
   uint64_t* qempty_bar = qfull_bar + 2;
-  int* s_last = reinterpret_cast<int*>(qempty_bar + 2);
+  uint64_t* rfull_bar = qempty_bar + 2;
+  uint64_t* rempty_bar = rfull_bar + 2;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (threadIdx.x == 0) {
     for (int i = 0; i < kX2Stages; ++i) {
@@ -428,6 +434,8 @@ cross_attention_tma_kernel(const Cross2Params p, const __grid_constant__ CUtenso
     for (int i = 0; i < 2; ++i) {
       mbar_init(&qfull_bar[i], 1);
       mbar_init(&qempty_bar[i], kX2Consumers);
+      mbar_init(&rfull_bar[i], kX2Consumers);
+      mbar_init(&rempty_bar[i], 1);
     }
     mbar_fence_init();
     tma_prefetch_desc(&mapQ);
@@ -463,11 +471,121 @@ cross_attention_tma_kernel(const Cross2Params p, const __grid_constant__ CUtenso
     }
     return;
   }
+  if (warp == kX2Consumers + 1) {
+    // ===================== epilogue warp =====================
+    const int g = lane >> 2, t4 = lane & 3;
+    int iq = 0;
+    for (int item = blockIdx.x; item < p.total_items; item += gridDim.x, ++iq) {
+      const int split = item % p.splits, ah = item / p.splits;
+      const int head = ah % H, audio = ah / H;
+      const int rb = iq & 1;
+      const float* rbuf = red + rb * kX2RedFloats;
+      x2_wait(&rfull_bar[rb], (iq >> 1) & 1);
+      float m0 = -INFINITY, m1 = -INFINITY;
+#pragma unroll
+      for (int w = 0; w < kX2Consumers; ++w) {
+        const float4 ml = *reinterpret_cast<const float4*>(rbuf + (w * 32 + lane) * 36 + 32);
+        m0 = fmaxf(m0, ml.x);
+        m1 = fmaxf(m1, ml.y);
+      }
+      float l0 = 0.f, l1 = 0.f, o[8][4];
+#pragma unroll
+      for (int i = 0; i < 8; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) o[i][j] = 0.f;
+#pragma unroll
+      for (int w = 0; w < kX2Consumers; ++w) {
+        const float* src = rbuf + (w * 32 + lane) * 36;
+        const float4 ml = *reinterpret_cast<const float4*>(src + 32);
+        const float f0 = ml.x == -INFINITY ? 0.f : fast_exp2(ml.x - m0);
+        const float f1 = ml.y == -INFINITY ? 0.f : fast_exp2(ml.y - m1);
+        l0 += ml.z * f0;
+        l1 += ml.w * f1;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const float4 v = *reinterpret_cast<const float4*>(src + i * 4);
+          o[i][0] += v.x * f0;
+          o[i][1] += v.y * f0;
+          o[i][2] += v.z * f1;
+          o[i][3] += v.w * f1;
+        }
+      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&rempty_bar[rb]);               // the consumers may refill this buffer
+      if (p.splits == 1) {
+        // the whole key range was here: normalise and store rows g and g + 8 of this (audio, head)
+        const float i0 = 1.0f / l0, i1 = 1.0f / l1;
+        T* o0 = reinterpret_cast<T*>(p.out) + (static_cast<long long>(audio) * p.n_q + g) * p.d + head * 64 + 2 * t4;
+        T* o1 = o0 + 8LL * p.d;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          if (g < p.n_q) *reinterpret_cast<uint32_t*>(o0 + i * 8) = Cvt<T>::pack2(o[i][0] * i0, o[i][1] * i0);
+          if (g + 8 < p.n_q) *reinterpret_cast<uint32_t*>(o1 + i * 8) = Cvt<T>::pack2(o[i][2] * i1, o[i][3] * i1);
+        }
+        continue;
+      }
+      const long long tile_id = ah;
+      float* part = p.partial + (tile_id * p.splits + split) * (16 * 66);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        *reinterpret_cast<float2*>(part + g * 66 + i * 8 + 2 * t4) = make_float2(o[i][0], o[i][1]);
+        *reinterpret_cast<float2*>(part + (g + 8) * 66 + i * 8 + 2 * t4) = make_float2(o[i][2], o[i][3]);
+      }
+      if (t4 == 0) {
+        *reinterpret_cast<float2*>(part + g * 66 + 64) = make_float2(m0, l0);
+        *reinterpret_cast<float2*>(part + (g + 8) * 66 + 64) = make_float2(m1, l1);
+      }
+      __threadfence();
+      __syncwarp();
+      int last = 0;
+      if (lane == 0) {
+        const int prev = atomicAdd(&p.counters[tile_id], 1);
+        last = (prev == p.splits - 1);
+        if (last) p.counters[tile_id] = 0;          // ready for the next launch
+      }
+      last = __shfl_sync(0xffffffffu, last, 0);
+      if (!last) continue;
+      __threadfence();
+      // ---- combine the splits: lane = (row = lane / 2, column half = lane % 2)
+      const int row = lane >> 1, c0 = (lane & 1) * 32;
+      if (row < p.n_q) {
+        const float* base = p.partial + tile_id * p.splits * (16 * 66) + row * 66;
+        float m = -INFINITY;
+        for (int sp = 0; sp < p.splits; ++sp) m = fmaxf(m, __ldcg(base + sp * 16 * 66 + 64));
+        float l = 0.f, acc[32];
+#pragma unroll
+        for (int e = 0; e < 32; ++e) acc[e] = 0.f;
+        for (int sp = 0; sp < p.splits; ++sp) {
+          const float* ps = base + sp * 16 * 66;
+          const float ms = __ldcg(ps + 64);
+          const float f = ms == -INFINITY ? 0.f : fast_exp2(ms - m);
+          l += __ldcg(ps + 65) * f;
+#pragma unroll
+          for (int e = 0; e < 32; e += 2) {
+            const float2 v = __ldcg(reinterpret_cast<const float2*>(ps + c0 + e));
+            acc[e] += v.x * f;
+            acc[e + 1] += v.y * f;
+          }
+        }
+        const float inv = 1.0f / l;
+        T* orow = reinterpret_cast<T*>(p.out) + (static_cast<long long>(audio) * p.n_q + row) * p.d + head * 64 + c0;
+#pragma unroll
+        for (int e = 0; e < 32; e += 8) {
+          uint4 u;
+          u.x = Cvt<T>::pack2(acc[e] * inv, acc[e + 1] * inv);
+          u.y = Cvt<T>::pack2(acc[e + 2] * inv, acc[e + 3] * inv);
+          u.z = Cvt<T>::pack2(acc[e + 4] * inv, acc[e + 5] * inv);
+          u.w = Cvt<T>::pack2(acc[e + 6] * inv, acc[e + 7] * inv);
+          *reinterpret_cast<uint4*>(orow + e) = u;
+        }
+      }
+    }
+    return;
+  }
   // ===================== consumers =====================
   int q = 0, iq = 0;
   for (int item = blockIdx.x; item < p.total_items; item += gridDim.x, ++iq) {
-    const int split = item % p.splits, ah = item / p.splits;
-    const int head = ah % H, audio = ah / H;
+    const int split = item % p.splits;
     const int qs = iq & 1;
     uint32_t qa[4][4];
     x2_wait(&qfull_bar[qs], (iq >> 1) & 1);
@@ -495,100 +613,21 @@ cross_attention_tma_kernel(const Cross2Params p, const __grid_constant__ CUtenso
       __syncwarp();
       if (lane == 0) mbar_arrive(&empty_bar[st]);
     }
-    // ---- merge the eight warps' (m, l, O) into warp 0
+    // ---- hand the fragment to the epilogue warp
 #pragma unroll
     for (int r = 0; r < 2; ++r) {
       acc.l[r] += __shfl_xor_sync(0xffffffffu, acc.l[r], 1);
       acc.l[r] += __shfl_xor_sync(0xffffffffu, acc.l[r], 2);
     }
-    {
-      float* mine = red + (warp * 32 + lane) * 40;
+    const int rb = iq & 1;
+    x2_wait(&rempty_bar[rb], ((iq >> 1) & 1) ^ 1);
+    float* mine = red + rb * kX2RedFloats + (warp * 32 + lane) * 36;
 #pragma unroll
-      for (int i = 0; i < 8; ++i)
-        *reinterpret_cast<float4*>(mine + i * 4) = make_float4(acc.o[i][0], acc.o[i][1], acc.o[i][2], acc.o[i][3]);
-      *reinterpret_cast<float4*>(mine + 32) = make_float4(acc.m[0], acc.m[1], acc.l[0], acc.l[1]);
-    }
-    asm volatile("bar.sync 1, 256;" ::: "memory");
-    const long long tile_id = ah;
-    const int g = lane >> 2, t4 = lane & 3;
-    if (warp == 0) {
-      float m0 = -INFINITY, m1 = -INFINITY;
-#pragma unroll
-      for (int w = 0; w < kX2Consumers; ++w) {
-        m0 = fmaxf(m0, red[(w * 32 + lane) * 40 + 32]);
-        m1 = fmaxf(m1, red[(w * 32 + lane) * 40 + 33]);
-      }
-      float l0 = 0.f, l1 = 0.f, o[8][4];
-#pragma unroll
-      for (int i = 0; i < 8; ++i)
-#pragma unroll
-        for (int j = 0; j < 4; ++j) o[i][j] = 0.f;
-#pragma unroll
-      for (int w = 0; w < kX2Consumers; ++w) {
-        const float* src = red + (w * 32 + lane) * 40;
-        const float4 ml = *reinterpret_cast<const float4*>(src + 32);
-        const float f0 = ml.x == -INFINITY ? 0.f : fast_exp2(ml.x - m0);
-        const float f1 = ml.y == -INFINITY ? 0.f : fast_exp2(ml.y - m1);
-        l0 += ml.z * f0;
-        l1 += ml.w * f1;
-#pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          const float4 v = *reinterpret_cast<const float4*>(src + i * 4);
-          o[i][0] += v.x * f0;
-          o[i][1] += v.y * f0;
-          o[i][2] += v.z * f1;
-          o[i][3] += v.w * f1;
-        }
-      }
-      float* part = p.partial + (tile_id * p.splits + split) * (16 * 66);
-#pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        *reinterpret_cast<float2*>(part + g * 66 + i * 8 + 2 * t4) = make_float2(o[i][0], o[i][1]);
-        *reinterpret_cast<float2*>(part + (g + 8) * 66 + i * 8 + 2 * t4) = make_float2(o[i][2], o[i][3]);
-      }
-      if (t4 == 0) {
-        *reinterpret_cast<float2*>(part + g * 66 + 64) = make_float2(m0, l0);
-        *reinterpret_cast<float2*>(part + (g + 8) * 66 + 64) = make_float2(m1, l1);
-      }
-      __threadfence();
-      __syncwarp();
-      if (lane == 0) {
-        const int prev = atomicAdd(&p.counters[tile_id], 1);
-        const int last = (prev == p.splits - 1);
-        if (last) p.counters[tile_id] = 0;          // ready for the next launch
-        *s_last = last;
-      }
-    }
-    asm volatile("bar.sync 1, 256;" ::: "memory");
-    if (*s_last && warp < 4) {
-      __threadfence();
-      // ---- combine the splits: 128 threads = 16 rows x 8 column groups of 8
-      const int row = threadIdx.x >> 3, cg = threadIdx.x & 7;
-      if (row < p.n_q) {
-        const float* base = p.partial + tile_id * p.splits * (16 * 66) + row * 66;
-        float m = -INFINITY;
-        for (int sp = 0; sp < p.splits; ++sp) m = fmaxf(m, __ldcg(base + sp * 16 * 66 + 64));
-        float l = 0.f, o[8];
-#pragma unroll
-        for (int e = 0; e < 8; ++e) o[e] = 0.f;
-        for (int sp = 0; sp < p.splits; ++sp) {
-          const float* ps = base + sp * 16 * 66;
-          const float ms = __ldcg(ps + 64);
-          const float f = ms == -INFINITY ? 0.f : fast_exp2(ms - m);
-          l += __ldcg(ps + 65) * f;
-#pragma unroll
-          for (int e = 0; e < 8; ++e) o[e] += __ldcg(ps + cg * 8 + e) * f;
-        }
-        const float inv = 1.0f / l;
-        T* orow = reinterpret_cast<T*>(p.out) + (static_cast<long long>(audio) * p.n_q + row) * p.d + head * 64 + cg * 8;
-        uint4 u;
-        u.x = Cvt<T>::pack2(o[0] * inv, o[1] * inv);
-        u.y = Cvt<T>::pack2(o[2] * inv, o[3] * inv);
-        u.z = Cvt<T>::pack2(o[4] * inv, o[5] * inv);
-        u.w = Cvt<T>::pack2(o[6] * inv, o[7] * inv);
-        *reinterpret_cast<uint4*>(orow) = u;
-      }
-    }
+    for (int i = 0; i < 8; ++i)
+      *reinterpret_cast<float4*>(mine + i * 4) = make_float4(acc.o[i][0], acc.o[i][1], acc.o[i][2], acc.o[i][3]);
+    *reinterpret_cast<float4*>(mine + 32) = make_float4(acc.m[0], acc.m[1], acc.l[0], acc.l[1]);
+    __syncwarp();
+    if (lane == 0) mbar_arrive(&rfull_bar[rb]);
   }
 }
 
@@ -975,7 +1014,7 @@ int launch_cross_attention_tma(int dtype, const void* q, const void* kv, void* o
     if (sp > 1 && (tps < 2 || (sp - 1) * tps >= p.total_tiles)) continue;
     const long long items = static_cast<long long>(pairs) * sp;
     const long long rounds = (items + sms - 1) / sms;
-    const double eff = static_cast<double>(items) / static_cast<double>(rounds * sms) - 0.01 * sp;
+    const double eff = static_cast<double>(items) / static_cast<double>(rounds * sms) - 0.03 * (sp - 1);   // a split costs a partial + ticket
     if (eff > best_eff) {
       best_eff = eff;
       best = sp;

@@ -180,18 +180,29 @@ dec_layer_kernel(const DLParams P, const __grid_constant__ DLMaps M) {
         mbar_expect_tx(&full_bar[prod], bytes);
         uint8_t* sa = tiles + prod * Cfg::kStageBytes;
         uint8_t* sb = sa + ks * kDLASub;
+        // ONE request per operand per stage: the tensor maps view [rows, K] as {64 k, rows, K / 64} so a box of `ks` k-blocks
+        // lands as `ks` consecutive 128B-swizzled [rows x 64] sub-tiles - the TMA unit serves one request per ~130-190 clk
+        // whatever its size (8 KB boxes: 37 B/clk/SM measured in this kernel; 32 KB boxes: 62 B/clk/SM)
         // weights first: they are constants, so the first stage of a phase streams them in while the grid barrier of the
         // previous phase is still closing; the activation rows follow once that phase is complete grid-wide
-        for (int sub = 0; sub < ks; ++sub)         // sub-blocks past K are zero-filled by TMA (full byte count)
-          tma_load_2d(sb + sub * bsub, &M.b[p], &full_bar[prod], (g * ks + sub) * 64, u0 * kDLUnit);
+        if (ph.kouter) {
+          tma_load_3d(sb, &M.b[p], &full_bar[prod], 0, u0 * kDLUnit, g * ks);
+        } else {
+          for (int sub = 0; sub < ks; ++sub)       // sub-blocks past K are zero-filled by TMA (full byte count)
+            tma_load_2d(sb + sub * bsub, &M.b[p], &full_bar[prod], (g * ks + sub) * 64, u0 * kDLUnit);
+        }
         if (!released) {
           dl_mbar_wait(&ready_bar[p], 0);
           fence_proxy_async_global();              // generic-proxy writes of other CTAs -> this thread's async-proxy (TMA) reads
           released = true;
         }
         if (prod == 0 && g == 0) stamp(p, 0);
-        for (int sub = 0; sub < ks; ++sub)
-          tma_load_2d(sa + sub * kDLASub, &M.a[p], &full_bar[prod], (g * ks + sub) * 64, m_blk * 64);
+        if (ph.kouter) {
+          tma_load_3d(sa, &M.a[p], &full_bar[prod], 0, m_blk * 64, g * ks);
+        } else {
+          for (int sub = 0; sub < ks; ++sub)
+            tma_load_2d(sa + sub * kDLASub, &M.a[p], &full_bar[prod], (g * ks + sub) * 64, m_blk * 64);
+        }
       }
     }
   } else if (warp == 1 && lane == 0) {
@@ -456,17 +467,36 @@ int dl_fill_phase(DLLaunch& L, int idx, int dtype, int R, int grid, const void* 
   if (box < 1) box = 1;
   if (box > kDLMaxUnits) return 5;
   ph.units_box = box;
-  {
-    uint64_t dims[2] = {static_cast<uint64_t>(K), static_cast<uint64_t>(R)};
-    uint64_t strides[1] = {static_cast<uint64_t>(lda * 2)};
-    uint32_t bx[2] = {64, 64};
-    if (make_tmap_16bit(&L.maps.a[idx], dtype, A, 2, dims, strides, bx)) return 2;
+  if (K % 64) return 6;
+  int ks = kDLSlotBytes / (kDLASub + box * kDLUnitBytes);      // must equal dl_ks(box) in the kernel
+  if (ks > kDLMaxKS) ks = kDLMaxKS;
+  static int kouter_ok = -1;          // the driver may refuse a k-block stride (128 B) below the row stride: fall back to 2-D
+  if (kouter_ok < 0) {
+    const char* e = getenv("WB200_DL_KOUTER");
+    kouter_ok = (e && e[0] == '0') ? 0 : 1;
   }
-  {
-    uint64_t dims[2] = {static_cast<uint64_t>(K), static_cast<uint64_t>(N)};
-    uint64_t strides[1] = {static_cast<uint64_t>(K) * 2};
-    uint32_t bx[2] = {64, static_cast<uint32_t>(box * kDLUnit)};
-    if (make_tmap_16bit(&L.maps.b[idx], dtype, W, 2, dims, strides, bx)) return 3;
+  ph.kouter = 0;
+  if (kouter_ok) {
+    uint64_t da[3] = {64, static_cast<uint64_t>(R), static_cast<uint64_t>(K / 64)};
+    uint64_t sa[2] = {static_cast<uint64_t>(lda * 2), 128};
+    uint32_t ba[3] = {64, 64, static_cast<uint32_t>(ks)};
+    uint64_t db[3] = {64, static_cast<uint64_t>(N), static_cast<uint64_t>(K / 64)};
+    uint64_t sb[2] = {static_cast<uint64_t>(K) * 2, 128};
+    uint32_t bb[3] = {64, static_cast<uint32_t>(box * kDLUnit), static_cast<uint32_t>(ks)};
+    if (make_tmap_16bit(&L.maps.a[idx], dtype, A, 3, da, sa, ba) == 0 && make_tmap_16bit(&L.maps.b[idx], dtype, W, 3, db, sb, bb) == 0)
+      ph.kouter = 1;
+    else
+      kouter_ok = 0;
+  }
+  if (!ph.kouter) {
+    uint64_t da[2] = {static_cast<uint64_t>(K), static_cast<uint64_t>(R)};
+    uint64_t sa[1] = {static_cast<uint64_t>(lda * 2)};
+    uint32_t ba[2] = {64, 64};
+    if (make_tmap_16bit(&L.maps.a[idx], dtype, A, 2, da, sa, ba)) return 2;
+    uint64_t db[2] = {static_cast<uint64_t>(K), static_cast<uint64_t>(N)};
+    uint64_t sb[1] = {static_cast<uint64_t>(K) * 2};
+    uint32_t bb[2] = {64, static_cast<uint32_t>(box * kDLUnit)};
+    if (make_tmap_16bit(&L.maps.b[idx], dtype, W, 2, db, sb, bb)) return 3;
   }
   return 0;
 }

@@ -19,6 +19,7 @@ struct DLPhase {
   int N, K;
   int flags;
   int units_box;          // rows of the weight box / 16 = the widest per-CTA share of the phase
+  int kouter;             // 1: the tensor maps are 3-D {64 k, rows, K / 64} and one request brings a whole stage of an operand
   const void* bias;       // T[N]   (phases without DL_FOLD)
   const float* c1;        // fp32 [N] (DL_FOLD)
   const float* c2;
@@ -42,8 +43,9 @@ struct DLParams {
 };
 
 struct alignas(64) DLMaps {
-  CUtensorMap a[kDLMaxPhases];        // activations [R, K], box 64 x 64
-  CUtensorMap b[kDLMaxPhases];        // weights [N, K], box 64 x 16 * units_box
+  // 3-D views {64 k, rows, K / 64}: one box = `ks` consecutive [rows x 64] k-blocks
+  CUtensorMap a[kDLMaxPhases];        // activations [R, K], box 64 x 64 rows x ks
+  CUtensorMap b[kDLMaxPhases];        // weights [N, K], box 64 x 16 * units_box rows x ks
 };
 
 struct DLLaunch {
