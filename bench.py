@@ -576,7 +576,7 @@ def bench_transcribe(args, model, tok, dims, dev, rank, world, local, timed, lib
     n = args.audio_seconds * 16000
     audio_host = torch.from_numpy(synthetic.synthetic_audio(1, n, seed=1234 + rank, kind="speechlike")[0]).pin_memory()
     audio_dev = audio_host.to(dev)
-    kw = dict(temperature=0.0, condition_on_previous_text=True, word_timestamps=False, language="en")
+    kw = dict(temperature=0.0, condition_on_previous_text=True, language="en")
 
     def run(audio):
         return model.transcribe(audio, **kw)

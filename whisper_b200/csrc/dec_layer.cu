@@ -59,16 +59,12 @@ __device__ __forceinline__ int dl_ks(int box) {
   return k > kDLMaxKS ? kDLMaxKS : k;
 }
 
-// Independent accumulation chains of a tile of nu units.  Consecutive tcgen05.mma into the SAME accumulator are a
-// dependent chain: measured here, a 64 x 48 x 16 MMA retires every ~90 clk although it occupies the tensor pipe for
-// 24 (profiles/r2_dec_layer_trace_v3.txt: 80 MMAs of the K = 1280 phases took 7400 clk, 320 of fc2 took 30000).  Narrow
-// tiles therefore spread their K steps round-robin over up to four accumulators (256 TMEM columns per buffer), summed
-// by the epilogue.
-__device__ __forceinline__ int dl_chains(int nu) {
-  const int c = 256 / (nu * kDLUnit);
-  return c > 4 ? 4 : (c < 1 ? 1 : c);
-}
-
+// Measured and rejected (profiles/r2_dec_layer_trace_v4_chains_rejected.txt): spreading the K steps of a narrow tile
+// round-robin over up to four accumulators, on the theory that back-to-back tcgen05.mma into ONE accumulator are a
+// latency-bound dependent chain.  They are not: alternating accumulators doubled the main-loop time (7400 -> 14900 clk
+// for the K = 1280 phases).  What the traces do show is the cost of UMMA M = 64 with both operands in shared memory:
+// ~40 + 1.1 x N clk per 16-deep MMA (N = 48: 92 clk, N = 144: 180, N = 176: 207) against the 0.5 x N of the
+// M = 128 form - the tensor pipe is ~2.3x slower per column at M = 64, which bounds the wide phases (QKV, fc1).
 template <int STAGES>
 struct DLCfg {
   static constexpr int kStageBytes = kDLSlotBytes;
@@ -233,9 +229,6 @@ dec_layer_kernel(const DLParams P, const __grid_constant__ DLMaps M) {
       dl_mbar_wait(&tmem_empty[acc], acc_par ^ 1);
       tc_fence_after();
       const uint32_t d_tmem = tmem_base + acc * 256;
-      const int chains = dl_chains(nu);
-      const uint32_t chain_cols = static_cast<uint32_t>(nu * kDLUnit);
-      int mi = 0;                                // MMA number within the phase: chain mi % chains
       for (int g = 0; g < groups; ++g, ++q) {
         const int stage = q % STAGES;
         dl_mbar_wait(&full_bar[stage], (q / STAGES) & 1);
@@ -247,8 +240,8 @@ dec_layer_kernel(const DLParams P, const __grid_constant__ DLMaps M) {
           const uint64_t adesc = umma_desc_sw128(sa + sub * kDLASub, 16, 1024);
           const uint64_t bdesc = umma_desc_sw128(sb + sub * bsub, 16, 1024);
 #pragma unroll
-          for (int k = 0; k < 4; ++k, ++mi)
-            umma_f16(d_tmem + (mi % chains) * chain_cols, adesc + 2 * k, bdesc + 2 * k, idesc, mi >= chains);
+          for (int k = 0; k < 4; ++k)
+            umma_f16(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (g != 0) || (sub != 0) || (k != 0));
         }
         umma_commit(&empty_bar[stage]);
       }
@@ -336,7 +329,6 @@ dec_layer_kernel(const DLParams P, const __grid_constant__ DLMaps M) {
         if (ct == 0) stamp(p, 3);
         tc_fence_after();
         const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + acc * 256;
-        const int chains = dl_chains(nu);
         for (int e = half, j = 0; e < nu; e += 2, ++j) {
           uint32_t r[16];
           tmem_ld16(taddr + e * kDLUnit, r);
@@ -344,12 +336,6 @@ dec_layer_kernel(const DLParams P, const __grid_constant__ DLMaps M) {
           float v[16];
 #pragma unroll
           for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
-          for (int c = 1; c < chains; ++c) {       // the other accumulation chains of this tile (warp-uniform)
-            tmem_ld16(taddr + c * nu * kDLUnit + e * kDLUnit, r);
-            tmem_ld_wait();
-#pragma unroll
-            for (int i = 0; i < 16; ++i) v[i] += __uint_as_float(r[i]);
-          }
           if (row_ok) {
             const int nb = (u0 + e) * kDLUnit;
             const float* v0 = s_vec + e * kDLUnit;
