@@ -90,3 +90,46 @@ def test_fused_layer_is_deterministic():
         b = model.decode(mel, opt)
         assert [r.tokens for r in a] == [r.tokens for r in b]
         assert [r.avg_logprob for r in a] == [r.avg_logprob for r in b]
+
+
+@pytest.mark.parametrize("dtype", [torch.float16, torch.bfloat16])
+def test_fused_layer_more_than_one_row_block(dtype):
+    """R = 14 audios x 5 beams = 70 rows: two 64-row blocks in the narrow phases, one 128-row block (UMMA M = 128) in the
+    wide ones (QKV, fc1), LN partials written by one split and read by the other."""
+    import whisper_b200 as wb
+    from oracle import audio as OA
+    from oracle import model as OM
+    from oracle import parity
+    from whisper_b200 import synthetic
+
+    meta, _ = load_model_fixture("test-multi")
+    dims, sd, _ = fixture_inputs(meta)
+    n_audio, opts = 14, dict(beam_size=5, sample_len=6)
+    audio = synthetic.synthetic_audio(n_audio, 480000, seed=99, kind="speechlike")
+    W = OM.to_weights(sd)
+    mel = torch.from_numpy(np.stack([OA.log_mel_spectrogram(a, dims["n_mels"]) for a in audio]))
+    feats = OM.encoder_forward(W, dims, mel)
+    rec = parity.oracle_record(W, dims, feats, opts, n_audio)
+    model = wb.Whisper(wb.ModelDimensions(**dims), sd, device="cuda", dtype=dtype)
+    g_mel = torch.stack([wb.log_mel_spectrogram(torch.from_numpy(a).cuda(), dims["n_mels"]) for a in audio])
+    g_feats = model.embed_audio(g_mel)
+    try:
+        _set_fused(False)
+        model.clear_sessions()
+        plain = _teacher_forced_logits(model, g_feats, rec, n_audio, opts)
+        _set_fused(True)
+        model.clear_sessions()
+        fused = _teacher_forced_logits(model, g_feats, rec, n_audio, opts)
+    finally:
+        _set_fused(True)
+        model.clear_sessions()
+    worst_pair = worst_ora = 0.0
+    for i, (a, b) in enumerate(zip(plain, fused)):
+        assert bool(torch.isfinite(b).all())
+        ref = rec["raw_logits"][i]
+        ref = ref[::5] if i == 0 else ref
+        scale = float(ref.abs().max())
+        worst_pair = max(worst_pair, float((a - b).abs().max()) / scale)
+        worst_ora = max(worst_ora, float((b - ref).abs().max()) / scale)
+    print(f"70 rows {dtype}: fused vs unfused {worst_pair:.5f}, fused vs oracle {worst_ora:.5f}")
+    assert worst_ora < LOGIT_TOL[dtype] and 0.0 < worst_pair < LOGIT_TOL[dtype]

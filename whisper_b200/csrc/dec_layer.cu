@@ -46,17 +46,17 @@ namespace wb {
 int g_fused_layer = -1;   // -1: read WB200_FUSED_LAYER on first use; wb200_set_fused_decoder_layer() overrides
 
 constexpr int kDLThreads = 416;                      // 13 warps
-constexpr int kDLASub = 64 * 128;                    // 64 rows x 64 x 16-bit
+constexpr int kDLRowBytes = 128;                     // one row of a 64-wide 16-bit k-block
 constexpr int kDLUnitBytes = kDLUnit * 128;          // 16 weight rows x 64 x 16-bit
 constexpr int kDLSlotBytes = 64 * 1024;              // one ring stage
 constexpr int kDLMaxKS = 4;
 constexpr int kDLTmemCols = 512;                     // two accumulator buffers of 256 columns
-static_assert(2 * (kDLASub + kDLMaxUnits * kDLUnitBytes) <= kDLSlotBytes, "a stage must hold two K sub-blocks of the widest tile");
+static_assert(2 * (64 * kDLRowBytes + kDLMaxUnits * kDLUnitBytes) <= kDLSlotBytes, "a stage must hold two K sub-blocks of the widest tile");
 
-// 64-wide K sub-blocks per ring stage for a weight box of `box` units (the same for every CTA of a phase)
-__device__ __forceinline__ int dl_ks(int box) {
-  const int k = kDLSlotBytes / (kDLASub + box * kDLUnitBytes);
-  return k > kDLMaxKS ? kDLMaxKS : k;
+// 64-wide K sub-blocks per ring stage for a row block of bm rows and a weight box of `box` units (per phase)
+__host__ __device__ __forceinline__ int dl_ks(int bm, int box) {
+  const int k = kDLSlotBytes / (bm * kDLRowBytes + box * kDLUnitBytes);
+  return k > kDLMaxKS ? kDLMaxKS : (k < 1 ? 1 : k);
 }
 
 // Measured and rejected (profiles/r2_dec_layer_trace_v4_chains_rejected.txt): spreading the K steps of a narrow tile
@@ -151,14 +151,21 @@ dec_layer_kernel(const DLParams P, const __grid_constant__ DLMaps M) {
     if (P.trace) P.trace[(static_cast<long long>(cta) * kDLMaxPhases + p) * 8 + slot_id] = clock64();
   };
 
-  // this CTA's share of a phase: row block m, columns [u0, u0 + nu) in units of 16
-  const int m_blk = cta % P.m_tiles;
-  const int slot = cta / P.m_tiles;
-  const int n_slots = (grid - m_blk + P.m_tiles - 1) / P.m_tiles;
-  auto share = [&](int p, int& u0, int& nu) {
+  // this CTA's share of a phase: row block m_blk (bm rows), columns [u0, u0 + nu) in units of 16; the CTAs of a row
+  // block are numbered by `slot`
+  struct Share {
+    int m_blk, slot, n_slots, u0, nu;
+  };
+  auto share = [&](int p) {
+    Share sh;
+    const int m_tiles = (P.R + P.ph[p].bm - 1) / P.ph[p].bm;
+    sh.m_blk = cta % m_tiles;
+    sh.slot = cta / m_tiles;
+    sh.n_slots = (grid - sh.m_blk + m_tiles - 1) / m_tiles;
     const int total = P.ph[p].N / kDLUnit;
-    u0 = static_cast<int>(static_cast<long long>(slot) * total / n_slots);
-    nu = static_cast<int>(static_cast<long long>(slot + 1) * total / n_slots) - u0;
+    sh.u0 = static_cast<int>(static_cast<long long>(sh.slot) * total / sh.n_slots);
+    sh.nu = static_cast<int>(static_cast<long long>(sh.slot + 1) * total / sh.n_slots) - sh.u0;
+    return sh;
   };
 
   const int prod = warp == 0 ? 0 : (warp == 2 ? 1 : (warp == 3 ? 2 : -1));
@@ -166,26 +173,27 @@ dec_layer_kernel(const DLParams P, const __grid_constant__ DLMaps M) {
     // ===================== TMA producers: producer j owns ring stage j =====================
     int q = 0;                                 // running stage number across phases (the ring never drains)
     for (int p = 0; p < n_phases; ++p) {
-      int u0, nu;
-      share(p, u0, nu);
+      const Share sh = share(p);
+      const int u0 = sh.u0, nu = sh.nu, m_blk = sh.m_blk;
       if (nu == 0) continue;
       const DLPhase& ph = P.ph[p];
+      const int asub = ph.bm * kDLRowBytes;
       // ONE weight box per K sub-block, as tall as the widest share of the phase (the TMA unit costs ~120 clk per request
       // whatever its size: a second 2 KB box for the odd unit cost as much as 8 KB of payload); rows past this CTA's own
       // share are loaded and ignored, rows past N are zero-filled
       const int box = ph.units_box;
-      const int ks = dl_ks(box);
+      const int ks = dl_ks(ph.bm, box);
       const int kblocks = (ph.K + 63) / 64;
       const int groups = (kblocks + ks - 1) / ks;
       const int bsub = box * kDLUnitBytes;
-      const uint32_t bytes = static_cast<uint32_t>(ks) * (kDLASub + bsub);
+      const uint32_t bytes = static_cast<uint32_t>(ks) * (asub + bsub);
       bool released = (p == 0);
       for (int g = 0; g < groups; ++g, ++q) {
         if (q % STAGES != prod) continue;
         dl_mbar_wait(&empty_bar[prod], ((q / STAGES) & 1) ^ 1);
         mbar_expect_tx(&full_bar[prod], bytes);
         uint8_t* sa = tiles + prod * Cfg::kStageBytes;
-        uint8_t* sb = sa + ks * kDLASub;
+        uint8_t* sb = sa + ks * asub;
         // ONE request per operand per stage: the tensor maps view [rows, K] as {64 k, rows, K / 64} so a box of `ks` k-blocks
         // lands as `ks` consecutive 128B-swizzled [rows x 64] sub-tiles - the TMA unit serves one request per ~130-190 clk
         // whatever its size (8 KB boxes: 37 B/clk/SM measured in this kernel; 32 KB boxes: 62 B/clk/SM)
@@ -204,10 +212,10 @@ dec_layer_kernel(const DLParams P, const __grid_constant__ DLMaps M) {
         }
         if (g == 0) stamp(p, 0);
         if (ph.kouter) {
-          tma_load_3d(sa, &M.a[p], &full_bar[prod], 0, m_blk * 64, g * ks);
+          tma_load_3d(sa, &M.a[p], &full_bar[prod], 0, m_blk * ph.bm, g * ks);
         } else {
           for (int sub = 0; sub < ks; ++sub)
-            tma_load_2d(sa + sub * kDLASub, &M.a[p], &full_bar[prod], (g * ks + sub) * 64, m_blk * 64);
+            tma_load_2d(sa + sub * asub, &M.a[p], &full_bar[prod], (g * ks + sub) * 64, m_blk * ph.bm);
         }
       }
     }
@@ -217,15 +225,16 @@ dec_layer_kernel(const DLParams P, const __grid_constant__ DLMaps M) {
     int acc = 0;
     uint32_t acc_par = 0;
     for (int p = 0; p < n_phases; ++p) {
-      int u0, nu;
-      share(p, u0, nu);
+      const Share sh = share(p);
+      const int nu = sh.nu;
       if (nu == 0) continue;
       const DLPhase& ph = P.ph[p];
-      const int ks = dl_ks(ph.units_box);
+      const int asub = ph.bm * kDLRowBytes;
+      const int ks = dl_ks(ph.bm, ph.units_box);
       const int kblocks = (ph.K + 63) / 64;
       const int groups = (kblocks + ks - 1) / ks;
       const int bsub = ph.units_box * kDLUnitBytes;
-      const uint32_t idesc = umma_idesc(Cvt<T>::kUmmaFmt, 64, static_cast<uint32_t>(nu * kDLUnit), 0, 0);
+      const uint32_t idesc = umma_idesc(Cvt<T>::kUmmaFmt, static_cast<uint32_t>(ph.bm), static_cast<uint32_t>(nu * kDLUnit), 0, 0);
       dl_mbar_wait(&tmem_empty[acc], acc_par ^ 1);
       tc_fence_after();
       const uint32_t d_tmem = tmem_base + acc * 256;
@@ -235,9 +244,9 @@ dec_layer_kernel(const DLParams P, const __grid_constant__ DLMaps M) {
         if (g == 0) stamp(p, 1);
         tc_fence_after();
         const uint32_t sa = smem_u32(tiles + stage * Cfg::kStageBytes);
-        const uint32_t sb = sa + ks * kDLASub;
+        const uint32_t sb = sa + ks * asub;
         for (int sub = 0; sub < ks; ++sub) {
-          const uint64_t adesc = umma_desc_sw128(sa + sub * kDLASub, 16, 1024);
+          const uint64_t adesc = umma_desc_sw128(sa + sub * asub, 16, 1024);
           const uint64_t bdesc = umma_desc_sw128(sb + sub * bsub, 16, 1024);
 #pragma unroll
           for (int k = 0; k < 4; ++k)
@@ -266,19 +275,20 @@ dec_layer_kernel(const DLParams P, const __grid_constant__ DLMaps M) {
     }
   } else if (warp >= 4 && warp < 12) {
     // ===================== epilogue =====================
-    // UMMA M = 64: accumulator row i sits in lane (i % 16) of TMEM quadrant i / 16, so lanes 16-31 of every warp idle.
+    // UMMA M = 64: accumulator row i sits in lane (i % 16) of TMEM quadrant i / 16, so lanes 16-31 of every warp idle;
+    // M = 128: row i = lane i.
     const int ct = threadIdx.x - 128;
     const int quad = warp & 3;
     const int half = (warp - 4) >> 2;
-    const int trow = quad * 16 + lane;                // row inside the 64-row block
-    const long long grow = static_cast<long long>(m_blk) * 64 + trow;
-    const bool row_ok = lane < 16 && grow < P.R;
     int acc = 0;
     uint32_t acc_par = 0;
     for (int p = 0; p < n_phases; ++p) {
-      int u0, nu;
-      share(p, u0, nu);
+      const Share sh = share(p);
+      const int u0 = sh.u0, nu = sh.nu, m_blk = sh.m_blk, slot = sh.slot;
       const DLPhase& ph = P.ph[p];
+      const int trow = ph.bm == 128 ? quad * 32 + lane : quad * 16 + lane;     // row inside the row block
+      const long long grow = static_cast<long long>(m_blk) * ph.bm + trow;
+      const bool row_ok = (ph.bm == 128 || lane < 16) && grow < P.R;
       const bool fold = (ph.flags & DL_FOLD) != 0;
       // ---- per-column vectors of this CTA's columns into shared memory while the main loop runs: c1 | c2 (LN fold) or
       //      the bias; constants of the model, so no need to wait for the previous phase
@@ -295,7 +305,9 @@ dec_layer_kernel(const DLParams P, const __grid_constant__ DLMaps M) {
       // ---- LayerNorm statistics of this row from the partials its producer left (model.py:39-41, eps 1e-5)
       float mean = 0.f, rstd = 0.f;
       if (fold && row_ok) {
-        const int slots = (p == 0 && P.ln_slots_in > 0) ? P.ln_slots_in : n_slots;
+        // partials were left by the writer's 64-row split: the CTAs of row block grow / 64
+        const int wt = (P.R + 63) / 64, wm = static_cast<int>(grow >> 6);
+        const int slots = (p == 0 && P.ln_slots_in > 0) ? P.ln_slots_in : (grid - wm + wt - 1) / wt;
         float n = 0.f, m2 = 0.f;
         for (int s0 = 0; s0 < slots; s0 += 16) {
           float4 part[16];
@@ -446,18 +458,33 @@ dec_layer_kernel(const DLParams P, const __grid_constant__ DLMaps M) {
 // -------------------------------------------------------------------------------------------------
 int dl_grid_size() { return sm_count(); }
 
+// rows per row block of a phase: the wide phases without LN partials (QKV, fc1) use UMMA M = 128 - at M = 64 the tensor
+// pipe runs at less than half its per-column rate and those phases were MMA-bound (profiles/r2_dec_layer_trace_v3.txt)
+static int dl_auto_bm(int R, int N, int K, int flags) {
+  return (!(flags & DL_STATS) && R > 64 && N >= 2 * K) ? 128 : 64;
+}
+
+static int dl_box_units(int R, int grid, int N, int bm) {
+  const int m_tiles = (R + bm - 1) / bm;
+  if (m_tiles > grid) return 1 << 20;
+  const int min_slots = grid / m_tiles;                         // fewest CTAs a row block gets
+  const int box = ((N / kDLUnit) + min_slots - 1) / min_slots;  // widest share: the weight box every CTA loads
+  return box < 1 ? 1 : box;
+}
+
 bool dl_supported(int R, int d, int grid) {
   if (R <= 0 || d % 64 != 0 || grid <= 0) return false;
-  const int m_tiles = (R + 63) / 64;
-  if (m_tiles > grid) return false;
-  const int min_slots = grid / m_tiles;                       // fewest CTAs a row block gets
-  const int widest = 4 * d / kDLUnit;                          // fc1
-  return (widest + min_slots - 1) / min_slots <= kDLMaxUnits;
+  const int shapes[4][3] = {{3 * d, d, DL_FOLD}, {d, d, DL_RESID | DL_STATS}, {4 * d, d, DL_FOLD | DL_GELU}, {d, 4 * d, DL_RESID | DL_STATS}};
+  for (auto& sh : shapes) {
+    const int bm = dl_auto_bm(R, sh[0], sh[1], sh[2]);
+    if (dl_box_units(R, grid, sh[0], bm) > kDLMaxUnits) return false;
+  }
+  return true;
 }
 
 int dl_fill_phase(DLLaunch& L, int idx, int dtype, int R, int grid, const void* A, long long lda, const void* W, int N, int K,
-                  const void* bias, const float* c1, const float* c2, int flags, void* out, long long ldo) {
-  if (idx >= kDLMaxPhases || N % kDLUnit || K % 8) return 1;
+                  const void* bias, const float* c1, const float* c2, int flags, void* out, long long ldo, int bm) {
+  if (idx >= kDLMaxPhases || N % kDLUnit || K % 64) return 1;
   DLPhase& ph = L.p.ph[idx];
   ph.N = N;
   ph.K = K;
@@ -467,15 +494,13 @@ int dl_fill_phase(DLLaunch& L, int idx, int dtype, int R, int grid, const void* 
   ph.c2 = c2;
   ph.out = out;
   ph.ldo = ldo;
-  const int m_tiles = (R + 63) / 64;
-  const int min_slots = grid / m_tiles;                         // fewest CTAs a row block gets
-  int box = ((N / kDLUnit) + min_slots - 1) / min_slots;        // widest share: the weight box every CTA loads
-  if (box < 1) box = 1;
+  if (bm == 0) bm = dl_auto_bm(R, N, K, flags);
+  if ((bm != 64 && bm != 128) || (bm == 128 && (flags & DL_STATS))) return 7;
+  ph.bm = bm;
+  const int box = dl_box_units(R, grid, N, bm);
   if (box > kDLMaxUnits) return 5;
   ph.units_box = box;
-  if (K % 64) return 6;
-  int ks = kDLSlotBytes / (kDLASub + box * kDLUnitBytes);      // must equal dl_ks(box) in the kernel
-  if (ks > kDLMaxKS) ks = kDLMaxKS;
+  const int ks = dl_ks(bm, box);
   static int kouter_ok = -1;          // the driver may refuse a k-block stride (128 B) below the row stride: fall back to 2-D
   if (kouter_ok < 0) {
     const char* e = getenv("WB200_DL_KOUTER");
@@ -485,7 +510,7 @@ int dl_fill_phase(DLLaunch& L, int idx, int dtype, int R, int grid, const void* 
   if (kouter_ok) {
     uint64_t da[3] = {64, static_cast<uint64_t>(R), static_cast<uint64_t>(K / 64)};
     uint64_t sa[2] = {static_cast<uint64_t>(lda * 2), 128};
-    uint32_t ba[3] = {64, 64, static_cast<uint32_t>(ks)};
+    uint32_t ba[3] = {64, static_cast<uint32_t>(bm), static_cast<uint32_t>(ks)};
     uint64_t db[3] = {64, static_cast<uint64_t>(N), static_cast<uint64_t>(K / 64)};
     uint64_t sb[2] = {static_cast<uint64_t>(K) * 2, 128};
     uint32_t bb[3] = {64, static_cast<uint32_t>(box * kDLUnit), static_cast<uint32_t>(ks)};
@@ -497,7 +522,7 @@ int dl_fill_phase(DLLaunch& L, int idx, int dtype, int R, int grid, const void* 
   if (!ph.kouter) {
     uint64_t da[2] = {static_cast<uint64_t>(K), static_cast<uint64_t>(R)};
     uint64_t sa[1] = {static_cast<uint64_t>(lda * 2)};
-    uint32_t ba[2] = {64, 64};
+    uint32_t ba[2] = {64, static_cast<uint32_t>(bm)};
     if (make_tmap_16bit(&L.maps.a[idx], dtype, A, 2, da, sa, ba)) return 2;
     uint64_t db[2] = {static_cast<uint64_t>(K), static_cast<uint64_t>(N)};
     uint64_t sb[1] = {static_cast<uint64_t>(K) * 2};

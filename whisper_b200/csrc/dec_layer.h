@@ -19,6 +19,7 @@ struct DLPhase {
   int N, K;
   int flags;
   int units_box;          // rows of the weight box / 16 = the widest per-CTA share of the phase
+  int bm;                 // rows per row block: 64 (UMMA M = 64) or 128 (UMMA M = 128, full tensor-pipe rate; wide phases)
   int kouter;             // 1: the tensor maps are 3-D {64 k, rows, K / 64} and one request brings a whole stage of an operand
   const void* bias;       // T[N]   (phases without DL_FOLD)
   const float* c1;        // fp32 [N] (DL_FOLD)
@@ -62,7 +63,7 @@ void dl_init_launch(DLLaunch& L, int dtype, int R, int grid, float4* ln_part, in
                     const int* skip_flag, int ln_slots_in);
 // appends nothing by itself: fills phase `idx` (caller sets p.n_phases)
 int dl_fill_phase(DLLaunch& L, int idx, int dtype, int R, int grid, const void* A, long long lda, const void* W, int N, int K,
-                  const void* bias, const float* c1, const float* c2, int flags, void* out, long long ldo);
+                  const void* bias, const float* c1, const float* c2, int flags, void* out, long long ldo, int bm = 0);
 int dl_launch(const DLLaunch& L, cudaStream_t s);
 
 }  // namespace wb
