@@ -688,14 +688,21 @@ __global__ void __launch_bounds__(640) self_attention_kernel(const SelfParams p,
   const uint8_t* qrow = reinterpret_cast<const uint8_t*>(p.qkv) + static_cast<long long>(row) * 3 * row_bytes + h * 128;
   const uint8_t* knew = qrow + row_bytes + c * 16;
   const uint8_t* vnew = qrow + 2 * row_bytes + c * 16;
-  // byte offset of (physical row, position) for this head: row-major [row][pos][d] or head-major [row][head][pos][64]
-  const long long pos_bytes = p.head_major ? 128 : row_bytes;
+  // byte offset of (physical row, position) for this head.  Row-major: [row][pos][d].  Head-major: the "beam window"
+  // layout [audio][head][pos][beam slot][64] - the G rows of an audio interleaved per position, so that the whole history
+  // of an (audio, head) is ONE contiguous block (what self_attention_tma_kernel streams); physical row = audio * G + slot.
+  const int Gw = p.head_major ? p.group : 1;
+  const long long pos_bytes = p.head_major ? 128LL * Gw : row_bytes;
   const long long row_stride = static_cast<long long>(p.max_ctx) * row_bytes;      // bytes per physical row, either layout
-  const long long head_off = p.head_major ? static_cast<long long>(h) * p.max_ctx * 128 : static_cast<long long>(h) * 128;
+  const long long head_off = p.head_major ? static_cast<long long>(h) * p.max_ctx * 128 * Gw : static_cast<long long>(h) * 128;
+  auto phys_off = [&](int ph) -> long long {       // offset of position 0 of physical row ph (before head_off)
+    return p.head_major ? static_cast<long long>(ph / Gw) * (row_stride * Gw) + static_cast<long long>(ph % Gw) * 128
+                        : static_cast<long long>(ph) * row_stride;
+  };
   uint8_t* kc = reinterpret_cast<uint8_t*>(p.kcache) + head_off + c * 16;
   uint8_t* vc = reinterpret_cast<uint8_t*>(p.vcache) + head_off + c * 16;
   if (step && lane < 16) {
-    const long long off = static_cast<long long>(row) * row_stride + pos_new * pos_bytes;
+    const long long off = phys_off(row) + pos_new * pos_bytes;
     if (lane < 8)
       *reinterpret_cast<uint4*>(kc + off) = *reinterpret_cast<const uint4*>(knew);
     else
@@ -734,7 +741,7 @@ __global__ void __launch_bounds__(640) self_attention_kernel(const SelfParams p,
       const bool valid = key < kv_len;
       const uint8_t *ks = knew, *vs = vnew;               // new token (or dummy address of a masked key)
       if (key < pos_new) {
-        const long long off = static_cast<long long>(ph[j]) * row_stride + key * pos_bytes;
+        const long long off = phys_off(ph[j]) + key * pos_bytes;
         ks = kc + off;
         vs = vc + off;
       }
@@ -861,7 +868,8 @@ __global__ void kv_append_kernel(const T* __restrict__ qkv, T* __restrict__ kcac
   const T* src = qkv + static_cast<long long>(row) * 3 * d + (1 + which) * d;
   T* cache = (which ? vcache : kcache) + static_cast<long long>(a) * group * max_ctx * d;   // physical row a * group
   for (int c = lane * 8; c < d; c += 256) {
-    T* dst = head_major ? cache + (static_cast<long long>(c >> 6) * max_ctx + i) * 64 + (c & 63)
+    // head-major = beam window [audio][head][pos][slot][64]: the prompt lives in slot 0 of its audio
+    T* dst = head_major ? cache + ((static_cast<long long>(c >> 6) * max_ctx + i) * group) * 64 + (c & 63)
                         : cache + static_cast<long long>(i) * d + c;
     *reinterpret_cast<uint4*>(dst) = *reinterpret_cast<const uint4*>(src + c);
   }

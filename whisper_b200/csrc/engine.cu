@@ -94,7 +94,8 @@ __global__ void gather_prefill_rows_kernel(const T* __restrict__ x, T* __restric
 __global__ void decoder_init_state_kernel(int* tokens0, int* tokens1, int* indir0, int* indir1, int max_ctx, int R,
                                           int group, int n_init, const int* __restrict__ init_tokens /*[n_audio,n_init]*/,
                                           float* sum_lp, int* len_ptr, int* done, int* cur, int* fin_count, int* fin_len,
-                                          int n_audio, int max_cand, int* counters, int n_counters, unsigned int* dl_sync) {
+                                          int n_audio, int max_cand, int* counters, int n_counters, unsigned int* dl_sync,
+                                          unsigned char* same0, unsigned char* same1) {
   const int tid = blockIdx.x * blockDim.x + threadIdx.x;
   const int stride = gridDim.x * blockDim.x;
   for (long long i = tid; i < static_cast<long long>(R) * max_ctx; i += stride) {
@@ -111,6 +112,10 @@ __global__ void decoder_init_state_kernel(int* tokens0, int* tokens1, int* indir
   for (int i = tid; i < n_audio; i += stride) fin_count[i] = 0;
   for (int i = tid; i < n_audio * max_cand; i += stride) fin_len[i] = 0;
   for (int i = tid; i < n_counters; i += stride) counters[i] = 0;
+  for (int i = tid; i < n_audio * 256; i += stride) {      // every beam starts from the same prompt
+    same0[i] = 1;
+    same1[i] = 1;
+  }
   if (tid == 0) {
     *len_ptr = n_init;
     *done = 0;
@@ -123,9 +128,16 @@ __global__ void decoder_init_state_kernel(int* tokens0, int* tokens1, int* indir
 }
 
 // teacher forcing: append given tokens (tests)
-__global__ void append_tokens_kernel(int* tokens, int max_ctx, int R, const int* __restrict__ next, int* len_ptr) {
+__global__ void append_tokens_kernel(int* tokens, int max_ctx, int R, const int* __restrict__ next, int* len_ptr,
+                                     unsigned char* same, int G) {
   const int L = *len_ptr;
   for (int r = threadIdx.x; r < R; r += blockDim.x) tokens[static_cast<long long>(r) * max_ctx + L] = next[r];
+  // beams keep their rows: two prefixes stay equal only if the appended tokens are equal too
+  if (same && G > 1)
+    for (int i = threadIdx.x; i < (R / G) * G * G; i += blockDim.x) {
+      const int a = i / (G * G), j1 = (i / G) % G, j2 = i % G;
+      if (next[a * G + j1] != next[a * G + j2]) same[a * 256 + j1 * 16 + j2] = 0;
+    }
   __syncthreads();
   if (threadIdx.x == 0) *len_ptr = L + 1;
 }
@@ -308,6 +320,7 @@ static void dec_carve(const Model* m, const wb200_decode_config& c, Arena& ar, D
   o->blank_mask = static_cast<uint32_t*>(ar.take(ldv / 8 + 64));
   o->init_tokens = static_cast<int*>(ar.take(P * 4 + 64));
   o->scalars = static_cast<int*>(ar.take(256));
+  for (int i = 0; i < 2; ++i) o->beam_same[i] = static_cast<unsigned char*>(ar.take(B * 256));
   // fused decoder-layer kernel: LN partial statistics [slots <= SMs][rows padded to 64] and its two counters
   o->ln_ld = static_cast<int>((R + 63) / 64 * 64);
   o->ln_part = static_cast<float4*>(ar.take(static_cast<size_t>(256) * o->ln_ld * sizeof(float4)));
@@ -549,7 +562,7 @@ int decoder_prefill(Decoder* D, const int32_t* init_tokens_host, cudaStream_t s)
   decoder_init_state_kernel<<<256, 256, 0, s>>>(D->tokens[0], D->tokens[1], D->indir[0], D->indir[1], ctx, R, G, c.n_init,
                                                 D->init_tokens, D->sum_lp, D->len_ptr, D->done_ptr, D->cur_ptr, D->fin_count, D->fin_len,
                                                 B, c.max_candidates > 0 ? c.max_candidates : 1, D->counters, D->n_counters + 256,
-                                                D->dl_sync);
+                                                D->dl_sync, D->beam_same[0], D->beam_same[1]);
   count_launch();
   if (dt == DT_BF16) launch_embed<__nv_bfloat16>(D, P, false, s); else launch_embed<__half>(D, P, false, s);
   WB_TRY(decoder_stack(D, P, false, s));
@@ -680,6 +693,8 @@ int decoder_select(Decoder* D, cudaStream_t s) {
     b.out_index = D->cur ^ 1;         // flag is up later launches are no-ops and the host view goes stale
     b.n_init = c.n_init;
     b.tickets = D->scalars + 24;
+    b.same_in = D->beam_same[D->cur];
+    b.same_out = D->beam_same[D->cur ^ 1];
     WB_TRY(launch_beam_update(b, s));
     D->cur ^= 1;
   }
@@ -691,7 +706,8 @@ int decoder_append(Decoder* D, const int32_t* next_host, cudaStream_t s) {
   const int R = D->cfg.n_audio * D->cfg.n_group;
   if (cudaMemcpyAsync(D->sources, next_host, static_cast<size_t>(R) * 4, cudaMemcpyHostToDevice, s) != cudaSuccess)
     return set_error(250, "append: upload failed");
-  append_tokens_kernel<<<1, 256, 0, s>>>(D->tokens[D->cur], D->m->dims.n_text_ctx, R, D->sources, D->len_ptr);
+  append_tokens_kernel<<<1, 256, 0, s>>>(D->tokens[D->cur], D->m->dims.n_text_ctx, R, D->sources, D->len_ptr,
+                                         D->cfg.beam_search ? D->beam_same[D->cur] : nullptr, D->cfg.n_group);
   count_launch();
   D->host_len += 1;
   return 0;

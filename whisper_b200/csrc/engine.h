@@ -72,6 +72,7 @@ struct Decoder {
   uint32_t* suppress_mask = nullptr;
   uint32_t* blank_mask = nullptr;
   int* init_tokens = nullptr;
+  unsigned char* beam_same[2] = {nullptr, nullptr};   // [n_audio][16][16] prefix-equality of beams (ping-pong with tokens)
   int* scalars = nullptr;      // [0] length, [8] done flag, [16] current ping-pong buffer
   int* len_ptr = nullptr;
   int* done_ptr = nullptr;

@@ -215,6 +215,10 @@ struct BeamParams {
   int out_index;
   int n_init;             // prompt length: positions < n_init were written by the prefill
   int* tickets;           // device int[2], zero between launches: arrival ticket, count of full audios
+  // [n_audio][16][16] bytes: same_in[a][j1][j2] != 0 iff beams j1, j2 of audio a hold the same token prefix (the keys
+  // of the reference's candidate dict, decoding.py:344); same_out receives the matrix of the new beams
+  const unsigned char* same_in;
+  unsigned char* same_out;
 };
 int launch_filter_topk(const FilterParams& p, int R, cudaStream_t s);
 int launch_no_speech(const float* logits, long long ld, int V, int no_speech, float* out, int rows,

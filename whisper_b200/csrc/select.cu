@@ -21,11 +21,6 @@ namespace wb {
 constexpr int kSelThreads = 512;
 constexpr int kMaxTopK = 17;  // beam <= 16
 
-struct TopK {
-  float v[kMaxTopK];
-  int i[kMaxTopK];
-};
-
 // total order used everywhere: larger value first, then smaller index
 __device__ __forceinline__ bool better(float va, int ia, float vb, int ib) {
   return va > vb || (va == vb && ia < ib);
@@ -78,6 +73,49 @@ __device__ __forceinline__ float gumbel_noise(uint32_t seed_lo, uint32_t seed_hi
   return -logf(-logf(u));
 }
 
+// Per-thread sorted list of the KM best (value, index) pairs, kept in registers: every index below is a compile-time
+// constant after unrolling (a runtime-indexed array would live in local memory - the first version of this kernel did,
+// and spent most of its 95 us there).
+template <int KM>
+struct TopList {
+  float v[KM];
+  int i[KM];
+  __device__ __forceinline__ void init() {
+#pragma unroll
+    for (int k = 0; k < KM; ++k) {
+      v[k] = -INFINITY;
+      i[k] = 0x7fffffff;
+    }
+  }
+  __device__ __forceinline__ void push(float val, int idx) {
+    if (!better(val, idx, v[KM - 1], i[KM - 1])) return;
+    v[KM - 1] = val;
+    i[KM - 1] = idx;
+#pragma unroll
+    for (int k = KM - 1; k > 0; --k) {
+      if (better(v[k], i[k], v[k - 1], i[k - 1])) {
+        const float tv = v[k];
+        const int ti = i[k];
+        v[k] = v[k - 1];
+        i[k] = i[k - 1];
+        v[k - 1] = tv;
+        i[k - 1] = ti;
+      }
+    }
+  }
+  // remove and return the head (static shifts)
+  __device__ __forceinline__ void pop() {
+#pragma unroll
+    for (int k = 0; k + 1 < KM; ++k) {
+      v[k] = v[k + 1];
+      i[k] = i[k + 1];
+    }
+    v[KM - 1] = -INFINITY;
+    i[KM - 1] = 0x7fffffff;
+  }
+};
+
+template <int KM>
 __global__ void __launch_bounds__(kSelThreads) filter_topk_kernel(const FilterParams p) {
   if (p.skip_flag && *p.skip_flag) return;
   const int r = blockIdx.x;
@@ -86,10 +124,11 @@ __global__ void __launch_bounds__(kSelThreads) filter_topk_kernel(const FilterPa
   const float* x = p.logits + static_cast<long long>(r / p.row_div) * p.ld;
   const int tb = p.timestamp_begin;
 
-  __shared__ int s_rule[4];      // ts_lo (mask [tb, ts_lo)), mask_all_ts, mask_text_below_eot, first_step
-  __shared__ float s_red[kSelThreads / 32][6];
-  __shared__ float s_fin[4];
-  __shared__ TopK s_top[kSelThreads / 32];
+  __shared__ int s_rule[4];      // ts_lo (mask [tb, ts_lo)), mask_all_ts, mask_text_below_eot, drop_text
+  __shared__ float s_red[kSelThreads / 32][4];
+  __shared__ float s_fin[2];
+  __shared__ float s_tv[kSelThreads / 32][KM];
+  __shared__ int s_ti[kSelThreads / 32][KM];
 
   const bool first = (L == p.sample_begin);
   if (tid == 0) {
@@ -115,10 +154,12 @@ __global__ void __launch_bounds__(kSelThreads) filter_topk_kernel(const FilterPa
   const int ts_lo = s_rule[0];
   const bool all_ts = s_rule[1], text_lt_eot = s_rule[2];
   const int ts_hi = (p.ts_rules && first && p.max_initial_ts >= 0) ? tb + p.max_initial_ts : p.V - 1;
+  const bool use_blank = p.suppress_blank && first;
 
-  auto masked = [&](int v) -> bool {
-    if ((p.suppress_mask[v >> 5] >> (v & 31)) & 1u) return true;
-    if (p.suppress_blank && first && ((p.blank_mask[v >> 5] >> (v & 31)) & 1u)) return true;
+  // rule mask of token v given the suppress / blank bitmap words that hold it
+  auto masked = [&](int v, uint32_t sup_word, uint32_t blank_word) -> bool {
+    if ((sup_word >> (v & 31)) & 1u) return true;
+    if (use_blank && ((blank_word >> (v & 31)) & 1u)) return true;
     if (p.ts_rules) {
       if (v >= tb) {
         if (all_ts || v < ts_lo || v > ts_hi) return true;
@@ -129,14 +170,29 @@ __global__ void __launch_bounds__(kSelThreads) filter_topk_kernel(const FilterPa
     }
     return false;
   };
+  // The row is walked four tokens per thread per step (one 16-byte load; the four tokens share their bitmap words);
+  // the <= 3 tokens past the last multiple of four are handled by the first threads.
+  const int V4 = p.V >> 2;
+  const float4* x4 = reinterpret_cast<const float4*>(x);
 
-  // ---- pass 1: (max, sum-exp) of the text part [0, tb) and the timestamp part [tb, V); text max
+  // ---- pass 1: (max, sum-exp) of the text part [0, tb) and the timestamp part [tb, V)
   float m_txt = -INFINITY, s_txt = 0.f, m_ts = -INFINITY, s_ts = 0.f;
-  for (int v = tid; v < p.V; v += kSelThreads) {
-    if (masked(v)) continue;
-    const float val = x[v];
-    if (val == -INFINITY) continue;
+  auto acc1 = [&](int v, float val, uint32_t sw, uint32_t bw) {
+    if (val == -INFINITY || masked(v, sw, bw)) return;
     if (v < tb) lse_merge(m_txt, s_txt, val, 1.f); else lse_merge(m_ts, s_ts, val, 1.f);
+  };
+  for (int q = tid; q < V4; q += kSelThreads) {
+    const float4 f = x4[q];
+    const int v = q << 2;
+    const uint32_t sw = __ldg(p.suppress_mask + (v >> 5)), bw = use_blank ? __ldg(p.blank_mask + (v >> 5)) : 0u;
+    acc1(v, f.x, sw, bw);
+    acc1(v + 1, f.y, sw, bw);
+    acc1(v + 2, f.z, sw, bw);
+    acc1(v + 3, f.w, sw, bw);
+  }
+  if (tid < (p.V & 3)) {
+    const int v = (V4 << 2) + tid;
+    acc1(v, x[v], __ldg(p.suppress_mask + (v >> 5)), use_blank ? __ldg(p.blank_mask + (v >> 5)) : 0u);
   }
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) {
@@ -174,64 +230,66 @@ __global__ void __launch_bounds__(kSelThreads) filter_topk_kernel(const FilterPa
   const float lse = s_fin[0];
   const bool drop_text = s_rule[3];
 
-  // ---- pass 2: top-K of the surviving logits
-  TopK mine;
-#pragma unroll
-  for (int k = 0; k < kMaxTopK; ++k) {
-    mine.v[k] = -INFINITY;
-    mine.i[k] = 0x7fffffff;
-  }
+  // ---- pass 2: top-K of the surviving logits (the row is L2 / L1 resident from pass 1)
+  TopList<KM> mine;
+  mine.init();
   const int K = p.K;
   const bool sampling = p.inv_temp > 0.f && K == 1;
-  for (int v = tid; v < p.V; v += kSelThreads) {
-    float val = x[v];
-    if (masked(v) || (drop_text && v < tb)) val = -INFINITY;
-    if (sampling && val != -INFINITY) val = fmaf(val, p.inv_temp, gumbel_noise(p.seed_lo, p.seed_hi, r, L, v));
-    if (better(val, v, mine.v[K - 1], mine.i[K - 1])) {
-      int k = K - 1;
-      while (k > 0 && better(val, v, mine.v[k - 1], mine.i[k - 1])) {
-        mine.v[k] = mine.v[k - 1];
-        mine.i[k] = mine.i[k - 1];
-        --k;
-      }
-      mine.v[k] = val;
-      mine.i[k] = v;
-    }
+  auto acc2 = [&](int v, float val, uint32_t sw, uint32_t bw) {
+    if (val == -INFINITY || masked(v, sw, bw) || (drop_text && v < tb)) return;
+    if (sampling) val = fmaf(val, p.inv_temp, gumbel_noise(p.seed_lo, p.seed_hi, r, L, v));
+    mine.push(val, v);
+  };
+  for (int q = tid; q < V4; q += kSelThreads) {
+    const float4 f = x4[q];
+    const int v = q << 2;
+    const uint32_t sw = __ldg(p.suppress_mask + (v >> 5)), bw = use_blank ? __ldg(p.blank_mask + (v >> 5)) : 0u;
+    acc2(v, f.x, sw, bw);
+    acc2(v + 1, f.y, sw, bw);
+    acc2(v + 2, f.z, sw, bw);
+    acc2(v + 3, f.w, sw, bw);
   }
-  // warp merge: K rounds of "pop the best head among lanes"
-  TopK wtop;
-  {
-    int head = 0;
-    for (int k = 0; k < K; ++k) {
-      float bv = head < K ? mine.v[head] : -INFINITY;
-      int bi = head < K ? mine.i[head] : 0x7fffffff;
-      float cv = bv;
-      int ci = bi;
+  if (tid < (p.V & 3)) {
+    const int v = (V4 << 2) + tid;
+    acc2(v, x[v], __ldg(p.suppress_mask + (v >> 5)), use_blank ? __ldg(p.blank_mask + (v >> 5)) : 0u);
+  }
+  // warp merge: K rounds of "pop the best head among the lanes"
+  for (int k = 0; k < K; ++k) {
+    const float bv = mine.v[0];
+    const int bi = mine.i[0];
+    float cv = bv;
+    int ci = bi;
 #pragma unroll
-      for (int o = 16; o > 0; o >>= 1) {
-        const float ov = __shfl_xor_sync(0xffffffffu, cv, o);
-        const int oi = __shfl_xor_sync(0xffffffffu, ci, o);
-        if (better(ov, oi, cv, ci)) {
-          cv = ov;
-          ci = oi;
-        }
+    for (int o = 16; o > 0; o >>= 1) {
+      const float ov = __shfl_xor_sync(0xffffffffu, cv, o);
+      const int oi = __shfl_xor_sync(0xffffffffu, ci, o);
+      if (better(ov, oi, cv, ci)) {
+        cv = ov;
+        ci = oi;
       }
-      if (ci == bi && cv == bv && head < K) ++head;             // this lane's head was taken
-      wtop.v[k] = cv;
-      wtop.i[k] = ci;
+    }
+    if (ci == bi && cv == bv && bi != 0x7fffffff) mine.pop();   // this lane's head was taken
+    if (lane == 0) {
+      s_tv[warp][k] = cv;
+      s_ti[warp][k] = ci;
     }
   }
-  if (lane == 0) s_top[warp] = wtop;
   __syncthreads();
   if (warp == 0) {
-    // lane w holds warp w's sorted list; same pop-the-best merge across lanes
-    TopK l;
-    if (lane < kSelThreads / 32) l = s_top[lane];
-    int head = 0;
-    const bool have = lane < kSelThreads / 32;
+    // lane w holds warp w's sorted list; the same pop-the-best merge across the 16 warps
+    TopList<KM> l;
+    l.init();
+    if (lane < kSelThreads / 32) {
+#pragma unroll
+      for (int k = 0; k < KM; ++k)
+        if (k < K) {
+          l.v[k] = s_tv[lane][k];
+          l.i[k] = s_ti[lane][k];
+        }
+    }
     for (int k = 0; k < K; ++k) {
-      float bv = (have && head < K) ? l.v[head] : -INFINITY;
-      int bi = (have && head < K) ? l.i[head] : 0x7fffffff;
+      const float bv = l.v[0];
+      const int bi = l.i[0];
       float cv = bv;
       int ci = bi;
 #pragma unroll
@@ -243,7 +301,7 @@ __global__ void __launch_bounds__(kSelThreads) filter_topk_kernel(const FilterPa
           ci = oi;
         }
       }
-      if (have && head < K && ci == bi && cv == bv) ++head;
+      if (ci == bi && cv == bv && bi != 0x7fffffff) l.pop();
       if (lane == 0) {
         // log-probability of the chosen token under the UN-tempered distribution (decoding.py:285-287)
         const float chosen = sampling ? ((ci >= 0 && ci < p.V) ? x[ci] : -INFINITY) : cv;
@@ -315,122 +373,120 @@ __global__ void __launch_bounds__(1024) greedy_update_kernel(const GreedyParams 
 constexpr int kMaxBeam = 16;
 constexpr int kMaxCand = kMaxBeam * (kMaxBeam + 1);
 
-constexpr int kBeamWarps = 1;   // one warp = one audio = one CTA; completion is reduced through a ticket
+constexpr int kBeamThreads = 256;
 
-__global__ void __launch_bounds__(kBeamWarps * 32) beam_update_kernel(const BeamParams p) {
+// One CTA per audio.  The candidate logic of decoding.py:335-360 is inherently sequential (dict insertion order, "last
+// writer wins", first G non-EOT survivors) and runs on thread 0 over shared memory; everything around it is parallel:
+// the G x (G+1) candidates are gathered by as many threads, finished hypotheses and the new token / parent-table rows
+// are copied by one warp each.  Whether two beams hold the same token prefix - what the reference's dict keys decide -
+// is NOT recomputed by comparing rows: it follows exactly from the previous step,
+//     same'[j1][j2] = same[src(j1)][src(j2)]  and  token(j1) == token(j2),
+// and is carried in a G x G byte matrix per audio (all ones after the prefill: every beam starts from the prompt).
+__global__ void __launch_bounds__(kBeamThreads) beam_update_kernel(const BeamParams p) {
   if (p.skip_flag && *p.skip_flag) return;
   __shared__ int s_all_done;
-  __shared__ float s_score[kBeamWarps][kMaxCand];
-  __shared__ short s_tok_row[kBeamWarps][kMaxCand];   // owning beam j
-  __shared__ int s_tok[kBeamWarps][kMaxCand];
-  __shared__ short s_order[kBeamWarps][kMaxCand];
-  __shared__ unsigned char s_same[kBeamWarps][kMaxBeam][kMaxBeam];
-  __shared__ int s_newsrc[kBeamWarps][kMaxBeam];
-  __shared__ int s_newtok[kBeamWarps][kMaxBeam];
-  if (threadIdx.x == 0) s_all_done = 1;
-  __syncthreads();
-  const int warp = 0, lane = threadIdx.x & 31;
+  __shared__ float s_score[kMaxCand];
+  __shared__ short s_tok_row[kMaxCand];   // owning beam j
+  __shared__ int s_tok[kMaxCand];
+  __shared__ short s_order[kMaxCand];
+  __shared__ unsigned char s_dead[kMaxCand];
+  __shared__ unsigned char s_same[kMaxBeam][kMaxBeam];
+  __shared__ int s_newsrc[kMaxBeam];
+  __shared__ int s_newtok[kMaxBeam];
+  __shared__ int s_fin_src[kMaxBeam + 1];  // newly finished hypotheses of this step: source row, slot
+  __shared__ int s_fin_slot[kMaxBeam + 1];
+  __shared__ int s_n_fin;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int L = *p.len_ptr;
   const int G = p.G, K = G + 1, N = G * K;
-  {
-    const int a = blockIdx.x;
-    const int r0 = a * G;
-    // prefix equality between beams (needed for the dict de-duplication of decoding.py:344-346)
-    for (int pair = 0; pair < G * G; ++pair) {
-      const int j1 = pair / G, j2 = pair % G;
-      if (j2 <= j1) {
-        if (lane == 0) s_same[warp][j1][j2] = (j1 == j2);
-        continue;
-      }
-      const int* a1 = p.tokens_in + static_cast<long long>(r0 + j1) * p.max_ctx;
-      const int* a2 = p.tokens_in + static_cast<long long>(r0 + j2) * p.max_ctx;
-      int diff = 0;
-      for (int i = lane; i < L; i += 32) diff |= (a1[i] != a2[i]);
-      diff = __any_sync(0xffffffffu, diff);
-      if (lane == 0) s_same[warp][j1][j2] = !diff;
-    }
-    __syncwarp();
-    int n_kept = 0;
-    if (lane == 0) {
-      // candidates in insertion order (j, then top-k rank); score = fp32(sum_lp + lp)
-      for (int c = 0; c < N; ++c) {
-        const int j = c / K;
-        s_score[warp][c] = p.sum_logprobs[r0 + j] + p.top_val[static_cast<long long>(r0 + j) * K + c % K];
-        s_tok[warp][c] = p.top_idx[static_cast<long long>(r0 + j) * K + c % K];
-        s_tok_row[warp][c] = static_cast<short>(j);
-      }
-      // dict semantics: a later duplicate (same prefix, same token) overwrites value and source but
-      // keeps the FIRST insertion position.  dead[c] marks removed later duplicates.
-      bool dead[kMaxCand];
-      for (int c = 0; c < N; ++c) dead[c] = false;
-      for (int c = 0; c < N; ++c) {
-        if (dead[c]) continue;
-        for (int c2 = c + 1; c2 < N; ++c2) {
-          if (dead[c2]) continue;
-          const int j1 = s_tok_row[warp][c], j2 = s_tok_row[warp][c2];
-          const int lo = j1 < j2 ? j1 : j2, hi = j1 < j2 ? j2 : j1;
-          const bool same_prefix = (lo == hi) ? true : s_same[warp][lo][hi];
-          if (same_prefix && s_tok[warp][c] == s_tok[warp][c2] && j1 != j2) {
-            s_score[warp][c] = s_score[warp][c2];       // last writer's value ...
-            s_tok_row[warp][c] = s_tok_row[warp][c2];   // ... and source
-            dead[c2] = true;
-          }
+  const int a = blockIdx.x;
+  const int r0 = a * G;
+  if (tid == 0) s_all_done = 1;
+  // candidates in insertion order (j, then top-k rank); score = fp32(sum_lp + lp)   (decoding.py:339-346)
+  for (int c = tid; c < N; c += kBeamThreads) {
+    const int j = c / K;
+    s_score[c] = p.sum_logprobs[r0 + j] + p.top_val[static_cast<long long>(r0 + j) * K + c % K];
+    s_tok[c] = p.top_idx[static_cast<long long>(r0 + j) * K + c % K];
+    s_tok_row[c] = static_cast<short>(j);
+    s_dead[c] = 0;
+  }
+  if (tid < G * G) s_same[tid / G][tid % G] = p.same_in[static_cast<long long>(a) * kMaxBeam * kMaxBeam + (tid / G) * kMaxBeam + tid % G];
+  __syncthreads();
+  if (tid == 0) {
+    // dict semantics: a later duplicate (same prefix, same token) overwrites value and source but
+    // keeps the FIRST insertion position.  s_dead[c] marks removed later duplicates.
+    for (int c = 0; c < N; ++c) {
+      if (s_dead[c]) continue;
+      for (int c2 = c + 1; c2 < N; ++c2) {
+        if (s_dead[c2]) continue;
+        const int j1 = s_tok_row[c], j2 = s_tok_row[c2];
+        if (j1 != j2 && s_tok[c] == s_tok[c2] && s_same[j1][j2]) {
+          s_score[c] = s_score[c2];       // last writer's value ...
+          s_tok_row[c] = s_tok_row[c2];   // ... and source
+          s_dead[c2] = 1;
         }
-      }
-      // stable descending sort of the live candidates (insertion sort; N <= 272)
-      int n_live = 0;
-      for (int c = 0; c < N; ++c) {
-        if (dead[c]) continue;
-        int pos = n_live++;
-        while (pos > 0 && s_score[warp][s_order[warp][pos - 1]] < s_score[warp][c]) {
-          s_order[warp][pos] = s_order[warp][pos - 1];
-          --pos;
-        }
-        s_order[warp][pos] = static_cast<short>(c);
-      }
-      // decoding.py:349-360: walk the ranking; EOT candidates met before the beam is full are finished
-      int fin_n = p.fin_count[a];
-      for (int q = 0; q < n_live && n_kept < G; ++q) {
-        const int c = s_order[warp][q];
-        const int tok = s_tok[warp][c];
-        const int src = r0 + s_tok_row[warp][c];
-        if (tok == p.eot) {
-          if (fin_n < p.max_candidates) {                    // decoding.py:372-375
-            const long long slot = static_cast<long long>(a) * p.max_candidates + fin_n;
-            p.fin_len[slot] = -(src + 1);                    // marks "copy prefix of row src" for the lanes below
-            p.fin_score[slot] = s_score[warp][c];
-            ++fin_n;
-          }
-        } else {
-          s_newsrc[warp][n_kept] = src;
-          s_newtok[warp][n_kept] = tok;
-          p.sum_logprobs[r0 + n_kept] = s_score[warp][c];    // decoding.py:354 (safe: scores were read above)
-          ++n_kept;
-        }
-      }
-      p.fin_count[a] = fin_n;
-      if (fin_n < p.max_candidates) atomicAnd(&s_all_done, 0);
-    }
-    __syncwarp();
-    // materialise newly finished hypotheses: prefix of the source row + EOT
-    for (int f = 0; f < p.max_candidates; ++f) {
-      const long long slot = static_cast<long long>(a) * p.max_candidates + f;
-      const int mark = p.fin_len[slot];
-      if (mark < 0) {
-        const int src = -mark - 1;
-        const int* srow = p.tokens_in + static_cast<long long>(src) * p.max_ctx;
-        int* drow = p.fin_tokens + slot * p.max_ctx;
-        for (int i = lane; i < L; i += 32) drow[i] = srow[i];
-        if (lane == 0) {
-          drow[L] = p.eot;
-          p.fin_len[slot] = L + 1;
-        }
-        __syncwarp();
       }
     }
-    // new beams: token rows and the kv-cache parent table
-    for (int j = 0; j < G; ++j) {
-      const int src = s_newsrc[warp][j];
+    // stable descending sort of the live candidates (insertion sort; N <= 272)
+    int n_live = 0;
+    for (int c = 0; c < N; ++c) {
+      if (s_dead[c]) continue;
+      int pos = n_live++;
+      while (pos > 0 && s_score[s_order[pos - 1]] < s_score[c]) {
+        s_order[pos] = s_order[pos - 1];
+        --pos;
+      }
+      s_order[pos] = static_cast<short>(c);
+    }
+    // decoding.py:349-360: walk the ranking; EOT candidates met before the beam is full are finished
+    int fin_n = p.fin_count[a], n_kept = 0, n_fin = 0;
+    for (int q = 0; q < n_live && n_kept < G; ++q) {
+      const int c = s_order[q];
+      const int tok = s_tok[c];
+      const int src = r0 + s_tok_row[c];
+      if (tok == p.eot) {
+        if (fin_n < p.max_candidates) {                    // decoding.py:372-375
+          const int slot = a * p.max_candidates + fin_n;
+          p.fin_score[slot] = s_score[c];
+          s_fin_src[n_fin] = src;
+          s_fin_slot[n_fin] = slot;
+          ++n_fin;
+          ++fin_n;
+        }
+      } else {
+        s_newsrc[n_kept] = src;
+        s_newtok[n_kept] = tok;
+        p.sum_logprobs[r0 + n_kept] = s_score[c];          // decoding.py:354 (safe: scores were gathered above)
+        ++n_kept;
+      }
+    }
+    s_n_fin = n_fin;
+    p.fin_count[a] = fin_n;
+    if (fin_n < p.max_candidates) s_all_done = 0;
+  }
+  __syncthreads();
+  // prefix-equality matrix of the new beams
+  if (tid < G * G) {
+    const int j1 = tid / G, j2 = tid % G;
+    const int s1 = s_newsrc[j1] - r0, s2 = s_newsrc[j2] - r0;
+    p.same_out[static_cast<long long>(a) * kMaxBeam * kMaxBeam + j1 * kMaxBeam + j2] =
+        (j1 == j2) ? 1 : (s_same[s1][s2] && s_newtok[j1] == s_newtok[j2]);
+  }
+  // work items for the warps: newly finished hypotheses (prefix of the source row + EOT), then the new beams (token
+  // row + kv-cache parent table)
+  const int n_fin = s_n_fin;
+  for (int item = warp; item < n_fin + G; item += kBeamThreads / 32) {
+    if (item < n_fin) {
+      const int* srow = p.tokens_in + static_cast<long long>(s_fin_src[item]) * p.max_ctx;
+      int* drow = p.fin_tokens + static_cast<long long>(s_fin_slot[item]) * p.max_ctx;
+      for (int i = lane; i < L; i += 32) drow[i] = srow[i];
+      if (lane == 0) {
+        drow[L] = p.eot;
+        p.fin_len[s_fin_slot[item]] = L + 1;
+      }
+    } else {
+      const int j = item - n_fin;
+      const int src = s_newsrc[j];
       const int* srow = p.tokens_in + static_cast<long long>(src) * p.max_ctx;
       const int* sind = p.indir_in + static_cast<long long>(src) * p.max_ctx;
       int* drow = p.tokens_out + static_cast<long long>(r0 + j) * p.max_ctx;
@@ -442,11 +498,10 @@ __global__ void __launch_bounds__(kBeamWarps * 32) beam_update_kernel(const Beam
         dind[i] = (i == L - 1 && i >= p.n_init) ? src : sind[i];
       }
       if (lane == 0) {
-        drow[L] = s_newtok[warp][j];
+        drow[L] = s_newtok[j];
         p.source_out[r0 + j] = src;
       }
     }
-    __syncwarp();
   }
   __syncthreads();
   if (threadIdx.x == 0) {
@@ -473,7 +528,10 @@ __global__ void __launch_bounds__(kBeamWarps * 32) beam_update_kernel(const Beam
 int launch_filter_topk(const FilterParams& p, int R, cudaStream_t s) {
   if (p.K < 1 || p.K > kMaxTopK) return 50;
   ProfileScope prof(PROF_SELECT, s);
-  filter_topk_kernel<<<R, kSelThreads, 0, s>>>(p);
+  if ((reinterpret_cast<uintptr_t>(p.logits) & 15) || (p.ld & 3)) return 50;      // rows are read with 16-byte loads
+  if (p.K == 1) filter_topk_kernel<1><<<R, kSelThreads, 0, s>>>(p);
+  else if (p.K <= 6) filter_topk_kernel<6><<<R, kSelThreads, 0, s>>>(p);
+  else filter_topk_kernel<kMaxTopK><<<R, kSelThreads, 0, s>>>(p);
   count_launch();
   return cudaGetLastError() == cudaSuccess ? 0 : 51;
 }
@@ -558,7 +616,7 @@ int launch_greedy_update(const GreedyParams& p, cudaStream_t s) {
 }
 int launch_beam_update(const BeamParams& p, cudaStream_t s) {
   if (p.G > kMaxBeam) return 54;
-  beam_update_kernel<<<p.n_audio, kBeamWarps * 32, 0, s>>>(p);
+  beam_update_kernel<<<p.n_audio, kBeamThreads, 0, s>>>(p);
   count_launch();
   return cudaGetLastError() == cudaSuccess ? 0 : 55;
 }
