@@ -76,8 +76,9 @@ int wb200_set_pdl(int enabled);
 int wb200_set_fused_decoder_layer(int enabled);
 /* Layout of the decoder's kv caches for sessions created AFTER the call (default 1, or WB200_KV_HEAD_MAJOR=0 in
  * the environment).  1: head-major - cross-attention K/V [n_audio, 2H, 1500, 64] (written that way by the K/V
- * projection's epilogue), self-attention caches [rows, H, 448, 64] - so every (audio, head) / (row, head) pair streams
- * one contiguous block, which is also what the TMA cross-attention kernel needs.  0: cross K/V [n_audio, 1500, 2d] and
+ * projection's epilogue), self-attention caches [n_audio, H, 448, n_group, 64] (the n_group rows of an audio interleaved
+ * per position: the "beam window") - so every (audio, head) streams one contiguous block, which is what the TMA
+ * attention kernels need.  0: cross K/V [n_audio, 1500, 2d] and
  * self caches [rows, 448, d], one head's 128 bytes per position strided by the model width.  With the cp.async
  * attention kernels the two layouts give bit-identical results (measured on B200: head-major +1 %,
  * profiles/r2_ab_switches.txt). */
@@ -87,6 +88,14 @@ int wb200_set_kv_head_major(int enabled);
  * through an mbarrier ring that stays full across (audio, head) work items; needs the head-major layout.  0 = the
  * cp.async kernel (always used for the prefill).  Takes effect at the next launch. */
 int wb200_set_cross_attention_tma(int enabled);
+/* Decoder-step self attention under beam search / best_of (2 <= n_group <= 8): 1 (default, WB200_SATTN_TMA=0 to
+ * disable) = the G rows of an audio are processed together by a persistent TMA-fed kernel that streams the audio's
+ * whole (position x beam-slot) history of a head as one contiguous block of the head-major ("beam window") cache and
+ * masks each row by the beam's parent table - the device form of PyTorchInference.rearrange_kv_cache
+ * (whisper/decoding.py:172-176) + the kv-cache hooks' torch.cat (whisper/model.py:327-333).  0 = one warp per
+ * (row, head) gathering 128-byte pieces through the parent table (always used for greedy decoding, the prefill and the
+ * position-major layout).  Takes effect at the next launch. */
+int wb200_set_self_attention_tma(int enabled);
 
 /* Same operator with split-K enabled for skinny problems (the 320-row decode-step GEMMs): `workspace`
  * holds fp32 partial slabs (up to 8 * M * N floats are used), `tickets` is an int32 array of n_tickets

@@ -113,6 +113,11 @@ int wb200_set_kv_head_major(int enabled) {
   return 0;
 }
 
+int wb200_set_self_attention_tma(int enabled) {
+  g_sattn_tma = enabled ? 1 : 0;
+  return 0;
+}
+
 int wb200_set_cross_attention_tma(int enabled) {
   g_xattn_tma = enabled ? 1 : 0;
   return 0;

@@ -856,6 +856,307 @@ static int dispatch_sa(const SelfParams& p, int n_rows, int n_head, int u, int s
   return 45;
 }
 
+// =================================================================================================
+// self attention, step mode, beams of an audio together, TMA-fed and persistent (beam-window layout only)
+// =================================================================================================
+// With beam search the G rows of an audio attend over histories that are piecewise the same physical cache rows, and
+// after a few reorders the physical row of consecutive positions of one lineage is effectively random: the warp-per-
+// (row, head) kernel above then gathers isolated 128-byte pieces (measured at the mean length of the headline run:
+// 148 MB of DRAM traffic per launch at 3.85 TB/s, 12 % L2 hits, profiles/r2_self_attn_midL_ncu_full_selected.csv).
+// In the beam-window layout [audio][head][pos][slot][64] the union of those histories is ONE contiguous block of
+// (length x G) rows per (audio, head), so this kernel does what the cross-attention kernel does - producer warp streams
+// 128-row K / V tiles by TMA through a ring that stays full across items, eight consumer warps run mma.sync tiles
+// with the G beams as the M rows, an epilogue warp merges and stores - plus a mask: beam b attends row (pos, slot) iff
+// its parent table says indir[b][pos] == slot (the reference gathers the caches instead, decoding.py:172-176).  The new
+// token's K / V come straight from the QKV projection's output (one 16-row tile per item), are used from shared
+// memory and appended to the cache by a consumer warp (the torch.cat of model.py:327-333).
+constexpr int kS2Consumers = 8;
+constexpr int kS2Threads = (kS2Consumers + 2) * 32;
+constexpr int kS2TileRows = 128;
+constexpr int kS2Stages = 3;
+constexpr int kS2TileBytes = kS2TileRows * 128;
+constexpr int kS2StageBytes = 2 * kS2TileBytes;
+constexpr int kS2MaxG = 8;
+constexpr int kS2IndBytes = 448 * 4;                              // one beam's parent table (n_text_ctx <= 448)
+constexpr int kS2MetaBytes = 3 * kX2QBytes + kS2MaxG * kS2IndBytes;   // Q | Knew | Vnew tiles + G parent tables
+constexpr int kS2RedFloats = kS2Consumers * 32 * 36;
+constexpr int kS2SmemBytes = kS2Stages * kS2StageBytes + 2 * kS2MetaBytes + 2 * kS2RedFloats * 4 + 256 + 1024;
+
+struct Self2Params {
+  void* out;              // [R, d]
+  void* kcache;           // this layer's K block [n_audio][H][ctx][G][64]
+  void* vcache;
+  const int* indir;       // [R, ctx]
+  const int* len_ptr;
+  const int* skip_flag;
+  int n_audio, n_head, G, ctx, d;
+};
+
+// 16 keys of a staged tile for the 16-row query tile, with a per-(query, key) mask; safe when a query has no valid key
+// in the slice.  valid(query_row, key) is evaluated for query rows g (and g + 8 only if two_halves).
+template <typename T, typename F>
+__device__ __forceinline__ void warp_tile_masked(const uint8_t* sK, const uint8_t* sV, int wrow0, const uint32_t (&qa)[4][4],
+                                                 WarpAcc& acc, F valid) {
+  const int lane = threadIdx.x & 31;
+  const int g = lane >> 2, t = lane & 3;
+  float s[2][4];
+#pragma unroll
+  for (int i = 0; i < 2; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) s[i][j] = 0.f;
+  {
+    const int m = lane >> 3;
+    const int krow = wrow0 + (m >> 1) * 8 + (lane & 7);
+#pragma unroll
+    for (int ks = 0; ks < 4; ++ks) {
+      const int chunk = ks * 2 + (m & 1);
+      uint32_t kb[4];
+      ldmatrix_x4(kb, sK + krow * 128 + ((chunk ^ (krow & 7)) << 4));
+      mma16816<T>(s[0], qa[ks], kb[0], kb[1]);
+      mma16816<T>(s[1], qa[ks], kb[2], kb[3]);
+    }
+  }
+#pragma unroll
+  for (int nt = 0; nt < 2; ++nt)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int key = nt * 8 + 2 * t + (j & 1);
+      const int qrow = g + (j >> 1) * 8;
+      if (!valid(qrow, key)) s[nt][j] = -INFINITY;
+    }
+  float mx0 = fmaxf(fmaxf(s[0][0], s[0][1]), fmaxf(s[1][0], s[1][1]));
+  float mx1 = fmaxf(fmaxf(s[0][2], s[0][3]), fmaxf(s[1][2], s[1][3]));
+  mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 1));
+  mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 2));
+  mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 1));
+  mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 2));
+  const float mn0 = fmaxf(acc.m[0], mx0 * kScaleLog2);
+  const float mn1 = fmaxf(acc.m[1], mx1 * kScaleLog2);
+  const float b0 = mn0 == -INFINITY ? 0.f : mn0;       // a row that has seen no key yet: keep everything at zero
+  const float b1 = mn1 == -INFINITY ? 0.f : mn1;
+  const float al0 = fast_exp2(acc.m[0] - b0);
+  const float al1 = fast_exp2(acc.m[1] - b1);
+  acc.m[0] = mn0;
+  acc.m[1] = mn1;
+  float p[2][4];
+#pragma unroll
+  for (int nt = 0; nt < 2; ++nt) {
+    p[nt][0] = fast_exp2(s[nt][0] * kScaleLog2 - b0);
+    p[nt][1] = fast_exp2(s[nt][1] * kScaleLog2 - b0);
+    p[nt][2] = fast_exp2(s[nt][2] * kScaleLog2 - b1);
+    p[nt][3] = fast_exp2(s[nt][3] * kScaleLog2 - b1);
+  }
+  acc.l[0] = acc.l[0] * al0 + (p[0][0] + p[0][1] + p[1][0] + p[1][1]);
+  acc.l[1] = acc.l[1] * al1 + (p[0][2] + p[0][3] + p[1][2] + p[1][3]);
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    acc.o[i][0] *= al0;
+    acc.o[i][1] *= al0;
+    acc.o[i][2] *= al1;
+    acc.o[i][3] *= al1;
+  }
+  uint32_t pa[4];
+  pa[0] = Cvt<T>::pack2(p[0][0], p[0][1]);
+  pa[1] = Cvt<T>::pack2(p[0][2], p[0][3]);
+  pa[2] = Cvt<T>::pack2(p[1][0], p[1][1]);
+  pa[3] = Cvt<T>::pack2(p[1][2], p[1][3]);
+  {
+    const int m = lane >> 3;
+    const int vrow = wrow0 + (m & 1) * 8 + (lane & 7);
+#pragma unroll
+    for (int np = 0; np < 4; ++np) {
+      const int chunk = np * 2 + (m >> 1);
+      uint32_t vb[4];
+      ldmatrix_x4_trans(vb, sV + vrow * 128 + ((chunk ^ (vrow & 7)) << 4));
+      mma16816<T>(acc.o[np * 2], pa, vb[0], vb[1]);
+      mma16816<T>(acc.o[np * 2 + 1], pa, vb[2], vb[3]);
+    }
+  }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(kS2Threads, 1)
+self_attention_tma_kernel(const Self2Params p, const __grid_constant__ CUtensorMap mapQKV,
+                          const __grid_constant__ CUtensorMap mapK, const __grid_constant__ CUtensorMap mapV) {
+  pdl_launch_dependents();
+  extern __shared__ uint8_t s2_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(s2_raw) + 1023) & ~static_cast<uintptr_t>(1023));
+  uint8_t* ring = smem;
+  uint8_t* meta = ring + kS2Stages * kS2StageBytes;              // [2][Q | Knew | Vnew | G parent tables]
+  float* red = reinterpret_cast<float*>(meta + 2 * kS2MetaBytes);
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(red + 2 * kS2RedFloats);
+  uint64_t* empty_bar = full_bar + kS2Stages;
+  uint64_t* mfull_bar = empty_bar + kS2Stages;
+  uint64_t* mempty_bar = mfull_bar + 2;
+  uint64_t* rfull_bar = mempty_bar + 2;
+  uint64_t* rempty_bar = rfull_bar + 2;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < kS2Stages; ++i) {
+      mbar_init(&full_bar[i], 1);
+      mbar_init(&empty_bar[i], kS2Consumers);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&mfull_bar[i], 1);
+      mbar_init(&mempty_bar[i], kS2Consumers);
+      mbar_init(&rfull_bar[i], kS2Consumers);
+      mbar_init(&rempty_bar[i], 1);
+    }
+    mbar_fence_init();
+    tma_prefetch_desc(&mapQKV);
+    tma_prefetch_desc(&mapK);
+    tma_prefetch_desc(&mapV);
+  }
+  __syncthreads();
+  pdl_wait();
+  if (p.skip_flag && *p.skip_flag) return;
+  const int H = p.n_head, G = p.G;
+  const int L = *p.len_ptr;                      // tokens per row including the new one
+  const int pos_new = L - 1;
+  const int cache_rows = pos_new * G;            // rows of an (audio, head) block that hold history
+  const int n_tiles = (cache_rows + kS2TileRows - 1) / kS2TileRows;
+  const int total_items = p.n_audio * H;
+  const uint32_t ind_bytes = static_cast<uint32_t>((pos_new * 4 + 15) & ~15);
+
+  if (warp == kS2Consumers) {
+    // ===================== producer =====================
+    if (lane == 0) {
+      int q = 0, iq = 0;
+      for (int item = blockIdx.x; item < total_items; item += gridDim.x, ++iq) {
+        const int head = item % H, audio = item / H;
+        const int ms = iq & 1;
+        uint8_t* mb = meta + ms * kS2MetaBytes;
+        x2_wait(&mempty_bar[ms], ((iq >> 1) & 1) ^ 1);
+        mbar_expect_tx(&mfull_bar[ms], 3 * kX2QBytes + G * ind_bytes);
+        tma_load_2d(mb, &mapQKV, &mfull_bar[ms], head * 64, audio * G);
+        tma_load_2d(mb + kX2QBytes, &mapQKV, &mfull_bar[ms], p.d + head * 64, audio * G);
+        tma_load_2d(mb + 2 * kX2QBytes, &mapQKV, &mfull_bar[ms], 2 * p.d + head * 64, audio * G);
+        if (ind_bytes)
+          for (int b = 0; b < G; ++b)
+            bulk_load_1d(mb + 3 * kX2QBytes + b * kS2IndBytes, p.indir + static_cast<long long>(audio * G + b) * p.ctx, ind_bytes,
+                         &mfull_bar[ms]);
+        for (int t = 0; t < n_tiles; ++t, ++q) {
+          const int st = q % kS2Stages;
+          x2_wait(&empty_bar[st], ((q / kS2Stages) & 1) ^ 1);
+          mbar_expect_tx(&full_bar[st], kS2StageBytes);
+          uint8_t* dst = ring + st * kS2StageBytes;
+          tma_load_3d(dst, &mapK, &full_bar[st], 0, t * kS2TileRows, audio * H + head);
+          tma_load_3d(dst + kS2TileBytes, &mapV, &full_bar[st], 0, t * kS2TileRows, audio * H + head);
+        }
+      }
+    }
+    return;
+  }
+  if (warp == kS2Consumers + 1) {
+    // ===================== epilogue warp: merge the eight fragments, normalise, store =====================
+    const int g = lane >> 2, t4 = lane & 3;
+    int iq = 0;
+    for (int item = blockIdx.x; item < total_items; item += gridDim.x, ++iq) {
+      const int head = item % H, audio = item / H;
+      const int rb = iq & 1;
+      const float* rbuf = red + rb * kS2RedFloats;
+      x2_wait(&rfull_bar[rb], (iq >> 1) & 1);
+      float m0 = -INFINITY;
+#pragma unroll
+      for (int w = 0; w < kS2Consumers; ++w) m0 = fmaxf(m0, rbuf[(w * 32 + lane) * 36 + 32]);
+      float l0 = 0.f, o[8][2];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) o[i][0] = o[i][1] = 0.f;
+#pragma unroll
+      for (int w = 0; w < kS2Consumers; ++w) {
+        const float* src = rbuf + (w * 32 + lane) * 36;
+        const float4 ml = *reinterpret_cast<const float4*>(src + 32);
+        const float f0 = ml.x == -INFINITY ? 0.f : fast_exp2(ml.x - m0);
+        l0 += ml.z * f0;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const float2 v = *reinterpret_cast<const float2*>(src + i * 4);
+          o[i][0] += v.x * f0;
+          o[i][1] += v.y * f0;
+        }
+      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&rempty_bar[rb]);
+      if (g < G) {                                   // G <= 8: only the rows g of the fragment are beams
+        const float i0 = 1.0f / l0;
+        T* o0 = reinterpret_cast<T*>(p.out) + (static_cast<long long>(audio) * G + g) * p.d + head * 64 + 2 * t4;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) *reinterpret_cast<uint32_t*>(o0 + i * 8) = Cvt<T>::pack2(o[i][0] * i0, o[i][1] * i0);
+      }
+    }
+    return;
+  }
+  // ===================== consumers =====================
+  int q = 0, iq = 0;
+  for (int item = blockIdx.x; item < total_items; item += gridDim.x, ++iq) {
+    const int head = item % H, audio = item / H;
+    const int ms = iq & 1;
+    const uint8_t* mb = meta + ms * kS2MetaBytes;
+    const int* s_ind = reinterpret_cast<const int*>(mb + 3 * kX2QBytes);      // [G][448]
+    uint32_t qa[4][4];
+    x2_wait(&mfull_bar[ms], (iq >> 1) & 1);
+    {
+      const int row = lane & 15;
+#pragma unroll
+      for (int ks = 0; ks < 4; ++ks) {
+        const int chunk = ks * 2 + (lane >> 4);
+        ldmatrix_x4(qa[ks], mb + row * 128 + ((chunk ^ (row & 7)) << 4));
+      }
+    }
+    WarpAcc acc;
+    acc_init(acc);
+    const int base_phys = audio * G;
+    for (int t = 0; t < n_tiles; ++t, ++q) {
+      const int st = q % kS2Stages;
+      x2_wait(&full_bar[st], (q / kS2Stages) & 1);
+      const uint8_t* sK = ring + st * kS2StageBytes;
+      const int row0 = t * kS2TileRows + warp * 16;          // first cache row of this warp's slice
+      if (row0 < cache_rows) {
+        auto valid = [&](int qrow, int key) -> bool {
+          const int kr = row0 + key;
+          const int pos = kr / G, slot = kr - pos * G;
+          return qrow < G && pos < pos_new && s_ind[qrow * (kS2IndBytes / 4) + pos] == base_phys + slot;
+        };
+        warp_tile_masked<T>(sK, sK + kS2TileBytes, warp * 16, qa, acc, valid);
+      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&empty_bar[st]);
+    }
+    if (warp == 0) {
+      // the new position: beam b attends its own new key (row b of the Knew / Vnew tiles)
+      auto valid = [&](int qrow, int key) -> bool { return qrow < G && key == qrow; };
+      warp_tile_masked<T>(mb + kX2QBytes, mb + 2 * kX2QBytes, 0, qa, acc, valid);
+    } else if (warp == 1) {
+      // append the new K / V rows to the cache: [audio][head][pos_new][slot b][64]
+      const long long blk = (static_cast<long long>(audio) * H + head) * p.ctx + pos_new;
+      uint8_t* kdst = reinterpret_cast<uint8_t*>(p.kcache) + blk * G * 128;
+      uint8_t* vdst = reinterpret_cast<uint8_t*>(p.vcache) + blk * G * 128;
+      for (int i = lane; i < G * 8; i += 32) {
+        const int b = i >> 3, c = i & 7;
+        const int soff = b * 128 + ((c ^ (b & 7)) << 4);
+        *reinterpret_cast<uint4*>(kdst + b * 128 + c * 16) = *reinterpret_cast<const uint4*>(mb + kX2QBytes + soff);
+        *reinterpret_cast<uint4*>(vdst + b * 128 + c * 16) = *reinterpret_cast<const uint4*>(mb + 2 * kX2QBytes + soff);
+      }
+    }
+    __syncwarp();
+    if (lane == 0) mbar_arrive(&mempty_bar[ms]);
+    // ---- hand the fragment to the epilogue warp
+    acc.l[0] += __shfl_xor_sync(0xffffffffu, acc.l[0], 1);
+    acc.l[0] += __shfl_xor_sync(0xffffffffu, acc.l[0], 2);
+    acc.l[1] += __shfl_xor_sync(0xffffffffu, acc.l[1], 1);
+    acc.l[1] += __shfl_xor_sync(0xffffffffu, acc.l[1], 2);
+    const int rb = iq & 1;
+    x2_wait(&rempty_bar[rb], ((iq >> 1) & 1) ^ 1);
+    float* mine = red + rb * kS2RedFloats + (warp * 32 + lane) * 36;
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+      *reinterpret_cast<float4*>(mine + i * 4) = make_float4(acc.o[i][0], acc.o[i][1], acc.o[i][2], acc.o[i][3]);
+    *reinterpret_cast<float4*>(mine + 32) = make_float4(acc.m[0], acc.m[1], acc.l[0], acc.l[1]);
+    __syncwarp();
+    if (lane == 0) mbar_arrive(&rfull_bar[rb]);
+  }
+}
+
 // Prefill-mode append: copy k|v of qkv[(a, i)] into cache[(a*group, i)].  One warp per (row, k/v).
 template <typename T>
 __global__ void kv_append_kernel(const T* __restrict__ qkv, T* __restrict__ kcache, T* __restrict__ vcache,
@@ -1066,6 +1367,58 @@ int launch_cross_attention_tma(int dtype, const void* q, const void* kv, void* o
   }
   count_launch();
   return (le == cudaSuccess && cudaGetLastError() == cudaSuccess) ? 0 : 49;
+}
+
+// Step-mode self attention of all beams of an audio together (beam-window kv layout, 2 <= G <= 8).  -1: not covered.
+int launch_self_attention_tma(int dtype, const void* qkv, void* kcache, void* vcache, void* out, const int* indir,
+                              const int* len_ptr, const int* skip_flag, int n_audio, int G, int n_head, int max_ctx,
+                              cudaStream_t s) {
+  const int sms = sm_count();
+  if (G < 2 || G > kS2MaxG || max_ctx * 4 > kS2IndBytes || n_audio * n_head * 2 < sms) return -1;
+  const int d = n_head * 64;
+  Self2Params p;
+  p.out = out;
+  p.kcache = kcache;
+  p.vcache = vcache;
+  p.indir = indir;
+  p.len_ptr = len_ptr;
+  p.skip_flag = skip_flag;
+  p.n_audio = n_audio;
+  p.n_head = n_head;
+  p.G = G;
+  p.ctx = max_ctx;
+  p.d = d;
+  CUtensorMap mapQKV, mapK, mapV;
+  {
+    uint64_t dims[2] = {static_cast<uint64_t>(3 * d), static_cast<uint64_t>(n_audio) * G};
+    uint64_t strides[1] = {static_cast<uint64_t>(3 * d) * 2};
+    uint32_t box[2] = {64, 16};
+    if (make_tmap_16bit(&mapQKV, dtype, qkv, 2, dims, strides, box)) return 57;
+  }
+  {
+    uint64_t dims[3] = {64, static_cast<uint64_t>(max_ctx) * G, static_cast<uint64_t>(n_audio) * n_head};
+    uint64_t strides[2] = {128, static_cast<uint64_t>(max_ctx) * G * 128};
+    uint32_t box[3] = {64, kS2TileRows, 1};
+    if (make_tmap_16bit(&mapK, dtype, kcache, 3, dims, strides, box)) return 58;
+    if (make_tmap_16bit(&mapV, dtype, vcache, 3, dims, strides, box)) return 58;
+  }
+  const int items = n_audio * n_head;
+  const int grid = items < sms ? items : sms;
+  ProfileScope prof(PROF_SELF_ATTN, s);
+  cudaError_t le;
+  if (dtype == DT_BF16) {
+    static SmemOptIn optin;
+    auto kern = self_attention_tma_kernel<__nv_bfloat16>;
+    if (!optin.ensure(kern, kS2SmemBytes)) return 59;
+    le = launch_pdl(kern, dim3(grid), dim3(kS2Threads), kS2SmemBytes, s, p, mapQKV, mapK, mapV);
+  } else {
+    static SmemOptIn optin;
+    auto kern = self_attention_tma_kernel<__half>;
+    if (!optin.ensure(kern, kS2SmemBytes)) return 59;
+    le = launch_pdl(kern, dim3(grid), dim3(kS2Threads), kS2SmemBytes, s, p, mapQKV, mapK, mapV);
+  }
+  count_launch();
+  return (le == cudaSuccess && cudaGetLastError() == cudaSuccess) ? 0 : 59;
 }
 
 }  // namespace wb

@@ -405,6 +405,10 @@ int decoder_create(const Model* m, const wb200_decode_config* c, void* ws, size_
     const char* e = getenv("WB200_XATTN_TMA");
     g_xattn_tma = (e && e[0] == '0') ? 0 : 1;
   }
+  if (g_sattn_tma < 0) {
+    const char* e = getenv("WB200_SATTN_TMA");
+    g_sattn_tma = (e && e[0] == '0') ? 0 : 1;
+  }
   D->kv_head_major = g_kv_head_major != 0;
   D->cfg.suppress_ids = nullptr;
   D->cfg.blank_ids = nullptr;
@@ -442,6 +446,17 @@ int decoder_create(const Model* m, const wb200_decode_config* c, void* ws, size_
     return set_error(215, "decoder: mask upload failed");
   }
   {
+    // the beam-window self-attention kernel reads whole tiles, including rows no beam refers to (masked to zero
+    // probability): those bytes must be finite, so the arenas start from zero instead of whatever the allocator left
+    const size_t self_bytes = static_cast<size_t>(m->dims.n_text_layer) * c->n_audio * c->n_group * m->dims.n_text_ctx *
+                              m->dims.n_text_state * 2;
+    if (cudaMemsetAsync(D->self_k, 0, self_bytes, s) != cudaSuccess || cudaMemsetAsync(D->self_v, 0, self_bytes, s) != cudaSuccess) {
+      cudaFreeHost(D->pinned);
+      delete D;
+      return set_error(218, "decoder: kv arena initialisation failed");
+    }
+  }
+  {
     int r = build_fused_plan(D);
     if (r) {
       cudaFreeHost(D->pinned);
@@ -467,6 +482,20 @@ int decoder_set_audio(Decoder* D, const void* features, cudaStream_t s) {
                   D->kv_head_major ? Ta : 0));
   }
   return 0;
+}
+
+// decoder self-attention of one layer in the step: all beams of an audio together through the beam-window TMA kernel
+// when the shape allows, else one warp per (row, head)
+static int self_attention_step(Decoder* D, void* kc, void* vc, cudaStream_t s) {
+  const Model* m = D->m;
+  const int H = m->dims.n_text_head, ctx = m->dims.n_text_ctx, B = D->cfg.n_audio, G = D->cfg.n_group;
+  if (D->kv_head_major && g_sattn_tma) {
+    const int r = launch_self_attention_tma(m->dtype, D->qkv, kc, vc, D->att, D->indir[D->cur], D->len_ptr, D->done_ptr, B, G, H,
+                                            ctx, s);
+    if (r >= 0) return r;
+  }
+  return launch_self_attention(m->dtype, D->qkv, kc, vc, D->att, D->indir[D->cur], D->len_ptr, D->done_ptr, B * G, H, ctx,
+                               D->cfg.n_init, G, s, D->kv_head_major ? 1 : 0);
 }
 
 // decoder cross-attention of one layer: the persistent TMA kernel for the step (head-major K/V, <= 16 queries per
@@ -500,8 +529,7 @@ static int decoder_stack(Decoder* D, int rows, bool step, cudaStream_t s) {
       void* vc = static_cast<uint8_t*>(D->self_v) + l * self_per_layer;
       const uint8_t* ckv = static_cast<const uint8_t*>(D->cross_kv) + l * cross_per_layer;
       if (l == 0) WB_TRY(dl_launch(D->dl_head[0], s));
-      WB_TRY(launch_self_attention(dt, D->qkv, kc, vc, D->att, D->indir[D->cur], D->len_ptr, skip, rows, H, ctx,
-                                   D->cfg.n_init, G, s, D->kv_head_major ? 1 : 0));
+      WB_TRY(self_attention_step(D, kc, vc, s));
       WB_TRY(dl_launch(D->dl_mid[l], s));
       WB_TRY(cross_attention(D, ckv, true, n_q, s));
       WB_TRY(dl_launch(D->dl_tail[l], s));
@@ -515,8 +543,11 @@ static int decoder_stack(Decoder* D, int rows, bool step, cudaStream_t s) {
     const uint8_t* ckv = static_cast<const uint8_t*>(D->cross_kv) + l * cross_per_layer;
     WB_TRY(launch_layernorm(dt, D->x, d, D->ln, d, (const float*)L[D_ATTN_LN_W], (const float*)L[D_ATTN_LN_B], rows, d, s, skip));
     WB_TRY(linear(m, D->ln, d, rows, L[D_QKV_W], 3 * d, d, L[D_QKV_B], nullptr, D->qkv, 3 * d, 0, 0, s, skip, D));
-    WB_TRY(launch_self_attention(dt, D->qkv, kc, vc, D->att, step ? D->indir[D->cur] : nullptr, D->len_ptr, skip, rows, H,
-                                 ctx, D->cfg.n_init, G, s, D->kv_head_major ? 1 : 0));
+    if (step)
+      WB_TRY(self_attention_step(D, kc, vc, s));
+    else
+      WB_TRY(launch_self_attention(dt, D->qkv, kc, vc, D->att, nullptr, D->len_ptr, skip, rows, H, ctx, D->cfg.n_init, G, s,
+                                   D->kv_head_major ? 1 : 0));
     WB_TRY(linear(m, D->att, d, rows, L[D_OUT_W], d, d, L[D_OUT_B], D->x, D->x, d, 0, 0, s, skip, D));
     WB_TRY(launch_layernorm(dt, D->x, d, D->ln, d, (const float*)L[D_CROSS_LN_W], (const float*)L[D_CROSS_LN_B], rows, d, s, skip));
     WB_TRY(linear(m, D->ln, d, rows, L[D_CQ_W], d, d, L[D_CQ_B], nullptr, D->q, d, 0, 0, s, skip, D));
