@@ -628,10 +628,20 @@ def bench_transcribe(args, model, tok, dims, dev, rank, world, local, timed, lib
         "transcribe_batch": {"files": n_files, "seconds_each": piece / 16000.0, "value": args.audio_seconds / (ms_b / 1000.0),
                              "unit": "x realtime", "ms": ms_b, "rounds": res_b[0].get("rounds"),
                              "note": "the same hour as 16 files advanced in lock-step (SURVEY 8f.1)"},
-        "roofline": {"kernel": "decode loop (batch 1)", "bound": "hbm",
-                     "achieved": None, "peak": peak_gbs, "unit": "GB/s", "frac": None, "peak_source": peak_src, "traffic": None,
-                     "note": "batch-1 long-form decode is launch / latency bound, not bandwidth bound; see phases_ms_per_step"},
     }
+    # HBM roofline of the batch-1 decoder iteration: every iteration streams the decoder's weights, the logits matrix and
+    # the window's cross K/V once; the mean self-attention history is tokens / decode call / 2
+    iters = loop_steps / max(1, args.steps)
+    alg = algorithmic_numbers(dims, 1, 1, max(1.0, tokens / max(1, n_decodes / max(1, args.steps)) / 2.0))
+    loop_ms = phases.get("decode_loop", 0.0) / args.steps
+    ach = alg["decode_step_bytes"] * iters / (loop_ms / 1000.0) / 1e9 if loop_ms > 0 else None
+    line["roofline"] = {"kernel": "decoder iteration (one audio, greedy): 3 fused-layer launches + 2 attention launches per layer, "
+                                  "logits GEMM, selection", "bound": "hbm", "achieved": ach, "peak": peak_gbs, "unit": "GB/s",
+                        "frac": (ach / peak_gbs) if ach else None, "peak_source": peak_src, "traffic": None,
+                        "algorithmic_bytes_per_iteration": alg["decode_step_bytes"],
+                        "us_per_iteration": 1000.0 * loop_ms / max(1.0, iters),
+                        "how": "weights of the decoder layers + logits matrix + the window's cross K/V + mean self K/V, x iterations, "
+                               "divided by the CUDA-event time of the device-resident decode loops of the hour"}
     if world == 1 and not args.no_cpu_baseline:
         threads = host_threads()
         s = reference_value(args, threads)

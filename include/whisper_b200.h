@@ -74,14 +74,20 @@ int wb200_set_pdl(int enabled);
  * into the consuming Linear.  On by default for sessions created AFTER the call (WB200_FUSED_LAYER=0 in the environment
  * or this call turns it off; the unfused kernels then run, as they always do for the prefill). */
 int wb200_set_fused_decoder_layer(int enabled);
+/* Few-rows form of the fused decoder-layer kernel (sessions with n_audio * n_group <= 8 rows: one audio decoded
+ * greedily as in whisper/transcribe.py:272-508, one audio with 5 beams): same phases and LayerNorm folding, the main
+ * loop a weight-stationary matrix-vector product (every SM bulk-copies its own slice of the weight rows into shared
+ * memory ahead of the grid barrier and runs mma.sync with the weight rows as the M operand).  On by default for
+ * sessions created AFTER the call (WB200_FUSED_ROWS=0 in the environment or this call: the 64-row tile form runs). */
+int wb200_set_fused_decoder_rows(int enabled);
 /* Layout of the decoder's kv caches for sessions created AFTER the call (default 1, or WB200_KV_HEAD_MAJOR=0 in
  * the environment).  1: head-major - cross-attention K/V [n_audio, 2H, 1500, 64] (written that way by the K/V
- * projection's epilogue), self-attention caches [n_audio, H, 448, n_group, 64] (the n_group rows of an audio interleaved
- * per position: the "beam window") - so every (audio, head) streams one contiguous block, which is what the TMA
- * attention kernels need.  0: cross K/V [n_audio, 1500, 2d] and
- * self caches [rows, 448, d], one head's 128 bytes per position strided by the model width.  With the cp.async
- * attention kernels the two layouts give bit-identical results (measured on B200: head-major +1 %,
- * profiles/r2_ab_switches.txt). */
+ * projection's epilogue), self-attention caches [rows, H, 448, 64] - or, in sessions that run the beam-window
+ * self-attention kernel (wb200_set_self_attention_tma), [n_audio, H, 448, n_group, 64]: the n_group rows of an audio
+ * interleaved per position - so every (audio, head) streams one contiguous block, which is what the TMA attention
+ * kernels need.  0: cross K/V [n_audio, 1500, 2d] and self caches [rows, 448, d], one head's 128 bytes per position
+ * strided by the model width.  With the cp.async attention kernels the layouts give bit-identical results (measured
+ * on B200: head-major +1 %, profiles/r2_ab_switches.txt). */
 int wb200_set_kv_head_major(int enabled);
 /* Decoder-step cross attention (whisper/model.py:101-109 + SDPA, one query per beam against the audio's 1500 cached
  * keys): 1 (default, WB200_XATTN_TMA=0 to disable) = persistent kernel, one CTA per SM, K/V tiles streamed by TMA
@@ -93,8 +99,9 @@ int wb200_set_cross_attention_tma(int enabled);
  * whole (position x beam-slot) history of a head as one contiguous block of the head-major ("beam window") cache and
  * masks each row by the beam's parent table - the device form of PyTorchInference.rearrange_kv_cache
  * (whisper/decoding.py:172-176) + the kv-cache hooks' torch.cat (whisper/model.py:327-333).  0 = one warp per
- * (row, head) gathering 128-byte pieces through the parent table (always used for greedy decoding, the prefill and the
- * position-major layout).  Takes effect at the next launch. */
+ * (row, head) gathering 128-byte pieces through the parent table (always used for greedy decoding, the prefill, the
+ * position-major layout and batches with fewer (audio, head) pairs than half the SMs).  The cache layout goes with
+ * the kernel, so the switch applies to sessions created AFTER the call. */
 int wb200_set_self_attention_tma(int enabled);
 
 /* Same operator with split-K enabled for skinny problems (the 320-row decode-step GEMMs): `workspace`

@@ -21,6 +21,12 @@ def _set_fused(on: bool):
     assert _lib.lib().wb200_set_fused_decoder_layer(int(on)) == 0
 
 
+def _set_rows(on: bool):
+    from whisper_b200 import _lib
+
+    assert _lib.lib().wb200_set_fused_decoder_rows(int(on)) == 0
+
+
 def _teacher_forced_logits(model, g_feats, rec, n_audio, opts):
     from oracle import parity
 
@@ -58,10 +64,12 @@ def test_fused_layer_matches_unfused_and_oracle(name, opts, dtype):
         model.clear_sessions()           # the switch applies to sessions created after it: drop the parked ones
         plain = _teacher_forced_logits(model, g_feats, rec, 2, opts)
         _set_fused(True)
+        _set_rows(False)                 # the 64-row tile form, whatever the row count
         model.clear_sessions()
         fused = _teacher_forced_logits(model, g_feats, rec, 2, opts)
     finally:
         _set_fused(True)
+        _set_rows(True)
         model.clear_sessions()
     worst_pair, worst_ora = 0.0, 0.0
     for i, (a, b) in enumerate(zip(plain, fused)):
@@ -133,3 +141,56 @@ def test_fused_layer_more_than_one_row_block(dtype):
         worst_ora = max(worst_ora, float((b - ref).abs().max()) / scale)
     print(f"70 rows {dtype}: fused vs unfused {worst_pair:.5f}, fused vs oracle {worst_ora:.5f}")
     assert worst_ora < LOGIT_TOL[dtype] and 0.0 < worst_pair < LOGIT_TOL[dtype]
+
+
+@pytest.mark.parametrize("dtype", [torch.float16, torch.bfloat16])
+@pytest.mark.parametrize("name,n_audio,opts", [("test-multi", 1, dict(sample_len=16)),          # R = 1
+                                               ("test-en", 1, dict(beam_size=5, sample_len=16)),  # R = 5
+                                               ("tiny.en", 2, dict(beam_size=3, sample_len=12)),  # R = 6
+                                               ("tiny.en", 2, dict(beam_size=4, sample_len=10)),  # R = 8
+                                               ("test-multi", 7, dict(sample_len=8))])            # R = 7
+def test_few_rows_form_matches_tile_form_and_oracle(name, n_audio, opts, dtype):
+    """Sessions with <= 8 rows run the weight-stationary form of the fused layer (dec_rows_kernel: bulk-copied weight
+    slabs, mma.sync with the weight rows as the M operand, K split over eight warps); same math as the tile form up to the
+    order of the fp32 sums."""
+    import whisper_b200 as wb
+    from oracle import audio as OA
+    from oracle import model as OM
+    from oracle import parity
+    from whisper_b200 import synthetic
+
+    meta, _ = load_model_fixture(name)
+    dims, sd, _ = fixture_inputs(meta)
+    audio = synthetic.synthetic_audio(n_audio, 480000, seed=7 + n_audio, kind="speechlike")
+    W = OM.to_weights(sd)
+    mel = torch.from_numpy(np.stack([OA.log_mel_spectrogram(a, dims["n_mels"]) for a in audio]))
+    feats = OM.encoder_forward(W, dims, mel)
+    rec = parity.oracle_record(W, dims, feats, opts, n_audio)
+    G = opts.get("beam_size") or 1
+    assert n_audio * G <= 8
+    model = wb.Whisper(wb.ModelDimensions(**dims), sd, device="cuda", dtype=dtype)
+    g_mel = torch.stack([wb.log_mel_spectrogram(torch.from_numpy(a).cuda(), dims["n_mels"]) for a in audio])
+    g_feats = model.embed_audio(g_mel)
+    try:
+        _set_rows(False)
+        model.clear_sessions()
+        tile = _teacher_forced_logits(model, g_feats, rec, n_audio, opts)
+        _set_rows(True)
+        model.clear_sessions()
+        rows = _teacher_forced_logits(model, g_feats, rec, n_audio, opts)
+        again = _teacher_forced_logits(model, g_feats, rec, n_audio, opts)
+    finally:
+        _set_rows(True)
+        model.clear_sessions()
+    worst_pair = worst_ora = 0.0
+    for i, (a, b, c) in enumerate(zip(tile, rows, again)):
+        assert bool(torch.isfinite(b).all()), f"step {i}: non-finite logits from the few-rows form"
+        assert torch.equal(b, c), f"step {i}: the few-rows form is not deterministic"
+        ref = rec["raw_logits"][i]
+        ref = ref[::G] if i == 0 else ref
+        scale = float(ref.abs().max())
+        worst_pair = max(worst_pair, float((a - b).abs().max()) / scale)
+        worst_ora = max(worst_ora, float((b - ref).abs().max()) / scale)
+    print(f"{name} R={n_audio * G} {dtype}: few-rows vs tile form {worst_pair:.5f}, few-rows vs oracle {worst_ora:.5f} "
+          f"(of max |logit|), {len(rows)} steps")
+    assert worst_ora < LOGIT_TOL[dtype] and worst_pair < LOGIT_TOL[dtype]      # differ by summation order only

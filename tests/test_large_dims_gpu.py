@@ -94,3 +94,61 @@ def test_baseline_dims_against_oracle(name, dtype):
     finally:
         del model
         torch.cuda.empty_cache()
+
+
+@pytest.mark.parametrize("dtype", [torch.float16, torch.bfloat16])
+@pytest.mark.parametrize("name,beam", [("turbo", None), ("large-v3", 5)])
+def test_few_rows_form_at_baseline_dims(name, beam, dtype):
+    """One audio (the shape of BASELINE configs[3]: turbo, greedy, batch 1 - and large-v3 with 5 beams): <= 8 rows, so the
+    step runs the weight-stationary form of the fused layer (dec_rows_kernel) with 8-35 weight rows of K = 1280 / 5120 per
+    SM.  Device logits along the oracle's trajectory, and the same run through the 64-row tile form."""
+    import whisper_b200 as wb
+    from oracle import model as OM
+    from oracle import parity
+    from whisper_b200 import _lib
+
+    dims, sd, audio, feats, _, _ = _oracle(name)
+    opts = dict(sample_len=7) if beam is None else dict(beam_size=beam, sample_len=7)
+    G = beam or 1
+    with torch.no_grad():
+        rec = parity.oracle_record(OM.to_weights(sd), dims, feats[:1], opts, 1)
+    model = wb.Whisper(wb.ModelDimensions(**dims), sd, device="cuda", dtype=dtype)
+
+    def run():
+        task, sess = parity.open_session(model, opts, 1, g_feats)
+        out = []
+        try:
+            for i in range(len(rec["raw_logits"])):
+                if i > 0:
+                    sess.step()
+                out.append(sess.get_logits(1 if i == 0 else G).float().cpu())
+                ref = rec["raw_logits"][i]
+                sess.set_logits(ref[::G] if i == 0 else ref)
+                sess.select()
+        finally:
+            sess.close()
+        return out
+
+    try:
+        mel = wb.log_mel_spectrogram(torch.from_numpy(audio[0]).cuda(), dims["n_mels"])[None]
+        g_feats = model.embed_audio(mel)
+        rows = run()
+        _lib.lib().wb200_set_fused_decoder_rows(0)
+        model.clear_sessions()
+        tile = run()
+        worst_pair = worst_ora = 0.0
+        for i, (a, b) in enumerate(zip(tile, rows)):
+            ref = rec["raw_logits"][i]
+            ref = ref[::G] if i == 0 else ref
+            scale = float(ref.abs().max())
+            worst_pair = max(worst_pair, float((a - b).abs().max()) / scale)
+            worst_ora = max(worst_ora, float((b - ref).abs().max()) / scale)
+        print(f"{name} beam={beam} {dtype}: few-rows vs tile form {worst_pair:.5f}, few-rows vs oracle {worst_ora:.5f} over "
+              f"{len(rows)} iterations")
+        assert worst_ora < LOGIT_TOL[dtype]
+        assert 0.0 < worst_pair < LOGIT_TOL[dtype]       # two different kernels, the same math
+    finally:
+        _lib.lib().wb200_set_fused_decoder_rows(1)
+        model.clear_sessions()
+        del model
+        torch.cuda.empty_cache()

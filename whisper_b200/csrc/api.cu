@@ -128,6 +128,11 @@ int wb200_set_fused_decoder_layer(int enabled) {
   return 0;
 }
 
+int wb200_set_fused_decoder_rows(int enabled) {
+  g_fused_rows = enabled ? 1 : 0;
+  return 0;
+}
+
 int wb200_set_pdl(int enabled) {
   g_pdl_on = enabled ? 1 : 0;
   return 0;

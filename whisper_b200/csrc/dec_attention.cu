@@ -645,7 +645,7 @@ struct SelfParams {
   int d, max_ctx;
   int n_init;           // prefill mode: tokens per audio (query row = audio * n_init + i)
   int group;            // prefill mode: physical row of audio a is a * group
-  int head_major;       // caches are [phys_row][head][max_ctx][64] instead of [phys_row][max_ctx][d]
+  int head_major;       // 0: [phys_row][max_ctx][d]; 1: [phys_row][head][max_ctx][64]; 2: beam window [audio][head][max_ctx][slot][64]
 };
 
 // One WARP per (row, head): with a single query there is nothing for a tensor-core tile to share, so
@@ -688,10 +688,11 @@ __global__ void __launch_bounds__(640) self_attention_kernel(const SelfParams p,
   const uint8_t* qrow = reinterpret_cast<const uint8_t*>(p.qkv) + static_cast<long long>(row) * 3 * row_bytes + h * 128;
   const uint8_t* knew = qrow + row_bytes + c * 16;
   const uint8_t* vnew = qrow + 2 * row_bytes + c * 16;
-  // byte offset of (physical row, position) for this head.  Row-major: [row][pos][d].  Head-major: the "beam window"
-  // layout [audio][head][pos][beam slot][64] - the G rows of an audio interleaved per position, so that the whole history
-  // of an (audio, head) is ONE contiguous block (what self_attention_tma_kernel streams); physical row = audio * G + slot.
-  const int Gw = p.head_major ? p.group : 1;
+  // byte offset of (physical row, position) for this head.  Row-major: [row][pos][d].  Head-major: [row][head][pos][64].
+  // Beam window: [audio][head][pos][beam slot][64] - the G rows of an audio interleaved per position, so that the whole
+  // history of an (audio, head) is ONE contiguous block (what self_attention_tma_kernel streams); physical row =
+  // audio * G + slot.
+  const int Gw = p.head_major == 2 ? p.group : 1;
   const long long pos_bytes = p.head_major ? 128LL * Gw : row_bytes;
   const long long row_stride = static_cast<long long>(p.max_ctx) * row_bytes;      // bytes per physical row, either layout
   const long long head_off = p.head_major ? static_cast<long long>(h) * p.max_ctx * 128 * Gw : static_cast<long long>(h) * 128;
@@ -873,13 +874,13 @@ static int dispatch_sa(const SelfParams& p, int n_rows, int n_head, int u, int s
 constexpr int kS2Consumers = 8;
 constexpr int kS2Threads = (kS2Consumers + 2) * 32;
 constexpr int kS2TileRows = 128;
-constexpr int kS2Stages = 3;
+constexpr int kS2Stages = 4;
 constexpr int kS2TileBytes = kS2TileRows * 128;
 constexpr int kS2StageBytes = 2 * kS2TileBytes;
 constexpr int kS2MaxG = 8;
 constexpr int kS2IndBytes = 448 * 4;                              // one beam's parent table (n_text_ctx <= 448)
 constexpr int kS2MetaBytes = 3 * kX2QBytes + kS2MaxG * kS2IndBytes;   // Q | Knew | Vnew tiles + G parent tables
-constexpr int kS2RedFloats = kS2Consumers * 32 * 36;
+constexpr int kS2RedFloats = kS2Consumers * 32 * 20;       // per lane: o of its beam row (16) | m | l | pad
 constexpr int kS2SmemBytes = kS2Stages * kS2StageBytes + 2 * kS2MetaBytes + 2 * kS2RedFloats * 4 + 256 + 1024;
 
 struct Self2Params {
@@ -890,15 +891,18 @@ struct Self2Params {
   const int* len_ptr;
   const int* skip_flag;
   int n_audio, n_head, G, ctx, d;
+  int g_magic;            // ceil(2^16 / G): (r * g_magic) >> 16 == r / G for every cache row index r < 9362
 };
 
-// 16 keys of a staged tile for the 16-row query tile, with a per-(query, key) mask; safe when a query has no valid key
-// in the slice.  valid(query_row, key) is evaluated for query rows g (and g + 8 only if two_halves).
-template <typename T, typename F>
-__device__ __forceinline__ void warp_tile_masked(const uint8_t* sK, const uint8_t* sV, int wrow0, const uint32_t (&qa)[4][4],
-                                                 WarpAcc& acc, F valid) {
+// 16 keys of a staged tile for a query tile whose rows 8..15 are padding (G <= 8 beams live in rows 0..7): only the
+// row-g half of every fragment carries scores, the other half is fed zero probabilities.  kmask[j] is the set of beams
+// (bit b) that attend this lane's j-th key (keys 2t, 2t + 1, 8 + 2t, 9 + 2t of the slice); safe when a beam has no
+// valid key in the slice (its running maximum stays -inf and everything stays zero).
+template <typename T>
+__device__ __forceinline__ void warp_tile_beams(const uint8_t* sK, const uint8_t* sV, int wrow0, const uint32_t (&qa)[4][4],
+                                                WarpAcc& acc, const uint32_t (&kmask)[4]) {
   const int lane = threadIdx.x & 31;
-  const int g = lane >> 2, t = lane & 3;
+  const int g = lane >> 2;
   float s[2][4];
 #pragma unroll
   for (int i = 0; i < 2; ++i)
@@ -916,50 +920,30 @@ __device__ __forceinline__ void warp_tile_masked(const uint8_t* sK, const uint8_
       mma16816<T>(s[1], qa[ks], kb[2], kb[3]);
     }
   }
-#pragma unroll
-  for (int nt = 0; nt < 2; ++nt)
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      const int key = nt * 8 + 2 * t + (j & 1);
-      const int qrow = g + (j >> 1) * 8;
-      if (!valid(qrow, key)) s[nt][j] = -INFINITY;
-    }
-  float mx0 = fmaxf(fmaxf(s[0][0], s[0][1]), fmaxf(s[1][0], s[1][1]));
-  float mx1 = fmaxf(fmaxf(s[0][2], s[0][3]), fmaxf(s[1][2], s[1][3]));
-  mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 1));
-  mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 2));
-  mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 1));
-  mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 2));
-  const float mn0 = fmaxf(acc.m[0], mx0 * kScaleLog2);
-  const float mn1 = fmaxf(acc.m[1], mx1 * kScaleLog2);
-  const float b0 = mn0 == -INFINITY ? 0.f : mn0;       // a row that has seen no key yet: keep everything at zero
-  const float b1 = mn1 == -INFINITY ? 0.f : mn1;
-  const float al0 = fast_exp2(acc.m[0] - b0);
-  const float al1 = fast_exp2(acc.m[1] - b1);
-  acc.m[0] = mn0;
-  acc.m[1] = mn1;
-  float p[2][4];
-#pragma unroll
-  for (int nt = 0; nt < 2; ++nt) {
-    p[nt][0] = fast_exp2(s[nt][0] * kScaleLog2 - b0);
-    p[nt][1] = fast_exp2(s[nt][1] * kScaleLog2 - b0);
-    p[nt][2] = fast_exp2(s[nt][2] * kScaleLog2 - b1);
-    p[nt][3] = fast_exp2(s[nt][3] * kScaleLog2 - b1);
-  }
-  acc.l[0] = acc.l[0] * al0 + (p[0][0] + p[0][1] + p[1][0] + p[1][1]);
-  acc.l[1] = acc.l[1] * al1 + (p[0][2] + p[0][3] + p[1][2] + p[1][3]);
+  float sc[4];
+  sc[0] = ((kmask[0] >> g) & 1u) ? s[0][0] * kScaleLog2 : -INFINITY;
+  sc[1] = ((kmask[1] >> g) & 1u) ? s[0][1] * kScaleLog2 : -INFINITY;
+  sc[2] = ((kmask[2] >> g) & 1u) ? s[1][0] * kScaleLog2 : -INFINITY;
+  sc[3] = ((kmask[3] >> g) & 1u) ? s[1][1] * kScaleLog2 : -INFINITY;
+  float mx = fmaxf(fmaxf(sc[0], sc[1]), fmaxf(sc[2], sc[3]));
+  mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 1));
+  mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 2));
+  const float mn = fmaxf(acc.m[0], mx);
+  const float b0 = mn == -INFINITY ? 0.f : mn;         // a row that has seen no key yet: keep everything at zero
+  const float al = fast_exp2(acc.m[0] - b0);
+  acc.m[0] = mn;
+  const float p0 = fast_exp2(sc[0] - b0), p1 = fast_exp2(sc[1] - b0), p2 = fast_exp2(sc[2] - b0), p3 = fast_exp2(sc[3] - b0);
+  acc.l[0] = acc.l[0] * al + ((p0 + p1) + (p2 + p3));
 #pragma unroll
   for (int i = 0; i < 8; ++i) {
-    acc.o[i][0] *= al0;
-    acc.o[i][1] *= al0;
-    acc.o[i][2] *= al1;
-    acc.o[i][3] *= al1;
+    acc.o[i][0] *= al;
+    acc.o[i][1] *= al;
   }
   uint32_t pa[4];
-  pa[0] = Cvt<T>::pack2(p[0][0], p[0][1]);
-  pa[1] = Cvt<T>::pack2(p[0][2], p[0][3]);
-  pa[2] = Cvt<T>::pack2(p[1][0], p[1][1]);
-  pa[3] = Cvt<T>::pack2(p[1][2], p[1][3]);
+  pa[0] = Cvt<T>::pack2(p0, p1);
+  pa[1] = 0u;
+  pa[2] = Cvt<T>::pack2(p2, p3);
+  pa[3] = 0u;
   {
     const int m = lane >> 3;
     const int vrow = wrow0 + (m & 1) * 8 + (lane & 7);
@@ -1058,21 +1042,23 @@ self_attention_tma_kernel(const Self2Params p, const __grid_constant__ CUtensorM
       x2_wait(&rfull_bar[rb], (iq >> 1) & 1);
       float m0 = -INFINITY;
 #pragma unroll
-      for (int w = 0; w < kS2Consumers; ++w) m0 = fmaxf(m0, rbuf[(w * 32 + lane) * 36 + 32]);
+      for (int w = 0; w < kS2Consumers; ++w) m0 = fmaxf(m0, rbuf[(w * 32 + lane) * 20 + 16]);
       float l0 = 0.f, o[8][2];
 #pragma unroll
       for (int i = 0; i < 8; ++i) o[i][0] = o[i][1] = 0.f;
 #pragma unroll
       for (int w = 0; w < kS2Consumers; ++w) {
-        const float* src = rbuf + (w * 32 + lane) * 36;
-        const float4 ml = *reinterpret_cast<const float4*>(src + 32);
+        const float* src = rbuf + (w * 32 + lane) * 20;
+        const float2 ml = *reinterpret_cast<const float2*>(src + 16);
         const float f0 = ml.x == -INFINITY ? 0.f : fast_exp2(ml.x - m0);
-        l0 += ml.z * f0;
+        l0 += ml.y * f0;
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          const float2 v = *reinterpret_cast<const float2*>(src + i * 4);
-          o[i][0] += v.x * f0;
-          o[i][1] += v.y * f0;
+        for (int i = 0; i < 4; ++i) {
+          const float4 v = *reinterpret_cast<const float4*>(src + i * 4);
+          o[2 * i][0] += v.x * f0;
+          o[2 * i][1] += v.y * f0;
+          o[2 * i + 1][0] += v.z * f0;
+          o[2 * i + 1][1] += v.w * f0;
         }
       }
       __syncwarp();
@@ -1106,27 +1092,44 @@ self_attention_tma_kernel(const Self2Params p, const __grid_constant__ CUtensorM
     WarpAcc acc;
     acc_init(acc);
     const int base_phys = audio * G;
+    const int t2 = (lane & 3) * 2;
     for (int t = 0; t < n_tiles; ++t, ++q) {
       const int st = q % kS2Stages;
       x2_wait(&full_bar[st], (q / kS2Stages) & 1);
       const uint8_t* sK = ring + st * kS2StageBytes;
       const int row0 = t * kS2TileRows + warp * 16;          // first cache row of this warp's slice
       if (row0 < cache_rows) {
-        auto valid = [&](int qrow, int key) -> bool {
-          const int kr = row0 + key;
-          const int pos = kr / G, slot = kr - pos * G;
-          return qrow < G && pos < pos_new && s_ind[qrow * (kS2IndBytes / 4) + pos] == base_phys + slot;
-        };
-        warp_tile_masked<T>(sK, sK + kS2TileBytes, warp * 16, qa, acc, valid);
+        // lanes i and i + 16: the set of beams whose parent table points at cache row row0 + i = (position, slot)
+        uint32_t bits = 0;
+        {
+          const int kr = row0 + (lane & 15);
+          const int pos = (kr * p.g_magic) >> 16, slot = kr - pos * G;
+          if (pos < pos_new) {
+            const int want = base_phys + slot;
+#pragma unroll
+            for (int b = 0; b < kS2MaxG; ++b)
+              if (b < G) bits |= static_cast<uint32_t>(s_ind[b * (kS2IndBytes / 4) + pos] == want) << b;
+          }
+        }
+        uint32_t kmask[4];
+        kmask[0] = __shfl_sync(0xffffffffu, bits, t2);
+        kmask[1] = __shfl_sync(0xffffffffu, bits, t2 + 1);
+        kmask[2] = __shfl_sync(0xffffffffu, bits, t2 + 8);
+        kmask[3] = __shfl_sync(0xffffffffu, bits, t2 + 9);
+        warp_tile_beams<T>(sK, sK + kS2TileBytes, warp * 16, qa, acc, kmask);
       }
       __syncwarp();
       if (lane == 0) mbar_arrive(&empty_bar[st]);
     }
-    if (warp == 0) {
-      // the new position: beam b attends its own new key (row b of the Knew / Vnew tiles)
-      auto valid = [&](int qrow, int key) -> bool { return qrow < G && key == qrow; };
-      warp_tile_masked<T>(mb + kX2QBytes, mb + 2 * kX2QBytes, 0, qa, acc, valid);
-    } else if (warp == 1) {
+    // the two warps with the emptiest slice of a ragged last tile take the new position
+    if (warp == kS2Consumers - 1) {
+      // beam b attends its own new key (row b of the Knew / Vnew tiles)
+      uint32_t kmask[4];
+      kmask[0] = t2 < G ? 1u << t2 : 0u;
+      kmask[1] = t2 + 1 < G ? 2u << t2 : 0u;
+      kmask[2] = kmask[3] = 0u;
+      warp_tile_beams<T>(mb + kX2QBytes, mb + 2 * kX2QBytes, 0, qa, acc, kmask);
+    } else if (warp == kS2Consumers - 2) {
       // append the new K / V rows to the cache: [audio][head][pos_new][slot b][64]
       const long long blk = (static_cast<long long>(audio) * H + head) * p.ctx + pos_new;
       uint8_t* kdst = reinterpret_cast<uint8_t*>(p.kcache) + blk * G * 128;
@@ -1140,18 +1143,16 @@ self_attention_tma_kernel(const Self2Params p, const __grid_constant__ CUtensorM
     }
     __syncwarp();
     if (lane == 0) mbar_arrive(&mempty_bar[ms]);
-    // ---- hand the fragment to the epilogue warp
+    // ---- hand the fragment (beam rows only) to the epilogue warp
     acc.l[0] += __shfl_xor_sync(0xffffffffu, acc.l[0], 1);
     acc.l[0] += __shfl_xor_sync(0xffffffffu, acc.l[0], 2);
-    acc.l[1] += __shfl_xor_sync(0xffffffffu, acc.l[1], 1);
-    acc.l[1] += __shfl_xor_sync(0xffffffffu, acc.l[1], 2);
     const int rb = iq & 1;
     x2_wait(&rempty_bar[rb], ((iq >> 1) & 1) ^ 1);
-    float* mine = red + rb * kS2RedFloats + (warp * 32 + lane) * 36;
+    float* mine = red + rb * kS2RedFloats + (warp * 32 + lane) * 20;
 #pragma unroll
-    for (int i = 0; i < 8; ++i)
-      *reinterpret_cast<float4*>(mine + i * 4) = make_float4(acc.o[i][0], acc.o[i][1], acc.o[i][2], acc.o[i][3]);
-    *reinterpret_cast<float4*>(mine + 32) = make_float4(acc.m[0], acc.m[1], acc.l[0], acc.l[1]);
+    for (int i = 0; i < 4; ++i)
+      *reinterpret_cast<float4*>(mine + i * 4) = make_float4(acc.o[2 * i][0], acc.o[2 * i][1], acc.o[2 * i + 1][0], acc.o[2 * i + 1][1]);
+    *reinterpret_cast<float4*>(mine + 16) = make_float4(acc.m[0], acc.l[0], 0.f, 0.f);
     __syncwarp();
     if (lane == 0) mbar_arrive(&rfull_bar[rb]);
   }
@@ -1169,8 +1170,8 @@ __global__ void kv_append_kernel(const T* __restrict__ qkv, T* __restrict__ kcac
   const T* src = qkv + static_cast<long long>(row) * 3 * d + (1 + which) * d;
   T* cache = (which ? vcache : kcache) + static_cast<long long>(a) * group * max_ctx * d;   // physical row a * group
   for (int c = lane * 8; c < d; c += 256) {
-    // head-major = beam window [audio][head][pos][slot][64]: the prompt lives in slot 0 of its audio
-    T* dst = head_major ? cache + ((static_cast<long long>(c >> 6) * max_ctx + i) * group) * 64 + (c & 63)
+    // head-major [row][head][pos][64]; beam window [audio][head][pos][slot][64]: the prompt lives in slot 0 of its audio
+    T* dst = head_major ? cache + ((static_cast<long long>(c >> 6) * max_ctx + i) * (head_major == 2 ? group : 1)) * 64 + (c & 63)
                         : cache + static_cast<long long>(i) * d + c;
     *reinterpret_cast<uint4*>(dst) = *reinterpret_cast<const uint4*>(src + c);
   }
@@ -1369,12 +1370,17 @@ int launch_cross_attention_tma(int dtype, const void* q, const void* kv, void* o
   return (le == cudaSuccess && cudaGetLastError() == cudaSuccess) ? 0 : 49;
 }
 
-// Step-mode self attention of all beams of an audio together (beam-window kv layout, 2 <= G <= 8).  -1: not covered.
+// Step-mode self attention of all beams of an audio together (beam-window kv layout, 2 <= G <= 8 and enough (audio,
+// head) items to occupy the SMs: the session picks the layout from self_attention_tma_covers at create).
+bool self_attention_tma_covers(int n_audio, int G, int n_head, int max_ctx) {
+  return G >= 2 && G <= kS2MaxG && max_ctx * 4 <= kS2IndBytes && n_audio * n_head * 2 >= sm_count();
+}
+
 int launch_self_attention_tma(int dtype, const void* qkv, void* kcache, void* vcache, void* out, const int* indir,
                               const int* len_ptr, const int* skip_flag, int n_audio, int G, int n_head, int max_ctx,
                               cudaStream_t s) {
   const int sms = sm_count();
-  if (G < 2 || G > kS2MaxG || max_ctx * 4 > kS2IndBytes || n_audio * n_head * 2 < sms) return -1;
+  if (!self_attention_tma_covers(n_audio, G, n_head, max_ctx)) return 56;
   const int d = n_head * 64;
   Self2Params p;
   p.out = out;
@@ -1388,6 +1394,7 @@ int launch_self_attention_tma(int dtype, const void* qkv, void* kcache, void* vc
   p.G = G;
   p.ctx = max_ctx;
   p.d = d;
+  p.g_magic = (65536 + G - 1) / G;
   CUtensorMap mapQKV, mapK, mapV;
   {
     uint64_t dims[2] = {static_cast<uint64_t>(3 * d), static_cast<uint64_t>(n_audio) * G};

@@ -36,6 +36,8 @@
 #include <stdio.h>
 #include <stdlib.h>
 
+#include <algorithm>
+
 #include "dec_layer.h"
 #include "kernels.h"
 #include "ptx.cuh"
@@ -44,6 +46,7 @@
 namespace wb {
 
 int g_fused_layer = -1;   // -1: read WB200_FUSED_LAYER on first use; wb200_set_fused_decoder_layer() overrides
+int g_fused_rows = -1;    // -1: read WB200_FUSED_ROWS on first use; wb200_set_fused_decoder_rows() overrides
 
 constexpr int kDLThreads = 416;                      // 13 warps
 constexpr int kDLRowBytes = 128;                     // one row of a 64-wide 16-bit k-block
@@ -453,6 +456,243 @@ dec_layer_kernel(const DLParams P, const __grid_constant__ DLMaps M) {
   if (warp == 2) tmem_dealloc(tmem_base, kDLTmemCols);
 }
 
+// =================================================================================================
+// few-rows form: R <= 8 (one audio greedy, one audio x 5 beams, a handful of streams)
+// =================================================================================================
+// With a handful of rows the tile form above is all fixed cost: a 64-row UMMA tile holds <= 8 real rows, every K = 16
+// step still costs ~58 clk of tensor-pipe issue at N = 16, and a phase takes 6-18 us for 20-90 KB of weights per SM
+// (measured on the turbo batch-1 run, profiles/r2_launches_turbo_b1.csv: 46 us per launch, 9 launches per token).
+// This form keeps the phase structure, the LayerNorm folding and the grid barrier, and replaces the main loop by a
+// weight-stationary matrix-vector product on mma.sync with the operands swapped:
+//   * every CTA owns N / grid consecutive output features (8-35 weight rows); ONE bulk copy per weight row brings its
+//     whole slab (<= 92 KB) into shared memory, issued by the 32 lanes of a control warp as soon as the previous
+//     phase's main loop has released the buffer - so the slab of phase p + 1 streams in from HBM while phase p runs its
+//     epilogue and the grid barrier closes (the slab of the first phase: before griddepcontrol.wait);
+//   * the <= 8 input rows (R x K 16-bit, <= 80 KB) follow by bulk copy once the barrier has opened;
+//   * D[16 features x 8 rows] += W[16 x 16] . X^T[16 x 8]: the weight rows are the M side of m16n8k16, the input rows the
+//     N side; the 8 compute warps split K eight ways (10 - 40 MMAs each), partial sums meet in shared memory.  Rows are
+//     padded by 16 bytes so that ldmatrix is conflict-free; features / input rows that do not exist read whatever the
+//     buffer holds and only ever reach accumulator entries nobody looks at.
+//   * epilogue per output element as in the tile form (fold / bias / erf-GELU / residual), LN partials per
+//     (row, CTA): count = this CTA's features, merged by the consumer with Chan's formula.
+constexpr int kDRComputeWarps = 8;
+constexpr int kDRThreads = (kDRComputeWarps + 1) * 32;
+constexpr int kDRMaxTiles = 3;                                  // 16-feature tiles per CTA and phase (N / grid <= 48)
+constexpr int kDRRedFloats = kDRComputeWarps * kDRMaxTiles * 16 * 8;
+constexpr int kDROutFloats = kDRMaxRows * kDRMaxTiles * 16;
+constexpr int kDRTailBytes = (kDRRedFloats + kDROutFloats + 2 * kDRMaxRows) * 4 + 3 * 8 + 64;
+
+template <typename T>
+__global__ void __launch_bounds__(kDRThreads, 1) dec_rows_kernel(const DLParams P) {
+  pdl_launch_dependents();
+  extern __shared__ uint8_t dr_smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(dr_smem_raw) + 127) & ~static_cast<uintptr_t>(127));
+  uint8_t* sW = smem;
+  uint8_t* sA = smem + P.dr_a_off;
+  float* s_red = reinterpret_cast<float*>(smem + P.dr_tail_off);   // [warp][tile][16 features][8 rows]
+  float* s_out = s_red + kDRRedFloats;                              // [row][feature]: the values as stored
+  float* s_stat = s_out + kDROutFloats;                             // mean[8] | rstd[8]
+  uint64_t* w_full = reinterpret_cast<uint64_t*>(s_stat + 2 * kDRMaxRows);
+  uint64_t* a_full = w_full + 1;
+  uint64_t* w_empty = w_full + 2;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, tid = threadIdx.x;
+  const int grid = gridDim.x, cta = blockIdx.x;
+  const int R = P.R;
+  if (tid == 0) {
+    mbar_init(w_full, 1);
+    mbar_init(a_full, 1);
+    mbar_init(w_empty, 1);
+    mbar_fence_init();
+  }
+  __syncthreads();
+  // this CTA's output features of a phase
+  auto first_col = [&](int p, int c) { return static_cast<int>(static_cast<long long>(c) * P.ph[p].N / grid); };
+
+  if (warp == kDRComputeWarps) {
+    // ===================== control warp: bulk copies and the grid barrier =====================
+    auto issue_w = [&](int p) {
+      const DLPhase& ph = P.ph[p];
+      const int n0 = first_col(p, cta), nc = first_col(p, cta + 1) - n0;
+      const uint32_t row_bytes = static_cast<uint32_t>(ph.K) * 2;
+      if (lane == 0) mbar_expect_tx(w_full, static_cast<uint32_t>(nc) * row_bytes);
+      __syncwarp();
+      for (int i = lane; i < nc; i += 32)
+        bulk_load_1d(sW + static_cast<size_t>(i) * (row_bytes + 16), static_cast<const uint8_t*>(ph.w) + static_cast<size_t>(n0 + i) * row_bytes,
+                     row_bytes, w_full);
+    };
+    issue_w(0);                 // weights are constants: the first slab streams in under the tail of the previous kernel
+    pdl_wait();
+    if (P.skip_flag && *P.skip_flag) {
+      dl_mbar_wait(w_full, 0);  // never leave with a copy into this CTA's shared memory in flight
+      return;
+    }
+    for (int p = 0; p < P.n_phases; ++p) {
+      const DLPhase& ph = P.ph[p];
+      if (p > 0) {
+        const unsigned int target = static_cast<unsigned int>(p) * static_cast<unsigned int>(grid);
+        long long spins = 0;
+        while (true) {
+          unsigned int v;
+          asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(P.sync) : "memory");
+          if (v >= target) break;
+          if (++spins > (1ll << 23)) __trap();
+        }
+      }
+      fence_proxy_async_global();        // other CTAs' generic-proxy stores -> this lane's bulk (async-proxy) reads
+      const uint32_t row_bytes = static_cast<uint32_t>(ph.K) * 2;
+      if (lane == 0) mbar_expect_tx(a_full, static_cast<uint32_t>(R) * row_bytes);
+      __syncwarp();
+      if (lane < R)
+        bulk_load_1d(sA + static_cast<size_t>(lane) * (row_bytes + 16), static_cast<const uint8_t*>(ph.a) + static_cast<size_t>(lane) * ph.lda * 2,
+                     row_bytes, a_full);
+      if (p + 1 < P.n_phases) {
+        dl_mbar_wait(w_empty, p & 1);    // every compute warp is done with the slab and the input rows of phase p
+        issue_w(p + 1);
+      }
+    }
+    return;
+  }
+
+  // ===================== compute warps =====================
+  pdl_wait();
+  if (P.skip_flag && *P.skip_flag) return;
+  const int g = lane >> 2, t4 = lane & 3;
+  for (int p = 0; p < P.n_phases; ++p) {
+    const DLPhase& ph = P.ph[p];
+    const int n0 = first_col(p, cta), nc = first_col(p, cta + 1) - n0;
+    const int n_tiles = (nc + 15) >> 4;
+    const int stride = ph.K * 2 + 16;
+    const bool fold = (ph.flags & DL_FOLD) != 0;
+    // ---- this thread's <= 2 output elements (row, feature) and their constants, before anything has to be waited for
+    const int n_out = nc * R;
+    int o_r[2], o_n[2];
+    float o_c1[2], o_c2[2];
+#pragma unroll
+    for (int j = 0; j < 2; ++j) {
+      const int o = tid + j * 256;
+      o_r[j] = o < n_out ? o / nc : -1;
+      o_n[j] = o < n_out ? o - o_r[j] * nc : 0;
+      o_c1[j] = o_c2[j] = 0.f;
+      if (o_r[j] >= 0) {
+        const int n = n0 + o_n[j];
+        if (fold) {
+          o_c1[j] = __ldg(ph.c1 + n);
+          o_c2[j] = __ldg(ph.c2 + n);
+        } else {
+          o_c1[j] = Cvt<T>::to_f(__ldg(reinterpret_cast<const T*>(ph.bias) + n));
+        }
+      }
+    }
+    dl_mbar_wait(a_full, p & 1);         // the previous phase is complete grid-wide (the control warp saw the barrier open)
+    // ---- LayerNorm statistics of row `warp` from the partials its producer left (model.py:39-41, eps 1e-5)
+    if (fold && warp < R) {
+      const int slots = (p == 0 && P.ln_slots_in > 0) ? P.ln_slots_in : grid;
+      float n = 0.f, mean = 0.f, m2 = 0.f;
+      for (int s0 = lane; s0 < slots; s0 += 32) {
+        const float4 part = __ldcg(P.ln_part + static_cast<long long>(s0) * P.ln_ld + warp);
+        chan_merge(n, mean, m2, part.x, part.y, part.z);
+      }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        const float nb = __shfl_xor_sync(0xffffffffu, n, o), mb = __shfl_xor_sync(0xffffffffu, mean, o),
+                    qb = __shfl_xor_sync(0xffffffffu, m2, o);
+        chan_merge(n, mean, m2, nb, mb, qb);
+      }
+      if (lane == 0) {
+        s_stat[warp] = mean;
+        s_stat[kDRMaxRows + warp] = rsqrtf(m2 / n + 1e-5f);
+      }
+    }
+    float o_x[2] = {0.f, 0.f};
+    if (ph.flags & DL_RESID) {
+#pragma unroll
+      for (int j = 0; j < 2; ++j)
+        if (o_r[j] >= 0) o_x[j] = Cvt<T>::to_f(__ldcg(reinterpret_cast<const T*>(ph.out) + o_r[j] * ph.ldo + n0 + o_n[j]));
+    }
+    // ---- main loop: this warp's eighth of K for every 16-feature tile
+    float acc[kDRMaxTiles][4];
+#pragma unroll
+    for (int t = 0; t < kDRMaxTiles; ++t)
+#pragma unroll
+      for (int i = 0; i < 4; ++i) acc[t][i] = 0.f;
+    dl_mbar_wait(w_full, p & 1);
+    {
+      const int kw = ph.K / kDRComputeWarps;
+      // ldmatrix x4 on the slab: matrices (features 0-7, k 0-7), (8-15, k 0-7), (0-7, k 8-15), (8-15, k 8-15) = a0..a3
+      const uint8_t* wrow = sW + static_cast<size_t>((lane & 7) + ((lane >> 3) & 1) * 8) * stride + (lane >> 4) * 16;
+      // ldmatrix x2 on the input rows: (rows 0-7, k 0-7), (rows 0-7, k 8-15) = b0, b1
+      const uint8_t* arow = sA + static_cast<size_t>(lane & 7) * stride + ((lane >> 3) & 1) * 16;
+      for (int k0 = warp * kw; k0 < (warp + 1) * kw; k0 += 16) {
+        uint32_t b[2];
+        ldmatrix_x2(b, arow + k0 * 2);
+#pragma unroll
+        for (int t = 0; t < kDRMaxTiles; ++t)
+          if (t < n_tiles) {
+            uint32_t a[4];
+            ldmatrix_x4(a, wrow + static_cast<size_t>(t) * 16 * stride + k0 * 2);
+            mma16816<T>(acc[t], a, b[0], b[1]);
+          }
+      }
+    }
+#pragma unroll
+    for (int t = 0; t < kDRMaxTiles; ++t)
+      if (t < n_tiles) {
+        float* dst = s_red + ((warp * kDRMaxTiles + t) * 16) * 8;
+        *reinterpret_cast<float2*>(dst + g * 8 + 2 * t4) = make_float2(acc[t][0], acc[t][1]);
+        *reinterpret_cast<float2*>(dst + (g + 8) * 8 + 2 * t4) = make_float2(acc[t][2], acc[t][3]);
+      }
+    asm volatile("bar.sync 1, 256;" ::: "memory");
+    if (tid == 0) mbar_arrive(w_empty);
+    // ---- epilogue
+#pragma unroll
+    for (int j = 0; j < 2; ++j)
+      if (o_r[j] >= 0) {
+        const int r = o_r[j], nl = o_n[j];
+        const float* src = s_red + ((nl >> 4) * 16 + (nl & 15)) * 8 + r;
+        float v = 0.f;
+#pragma unroll
+        for (int w = 0; w < kDRComputeWarps; ++w) v += src[w * kDRMaxTiles * 16 * 8];
+        if (fold)
+          v = fmaf(s_stat[kDRMaxRows + r], v - s_stat[r] * o_c1[j], o_c2[j]);
+        else
+          v += o_c1[j];
+        if (ph.flags & DL_GELU) v = gelu_erf(round_to<T>(v));
+        if (ph.flags & DL_RESID) v = round_to<T>(v) + o_x[j];
+        const T tv = Cvt<T>::from_f(v);
+        reinterpret_cast<T*>(ph.out)[r * ph.ldo + n0 + nl] = tv;
+        s_out[r * (kDRMaxTiles * 16) + nl] = Cvt<T>::to_f(tv);
+      }
+    if (ph.flags & DL_STATS) {
+      asm volatile("bar.sync 1, 256;" ::: "memory");
+      if (tid < R) {
+        // statistics of the STORED (16-bit rounded) values: what the next LayerNorm would read
+        const float* row = s_out + tid * (kDRMaxTiles * 16);
+        float sum = 0.f;
+        for (int i = 0; i < nc; ++i) sum += row[i];
+        const float mean = nc > 0 ? sum / static_cast<float>(nc) : 0.f;
+        float m2 = 0.f;
+        for (int i = 0; i < nc; ++i) {
+          const float d = row[i] - mean;
+          m2 = fmaf(d, d, m2);
+        }
+        __stcg(P.ln_part + static_cast<long long>(cta) * P.ln_ld + tid, make_float4(static_cast<float>(nc), mean, m2, 0.f));
+      }
+    }
+    if (p + 1 < P.n_phases) {
+      asm volatile("bar.sync 1, 256;" ::: "memory");
+      if (tid == 0) asm volatile("red.release.gpu.global.add.u32 [%0], %1;" ::"l"(P.sync), "r"(1u) : "memory");
+    }
+  }
+  if (tid == 0 && P.n_phases > 1) {
+    const unsigned int prev = atomicAdd(P.sync + 1, 1u);
+    if (prev == static_cast<unsigned int>(grid) - 1) {
+      P.sync[0] = 0;
+      P.sync[1] = 0;
+      __threadfence();
+    }
+  }
+}
+
 // -------------------------------------------------------------------------------------------------
 // host side
 // -------------------------------------------------------------------------------------------------
@@ -494,6 +734,9 @@ int dl_fill_phase(DLLaunch& L, int idx, int dtype, int R, int grid, const void* 
   ph.c2 = c2;
   ph.out = out;
   ph.ldo = ldo;
+  ph.a = A;
+  ph.lda = lda;
+  ph.w = W;
   if (bm == 0) bm = dl_auto_bm(R, N, K, flags);
   if ((bm != 64 && bm != 128) || (bm == 128 && (flags & DL_STATS))) return 7;
   ph.bm = bm;
@@ -545,6 +788,37 @@ void dl_init_launch(DLLaunch& L, int dtype, int R, int grid, float4* ln_part, in
   L.p.sync = sync;
   L.p.skip_flag = skip_flag;
   L.p.trace = nullptr;
+  L.p.dr_a_off = L.p.dr_tail_off = 0;
+  L.rows_smem = 0;
+}
+
+bool dl_use_rows_form(DLLaunch& L) {
+  if (g_fused_rows < 0) {
+    const char* e = getenv("WB200_FUSED_ROWS");
+    g_fused_rows = (e && e[0] == '0') ? 0 : 1;
+  }
+  L.rows_smem = 0;
+  const DLParams& P = L.p;
+  if (!g_fused_rows || P.R > kDRMaxRows || P.n_phases <= 0) return false;
+  long long w_bytes = 0, extent = 0, a_bytes = 0;
+  for (int p = 0; p < P.n_phases; ++p) {
+    const DLPhase& ph = P.ph[p];
+    if (ph.K % (16 * kDRComputeWarps) || ph.N < 1) return false;
+    const long long stride = ph.K * 2LL + 16;
+    const int nc_max = (ph.N + L.grid - 1) / L.grid;
+    if (nc_max > kDRMaxTiles * 16) return false;
+    w_bytes = std::max(w_bytes, nc_max * stride);
+    extent = std::max(extent, ((nc_max + 15) / 16 * 16) * stride);     // ldmatrix reads whole 16-row tiles
+    a_bytes = std::max(a_bytes, kDRMaxRows * stride);
+  }
+  const long long a_off = (w_bytes + 127) / 128 * 128;
+  const long long tail_off = (std::max(a_off + a_bytes, extent) + 127) / 128 * 128;
+  const long long total = tail_off + kDRTailBytes + 128;
+  if (total > 227 * 1024) return false;
+  L.p.dr_a_off = static_cast<int>(a_off);
+  L.p.dr_tail_off = static_cast<int>(tail_off);
+  L.rows_smem = static_cast<int>(total);
+  return true;
 }
 
 template <typename T>
@@ -560,8 +834,20 @@ static int dl_launch_t(const DLLaunch& L, cudaStream_t s) {
   return (le == cudaSuccess && cudaGetLastError() == cudaSuccess) ? 0 : 61;
 }
 
+template <typename T>
+static int dr_launch_t(const DLLaunch& L, cudaStream_t s) {
+  auto kern = dec_rows_kernel<T>;
+  static SmemOptIn optin;
+  if (!optin.ensure(kern, 227 * 1024)) return 62;
+  ProfileScope prof(PROF_DEC_LAYER, s);
+  const cudaError_t le = launch_pdl(kern, dim3(L.grid), dim3(kDRThreads), L.rows_smem, s, L.p);
+  count_launch();
+  return (le == cudaSuccess && cudaGetLastError() == cudaSuccess) ? 0 : 63;
+}
+
 int dl_launch(const DLLaunch& L, cudaStream_t s) {
   if (L.p.n_phases <= 0) return 0;
+  if (L.rows_smem > 0) return L.dtype == DT_BF16 ? dr_launch_t<__nv_bfloat16>(L, s) : dr_launch_t<__half>(L, s);
   return L.dtype == DT_BF16 ? dl_launch_t<__nv_bfloat16>(L, s) : dl_launch_t<__half>(L, s);
 }
 

@@ -26,6 +26,9 @@ struct DLPhase {
   const float* c2;
   void* out;              // T [R, ldo]
   long long ldo;
+  const void* a;          // T [R, lda] input rows and T [N, K] weights as plain pointers (few-rows form; the tile form
+  long long lda;          // reads them through the tensor maps)
+  const void* w;
 };
 
 struct DLParams {
@@ -40,6 +43,7 @@ struct DLParams {
   // 2 last MMA committed, 3 accumulator seen by the epilogue, 4 stores done, 5 arrived on the grid barrier,
   // 6 next phase released (poller), 7 LN statistics gathered
   unsigned long long* trace;
+  int dr_a_off, dr_tail_off;   // few-rows form: shared-memory offsets of the input rows and of the scratch tail
   DLPhase ph[kDLMaxPhases];
 };
 
@@ -52,11 +56,15 @@ struct alignas(64) DLMaps {
 struct DLLaunch {
   int dtype = 0;
   int grid = 0;
+  int rows_smem = 0;      // > 0: launch the few-rows form (dec_rows_kernel) with this much dynamic shared memory
   DLParams p;
   DLMaps maps;
 };
 
+constexpr int kDRMaxRows = 8;      // the few-rows form covers R <= 8 (one mma.sync n = 8 operand)
+
 extern int g_fused_layer;
+extern int g_fused_rows;           // few-rows form for R <= kDRMaxRows (wb200_set_fused_decoder_rows / WB200_FUSED_ROWS, default on)
 int dl_grid_size();
 bool dl_supported(int R, int d, int grid);
 void dl_init_launch(DLLaunch& L, int dtype, int R, int grid, float4* ln_part, int ln_ld, unsigned int* sync,
@@ -64,6 +72,9 @@ void dl_init_launch(DLLaunch& L, int dtype, int R, int grid, float4* ln_part, in
 // appends nothing by itself: fills phase `idx` (caller sets p.n_phases)
 int dl_fill_phase(DLLaunch& L, int idx, int dtype, int R, int grid, const void* A, long long lda, const void* W, int N, int K,
                   const void* bias, const float* c1, const float* c2, int flags, void* out, long long ldo, int bm = 0);
+// after every phase is filled: switch the launch to the few-rows form if it applies (R <= kDRMaxRows, shapes fit);
+// returns true when it did
+bool dl_use_rows_form(DLLaunch& L);
 int dl_launch(const DLLaunch& L, cudaStream_t s);
 
 }  // namespace wb

@@ -362,6 +362,7 @@ static int build_fused_plan(Decoder* D) {
     dl_init_launch(H, dt, R, grid, D->ln_part, D->ln_ld, D->dl_sync, skip, l == 0 ? 1 : 0);
     if (int r = qkv_phase(H, 0, L)) return 10 + r;
     H.p.n_phases = 1;
+    dl_use_rows_form(H);
     DLLaunch& Mi = D->dl_mid[l];
     dl_init_launch(Mi, dt, R, grid, D->ln_part, D->ln_ld, D->dl_sync, skip, 0);
     if (int r = dl_fill_phase(Mi, 0, dt, R, grid, D->att, d, L[D_OUT_W], d, d, L[D_OUT_B], nullptr, nullptr,
@@ -369,6 +370,7 @@ static int build_fused_plan(Decoder* D) {
     if (int r = dl_fill_phase(Mi, 1, dt, R, grid, D->x, d, L[D_CQ_WF], d, d, nullptr, (const float*)L[D_CQ_C1],
                               (const float*)L[D_CQ_C2], DL_FOLD, D->q, d)) return 30 + r;
     Mi.p.n_phases = 2;
+    dl_use_rows_form(Mi);
     DLLaunch& Ta = D->dl_tail[l];
     dl_init_launch(Ta, dt, R, grid, D->ln_part, D->ln_ld, D->dl_sync, skip, 0);
     if (int r = dl_fill_phase(Ta, 0, dt, R, grid, D->att, d, L[D_COUT_W], d, d, L[D_COUT_B], nullptr, nullptr,
@@ -382,6 +384,7 @@ static int build_fused_plan(Decoder* D) {
       if (int r = qkv_phase(Ta, 3, m->dec_layer(l + 1))) return 70 + r;
       Ta.p.n_phases = 4;
     }
+    dl_use_rows_form(Ta);
   }
   D->fused = true;
   return 0;
@@ -410,6 +413,9 @@ int decoder_create(const Model* m, const wb200_decode_config* c, void* ws, size_
     g_sattn_tma = (e && e[0] == '0') ? 0 : 1;
   }
   D->kv_head_major = g_kv_head_major != 0;
+  // beam-window self caches only where the kernel that wants them runs (fixed per session: the layout cannot change later)
+  D->kv_window = D->kv_head_major && g_sattn_tma &&
+                 self_attention_tma_covers(c->n_audio, c->n_group, m->dims.n_text_head, m->dims.n_text_ctx);
   D->cfg.suppress_ids = nullptr;
   D->cfg.blank_ids = nullptr;
   Arena ar{static_cast<uint8_t*>(ws), 0, ws_bytes};
@@ -489,11 +495,8 @@ int decoder_set_audio(Decoder* D, const void* features, cudaStream_t s) {
 static int self_attention_step(Decoder* D, void* kc, void* vc, cudaStream_t s) {
   const Model* m = D->m;
   const int H = m->dims.n_text_head, ctx = m->dims.n_text_ctx, B = D->cfg.n_audio, G = D->cfg.n_group;
-  if (D->kv_head_major && g_sattn_tma) {
-    const int r = launch_self_attention_tma(m->dtype, D->qkv, kc, vc, D->att, D->indir[D->cur], D->len_ptr, D->done_ptr, B, G, H,
-                                            ctx, s);
-    if (r >= 0) return r;
-  }
+  if (D->kv_window)
+    return launch_self_attention_tma(m->dtype, D->qkv, kc, vc, D->att, D->indir[D->cur], D->len_ptr, D->done_ptr, B, G, H, ctx, s);
   return launch_self_attention(m->dtype, D->qkv, kc, vc, D->att, D->indir[D->cur], D->len_ptr, D->done_ptr, B * G, H, ctx,
                                D->cfg.n_init, G, s, D->kv_head_major ? 1 : 0);
 }
@@ -547,7 +550,7 @@ static int decoder_stack(Decoder* D, int rows, bool step, cudaStream_t s) {
       WB_TRY(self_attention_step(D, kc, vc, s));
     else
       WB_TRY(launch_self_attention(dt, D->qkv, kc, vc, D->att, nullptr, D->len_ptr, skip, rows, H, ctx, D->cfg.n_init, G, s,
-                                   D->kv_head_major ? 1 : 0));
+                                   D->kv_window ? 2 : D->kv_head_major ? 1 : 0));
     WB_TRY(linear(m, D->att, d, rows, L[D_OUT_W], d, d, L[D_OUT_B], D->x, D->x, d, 0, 0, s, skip, D));
     WB_TRY(launch_layernorm(dt, D->x, d, D->ln, d, (const float*)L[D_CROSS_LN_W], (const float*)L[D_CROSS_LN_B], rows, d, s, skip));
     WB_TRY(linear(m, D->ln, d, rows, L[D_CQ_W], d, d, L[D_CQ_B], nullptr, D->q, d, 0, 0, s, skip, D));

@@ -95,6 +95,7 @@ struct Decoder {
   int pair_graph_cur = -1;          // value of `cur` the graph was captured at
   int launches_per_pair = 0;        // kernels inside one replay (for wb200_launch_count)
   bool kv_head_major = false;       // kv caches stored per head ([.., head, position, 64]); fixed at create
+  bool kv_window = false;           // self caches in the beam-window layout [audio][head][position][slot][64]; fixed at create
   // fused decoder-layer GEMM chain of the step path (dec_layer.cu): per layer [QKV] (layer 0 only; later layers get
   // theirs from the previous layer's tail), [out-proj, cross-query], [cross-out, fc1, fc2, next layer's QKV]
   bool fused = false;

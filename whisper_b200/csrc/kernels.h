@@ -157,7 +157,9 @@ int launch_cross_attention(int dtype, const void* q, const void* k, const void* 
 int launch_cross_attention_tma(int dtype, const void* q, const void* kv, void* out, float* partial, int* counters,
                                const int* skip_flag, int n_audio, int n_q, int T, int n_head, cudaStream_t s);
 // Step-mode self attention of all beams of an audio together (beam-window kv layout, 2 <= group <= 8, enough
-// (audio, head) items to fill the SMs); appends the new K / V.  -1: not covered, use launch_self_attention.
+// (audio, head) items to fill the SMs - self_attention_tma_covers, which the session consults when it fixes the cache
+// layout); appends the new K / V.
+bool self_attention_tma_covers(int n_audio, int G, int n_head, int max_ctx);
 int launch_self_attention_tma(int dtype, const void* qkv, void* kcache, void* vcache, void* out, const int* indir,
                               const int* len_ptr, const int* skip_flag, int n_audio, int G, int n_head, int max_ctx,
                               cudaStream_t s);
@@ -166,7 +168,7 @@ extern int g_sattn_tma;       // wb200_set_self_attention_tma / WB200_SATTN_TMA 
 // (indir == null): n_init positions per audio, causal, cache rows a*group.
 int launch_self_attention(int dtype, const void* qkv, void* kcache, void* vcache, void* out,
                           const int* indir, const int* len_ptr, const int* skip_flag, int n_rows,
-                          int n_head, int max_ctx, int n_init, int group, cudaStream_t s, int head_major = 0);
+                          int n_head, int max_ctx, int n_init, int group, cudaStream_t s, int head_major = 0);   // 2: beam window
 
 // ---- token selection (select.cu)
 struct FilterParams {

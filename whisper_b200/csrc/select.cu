@@ -20,6 +20,7 @@ namespace wb {
 
 constexpr int kSelThreads = 512;
 constexpr int kMaxTopK = 17;  // beam <= 16
+constexpr int kSelCluster = 8; // CTAs per row when there are few rows (portable cluster size)
 
 // total order used everywhere: larger value first, then smaller index
 __device__ __forceinline__ bool better(float va, int ia, float vb, int ib) {
@@ -115,10 +116,54 @@ struct TopList {
   }
 };
 
-template <int KM>
+// K rounds of "pop the best head among the 32 lanes' sorted lists"; lane 0 hands every winner to emit(k, value, index)
+template <int KM, typename Emit>
+__device__ __forceinline__ void warp_merge_lists(TopList<KM>& l, int K, Emit emit) {
+  const int lane = threadIdx.x & 31;
+  for (int k = 0; k < K; ++k) {
+    const float bv = l.v[0];
+    const int bi = l.i[0];
+    float cv = bv;
+    int ci = bi;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      const float ov = __shfl_xor_sync(0xffffffffu, cv, o);
+      const int oi = __shfl_xor_sync(0xffffffffu, ci, o);
+      if (better(ov, oi, cv, ci)) {
+        cv = ov;
+        ci = oi;
+      }
+    }
+    if (ci == bi && cv == bv && bi != 0x7fffffff) l.pop();   // this lane's head was taken
+    if (lane == 0) emit(k, cv, ci);
+  }
+}
+
+// thread-block cluster helpers (CL CTAs share one row: partial results are read from the peers' shared memory)
+__device__ __forceinline__ uint32_t cluster_rank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ uint32_t peer_u32(const void* own_smem, uint32_t rank) {
+  uint32_t ra, v;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(ra) : "r"(smem_u32(own_smem)), "r"(rank));
+  asm volatile("ld.shared::cluster.u32 %0, [%1];" : "=r"(v) : "r"(ra) : "memory");
+  return v;
+}
+__device__ __forceinline__ float peer_f32(const void* own_smem, uint32_t rank) { return __uint_as_float(peer_u32(own_smem, rank)); }
+
+// CL = 1: one CTA per row.  CL = 8 (few rows: one audio decoded greedily would otherwise scan its 51 866 logits with a
+// single CTA - 48 us measured, profiles/r2_launches_turbo_b1.csv): a cluster of 8 CTAs per row, each scanning an eighth
+// of the vocabulary; the (max, sum-exp) partials and the per-CTA top-K lists are merged through distributed shared memory.
+template <int KM, int CL>
 __global__ void __launch_bounds__(kSelThreads) filter_topk_kernel(const FilterParams p) {
   if (p.skip_flag && *p.skip_flag) return;
-  const int r = blockIdx.x;
+  const int r = CL > 1 ? blockIdx.x / CL : blockIdx.x;
+  const uint32_t crank = CL > 1 ? cluster_rank() : 0u;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int L = *p.len_ptr;
   const float* x = p.logits + static_cast<long long>(r / p.row_div) * p.ld;
@@ -129,6 +174,9 @@ __global__ void __launch_bounds__(kSelThreads) filter_topk_kernel(const FilterPa
   __shared__ float s_fin[2];
   __shared__ float s_tv[kSelThreads / 32][KM];
   __shared__ int s_ti[kSelThreads / 32][KM];
+  __shared__ float s_part[4];    // this CTA's (m_txt, s_txt, m_ts, s_ts), read by the cluster peers
+  __shared__ float s_cv[KM];     // this CTA's top-K, read by rank 0
+  __shared__ int s_ci[KM];
 
   const bool first = (L == p.sample_begin);
   if (tid == 0) {
@@ -174,6 +222,9 @@ __global__ void __launch_bounds__(kSelThreads) filter_topk_kernel(const FilterPa
   // the <= 3 tokens past the last multiple of four are handled by the first threads.
   const int V4 = p.V >> 2;
   const float4* x4 = reinterpret_cast<const float4*>(x);
+  const int q_lo = CL > 1 ? static_cast<int>(static_cast<long long>(V4) * crank / CL) : 0;
+  const int q_hi = CL > 1 ? static_cast<int>(static_cast<long long>(V4) * (crank + 1) / CL) : V4;
+  const bool has_tail = crank == CL - 1;
 
   // ---- pass 1: (max, sum-exp) of the text part [0, tb) and the timestamp part [tb, V)
   float m_txt = -INFINITY, s_txt = 0.f, m_ts = -INFINITY, s_ts = 0.f;
@@ -181,7 +232,7 @@ __global__ void __launch_bounds__(kSelThreads) filter_topk_kernel(const FilterPa
     if (val == -INFINITY || masked(v, sw, bw)) return;
     if (v < tb) lse_merge(m_txt, s_txt, val, 1.f); else lse_merge(m_ts, s_ts, val, 1.f);
   };
-  for (int q = tid; q < V4; q += kSelThreads) {
+  for (int q = q_lo + tid; q < q_hi; q += kSelThreads) {
     const float4 f = x4[q];
     const int v = q << 2;
     const uint32_t sw = __ldg(p.suppress_mask + (v >> 5)), bw = use_blank ? __ldg(p.blank_mask + (v >> 5)) : 0u;
@@ -190,7 +241,7 @@ __global__ void __launch_bounds__(kSelThreads) filter_topk_kernel(const FilterPa
     acc1(v + 2, f.z, sw, bw);
     acc1(v + 3, f.w, sw, bw);
   }
-  if (tid < (p.V & 3)) {
+  if (has_tail && tid < (p.V & 3)) {
     const int v = (V4 << 2) + tid;
     acc1(v, x[v], __ldg(p.suppress_mask + (v >> 5)), use_blank ? __ldg(p.blank_mask + (v >> 5)) : 0u);
   }
@@ -206,11 +257,32 @@ __global__ void __launch_bounds__(kSelThreads) filter_topk_kernel(const FilterPa
     s_red[warp][3] = s_ts;
   }
   __syncthreads();
+  if (CL > 1) {
+    if (tid == 0) {
+      float a = -INFINITY, b = 0.f, c = -INFINITY, d = 0.f;
+      for (int w = 0; w < kSelThreads / 32; ++w) {
+        lse_merge(a, b, s_red[w][0], s_red[w][1]);
+        lse_merge(c, d, s_red[w][2], s_red[w][3]);
+      }
+      s_part[0] = a;
+      s_part[1] = b;
+      s_part[2] = c;
+      s_part[3] = d;
+    }
+    cluster_sync_all();
+  }
   if (tid == 0) {
     float a = -INFINITY, b = 0.f, c = -INFINITY, d = 0.f;
-    for (int w = 0; w < kSelThreads / 32; ++w) {
-      lse_merge(a, b, s_red[w][0], s_red[w][1]);
-      lse_merge(c, d, s_red[w][2], s_red[w][3]);
+    if (CL > 1) {
+      for (uint32_t k = 0; k < CL; ++k) {          // the same order in every CTA of the cluster: identical results
+        lse_merge(a, b, peer_f32(&s_part[0], k), peer_f32(&s_part[1], k));
+        lse_merge(c, d, peer_f32(&s_part[2], k), peer_f32(&s_part[3], k));
+      }
+    } else {
+      for (int w = 0; w < kSelThreads / 32; ++w) {
+        lse_merge(a, b, s_red[w][0], s_red[w][1]);
+        lse_merge(c, d, s_red[w][2], s_red[w][3]);
+      }
     }
     float mt = a, st = b;
     lse_merge(mt, st, c, d);                                   // everything
@@ -240,7 +312,7 @@ __global__ void __launch_bounds__(kSelThreads) filter_topk_kernel(const FilterPa
     if (sampling) val = fmaf(val, p.inv_temp, gumbel_noise(p.seed_lo, p.seed_hi, r, L, v));
     mine.push(val, v);
   };
-  for (int q = tid; q < V4; q += kSelThreads) {
+  for (int q = q_lo + tid; q < q_hi; q += kSelThreads) {
     const float4 f = x4[q];
     const int v = q << 2;
     const uint32_t sw = __ldg(p.suppress_mask + (v >> 5)), bw = use_blank ? __ldg(p.blank_mask + (v >> 5)) : 0u;
@@ -249,34 +321,23 @@ __global__ void __launch_bounds__(kSelThreads) filter_topk_kernel(const FilterPa
     acc2(v + 2, f.z, sw, bw);
     acc2(v + 3, f.w, sw, bw);
   }
-  if (tid < (p.V & 3)) {
+  if (has_tail && tid < (p.V & 3)) {
     const int v = (V4 << 2) + tid;
     acc2(v, x[v], __ldg(p.suppress_mask + (v >> 5)), use_blank ? __ldg(p.blank_mask + (v >> 5)) : 0u);
   }
-  // warp merge: K rounds of "pop the best head among the lanes"
-  for (int k = 0; k < K; ++k) {
-    const float bv = mine.v[0];
-    const int bi = mine.i[0];
-    float cv = bv;
-    int ci = bi;
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-      const float ov = __shfl_xor_sync(0xffffffffu, cv, o);
-      const int oi = __shfl_xor_sync(0xffffffffu, ci, o);
-      if (better(ov, oi, cv, ci)) {
-        cv = ov;
-        ci = oi;
-      }
-    }
-    if (ci == bi && cv == bv && bi != 0x7fffffff) mine.pop();   // this lane's head was taken
-    if (lane == 0) {
-      s_tv[warp][k] = cv;
-      s_ti[warp][k] = ci;
-    }
-  }
+  // warp merge, then lane w of warp 0 holds warp w's sorted list and the same merge runs across the 16 warps
+  warp_merge_lists<KM>(mine, K, [&](int k, float cv, int ci) {
+    s_tv[warp][k] = cv;
+    s_ti[warp][k] = ci;
+  });
   __syncthreads();
+  auto emit_final = [&](int k, float cv, int ci) {
+    // log-probability of the chosen token under the UN-tempered distribution (decoding.py:285-287)
+    const float chosen = sampling ? ((ci >= 0 && ci < p.V) ? x[ci] : -INFINITY) : cv;
+    p.top_val[static_cast<long long>(r) * K + k] = chosen - lse;
+    p.top_idx[static_cast<long long>(r) * K + k] = ci;
+  };
   if (warp == 0) {
-    // lane w holds warp w's sorted list; the same pop-the-best merge across the 16 warps
     TopList<KM> l;
     l.init();
     if (lane < kSelThreads / 32) {
@@ -287,28 +348,31 @@ __global__ void __launch_bounds__(kSelThreads) filter_topk_kernel(const FilterPa
           l.i[k] = s_ti[lane][k];
         }
     }
-    for (int k = 0; k < K; ++k) {
-      const float bv = l.v[0];
-      const int bi = l.i[0];
-      float cv = bv;
-      int ci = bi;
+    if (CL > 1)
+      warp_merge_lists<KM>(l, K, [&](int k, float cv, int ci) {
+        s_cv[k] = cv;
+        s_ci[k] = ci;
+      });
+    else
+      warp_merge_lists<KM>(l, K, emit_final);
+  }
+  if (CL > 1) {
+    cluster_sync_all();
+    if (crank == 0 && warp == 0) {
+      // lane c holds the sorted list of cluster rank c
+      TopList<KM> l;
+      l.init();
+      if (lane < CL) {
 #pragma unroll
-      for (int o = 16; o > 0; o >>= 1) {
-        const float ov = __shfl_xor_sync(0xffffffffu, cv, o);
-        const int oi = __shfl_xor_sync(0xffffffffu, ci, o);
-        if (better(ov, oi, cv, ci)) {
-          cv = ov;
-          ci = oi;
-        }
+        for (int k = 0; k < KM; ++k)
+          if (k < K) {
+            l.v[k] = peer_f32(&s_cv[k], lane);
+            l.i[k] = static_cast<int>(peer_u32(&s_ci[k], lane));
+          }
       }
-      if (ci == bi && cv == bv && bi != 0x7fffffff) l.pop();
-      if (lane == 0) {
-        // log-probability of the chosen token under the UN-tempered distribution (decoding.py:285-287)
-        const float chosen = sampling ? ((ci >= 0 && ci < p.V) ? x[ci] : -INFINITY) : cv;
-        p.top_val[static_cast<long long>(r) * K + k] = chosen - lse;
-        p.top_idx[static_cast<long long>(r) * K + k] = ci;
-      }
+      warp_merge_lists<KM>(l, K, emit_final);
     }
+    cluster_sync_all();          // nobody leaves while rank 0 still reads its shared memory
   }
 }
 
@@ -529,9 +593,29 @@ int launch_filter_topk(const FilterParams& p, int R, cudaStream_t s) {
   if (p.K < 1 || p.K > kMaxTopK) return 50;
   ProfileScope prof(PROF_SELECT, s);
   if ((reinterpret_cast<uintptr_t>(p.logits) & 15) || (p.ld & 3)) return 50;      // rows are read with 16-byte loads
-  if (p.K == 1) filter_topk_kernel<1><<<R, kSelThreads, 0, s>>>(p);
-  else if (p.K <= 6) filter_topk_kernel<6><<<R, kSelThreads, 0, s>>>(p);
-  else filter_topk_kernel<kMaxTopK><<<R, kSelThreads, 0, s>>>(p);
+  if (R * kSelCluster <= sm_count()) {
+    // few rows: a cluster of CTAs per row
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(R * kSelCluster);
+    cfg.blockDim = dim3(kSelThreads);
+    cfg.stream = s;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = kSelCluster;
+    at[0].val.clusterDim.y = 1;
+    at[0].val.clusterDim.z = 1;
+    cfg.attrs = at;
+    cfg.numAttrs = 1;
+    cudaError_t e;
+    if (p.K == 1) e = cudaLaunchKernelEx(&cfg, filter_topk_kernel<1, kSelCluster>, p);
+    else if (p.K <= 6) e = cudaLaunchKernelEx(&cfg, filter_topk_kernel<6, kSelCluster>, p);
+    else e = cudaLaunchKernelEx(&cfg, filter_topk_kernel<kMaxTopK, kSelCluster>, p);
+    count_launch();
+    return (e == cudaSuccess && cudaGetLastError() == cudaSuccess) ? 0 : 51;
+  }
+  if (p.K == 1) filter_topk_kernel<1, 1><<<R, kSelThreads, 0, s>>>(p);
+  else if (p.K <= 6) filter_topk_kernel<6, 1><<<R, kSelThreads, 0, s>>>(p);
+  else filter_topk_kernel<kMaxTopK, 1><<<R, kSelThreads, 0, s>>>(p);
   count_launch();
   return cudaGetLastError() == cudaSuccess ? 0 : 51;
 }
