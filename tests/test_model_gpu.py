@@ -332,7 +332,8 @@ def test_decode_end_to_end(name, case, dtype):
 
 def test_batched_beam_equals_per_audio():
     """The reference cannot run beam search on a batch (decoding.py:734,740); our batched result must
-    equal running each audio alone."""
+    equal running each audio alone.  Tokens exactly; the scores to 16-bit noise only - the number of rows selects the
+    form of the fused decoder layer (few-rows / 64-row tiles), which differ in the order of their fp32 sums."""
     from whisper_b200.decoding import DecodingOptions
 
     model = gpu_model("test-en", torch.float16)
@@ -341,7 +342,7 @@ def test_batched_beam_equals_per_audio():
     both = model.decode(mel, opt)
     for a in range(2):
         alone = model.decode(mel[a], opt)
-        assert alone.tokens == both[a].tokens and abs(alone.avg_logprob - both[a].avg_logprob) < 1e-5
+        assert alone.tokens == both[a].tokens and abs(alone.avg_logprob - both[a].avg_logprob) < 2e-3
 
 
 def test_detect_language():

@@ -692,13 +692,15 @@ __global__ void __launch_bounds__(640) self_attention_kernel(const SelfParams p,
   // Beam window: [audio][head][pos][beam slot][64] - the G rows of an audio interleaved per position, so that the whole
   // history of an (audio, head) is ONE contiguous block (what self_attention_tma_kernel streams); physical row =
   // audio * G + slot.
-  const int Gw = p.head_major == 2 ? p.group : 1;
+  const bool window = p.head_major == 2;
+  const int Gw = window ? p.group : 1;
   const long long pos_bytes = p.head_major ? 128LL * Gw : row_bytes;
   const long long row_stride = static_cast<long long>(p.max_ctx) * row_bytes;      // bytes per physical row, either layout
   const long long head_off = p.head_major ? static_cast<long long>(h) * p.max_ctx * 128 * Gw : static_cast<long long>(h) * 128;
   auto phys_off = [&](int ph) -> long long {       // offset of position 0 of physical row ph (before head_off)
-    return p.head_major ? static_cast<long long>(ph / Gw) * (row_stride * Gw) + static_cast<long long>(ph % Gw) * 128
-                        : static_cast<long long>(ph) * row_stride;
+    // (the division sits in the dependent address chain of every key: only the window layout pays for it)
+    return window ? static_cast<long long>(ph / Gw) * (row_stride * Gw) + static_cast<long long>(ph % Gw) * 128
+                  : static_cast<long long>(ph) * row_stride;
   };
   uint8_t* kc = reinterpret_cast<uint8_t*>(p.kcache) + head_off + c * 16;
   uint8_t* vc = reinterpret_cast<uint8_t*>(p.vcache) + head_off + c * 16;

@@ -457,7 +457,7 @@ dec_layer_kernel(const DLParams P, const __grid_constant__ DLMaps M) {
 }
 
 // =================================================================================================
-// few-rows form: R <= 8 (one audio greedy, one audio x 5 beams, a handful of streams)
+// few-rows form: R <= 32 where it fits (one audio greedy, one audio x 5 beams, 32 streams of a small model)
 // =================================================================================================
 // With a handful of rows the tile form above is all fixed cost: a 64-row UMMA tile holds <= 8 real rows, every K = 16
 // step still costs ~58 clk of tensor-pipe issue at N = 16, and a phase takes 6-18 us for 20-90 KB of weights per SM
@@ -468,9 +468,10 @@ dec_layer_kernel(const DLParams P, const __grid_constant__ DLMaps M) {
 //     whole slab (<= 92 KB) into shared memory, issued by the 32 lanes of a control warp as soon as the previous
 //     phase's main loop has released the buffer - so the slab of phase p + 1 streams in from HBM while phase p runs its
 //     epilogue and the grid barrier closes (the slab of the first phase: before griddepcontrol.wait);
-//   * the <= 8 input rows (R x K 16-bit, <= 80 KB) follow by bulk copy once the barrier has opened;
-//   * D[16 features x 8 rows] += W[16 x 16] . X^T[16 x 8]: the weight rows are the M side of m16n8k16, the input rows the
-//     N side; the 8 compute warps split K eight ways (10 - 40 MMAs each), partial sums meet in shared memory.  Rows are
+//   * the input rows (R x K 16-bit; R <= 8 for the large models, up to 32 where slab + rows fit in 227 KB) follow by bulk
+//     copy once the barrier has opened;
+//   * D[16 features x 8 rows] += W[16 x 16] . X^T[16 x 8] per 8-row operand tile: the weight rows are the M side of
+//     m16n8k16, the input rows the N side; the 8 compute warps split K eight ways, partial sums meet in shared memory.  Rows are
 //     padded by 16 bytes so that ldmatrix is conflict-free; features / input rows that do not exist read whatever the
 //     buffer holds and only ever reach accumulator entries nobody looks at.
 //   * epilogue per output element as in the tile form (fold / bias / erf-GELU / residual), LN partials per
@@ -478,21 +479,25 @@ dec_layer_kernel(const DLParams P, const __grid_constant__ DLMaps M) {
 constexpr int kDRComputeWarps = 8;
 constexpr int kDRThreads = (kDRComputeWarps + 1) * 32;
 constexpr int kDRMaxTiles = 3;                                  // 16-feature tiles per CTA and phase (N / grid <= 48)
-constexpr int kDRRedFloats = kDRComputeWarps * kDRMaxTiles * 16 * 8;
-constexpr int kDROutFloats = kDRMaxRows * kDRMaxTiles * 16;
-constexpr int kDRTailBytes = (kDRRedFloats + kDROutFloats + 2 * kDRMaxRows) * 4 + 3 * 8 + 64;
+constexpr int kDRCols = kDRMaxTiles * 16;
+// scratch tail for NT 8-row operand tiles (R <= 8 NT): fp32 partial sums [warp][tile][16][8 NT], stored values
+// [8 NT][48], mean | rstd per row, three mbarriers
+__host__ __device__ constexpr int dr_red_floats(int nt) { return kDRComputeWarps * kDRMaxTiles * 16 * 8 * nt; }
+__host__ __device__ constexpr int dr_tail_bytes(int nt) { return (dr_red_floats(nt) + 8 * nt * kDRCols + 2 * 8 * nt) * 4 + 3 * 8 + 64; }
 
-template <typename T>
+template <typename T, int NT>
 __global__ void __launch_bounds__(kDRThreads, 1) dec_rows_kernel(const DLParams P) {
+  constexpr int RMAX = 8 * NT;
+  constexpr int J = (kDRCols * RMAX + 255) / 256;             // output elements per thread
   pdl_launch_dependents();
   extern __shared__ uint8_t dr_smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(dr_smem_raw) + 127) & ~static_cast<uintptr_t>(127));
   uint8_t* sW = smem;
   uint8_t* sA = smem + P.dr_a_off;
-  float* s_red = reinterpret_cast<float*>(smem + P.dr_tail_off);   // [warp][tile][16 features][8 rows]
-  float* s_out = s_red + kDRRedFloats;                              // [row][feature]: the values as stored
-  float* s_stat = s_out + kDROutFloats;                             // mean[8] | rstd[8]
-  uint64_t* w_full = reinterpret_cast<uint64_t*>(s_stat + 2 * kDRMaxRows);
+  float* s_red = reinterpret_cast<float*>(smem + P.dr_tail_off);   // [warp][tile][16 features][RMAX rows]
+  float* s_out = s_red + dr_red_floats(NT);                         // [row][feature]: the values as stored
+  float* s_stat = s_out + RMAX * kDRCols;                           // mean[RMAX] | rstd[RMAX]
+  uint64_t* w_full = reinterpret_cast<uint64_t*>(s_stat + 2 * RMAX);
   uint64_t* a_full = w_full + 1;
   uint64_t* w_empty = w_full + 2;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, tid = threadIdx.x;
@@ -542,7 +547,7 @@ __global__ void __launch_bounds__(kDRThreads, 1) dec_rows_kernel(const DLParams 
       const uint32_t row_bytes = static_cast<uint32_t>(ph.K) * 2;
       if (lane == 0) mbar_expect_tx(a_full, static_cast<uint32_t>(R) * row_bytes);
       __syncwarp();
-      if (lane < R)
+      if (lane < R)                      // R <= 32: one input row per lane
         bulk_load_1d(sA + static_cast<size_t>(lane) * (row_bytes + 16), static_cast<const uint8_t*>(ph.a) + static_cast<size_t>(lane) * ph.lda * 2,
                      row_bytes, a_full);
       if (p + 1 < P.n_phases) {
@@ -563,12 +568,12 @@ __global__ void __launch_bounds__(kDRThreads, 1) dec_rows_kernel(const DLParams 
     const int n_tiles = (nc + 15) >> 4;
     const int stride = ph.K * 2 + 16;
     const bool fold = (ph.flags & DL_FOLD) != 0;
-    // ---- this thread's <= 2 output elements (row, feature) and their constants, before anything has to be waited for
+    // ---- this thread's <= J output elements (row, feature) and their constants, before anything has to be waited for
     const int n_out = nc * R;
-    int o_r[2], o_n[2];
-    float o_c1[2], o_c2[2];
+    int o_r[J], o_n[J];
+    float o_c1[J], o_c2[J];
 #pragma unroll
-    for (int j = 0; j < 2; ++j) {
+    for (int j = 0; j < J; ++j) {
       const int o = tid + j * 256;
       o_r[j] = o < n_out ? o / nc : -1;
       o_n[j] = o < n_out ? o - o_r[j] * nc : 0;
@@ -584,89 +589,99 @@ __global__ void __launch_bounds__(kDRThreads, 1) dec_rows_kernel(const DLParams 
       }
     }
     dl_mbar_wait(a_full, p & 1);         // the previous phase is complete grid-wide (the control warp saw the barrier open)
-    // ---- LayerNorm statistics of row `warp` from the partials its producer left (model.py:39-41, eps 1e-5)
-    if (fold && warp < R) {
+    // ---- LayerNorm statistics of rows warp, warp + 8, .. from the partials their producer left (model.py:39-41, eps 1e-5)
+    if (fold) {
       const int slots = (p == 0 && P.ln_slots_in > 0) ? P.ln_slots_in : grid;
-      float n = 0.f, mean = 0.f, m2 = 0.f;
-      for (int s0 = lane; s0 < slots; s0 += 32) {
-        const float4 part = __ldcg(P.ln_part + static_cast<long long>(s0) * P.ln_ld + warp);
-        chan_merge(n, mean, m2, part.x, part.y, part.z);
-      }
+      for (int r = warp; r < R; r += kDRComputeWarps) {
+        float n = 0.f, mean = 0.f, m2 = 0.f;
+        for (int s0 = lane; s0 < slots; s0 += 32) {
+          const float4 part = __ldcg(P.ln_part + static_cast<long long>(s0) * P.ln_ld + r);
+          chan_merge(n, mean, m2, part.x, part.y, part.z);
+        }
 #pragma unroll
-      for (int o = 16; o > 0; o >>= 1) {
-        const float nb = __shfl_xor_sync(0xffffffffu, n, o), mb = __shfl_xor_sync(0xffffffffu, mean, o),
-                    qb = __shfl_xor_sync(0xffffffffu, m2, o);
-        chan_merge(n, mean, m2, nb, mb, qb);
-      }
-      if (lane == 0) {
-        s_stat[warp] = mean;
-        s_stat[kDRMaxRows + warp] = rsqrtf(m2 / n + 1e-5f);
+        for (int o = 16; o > 0; o >>= 1) {
+          const float nb = __shfl_xor_sync(0xffffffffu, n, o), mb = __shfl_xor_sync(0xffffffffu, mean, o),
+                      qb = __shfl_xor_sync(0xffffffffu, m2, o);
+          chan_merge(n, mean, m2, nb, mb, qb);
+        }
+        if (lane == 0) {
+          s_stat[r] = mean;
+          s_stat[RMAX + r] = rsqrtf(m2 / n + 1e-5f);
+        }
       }
     }
-    float o_x[2] = {0.f, 0.f};
-    if (ph.flags & DL_RESID) {
+    float o_x[J];
 #pragma unroll
-      for (int j = 0; j < 2; ++j)
-        if (o_r[j] >= 0) o_x[j] = Cvt<T>::to_f(__ldcg(reinterpret_cast<const T*>(ph.out) + o_r[j] * ph.ldo + n0 + o_n[j]));
+    for (int j = 0; j < J; ++j) {
+      o_x[j] = 0.f;
+      if ((ph.flags & DL_RESID) && o_r[j] >= 0)
+        o_x[j] = Cvt<T>::to_f(__ldcg(reinterpret_cast<const T*>(ph.out) + o_r[j] * ph.ldo + n0 + o_n[j]));
     }
     // ---- main loop: this warp's eighth of K for every 16-feature tile
-    float acc[kDRMaxTiles][4];
+    float acc[kDRMaxTiles][NT][4];
 #pragma unroll
     for (int t = 0; t < kDRMaxTiles; ++t)
 #pragma unroll
-      for (int i = 0; i < 4; ++i) acc[t][i] = 0.f;
+      for (int u = 0; u < NT; ++u)
+#pragma unroll
+        for (int i = 0; i < 4; ++i) acc[t][u][i] = 0.f;
     dl_mbar_wait(w_full, p & 1);
     {
       const int kw = ph.K / kDRComputeWarps;
       // ldmatrix x4 on the slab: matrices (features 0-7, k 0-7), (8-15, k 0-7), (0-7, k 8-15), (8-15, k 8-15) = a0..a3
       const uint8_t* wrow = sW + static_cast<size_t>((lane & 7) + ((lane >> 3) & 1) * 8) * stride + (lane >> 4) * 16;
-      // ldmatrix x2 on the input rows: (rows 0-7, k 0-7), (rows 0-7, k 8-15) = b0, b1
+      // ldmatrix x2 on 8 input rows: (rows 0-7, k 0-7), (rows 0-7, k 8-15) = b0, b1
       const uint8_t* arow = sA + static_cast<size_t>(lane & 7) * stride + ((lane >> 3) & 1) * 16;
       for (int k0 = warp * kw; k0 < (warp + 1) * kw; k0 += 16) {
-        uint32_t b[2];
-        ldmatrix_x2(b, arow + k0 * 2);
+        uint32_t b[NT][2];
+#pragma unroll
+        for (int u = 0; u < NT; ++u) ldmatrix_x2(b[u], arow + static_cast<size_t>(u) * 8 * stride + k0 * 2);
 #pragma unroll
         for (int t = 0; t < kDRMaxTiles; ++t)
           if (t < n_tiles) {
             uint32_t a[4];
             ldmatrix_x4(a, wrow + static_cast<size_t>(t) * 16 * stride + k0 * 2);
-            mma16816<T>(acc[t], a, b[0], b[1]);
+#pragma unroll
+            for (int u = 0; u < NT; ++u) mma16816<T>(acc[t][u], a, b[u][0], b[u][1]);
           }
       }
     }
 #pragma unroll
     for (int t = 0; t < kDRMaxTiles; ++t)
       if (t < n_tiles) {
-        float* dst = s_red + ((warp * kDRMaxTiles + t) * 16) * 8;
-        *reinterpret_cast<float2*>(dst + g * 8 + 2 * t4) = make_float2(acc[t][0], acc[t][1]);
-        *reinterpret_cast<float2*>(dst + (g + 8) * 8 + 2 * t4) = make_float2(acc[t][2], acc[t][3]);
+        float* dst = s_red + ((warp * kDRMaxTiles + t) * 16) * RMAX;
+#pragma unroll
+        for (int u = 0; u < NT; ++u) {
+          *reinterpret_cast<float2*>(dst + g * RMAX + u * 8 + 2 * t4) = make_float2(acc[t][u][0], acc[t][u][1]);
+          *reinterpret_cast<float2*>(dst + (g + 8) * RMAX + u * 8 + 2 * t4) = make_float2(acc[t][u][2], acc[t][u][3]);
+        }
       }
     asm volatile("bar.sync 1, 256;" ::: "memory");
     if (tid == 0) mbar_arrive(w_empty);
     // ---- epilogue
 #pragma unroll
-    for (int j = 0; j < 2; ++j)
+    for (int j = 0; j < J; ++j)
       if (o_r[j] >= 0) {
         const int r = o_r[j], nl = o_n[j];
-        const float* src = s_red + ((nl >> 4) * 16 + (nl & 15)) * 8 + r;
+        const float* src = s_red + ((nl >> 4) * 16 + (nl & 15)) * RMAX + r;
         float v = 0.f;
 #pragma unroll
-        for (int w = 0; w < kDRComputeWarps; ++w) v += src[w * kDRMaxTiles * 16 * 8];
+        for (int w = 0; w < kDRComputeWarps; ++w) v += src[w * kDRMaxTiles * 16 * RMAX];
         if (fold)
-          v = fmaf(s_stat[kDRMaxRows + r], v - s_stat[r] * o_c1[j], o_c2[j]);
+          v = fmaf(s_stat[RMAX + r], v - s_stat[r] * o_c1[j], o_c2[j]);
         else
           v += o_c1[j];
         if (ph.flags & DL_GELU) v = gelu_erf(round_to<T>(v));
         if (ph.flags & DL_RESID) v = round_to<T>(v) + o_x[j];
         const T tv = Cvt<T>::from_f(v);
         reinterpret_cast<T*>(ph.out)[r * ph.ldo + n0 + nl] = tv;
-        s_out[r * (kDRMaxTiles * 16) + nl] = Cvt<T>::to_f(tv);
+        s_out[r * kDRCols + nl] = Cvt<T>::to_f(tv);
       }
     if (ph.flags & DL_STATS) {
       asm volatile("bar.sync 1, 256;" ::: "memory");
       if (tid < R) {
         // statistics of the STORED (16-bit rounded) values: what the next LayerNorm would read
-        const float* row = s_out + tid * (kDRMaxTiles * 16);
+        const float* row = s_out + tid * kDRCols;
         float sum = 0.f;
         for (int i = 0; i < nc; ++i) sum += row[i];
         const float mean = nc > 0 ? sum / static_cast<float>(nc) : 0.f;
@@ -800,6 +815,7 @@ bool dl_use_rows_form(DLLaunch& L) {
   L.rows_smem = 0;
   const DLParams& P = L.p;
   if (!g_fused_rows || P.R > kDRMaxRows || P.n_phases <= 0) return false;
+  const int nt = P.R <= 8 ? 1 : (P.R <= 16 ? 2 : 4);       // 8-row operand tiles of the input rows
   long long w_bytes = 0, extent = 0, a_bytes = 0;
   for (int p = 0; p < P.n_phases; ++p) {
     const DLPhase& ph = P.ph[p];
@@ -809,11 +825,11 @@ bool dl_use_rows_form(DLLaunch& L) {
     if (nc_max > kDRMaxTiles * 16) return false;
     w_bytes = std::max(w_bytes, nc_max * stride);
     extent = std::max(extent, ((nc_max + 15) / 16 * 16) * stride);     // ldmatrix reads whole 16-row tiles
-    a_bytes = std::max(a_bytes, kDRMaxRows * stride);
+    a_bytes = std::max(a_bytes, 8LL * nt * stride);
   }
   const long long a_off = (w_bytes + 127) / 128 * 128;
   const long long tail_off = (std::max(a_off + a_bytes, extent) + 127) / 128 * 128;
-  const long long total = tail_off + kDRTailBytes + 128;
+  const long long total = tail_off + dr_tail_bytes(nt) + 128;
   if (total > 227 * 1024) return false;
   L.p.dr_a_off = static_cast<int>(a_off);
   L.p.dr_tail_off = static_cast<int>(tail_off);
@@ -834,9 +850,9 @@ static int dl_launch_t(const DLLaunch& L, cudaStream_t s) {
   return (le == cudaSuccess && cudaGetLastError() == cudaSuccess) ? 0 : 61;
 }
 
-template <typename T>
+template <typename T, int NT>
 static int dr_launch_t(const DLLaunch& L, cudaStream_t s) {
-  auto kern = dec_rows_kernel<T>;
+  auto kern = dec_rows_kernel<T, NT>;
   static SmemOptIn optin;
   if (!optin.ensure(kern, 227 * 1024)) return 62;
   ProfileScope prof(PROF_DEC_LAYER, s);
@@ -847,7 +863,12 @@ static int dr_launch_t(const DLLaunch& L, cudaStream_t s) {
 
 int dl_launch(const DLLaunch& L, cudaStream_t s) {
   if (L.p.n_phases <= 0) return 0;
-  if (L.rows_smem > 0) return L.dtype == DT_BF16 ? dr_launch_t<__nv_bfloat16>(L, s) : dr_launch_t<__half>(L, s);
+  if (L.rows_smem > 0) {
+    const bool bf = L.dtype == DT_BF16;
+    if (L.p.R <= 8) return bf ? dr_launch_t<__nv_bfloat16, 1>(L, s) : dr_launch_t<__half, 1>(L, s);
+    if (L.p.R <= 16) return bf ? dr_launch_t<__nv_bfloat16, 2>(L, s) : dr_launch_t<__half, 2>(L, s);
+    return bf ? dr_launch_t<__nv_bfloat16, 4>(L, s) : dr_launch_t<__half, 4>(L, s);
+  }
   return L.dtype == DT_BF16 ? dl_launch_t<__nv_bfloat16>(L, s) : dl_launch_t<__half>(L, s);
 }
 

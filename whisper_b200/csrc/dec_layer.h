@@ -61,7 +61,7 @@ struct DLLaunch {
   DLMaps maps;
 };
 
-constexpr int kDRMaxRows = 8;      // the few-rows form covers R <= 8 (one mma.sync n = 8 operand)
+constexpr int kDRMaxRows = 32;     // the few-rows form covers R <= 32 (1, 2 or 4 mma.sync n = 8 operand tiles) where shared memory allows
 
 extern int g_fused_layer;
 extern int g_fused_rows;           // few-rows form for R <= kDRMaxRows (wb200_set_fused_decoder_rows / WB200_FUSED_ROWS, default on)
@@ -72,7 +72,7 @@ void dl_init_launch(DLLaunch& L, int dtype, int R, int grid, float4* ln_part, in
 // appends nothing by itself: fills phase `idx` (caller sets p.n_phases)
 int dl_fill_phase(DLLaunch& L, int idx, int dtype, int R, int grid, const void* A, long long lda, const void* W, int N, int K,
                   const void* bias, const float* c1, const float* c2, int flags, void* out, long long ldo, int bm = 0);
-// after every phase is filled: switch the launch to the few-rows form if it applies (R <= kDRMaxRows, shapes fit);
+// after every phase is filled: switch the launch to the few-rows form if it applies (R <= kDRMaxRows, slab + rows fit);
 // returns true when it did
 bool dl_use_rows_form(DLLaunch& L);
 int dl_launch(const DLLaunch& L, cudaStream_t s);
