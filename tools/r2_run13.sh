@@ -2,7 +2,7 @@ cd $GRAFT_REPO_ROOT
 # few-rows form generalised to <= 32 rows; self-attention A/B after removing the division from the gather kernel
 timeout 900 python -m pytest tests/test_fused_layer_gpu.py "tests/test_model_gpu.py::test_batched_beam_equals_per_audio" tests/test_zz_kv_layout_gpu.py -x -q -s 2>&1 | grep -v "^$" | tail -40 > gpurun_out/r2_run13_tests_a.log; cat gpurun_out/r2_run13_tests_a.log | cut -c1-200
 if grep -q "passed" gpurun_out/r2_run13_tests_a.log && ! grep -q "failed\|error" gpurun_out/r2_run13_tests_a.log; then
-  timeout 1800 python -m pytest tests/test_model_gpu.py tests/test_large_dims_gpu.py tests/test_zz_decode_options_gpu.py tests/test_zz_transcribe_batch_gpu.py tests/test_alignment_gpu.py -x -q 2>&1 | tail -8 > gpurun_out/r2_run13_tests_b.log; cat gpurun_out/r2_run13_tests_b.log
+  timeout 1800 python -m pytest tests/test_model_gpu.py tests/test_large_dims_gpu.py tests/test_zz_decode_options_gpu.py tests/test_zz_transcribe_batch_gpu.py -x -q 2>&1 | tail -8 > gpurun_out/r2_run13_tests_b.log; cat gpurun_out/r2_run13_tests_b.log
 fi
 for sa in 0 1; do
   WB200_SATTN_TMA=$sa timeout 400 python bench.py --steps 2 --warmup 3 --no-cpu-baseline --no-gpu-baseline --breakdown --breakdown-ids 2 2> gpurun_out/r2_run13_bench_$sa.err > gpurun_out/r2_run13_bench_$sa.json
