@@ -80,6 +80,12 @@ int wb200_set_fused_decoder_layer(int enabled);
  * memory ahead of the grid barrier and runs mma.sync with the weight rows as the M operand).  On by default for
  * sessions created AFTER the call (WB200_FUSED_ROWS=0 in the environment or this call: the 64-row tile form runs). */
 int wb200_set_fused_decoder_rows(int enabled);
+/* Few-rows sessions with head-major kv caches: ONE launch per decoder iteration for the whole stack - the kernel above
+ * walks a phase table that strings every layer's Linear chains together with its self-attention (kv append + attention
+ * over the rows' lineages through the parent table, whisper/model.py:124-127,327-333 + decoding.py:172-176) and its
+ * cross-attention (key slices + merge) as further grid-barrier phases.  On by default for sessions created AFTER the
+ * call (WB200_FUSED_STACK=0 or this call: three few-rows launches per layer around the two attention kernels). */
+int wb200_set_fused_decoder_stack(int enabled);
 /* Layout of the decoder's kv caches for sessions created AFTER the call (default 1, or WB200_KV_HEAD_MAJOR=0 in
  * the environment).  1: head-major - cross-attention K/V [n_audio, 2H, 1500, 64] (written that way by the K/V
  * projection's epilogue), self-attention caches [rows, H, 448, 64] - or, in sessions that run the beam-window
@@ -94,11 +100,12 @@ int wb200_set_kv_head_major(int enabled);
  * through an mbarrier ring that stays full across (audio, head) work items; needs the head-major layout.  0 = the
  * cp.async kernel (always used for the prefill).  Takes effect at the next launch. */
 int wb200_set_cross_attention_tma(int enabled);
-/* Decoder-step self attention under beam search / best_of (2 <= n_group <= 8): 1 (default, WB200_SATTN_TMA=0 to
- * disable) = the G rows of an audio are processed together by a persistent TMA-fed kernel that streams the audio's
+/* Decoder-step self attention under beam search / best_of (2 <= n_group <= 8): 1 (opt-in, or WB200_SATTN_TMA=1 in the
+ * environment; measured 10 % slower than the default at the headline shape because it cannot profit from beams that
+ * share ancestors, profiles/r2_summary.md) = the G rows of an audio are processed together by a persistent TMA-fed kernel that streams the audio's
  * whole (position x beam-slot) history of a head as one contiguous block of the head-major ("beam window") cache and
  * masks each row by the beam's parent table - the device form of PyTorchInference.rearrange_kv_cache
- * (whisper/decoding.py:172-176) + the kv-cache hooks' torch.cat (whisper/model.py:327-333).  0 = one warp per
+ * (whisper/decoding.py:172-176) + the kv-cache hooks' torch.cat (whisper/model.py:327-333).  0 (default) = one warp per
  * (row, head) gathering 128-byte pieces through the parent table (always used for greedy decoding, the prefill, the
  * position-major layout and batches with fewer (audio, head) pairs than half the SMs).  The cache layout goes with
  * the kernel, so the switch applies to sessions created AFTER the call. */

@@ -132,22 +132,28 @@ def test_few_rows_form_at_baseline_dims(name, beam, dtype):
     try:
         mel = wb.log_mel_spectrogram(torch.from_numpy(audio[0]).cuda(), dims["n_mels"])[None]
         g_feats = model.embed_audio(mel)
-        rows = run()
+        stack = run()                                   # default: the whole stack as one launch per iteration
+        _lib.lib().wb200_set_fused_decoder_stack(0)
+        model.clear_sessions()
+        rows = run()                                    # few-rows chains around the separate attention kernels
         _lib.lib().wb200_set_fused_decoder_rows(0)
         model.clear_sessions()
         tile = run()
-        worst_pair = worst_ora = 0.0
-        for i, (a, b) in enumerate(zip(tile, rows)):
+        worst_pair = worst_stack = worst_ora = 0.0
+        for i, (a, b, c) in enumerate(zip(tile, rows, stack)):
             ref = rec["raw_logits"][i]
             ref = ref[::G] if i == 0 else ref
             scale = float(ref.abs().max())
             worst_pair = max(worst_pair, float((a - b).abs().max()) / scale)
-            worst_ora = max(worst_ora, float((b - ref).abs().max()) / scale)
-        print(f"{name} beam={beam} {dtype}: few-rows vs tile form {worst_pair:.5f}, few-rows vs oracle {worst_ora:.5f} over "
-              f"{len(rows)} iterations")
+            worst_stack = max(worst_stack, float((b - c).abs().max()) / scale)
+            worst_ora = max(worst_ora, float((b - ref).abs().max()) / scale, float((c - ref).abs().max()) / scale)
+        print(f"{name} beam={beam} {dtype}: few-rows vs tile form {worst_pair:.5f}, one-launch stack vs per-layer launches "
+              f"{worst_stack:.5f}, vs oracle {worst_ora:.5f} over {len(rows)} iterations")
         assert worst_ora < LOGIT_TOL[dtype]
         assert 0.0 < worst_pair < LOGIT_TOL[dtype]       # two different kernels, the same math
+        assert 0.0 < worst_stack < LOGIT_TOL[dtype]
     finally:
+        _lib.lib().wb200_set_fused_decoder_stack(1)
         _lib.lib().wb200_set_fused_decoder_rows(1)
         model.clear_sessions()
         del model

@@ -133,6 +133,11 @@ int wb200_set_fused_decoder_rows(int enabled) {
   return 0;
 }
 
+int wb200_set_fused_decoder_stack(int enabled) {
+  g_fused_stack = enabled ? 1 : 0;
+  return 0;
+}
+
 int wb200_set_pdl(int enabled) {
   g_pdl_on = enabled ? 1 : 0;
   return 0;

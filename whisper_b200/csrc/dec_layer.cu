@@ -47,6 +47,7 @@ namespace wb {
 
 int g_fused_layer = -1;   // -1: read WB200_FUSED_LAYER on first use; wb200_set_fused_decoder_layer() overrides
 int g_fused_rows = -1;    // -1: read WB200_FUSED_ROWS on first use; wb200_set_fused_decoder_rows() overrides
+int g_fused_stack = -1;   // -1: read WB200_FUSED_STACK on first use; wb200_set_fused_decoder_stack() overrides
 
 constexpr int kDLThreads = 416;                      // 13 warps
 constexpr int kDLRowBytes = 128;                     // one row of a 64-wide 16-bit k-block
@@ -485,6 +486,112 @@ constexpr int kDRCols = kDRMaxTiles * 16;
 __host__ __device__ constexpr int dr_red_floats(int nt) { return kDRComputeWarps * kDRMaxTiles * 16 * 8 * nt; }
 __host__ __device__ constexpr int dr_tail_bytes(int nt) { return (dr_red_floats(nt) + 8 * nt * kDRCols + 2 * 8 * nt) * 4 + 3 * 8 + 64; }
 
+// ---- attention inside the few-rows kernel: one query row, keys in blocks of four per warp.  Lane = (key of the block
+// g = lane / 8, 16-byte chunk c = lane % 8 of the 64-wide head): every load instruction fetches four complete 128-byte K
+// (or V) rows, the dot product finishes with three xor-shuffles inside the 8-lane group, every group keeps an online
+// softmax state that is merged across the groups, then across the warps through shared memory.
+constexpr float kDRScaleLog2 = 0.125f * 1.4426950408889634f;      // (1 / sqrt(64)) * log2(e)
+struct AttAcc {
+  float m, l, o[8];
+};
+__device__ __forceinline__ void att_init(AttAcc& a) {
+  a.m = -INFINITY;
+  a.l = 0.f;
+#pragma unroll
+  for (int e = 0; e < 8; ++e) a.o[e] = 0.f;
+}
+template <typename T>
+__device__ __forceinline__ void att_load_q(float (&q)[8], const void* src) {
+  const uint4 u = __ldcg(reinterpret_cast<const uint4*>(src));
+  const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+  for (int e = 0; e < 4; ++e) {
+    const float2 f = Cvt<T>::unpack2(w[e]);
+    q[2 * e] = f.x * kDRScaleLog2;
+    q[2 * e + 1] = f.y * kDRScaleLog2;
+  }
+}
+// one key per 8-lane group (all 32 lanes call this together)
+template <typename T>
+__device__ __forceinline__ void att_update(AttAcc& a, const float (&q)[8], uint4 kk, uint4 vv, bool valid) {
+  const uint32_t wk[4] = {kk.x, kk.y, kk.z, kk.w};
+  float s = 0.f;
+#pragma unroll
+  for (int e = 0; e < 4; ++e) {
+    const float2 f = Cvt<T>::unpack2(wk[e]);
+    s = fmaf(q[2 * e], f.x, s);
+    s = fmaf(q[2 * e + 1], f.y, s);
+  }
+  s += __shfl_xor_sync(0xffffffffu, s, 1);
+  s += __shfl_xor_sync(0xffffffffu, s, 2);
+  s += __shfl_xor_sync(0xffffffffu, s, 4);
+  if (!valid) return;
+  const float mn = fmaxf(a.m, s);
+  const float al = fast_exp2(a.m - mn);           // first key: exp2(-inf) = 0
+  const float pr = fast_exp2(s - mn);
+  a.m = mn;
+  a.l = fmaf(a.l, al, pr);
+  const uint32_t wv[4] = {vv.x, vv.y, vv.z, vv.w};
+#pragma unroll
+  for (int e = 0; e < 4; ++e) {
+    const float2 f = Cvt<T>::unpack2(wv[e]);
+    a.o[2 * e] = fmaf(a.o[2 * e], al, pr * f.x);
+    a.o[2 * e + 1] = fmaf(a.o[2 * e + 1], al, pr * f.y);
+  }
+}
+__device__ __forceinline__ void att_merge(float& m, float& l, float (&o)[8], float m2, float l2, const float (&o2)[8]) {
+  const float mn = fmaxf(m, m2);
+  const float a1 = m == -INFINITY ? 0.f : fast_exp2(m - mn);
+  const float a2 = m2 == -INFINITY ? 0.f : fast_exp2(m2 - mn);
+  l = l * a1 + l2 * a2;
+#pragma unroll
+  for (int e = 0; e < 8; ++e) o[e] = o[e] * a1 + o2[e] * a2;
+  m = mn;
+}
+// the four key groups of a warp -> every lane holds the warp's state for its chunk; lanes 0-7 park it in shared memory
+__device__ __forceinline__ void att_park(AttAcc& a, float* slot /* [68] of this warp */) {
+  const int lane = threadIdx.x & 31;
+#pragma unroll
+  for (int sh = 8; sh <= 16; sh <<= 1) {
+    const float m2 = __shfl_xor_sync(0xffffffffu, a.m, sh), l2 = __shfl_xor_sync(0xffffffffu, a.l, sh);
+    float o2[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) o2[e] = __shfl_xor_sync(0xffffffffu, a.o[e], sh);
+    att_merge(a.m, a.l, a.o, m2, l2, o2);
+  }
+  if (lane < 8) {
+#pragma unroll
+    for (int e = 0; e < 8; ++e) slot[lane * 8 + e] = a.o[e];
+  }
+  if (lane == 0) {
+    slot[64] = a.m;
+    slot[65] = a.l;
+  }
+}
+// lanes 0-7 of one warp: merge the parked states of the compute warps for chunk c = lane
+__device__ __forceinline__ void att_gather(const float* slots, int n_warps, int c, float& m, float& l, float (&o)[8]) {
+  m = -INFINITY;
+  l = 0.f;
+#pragma unroll
+  for (int e = 0; e < 8; ++e) o[e] = 0.f;
+  for (int w = 0; w < n_warps; ++w) {
+    const float* sl = slots + w * 68;
+    float o2[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) o2[e] = sl[c * 8 + e];
+    att_merge(m, l, o, sl[64], sl[65], o2);
+  }
+}
+template <typename T>
+__device__ __forceinline__ uint4 att_pack(const float (&o)[8], float inv) {
+  uint4 u;
+  u.x = Cvt<T>::pack2(o[0] * inv, o[1] * inv);
+  u.y = Cvt<T>::pack2(o[2] * inv, o[3] * inv);
+  u.z = Cvt<T>::pack2(o[4] * inv, o[5] * inv);
+  u.w = Cvt<T>::pack2(o[6] * inv, o[7] * inv);
+  return u;
+}
+
 template <typename T, int NT>
 __global__ void __launch_bounds__(kDRThreads, 1) dec_rows_kernel(const DLParams P) {
   constexpr int RMAX = 8 * NT;
@@ -494,7 +601,7 @@ __global__ void __launch_bounds__(kDRThreads, 1) dec_rows_kernel(const DLParams 
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(dr_smem_raw) + 127) & ~static_cast<uintptr_t>(127));
   uint8_t* sW = smem;
   uint8_t* sA = smem + P.dr_a_off;
-  float* s_red = reinterpret_cast<float*>(smem + P.dr_tail_off);   // [warp][tile][16 features][RMAX rows]
+  float* s_red = reinterpret_cast<float*>(smem + P.dr_tail_off);   // [warp][tile][16 features][RMAX rows]; attention: [warp][68]
   float* s_out = s_red + dr_red_floats(NT);                         // [row][feature]: the values as stored
   float* s_stat = s_out + RMAX * kDRCols;                           // mean[RMAX] | rstd[RMAX]
   uint64_t* w_full = reinterpret_cast<uint64_t*>(s_stat + 2 * RMAX);
@@ -510,14 +617,23 @@ __global__ void __launch_bounds__(kDRThreads, 1) dec_rows_kernel(const DLParams 
     mbar_fence_init();
   }
   __syncthreads();
-  // this CTA's output features of a phase
-  auto first_col = [&](int p, int c) { return static_cast<int>(static_cast<long long>(c) * P.ph[p].N / grid); };
+  // phase p: from the kernel parameters (a chain of Linears) or from the table in global memory (a whole decoder stack)
+  auto phase = [&](int p) -> DLPhase {
+    if (P.table) return P.table[p];
+    return P.ph[p];
+  };
+  auto phase_type = [&](int p) -> int { return P.table ? P.table[p].type : DS_LINEAR; };
+  auto next_linear = [&](int p) {        // first Linear phase at or after p (n_phases if none)
+    while (p < P.n_phases && phase_type(p) != DS_LINEAR) ++p;
+    return p;
+  };
 
   if (warp == kDRComputeWarps) {
     // ===================== control warp: bulk copies and the grid barrier =====================
     auto issue_w = [&](int p) {
-      const DLPhase& ph = P.ph[p];
-      const int n0 = first_col(p, cta), nc = first_col(p, cta + 1) - n0;
+      const DLPhase ph = phase(p);
+      const int n0 = static_cast<int>(static_cast<long long>(cta) * ph.N / grid);
+      const int nc = static_cast<int>(static_cast<long long>(cta + 1) * ph.N / grid) - n0;
       const uint32_t row_bytes = static_cast<uint32_t>(ph.K) * 2;
       if (lane == 0) mbar_expect_tx(w_full, static_cast<uint32_t>(nc) * row_bytes);
       __syncwarp();
@@ -525,14 +641,15 @@ __global__ void __launch_bounds__(kDRThreads, 1) dec_rows_kernel(const DLParams 
         bulk_load_1d(sW + static_cast<size_t>(i) * (row_bytes + 16), static_cast<const uint8_t*>(ph.w) + static_cast<size_t>(n0 + i) * row_bytes,
                      row_bytes, w_full);
     };
-    issue_w(0);                 // weights are constants: the first slab streams in under the tail of the previous kernel
+    int lin = next_linear(0);            // the Linear phase whose slab is in flight / resident
+    if (lin < P.n_phases) issue_w(lin);  // weights are constants: the first slab streams in under the tail of the previous kernel
     pdl_wait();
     if (P.skip_flag && *P.skip_flag) {
-      dl_mbar_wait(w_full, 0);  // never leave with a copy into this CTA's shared memory in flight
+      if (lin < P.n_phases) dl_mbar_wait(w_full, 0);  // never leave with a copy into this CTA's shared memory in flight
       return;
     }
+    int slab = 0;
     for (int p = 0; p < P.n_phases; ++p) {
-      const DLPhase& ph = P.ph[p];
       if (p > 0) {
         const unsigned int target = static_cast<unsigned int>(p) * static_cast<unsigned int>(grid);
         long long spins = 0;
@@ -543,6 +660,12 @@ __global__ void __launch_bounds__(kDRThreads, 1) dec_rows_kernel(const DLParams 
           if (++spins > (1ll << 23)) __trap();
         }
       }
+      if (p != lin) {                    // an attention phase: nothing to stage, just let the compute warps go
+        __syncwarp();
+        if (lane == 0) mbar_arrive(a_full);
+        continue;
+      }
+      const DLPhase ph = phase(p);
       fence_proxy_async_global();        // other CTAs' generic-proxy stores -> this lane's bulk (async-proxy) reads
       const uint32_t row_bytes = static_cast<uint32_t>(ph.K) * 2;
       if (lane == 0) mbar_expect_tx(a_full, static_cast<uint32_t>(R) * row_bytes);
@@ -550,10 +673,12 @@ __global__ void __launch_bounds__(kDRThreads, 1) dec_rows_kernel(const DLParams 
       if (lane < R)                      // R <= 32: one input row per lane
         bulk_load_1d(sA + static_cast<size_t>(lane) * (row_bytes + 16), static_cast<const uint8_t*>(ph.a) + static_cast<size_t>(lane) * ph.lda * 2,
                      row_bytes, a_full);
-      if (p + 1 < P.n_phases) {
-        dl_mbar_wait(w_empty, p & 1);    // every compute warp is done with the slab and the input rows of phase p
-        issue_w(p + 1);
+      lin = next_linear(p + 1);
+      if (lin < P.n_phases) {
+        dl_mbar_wait(w_empty, slab & 1); // every compute warp is done with the slab and the input rows of phase p
+        issue_w(lin);                    // streams in while phase p finishes and the attention phases in between run
       }
+      ++slab;
     }
     return;
   }
@@ -562,135 +687,266 @@ __global__ void __launch_bounds__(kDRThreads, 1) dec_rows_kernel(const DLParams 
   pdl_wait();
   if (P.skip_flag && *P.skip_flag) return;
   const int g = lane >> 2, t4 = lane & 3;
+  const int g4 = lane >> 3, c8 = lane & 7;                    // attention: key of the block, 16-byte chunk
+  int slab = 0;
   for (int p = 0; p < P.n_phases; ++p) {
-    const DLPhase& ph = P.ph[p];
-    const int n0 = first_col(p, cta), nc = first_col(p, cta + 1) - n0;
-    const int n_tiles = (nc + 15) >> 4;
-    const int stride = ph.K * 2 + 16;
-    const bool fold = (ph.flags & DL_FOLD) != 0;
-    // ---- this thread's <= J output elements (row, feature) and their constants, before anything has to be waited for
-    const int n_out = nc * R;
-    int o_r[J], o_n[J];
-    float o_c1[J], o_c2[J];
+    const DLPhase ph = phase(p);
+    if (ph.type == DS_LINEAR) {
+      const int n0 = static_cast<int>(static_cast<long long>(cta) * ph.N / grid);
+      const int nc = static_cast<int>(static_cast<long long>(cta + 1) * ph.N / grid) - n0;
+      const int n_tiles = (nc + 15) >> 4;
+      const int stride = ph.K * 2 + 16;
+      const bool fold = (ph.flags & DL_FOLD) != 0;
+      // ---- this thread's <= J output elements (row, feature) and their constants, before anything has to be waited for
+      const int n_out = nc * R;
+      int o_r[J], o_n[J];
+      float o_c1[J], o_c2[J];
 #pragma unroll
-    for (int j = 0; j < J; ++j) {
-      const int o = tid + j * 256;
-      o_r[j] = o < n_out ? o / nc : -1;
-      o_n[j] = o < n_out ? o - o_r[j] * nc : 0;
-      o_c1[j] = o_c2[j] = 0.f;
-      if (o_r[j] >= 0) {
-        const int n = n0 + o_n[j];
-        if (fold) {
-          o_c1[j] = __ldg(ph.c1 + n);
-          o_c2[j] = __ldg(ph.c2 + n);
-        } else {
-          o_c1[j] = Cvt<T>::to_f(__ldg(reinterpret_cast<const T*>(ph.bias) + n));
-        }
-      }
-    }
-    dl_mbar_wait(a_full, p & 1);         // the previous phase is complete grid-wide (the control warp saw the barrier open)
-    // ---- LayerNorm statistics of rows warp, warp + 8, .. from the partials their producer left (model.py:39-41, eps 1e-5)
-    if (fold) {
-      const int slots = (p == 0 && P.ln_slots_in > 0) ? P.ln_slots_in : grid;
-      for (int r = warp; r < R; r += kDRComputeWarps) {
-        float n = 0.f, mean = 0.f, m2 = 0.f;
-        for (int s0 = lane; s0 < slots; s0 += 32) {
-          const float4 part = __ldcg(P.ln_part + static_cast<long long>(s0) * P.ln_ld + r);
-          chan_merge(n, mean, m2, part.x, part.y, part.z);
-        }
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) {
-          const float nb = __shfl_xor_sync(0xffffffffu, n, o), mb = __shfl_xor_sync(0xffffffffu, mean, o),
-                      qb = __shfl_xor_sync(0xffffffffu, m2, o);
-          chan_merge(n, mean, m2, nb, mb, qb);
-        }
-        if (lane == 0) {
-          s_stat[r] = mean;
-          s_stat[RMAX + r] = rsqrtf(m2 / n + 1e-5f);
-        }
-      }
-    }
-    float o_x[J];
-#pragma unroll
-    for (int j = 0; j < J; ++j) {
-      o_x[j] = 0.f;
-      if ((ph.flags & DL_RESID) && o_r[j] >= 0)
-        o_x[j] = Cvt<T>::to_f(__ldcg(reinterpret_cast<const T*>(ph.out) + o_r[j] * ph.ldo + n0 + o_n[j]));
-    }
-    // ---- main loop: this warp's eighth of K for every 16-feature tile
-    float acc[kDRMaxTiles][NT][4];
-#pragma unroll
-    for (int t = 0; t < kDRMaxTiles; ++t)
-#pragma unroll
-      for (int u = 0; u < NT; ++u)
-#pragma unroll
-        for (int i = 0; i < 4; ++i) acc[t][u][i] = 0.f;
-    dl_mbar_wait(w_full, p & 1);
-    {
-      const int kw = ph.K / kDRComputeWarps;
-      // ldmatrix x4 on the slab: matrices (features 0-7, k 0-7), (8-15, k 0-7), (0-7, k 8-15), (8-15, k 8-15) = a0..a3
-      const uint8_t* wrow = sW + static_cast<size_t>((lane & 7) + ((lane >> 3) & 1) * 8) * stride + (lane >> 4) * 16;
-      // ldmatrix x2 on 8 input rows: (rows 0-7, k 0-7), (rows 0-7, k 8-15) = b0, b1
-      const uint8_t* arow = sA + static_cast<size_t>(lane & 7) * stride + ((lane >> 3) & 1) * 16;
-      for (int k0 = warp * kw; k0 < (warp + 1) * kw; k0 += 16) {
-        uint32_t b[NT][2];
-#pragma unroll
-        for (int u = 0; u < NT; ++u) ldmatrix_x2(b[u], arow + static_cast<size_t>(u) * 8 * stride + k0 * 2);
-#pragma unroll
-        for (int t = 0; t < kDRMaxTiles; ++t)
-          if (t < n_tiles) {
-            uint32_t a[4];
-            ldmatrix_x4(a, wrow + static_cast<size_t>(t) * 16 * stride + k0 * 2);
-#pragma unroll
-            for (int u = 0; u < NT; ++u) mma16816<T>(acc[t][u], a, b[u][0], b[u][1]);
+      for (int j = 0; j < J; ++j) {
+        const int o = tid + j * 256;
+        o_r[j] = o < n_out ? o / nc : -1;
+        o_n[j] = o < n_out ? o - o_r[j] * nc : 0;
+        o_c1[j] = o_c2[j] = 0.f;
+        if (o_r[j] >= 0) {
+          const int n = n0 + o_n[j];
+          if (fold) {
+            o_c1[j] = __ldg(ph.c1 + n);
+            o_c2[j] = __ldg(ph.c2 + n);
+          } else {
+            o_c1[j] = Cvt<T>::to_f(__ldg(reinterpret_cast<const T*>(ph.bias) + n));
           }
-      }
-    }
-#pragma unroll
-    for (int t = 0; t < kDRMaxTiles; ++t)
-      if (t < n_tiles) {
-        float* dst = s_red + ((warp * kDRMaxTiles + t) * 16) * RMAX;
-#pragma unroll
-        for (int u = 0; u < NT; ++u) {
-          *reinterpret_cast<float2*>(dst + g * RMAX + u * 8 + 2 * t4) = make_float2(acc[t][u][0], acc[t][u][1]);
-          *reinterpret_cast<float2*>(dst + (g + 8) * RMAX + u * 8 + 2 * t4) = make_float2(acc[t][u][2], acc[t][u][3]);
         }
       }
-    asm volatile("bar.sync 1, 256;" ::: "memory");
-    if (tid == 0) mbar_arrive(w_empty);
-    // ---- epilogue
+      dl_mbar_wait(a_full, p & 1);         // the previous phase is complete grid-wide (the control warp saw the barrier open)
+      // ---- LayerNorm statistics of rows warp, warp + 8, .. from the partials their producer left (model.py:39-41, eps 1e-5)
+      if (fold) {
+        const int slots = (p == 0 && P.ln_slots_in > 0) ? P.ln_slots_in : grid;
+        for (int r = warp; r < R; r += kDRComputeWarps) {
+          float n = 0.f, mean = 0.f, m2 = 0.f;
+          for (int s0 = lane; s0 < slots; s0 += 32) {
+            const float4 part = __ldcg(P.ln_part + static_cast<long long>(s0) * P.ln_ld + r);
+            chan_merge(n, mean, m2, part.x, part.y, part.z);
+          }
 #pragma unroll
-    for (int j = 0; j < J; ++j)
-      if (o_r[j] >= 0) {
-        const int r = o_r[j], nl = o_n[j];
-        const float* src = s_red + ((nl >> 4) * 16 + (nl & 15)) * RMAX + r;
-        float v = 0.f;
-#pragma unroll
-        for (int w = 0; w < kDRComputeWarps; ++w) v += src[w * kDRMaxTiles * 16 * RMAX];
-        if (fold)
-          v = fmaf(s_stat[RMAX + r], v - s_stat[r] * o_c1[j], o_c2[j]);
-        else
-          v += o_c1[j];
-        if (ph.flags & DL_GELU) v = gelu_erf(round_to<T>(v));
-        if (ph.flags & DL_RESID) v = round_to<T>(v) + o_x[j];
-        const T tv = Cvt<T>::from_f(v);
-        reinterpret_cast<T*>(ph.out)[r * ph.ldo + n0 + nl] = tv;
-        s_out[r * kDRCols + nl] = Cvt<T>::to_f(tv);
+          for (int o = 16; o > 0; o >>= 1) {
+            const float nb = __shfl_xor_sync(0xffffffffu, n, o), mb = __shfl_xor_sync(0xffffffffu, mean, o),
+                        qb = __shfl_xor_sync(0xffffffffu, m2, o);
+            chan_merge(n, mean, m2, nb, mb, qb);
+          }
+          if (lane == 0) {
+            s_stat[r] = mean;
+            s_stat[RMAX + r] = rsqrtf(m2 / n + 1e-5f);
+          }
+        }
       }
-    if (ph.flags & DL_STATS) {
+      float o_x[J];
+#pragma unroll
+      for (int j = 0; j < J; ++j) {
+        o_x[j] = 0.f;
+        if ((ph.flags & DL_RESID) && o_r[j] >= 0)
+          o_x[j] = Cvt<T>::to_f(__ldcg(reinterpret_cast<const T*>(ph.out) + o_r[j] * ph.ldo + n0 + o_n[j]));
+      }
+      // ---- main loop: this warp's eighth of K for every 16-feature tile
+      float acc[kDRMaxTiles][NT][4];
+#pragma unroll
+      for (int t = 0; t < kDRMaxTiles; ++t)
+#pragma unroll
+        for (int u = 0; u < NT; ++u)
+#pragma unroll
+          for (int i = 0; i < 4; ++i) acc[t][u][i] = 0.f;
+      dl_mbar_wait(w_full, slab & 1);
+      {
+        const int kw = ph.K / kDRComputeWarps;
+        // ldmatrix x4 on the slab: matrices (features 0-7, k 0-7), (8-15, k 0-7), (0-7, k 8-15), (8-15, k 8-15) = a0..a3
+        const uint8_t* wrow = sW + static_cast<size_t>((lane & 7) + ((lane >> 3) & 1) * 8) * stride + (lane >> 4) * 16;
+        // ldmatrix x2 on 8 input rows: (rows 0-7, k 0-7), (rows 0-7, k 8-15) = b0, b1
+        const uint8_t* arow = sA + static_cast<size_t>(lane & 7) * stride + ((lane >> 3) & 1) * 16;
+        for (int k0 = warp * kw; k0 < (warp + 1) * kw; k0 += 16) {
+          uint32_t b[NT][2];
+#pragma unroll
+          for (int u = 0; u < NT; ++u) ldmatrix_x2(b[u], arow + static_cast<size_t>(u) * 8 * stride + k0 * 2);
+#pragma unroll
+          for (int t = 0; t < kDRMaxTiles; ++t)
+            if (t < n_tiles) {
+              uint32_t a[4];
+              ldmatrix_x4(a, wrow + static_cast<size_t>(t) * 16 * stride + k0 * 2);
+#pragma unroll
+              for (int u = 0; u < NT; ++u) mma16816<T>(acc[t][u], a, b[u][0], b[u][1]);
+            }
+        }
+      }
+#pragma unroll
+      for (int t = 0; t < kDRMaxTiles; ++t)
+        if (t < n_tiles) {
+          float* dst = s_red + ((warp * kDRMaxTiles + t) * 16) * RMAX;
+#pragma unroll
+          for (int u = 0; u < NT; ++u) {
+            *reinterpret_cast<float2*>(dst + g * RMAX + u * 8 + 2 * t4) = make_float2(acc[t][u][0], acc[t][u][1]);
+            *reinterpret_cast<float2*>(dst + (g + 8) * RMAX + u * 8 + 2 * t4) = make_float2(acc[t][u][2], acc[t][u][3]);
+          }
+        }
       asm volatile("bar.sync 1, 256;" ::: "memory");
-      if (tid < R) {
-        // statistics of the STORED (16-bit rounded) values: what the next LayerNorm would read
-        const float* row = s_out + tid * kDRCols;
-        float sum = 0.f;
-        for (int i = 0; i < nc; ++i) sum += row[i];
-        const float mean = nc > 0 ? sum / static_cast<float>(nc) : 0.f;
-        float m2 = 0.f;
-        for (int i = 0; i < nc; ++i) {
-          const float d = row[i] - mean;
-          m2 = fmaf(d, d, m2);
+      if (tid == 0) mbar_arrive(w_empty);
+      ++slab;
+      // ---- epilogue
+#pragma unroll
+      for (int j = 0; j < J; ++j)
+        if (o_r[j] >= 0) {
+          const int r = o_r[j], nl = o_n[j];
+          const float* src = s_red + ((nl >> 4) * 16 + (nl & 15)) * RMAX + r;
+          float v = 0.f;
+#pragma unroll
+          for (int w = 0; w < kDRComputeWarps; ++w) v += src[w * kDRMaxTiles * 16 * RMAX];
+          if (fold)
+            v = fmaf(s_stat[RMAX + r], v - s_stat[r] * o_c1[j], o_c2[j]);
+          else
+            v += o_c1[j];
+          if (ph.flags & DL_GELU) v = gelu_erf(round_to<T>(v));
+          if (ph.flags & DL_RESID) v = round_to<T>(v) + o_x[j];
+          const T tv = Cvt<T>::from_f(v);
+          reinterpret_cast<T*>(ph.out)[r * ph.ldo + n0 + nl] = tv;
+          s_out[r * kDRCols + nl] = Cvt<T>::to_f(tv);
         }
-        __stcg(P.ln_part + static_cast<long long>(cta) * P.ln_ld + tid, make_float4(static_cast<float>(nc), mean, m2, 0.f));
+      if (ph.flags & DL_STATS) {
+        asm volatile("bar.sync 1, 256;" ::: "memory");
+        if (tid < R) {
+          // statistics of the STORED (16-bit rounded) values: what the next LayerNorm would read
+          const float* row = s_out + tid * kDRCols;
+          float sum = 0.f;
+          for (int i = 0; i < nc; ++i) sum += row[i];
+          const float mean = nc > 0 ? sum / static_cast<float>(nc) : 0.f;
+          float m2 = 0.f;
+          for (int i = 0; i < nc; ++i) {
+            const float d = row[i] - mean;
+            m2 = fmaf(d, d, m2);
+          }
+          __stcg(P.ln_part + static_cast<long long>(cta) * P.ln_ld + tid, make_float4(static_cast<float>(nc), mean, m2, 0.f));
+        }
+      }
+    } else if (ph.type == DS_SELF) {
+      // ---- self-attention of the new position of every (row, head) over the row's lineage + kv append: model.py:124-127
+      //      with the cache of model.py:327-333 read through the parent table (decoding.py:172-176)
+      dl_mbar_wait(a_full, p & 1);
+      const int H = P.n_head, ctx = P.ctx, d = P.d;
+      const int L = *P.len_ptr, pos_new = L - 1;
+      const long long row_stride = static_cast<long long>(H) * ctx * 128;
+      for (int pair = cta; pair < R * H; pair += grid) {
+        const int row = pair / H, h = pair - row * H;
+        const uint8_t* qrow = static_cast<const uint8_t*>(P.qkv) + (static_cast<long long>(row) * 3 * d + h * 64) * 2 + c8 * 16;
+        float q[8];
+        att_load_q<T>(q, qrow);
+        const int* ind = P.indir + static_cast<long long>(row) * ctx;
+        uint8_t* kc = static_cast<uint8_t*>(ph.kc) + static_cast<long long>(h) * ctx * 128 + c8 * 16;
+        uint8_t* vc = static_cast<uint8_t*>(ph.vc) + static_cast<long long>(h) * ctx * 128 + c8 * 16;
+        AttAcc a;
+        att_init(a);
+        for (int b = warp; b * 4 < L; b += 2 * kDRComputeWarps) {          // two blocks of four keys in flight
+          uint4 kk[2], vv[2];
+          bool ok[2];
+#pragma unroll
+          for (int u = 0; u < 2; ++u) {
+            const int key = (b + u * kDRComputeWarps) * 4 + g4;
+            ok[u] = key < L;
+            kk[u] = vv[u] = make_uint4(0u, 0u, 0u, 0u);
+            if (key < pos_new) {
+              const long long off = static_cast<long long>(__ldg(ind + key)) * row_stride + static_cast<long long>(key) * 128;
+              kk[u] = __ldcg(reinterpret_cast<const uint4*>(kc + off));
+              vv[u] = __ldcg(reinterpret_cast<const uint4*>(vc + off));
+            } else if (key == pos_new) {
+              kk[u] = __ldcg(reinterpret_cast<const uint4*>(qrow + static_cast<long long>(d) * 2));
+              vv[u] = __ldcg(reinterpret_cast<const uint4*>(qrow + static_cast<long long>(d) * 4));
+            }
+          }
+#pragma unroll
+          for (int u = 0; u < 2; ++u) att_update<T>(a, q, kk[u], vv[u], ok[u]);
+        }
+        att_park(a, s_red + warp * 68);
+        asm volatile("bar.sync 1, 256;" ::: "memory");
+        if (warp == 0 && lane < 8) {
+          float m, l, o[8];
+          att_gather(s_red, kDRComputeWarps, lane, m, l, o);
+          *reinterpret_cast<uint4*>(static_cast<uint8_t*>(P.att) + (static_cast<long long>(row) * d + h * 64) * 2 + lane * 16) =
+              att_pack<T>(o, 1.0f / l);
+        } else if (warp == 1 && lane < 16) {
+          // the new position joins the cache of its own row (torch.cat of model.py:327-333)
+          const long long off = static_cast<long long>(row) * row_stride + static_cast<long long>(pos_new) * 128;
+          const uint4 v = __ldcg(reinterpret_cast<const uint4*>(qrow + static_cast<long long>(d) * (lane < 8 ? 2 : 4)));
+          *reinterpret_cast<uint4*>((lane < 8 ? kc : vc) + off) = v;
+        }
+        asm volatile("bar.sync 1, 256;" ::: "memory");
+      }
+    } else if (ph.type == DS_CROSS) {
+      // ---- cross-attention (model.py:101-109 + SDPA) of every (row, head) over a slice of the audio's keys; with one slice
+      //      the output is final, otherwise (m, l, o) partials for the DS_COMBINE phase
+      dl_mbar_wait(a_full, p & 1);
+      const int H = P.n_head, d = P.d, S = P.splits, Tn = P.T;
+      for (int item = cta; item < R * H * S; item += grid) {
+        const int pair = item / S, sp = item - pair * S;
+        const int row = pair / H, h = pair - row * H, audio = row / P.G;
+        const int k0 = static_cast<int>(static_cast<long long>(sp) * Tn / S), k1 = static_cast<int>(static_cast<long long>(sp + 1) * Tn / S);
+        float q[8];
+        att_load_q<T>(q, static_cast<const uint8_t*>(P.q) + (static_cast<long long>(row) * d + h * 64) * 2 + c8 * 16);
+        const uint8_t* kb = static_cast<const uint8_t*>(ph.kc) + (static_cast<long long>(audio) * 2 * H + h) * Tn * 128 + c8 * 16;
+        const uint8_t* vb = kb + static_cast<long long>(H) * Tn * 128;
+        AttAcc a;
+        att_init(a);
+        for (int b = warp; k0 + b * 4 < k1; b += 4 * kDRComputeWarps) {    // four blocks of four keys in flight
+          uint4 kk[4], vv[4];
+          bool ok[4];
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            const int key = k0 + (b + u * kDRComputeWarps) * 4 + g4;
+            ok[u] = key < k1;
+            kk[u] = vv[u] = make_uint4(0u, 0u, 0u, 0u);
+            if (ok[u]) {
+              kk[u] = __ldg(reinterpret_cast<const uint4*>(kb + static_cast<long long>(key) * 128));
+              vv[u] = __ldg(reinterpret_cast<const uint4*>(vb + static_cast<long long>(key) * 128));
+            }
+          }
+#pragma unroll
+          for (int u = 0; u < 4; ++u) att_update<T>(a, q, kk[u], vv[u], ok[u]);
+        }
+        att_park(a, s_red + warp * 68);
+        asm volatile("bar.sync 1, 256;" ::: "memory");
+        if (warp == 0 && lane < 8) {
+          float m, l, o[8];
+          att_gather(s_red, kDRComputeWarps, lane, m, l, o);
+          if (S == 1) {
+            *reinterpret_cast<uint4*>(static_cast<uint8_t*>(P.att) + (static_cast<long long>(row) * d + h * 64) * 2 + lane * 16) =
+                att_pack<T>(o, 1.0f / l);
+          } else {
+            float* dst = P.xpart + static_cast<long long>(item) * 66;
+#pragma unroll
+            for (int e = 0; e < 8; ++e) __stcg(dst + lane * 8 + e, o[e]);
+            if (lane == 0) {
+              __stcg(dst + 64, m);
+              __stcg(dst + 65, l);
+            }
+          }
+        }
+        asm volatile("bar.sync 1, 256;" ::: "memory");
+      }
+    } else {
+      // ---- DS_COMBINE: merge the key slices of every (row, head); a warp per pair, two output features per lane
+      dl_mbar_wait(a_full, p & 1);
+      const int H = P.n_head, d = P.d, S = P.splits;
+      for (int pair = cta + warp * grid; pair < R * H; pair += grid * kDRComputeWarps) {
+        const int row = pair / H, h = pair - row * H;
+        const float* src = P.xpart + static_cast<long long>(pair) * S * 66;
+        float m = -INFINITY;
+        for (int sp = 0; sp < S; ++sp) m = fmaxf(m, __ldcg(src + sp * 66 + 64));
+        float l = 0.f, o0 = 0.f, o1 = 0.f;
+        for (int sp = 0; sp < S; ++sp) {
+          const float ms = __ldcg(src + sp * 66 + 64);
+          const float f = ms == -INFINITY ? 0.f : fast_exp2(ms - m);
+          l = fmaf(__ldcg(src + sp * 66 + 65), f, l);
+          const float2 v = __ldcg(reinterpret_cast<const float2*>(src + sp * 66 + 2 * lane));
+          o0 = fmaf(v.x, f, o0);
+          o1 = fmaf(v.y, f, o1);
+        }
+        const float inv = 1.0f / l;
+        *reinterpret_cast<uint32_t*>(static_cast<uint8_t*>(P.att) + (static_cast<long long>(row) * d + h * 64 + 2 * lane) * 2) =
+            Cvt<T>::pack2(o0 * inv, o1 * inv);
       }
     }
     if (p + 1 < P.n_phases) {
@@ -752,6 +1008,8 @@ int dl_fill_phase(DLLaunch& L, int idx, int dtype, int R, int grid, const void* 
   ph.a = A;
   ph.lda = lda;
   ph.w = W;
+  ph.type = DS_LINEAR;
+  ph.kc = ph.vc = nullptr;
   if (bm == 0) bm = dl_auto_bm(R, N, K, flags);
   if ((bm != 64 && bm != 128) || (bm == 128 && (flags & DL_STATS))) return 7;
   ph.bm = bm;
@@ -804,36 +1062,64 @@ void dl_init_launch(DLLaunch& L, int dtype, int R, int grid, float4* ln_part, in
   L.p.skip_flag = skip_flag;
   L.p.trace = nullptr;
   L.p.dr_a_off = L.p.dr_tail_off = 0;
+  L.p.table = nullptr;
+  L.p.qkv = L.p.q = nullptr;
+  L.p.att = nullptr;
+  L.p.indir = L.p.len_ptr = nullptr;
+  L.p.xpart = nullptr;
+  L.p.n_head = L.p.ctx = L.p.T = L.p.G = L.p.splits = L.p.d = 0;
   L.rows_smem = 0;
 }
 
-bool dl_use_rows_form(DLLaunch& L) {
-  if (g_fused_rows < 0) {
-    const char* e = getenv("WB200_FUSED_ROWS");
-    g_fused_rows = (e && e[0] == '0') ? 0 : 1;
-  }
-  L.rows_smem = 0;
-  const DLParams& P = L.p;
-  if (!g_fused_rows || P.R > kDRMaxRows || P.n_phases <= 0) return false;
-  const int nt = P.R <= 8 ? 1 : (P.R <= 16 ? 2 : 4);       // 8-row operand tiles of the input rows
+// shared-memory layout of the few-rows form over a set of Linear phases; 0 if it does not fit
+static int dr_layout(const DLPhase* ph, int n, int R, int grid, int* a_off_out, int* tail_off_out) {
+  const int nt = R <= 8 ? 1 : (R <= 16 ? 2 : 4);       // 8-row operand tiles of the input rows
   long long w_bytes = 0, extent = 0, a_bytes = 0;
-  for (int p = 0; p < P.n_phases; ++p) {
-    const DLPhase& ph = P.ph[p];
-    if (ph.K % (16 * kDRComputeWarps) || ph.N < 1) return false;
-    const long long stride = ph.K * 2LL + 16;
-    const int nc_max = (ph.N + L.grid - 1) / L.grid;
-    if (nc_max > kDRMaxTiles * 16) return false;
+  int n_linear = 0;
+  for (int p = 0; p < n; ++p) {
+    if (ph[p].type != DS_LINEAR) continue;
+    ++n_linear;
+    if (ph[p].K % (16 * kDRComputeWarps) || ph[p].N < 1) return 0;
+    const long long stride = ph[p].K * 2LL + 16;
+    const int nc_max = (ph[p].N + grid - 1) / grid;
+    if (nc_max > kDRCols) return 0;
     w_bytes = std::max(w_bytes, nc_max * stride);
     extent = std::max(extent, ((nc_max + 15) / 16 * 16) * stride);     // ldmatrix reads whole 16-row tiles
     a_bytes = std::max(a_bytes, 8LL * nt * stride);
   }
+  if (!n_linear) return 0;
   const long long a_off = (w_bytes + 127) / 128 * 128;
   const long long tail_off = (std::max(a_off + a_bytes, extent) + 127) / 128 * 128;
   const long long total = tail_off + dr_tail_bytes(nt) + 128;
-  if (total > 227 * 1024) return false;
-  L.p.dr_a_off = static_cast<int>(a_off);
-  L.p.dr_tail_off = static_cast<int>(tail_off);
-  L.rows_smem = static_cast<int>(total);
+  if (total > 227 * 1024) return 0;
+  *a_off_out = static_cast<int>(a_off);
+  *tail_off_out = static_cast<int>(tail_off);
+  return static_cast<int>(total);
+}
+
+static bool rows_form_enabled() {
+  if (g_fused_rows < 0) {
+    const char* e = getenv("WB200_FUSED_ROWS");
+    g_fused_rows = (e && e[0] == '0') ? 0 : 1;
+  }
+  return g_fused_rows != 0;
+}
+
+bool dl_use_rows_form(DLLaunch& L) {
+  L.rows_smem = 0;
+  L.p.table = nullptr;
+  if (!rows_form_enabled() || L.p.R > kDRMaxRows || L.p.n_phases <= 0) return false;
+  L.rows_smem = dr_layout(L.p.ph, L.p.n_phases, L.p.R, L.grid, &L.p.dr_a_off, &L.p.dr_tail_off);
+  return L.rows_smem > 0;
+}
+
+bool dl_plan_stack(DLLaunch& L, const DLPhase* host_table, int n, const DLPhase* device_table) {
+  L.rows_smem = 0;
+  if (!rows_form_enabled() || L.p.R > kDRMaxRows || n <= 0) return false;
+  L.rows_smem = dr_layout(host_table, n, L.p.R, L.grid, &L.p.dr_a_off, &L.p.dr_tail_off);
+  if (L.rows_smem <= 0) return false;
+  L.p.table = device_table;
+  L.p.n_phases = n;
   return true;
 }
 

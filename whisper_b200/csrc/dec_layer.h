@@ -11,6 +11,9 @@ constexpr int kDLUnit = 16;        // output columns per work unit (one tcgen05.
 constexpr int kDLMaxUnits = 12;    // widest per-CTA tile: 192 columns
 
 enum { DL_FOLD = 1, DL_GELU = 2, DL_RESID = 4, DL_STATS = 8 };
+// phase kinds (few-rows form only; the tile form knows Linear phases): Linear, self-attention + kv append over the
+// rows' lineages, cross-attention partials over a slice of the audio keys, merge of those partials
+enum { DS_LINEAR = 0, DS_SELF = 1, DS_CROSS = 2, DS_COMBINE = 3 };
 
 // One Linear of the chain.  DL_FOLD: the input is LayerNorm(x) - W holds W (.) gamma, c1 / c2 the fold vectors, the row
 // statistics come from the LN partials left by the producer of x.  DL_RESID: out is the residual stream,
@@ -29,6 +32,9 @@ struct DLPhase {
   const void* a;          // T [R, lda] input rows and T [N, K] weights as plain pointers (few-rows form; the tile form
   long long lda;          // reads them through the tensor maps)
   const void* w;
+  int type;               // DS_*
+  void* kc;               // DS_SELF: this layer's self K / V caches [row][H][ctx][64]; DS_CROSS: kc = the layer's cross K/V
+  void* vc;               //          block [audio][2H][T][64]
 };
 
 struct DLParams {
@@ -44,6 +50,16 @@ struct DLParams {
   // 6 next phase released (poller), 7 LN statistics gathered
   unsigned long long* trace;
   int dr_a_off, dr_tail_off;   // few-rows form: shared-memory offsets of the input rows and of the scratch tail
+  // few-rows form, whole decoder stack in one launch: the phases come from a table in global memory (n_phases entries)
+  // and include the attention of every layer
+  const DLPhase* table;
+  const void* qkv;             // [R, 3d] q | k | v of the new position (output of the QKV phases)
+  const void* q;               // [R, d]  cross-attention queries
+  void* att;                   // [R, d]  attention output
+  const int* indir;            // [R, ctx] position -> physical cache row
+  const int* len_ptr;          // tokens per row including the new one
+  float* xpart;                // [R * H][splits][66] cross-attention partials (m, l, o[64])
+  int n_head, ctx, T, G, splits, d;
   DLPhase ph[kDLMaxPhases];
 };
 
@@ -56,6 +72,7 @@ struct alignas(64) DLMaps {
 struct DLLaunch {
   int dtype = 0;
   int grid = 0;
+  int max_k = 0, max_cols = 0;   // few-rows stack form: extremes over the table's Linear phases (shared-memory layout)
   int rows_smem = 0;      // > 0: launch the few-rows form (dec_rows_kernel) with this much dynamic shared memory
   DLParams p;
   DLMaps maps;
@@ -64,6 +81,7 @@ struct DLLaunch {
 constexpr int kDRMaxRows = 32;     // the few-rows form covers R <= 32 (1, 2 or 4 mma.sync n = 8 operand tiles) where shared memory allows
 
 extern int g_fused_layer;
+extern int g_fused_stack;          // few-rows sessions: whole stack in one launch (wb200_set_fused_decoder_stack / WB200_FUSED_STACK, default on)
 extern int g_fused_rows;           // few-rows form for R <= kDRMaxRows (wb200_set_fused_decoder_rows / WB200_FUSED_ROWS, default on)
 int dl_grid_size();
 bool dl_supported(int R, int d, int grid);
@@ -75,6 +93,9 @@ int dl_fill_phase(DLLaunch& L, int idx, int dtype, int R, int grid, const void* 
 // after every phase is filled: switch the launch to the few-rows form if it applies (R <= kDRMaxRows, slab + rows fit);
 // returns true when it did
 bool dl_use_rows_form(DLLaunch& L);
+// whole-stack launch of the few-rows form: `host_table` (n entries, Linear phases filled with dl_fill_phase-compatible
+// fields, attention phases with type / kc / vc) is checked for shared-memory fit; returns false if the form does not apply
+bool dl_plan_stack(DLLaunch& L, const DLPhase* host_table, int n, const DLPhase* device_table);
 int dl_launch(const DLLaunch& L, cudaStream_t s);
 
 }  // namespace wb

@@ -325,6 +325,7 @@ static void dec_carve(const Model* m, const wb200_decode_config& c, Arena& ar, D
   o->ln_ld = static_cast<int>((R + 63) / 64 * 64);
   o->ln_part = static_cast<float4*>(ar.take(static_cast<size_t>(256) * o->ln_ld * sizeof(float4)));
   o->dl_sync = static_cast<unsigned int*>(ar.take(256));
+  o->stack_table = static_cast<DLPhase*>(ar.take((static_cast<size_t>(9) * NL + 2) * sizeof(DLPhase)));
 }
 
 size_t decoder_workspace_bytes(const Model* m, const wb200_decode_config* c) {
@@ -337,7 +338,69 @@ size_t decoder_workspace_bytes(const Model* m, const wb200_decode_config* c) {
 //   head[l] = {QKV}                                   (used for layer 0 only; other layers get it from the previous tail)
 //   mid[l]  = {out-proj + residual, cross-query}
 //   tail[l] = {cross-out + residual, fc1 + GELU, fc2 + residual, QKV of layer l + 1}
-static int build_fused_plan(Decoder* D) {
+// Few-rows sessions (every chain of the plan in the few-rows form, head-major caches): string the chains and the two
+// attentions of every layer into ONE phase table - [QKV0] then per layer {self-attention, out-proj, cross-query,
+// cross-attention (+ merge of its key slices), cross-out, fc1, fc2, next layer's QKV} - for a single launch per iteration.
+static int build_stack_plan(Decoder* D, cudaStream_t s) {
+  const Model* m = D->m;
+  D->stack_ready = false;
+  if (g_fused_stack < 0) {
+    const char* e = getenv("WB200_FUSED_STACK");
+    g_fused_stack = (e && e[0] == '0') ? 0 : 1;
+  }
+  const int NL = m->dims.n_text_layer, H = m->dims.n_text_head, d = m->dims.n_text_state, ctx = m->dims.n_text_ctx;
+  const int Ta = m->dims.n_audio_ctx, B = D->cfg.n_audio, G = D->cfg.n_group, R = B * G;
+  if (!g_fused_stack || !D->kv_head_major || D->kv_window || d != H * 64) return 0;
+  for (int l = 0; l < NL; ++l)
+    if (D->dl_mid[l].rows_smem <= 0 || D->dl_tail[l].rows_smem <= 0 || (l == 0 && D->dl_head[0].rows_smem <= 0)) return 0;
+  const int grid = D->dl_head[0].grid;
+  const int pairs = R * H;
+  int splits = grid / pairs;                       // key slices per (row, head) of the cross-attention
+  if (splits < 1) splits = 1;
+  if (splits > Ta / 64) splits = Ta / 64 > 0 ? Ta / 64 : 1;
+  const size_t nq = D->cfg.n_init > G ? D->cfg.n_init : G;
+  if (static_cast<size_t>(pairs) * splits * 66 > cross_attention_partial_floats(B, static_cast<int>(nq), H, Ta)) return 0;
+  const size_t cross_per_layer = static_cast<size_t>(B) * Ta * 2 * d * 2;
+  const size_t self_per_layer = static_cast<size_t>(R) * ctx * d * 2;
+  std::vector<DLPhase>& tab = D->stack_host;
+  tab.clear();
+  auto attention = [&](int type, void* kc, void* vc) {
+    DLPhase ph = {};
+    ph.type = type;
+    ph.kc = kc;
+    ph.vc = vc;
+    tab.push_back(ph);
+  };
+  tab.push_back(D->dl_head[0].p.ph[0]);
+  for (int l = 0; l < NL; ++l) {
+    attention(DS_SELF, static_cast<uint8_t*>(D->self_k) + l * self_per_layer, static_cast<uint8_t*>(D->self_v) + l * self_per_layer);
+    for (int i = 0; i < D->dl_mid[l].p.n_phases; ++i) tab.push_back(D->dl_mid[l].p.ph[i]);
+    attention(DS_CROSS, static_cast<uint8_t*>(D->cross_kv) + l * cross_per_layer, nullptr);
+    if (splits > 1) attention(DS_COMBINE, nullptr, nullptr);
+    for (int i = 0; i < D->dl_tail[l].p.n_phases; ++i) tab.push_back(D->dl_tail[l].p.ph[i]);
+  }
+  if (tab.size() > static_cast<size_t>(9) * NL + 2) return 80;
+  DLLaunch& S = D->dl_stack;
+  dl_init_launch(S, m->dtype, R, grid, D->ln_part, D->ln_ld, D->dl_sync, D->done_ptr, 1);
+  if (!dl_plan_stack(S, tab.data(), static_cast<int>(tab.size()), D->stack_table)) return 0;
+  if (cudaMemcpyAsync(D->stack_table, tab.data(), tab.size() * sizeof(DLPhase), cudaMemcpyHostToDevice, s) != cudaSuccess) return 81;
+  S.p.qkv = D->qkv;
+  S.p.q = D->q;
+  S.p.att = D->att;
+  S.p.indir = D->indir[0];                // set per launch (the parent tables ping-pong)
+  S.p.len_ptr = D->len_ptr;
+  S.p.xpart = D->partial;
+  S.p.n_head = H;
+  S.p.ctx = ctx;
+  S.p.T = Ta;
+  S.p.G = G;
+  S.p.splits = splits;
+  S.p.d = d;
+  D->stack_ready = true;
+  return 0;
+}
+
+static int build_fused_plan(Decoder* D, cudaStream_t s) {
   const Model* m = D->m;
   D->fused = false;
   if (g_fused_layer < 0) {
@@ -387,7 +450,7 @@ static int build_fused_plan(Decoder* D) {
     dl_use_rows_form(Ta);
   }
   D->fused = true;
-  return 0;
+  return build_stack_plan(D, s);
 }
 
 int decoder_create(const Model* m, const wb200_decode_config* c, void* ws, size_t ws_bytes, Decoder** out,
@@ -409,8 +472,9 @@ int decoder_create(const Model* m, const wb200_decode_config* c, void* ws, size_
     g_xattn_tma = (e && e[0] == '0') ? 0 : 1;
   }
   if (g_sattn_tma < 0) {
+    // opt-in: measured slower than the gather kernel at the headline shape (profiles/r2_summary.md section 4)
     const char* e = getenv("WB200_SATTN_TMA");
-    g_sattn_tma = (e && e[0] == '0') ? 0 : 1;
+    g_sattn_tma = (e && e[0] == '1') ? 1 : 0;
   }
   D->kv_head_major = g_kv_head_major != 0;
   // beam-window self caches only where the kernel that wants them runs (fixed per session: the layout cannot change later)
@@ -463,7 +527,7 @@ int decoder_create(const Model* m, const wb200_decode_config* c, void* ws, size_
     }
   }
   {
-    int r = build_fused_plan(D);
+    int r = build_fused_plan(D, s);
     if (r) {
       cudaFreeHost(D->pinned);
       delete D;
@@ -525,6 +589,11 @@ static int decoder_stack(Decoder* D, int rows, bool step, cudaStream_t s) {
   const size_t cross_per_layer = static_cast<size_t>(B) * Ta * 2 * d * 2;
   const size_t self_per_layer = static_cast<size_t>(R) * ctx * d * 2;
   const int n_q = step ? G : D->cfg.n_init;
+  if (step && D->fused && D->stack_ready) {
+    // few rows: the whole stack - Linear chains and both attentions of every layer - in one persistent launch
+    D->dl_stack.p.indir = D->indir[D->cur];
+    return dl_launch(D->dl_stack, s);
+  }
   if (step && D->fused) {
     // fused GEMM chains (dec_layer.cu) around the two attention kernels: 4 launches per layer instead of 11
     for (int l = 0; l < m->dims.n_text_layer; ++l) {

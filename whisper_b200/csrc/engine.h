@@ -100,6 +100,12 @@ struct Decoder {
   // theirs from the previous layer's tail), [out-proj, cross-query], [cross-out, fc1, fc2, next layer's QKV]
   bool fused = false;
   std::vector<DLLaunch> dl_head, dl_mid, dl_tail;
+  // few-rows sessions: the whole decoder stack of an iteration (every Linear chain AND both attentions of every layer) as
+  // ONE launch of dec_rows_kernel driven by a phase table in device memory
+  bool stack_ready = false;
+  DLLaunch dl_stack;
+  std::vector<DLPhase> stack_host;
+  DLPhase* stack_table = nullptr;   // device copy of stack_host
   float4* ln_part = nullptr;        // LN partial statistics of the residual stream
   int ln_ld = 0;
   unsigned int* dl_sync = nullptr;  // grid-barrier / exit counters of the fused kernel

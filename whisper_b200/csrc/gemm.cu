@@ -26,7 +26,7 @@ namespace wb {
 
 int g_pdl_on = -1;      // -1: read WB200_PDL on first use (default on); wb200_set_pdl() overrides
 int g_kv_head_major = -1;   // -1: read WB200_KV_HEAD_MAJOR on first decoder_create (default on)
-int g_sattn_tma = -1;       // -1: read WB200_SATTN_TMA on first decoder_create (default on)
+int g_sattn_tma = -1;       // -1: read WB200_SATTN_TMA on first decoder_create (default off)
 int g_xattn_tma = -1;       // -1: read WB200_XATTN_TMA on first decoder_create (default on)
 int g_bm64_on = 1;      // wb200_set_option("bm64", 0/1): 64-row tiles for skinny problems
 int g_splitk_on = -1;   // -1: read WB200_SPLITK on first use; wb200_set_splitk() overrides

@@ -163,7 +163,7 @@ bool self_attention_tma_covers(int n_audio, int G, int n_head, int max_ctx);
 int launch_self_attention_tma(int dtype, const void* qkv, void* kcache, void* vcache, void* out, const int* indir,
                               const int* len_ptr, const int* skip_flag, int n_audio, int G, int n_head, int max_ctx,
                               cudaStream_t s);
-extern int g_sattn_tma;       // wb200_set_self_attention_tma / WB200_SATTN_TMA (default on)
+extern int g_sattn_tma;       // wb200_set_self_attention_tma / WB200_SATTN_TMA=1 (default off: measured slower)
 // step mode (indir != null): one new position per row, appended to the cache; prefill mode
 // (indir == null): n_init positions per audio, causal, cache rows a*group.
 int launch_self_attention(int dtype, const void* qkv, void* kcache, void* vcache, void* out,

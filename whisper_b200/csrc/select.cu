@@ -21,6 +21,7 @@ namespace wb {
 constexpr int kSelThreads = 512;
 constexpr int kMaxTopK = 17;  // beam <= 16
 constexpr int kSelCluster = 8; // CTAs per row when there are few rows (portable cluster size)
+constexpr int kSelUnroll = 4;  // 16-byte loads in flight per thread in the vocabulary scans
 
 // total order used everywhere: larger value first, then smaller index
 __device__ __forceinline__ bool better(float va, int ia, float vb, int ib) {
@@ -232,14 +233,30 @@ __global__ void __launch_bounds__(kSelThreads) filter_topk_kernel(const FilterPa
     if (val == -INFINITY || masked(v, sw, bw)) return;
     if (v < tb) lse_merge(m_txt, s_txt, val, 1.f); else lse_merge(m_ts, s_ts, val, 1.f);
   };
-  for (int q = q_lo + tid; q < q_hi; q += kSelThreads) {
-    const float4 f = x4[q];
-    const int v = q << 2;
-    const uint32_t sw = __ldg(p.suppress_mask + (v >> 5)), bw = use_blank ? __ldg(p.blank_mask + (v >> 5)) : 0u;
-    acc1(v, f.x, sw, bw);
-    acc1(v + 1, f.y, sw, bw);
-    acc1(v + 2, f.z, sw, bw);
-    acc1(v + 3, f.w, sw, bw);
+  // four independent 16-byte loads in flight per thread: the scan is latency-bound (one CTA reads a 207 KB row)
+  for (int q = q_lo + tid; q < q_hi; q += kSelUnroll * kSelThreads) {
+    float4 f[kSelUnroll];
+    uint32_t sw[kSelUnroll], bw[kSelUnroll];
+#pragma unroll
+    for (int u = 0; u < kSelUnroll; ++u) {
+      const int qq = q + u * kSelThreads;
+      if (qq < q_hi) {
+        f[u] = x4[qq];
+        sw[u] = __ldg(p.suppress_mask + (qq >> 3));
+        bw[u] = use_blank ? __ldg(p.blank_mask + (qq >> 3)) : 0u;
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < kSelUnroll; ++u) {
+      const int qq = q + u * kSelThreads;
+      if (qq < q_hi) {
+        const int v = qq << 2;
+        acc1(v, f[u].x, sw[u], bw[u]);
+        acc1(v + 1, f[u].y, sw[u], bw[u]);
+        acc1(v + 2, f[u].z, sw[u], bw[u]);
+        acc1(v + 3, f[u].w, sw[u], bw[u]);
+      }
+    }
   }
   if (has_tail && tid < (p.V & 3)) {
     const int v = (V4 << 2) + tid;
@@ -312,14 +329,29 @@ __global__ void __launch_bounds__(kSelThreads) filter_topk_kernel(const FilterPa
     if (sampling) val = fmaf(val, p.inv_temp, gumbel_noise(p.seed_lo, p.seed_hi, r, L, v));
     mine.push(val, v);
   };
-  for (int q = q_lo + tid; q < q_hi; q += kSelThreads) {
-    const float4 f = x4[q];
-    const int v = q << 2;
-    const uint32_t sw = __ldg(p.suppress_mask + (v >> 5)), bw = use_blank ? __ldg(p.blank_mask + (v >> 5)) : 0u;
-    acc2(v, f.x, sw, bw);
-    acc2(v + 1, f.y, sw, bw);
-    acc2(v + 2, f.z, sw, bw);
-    acc2(v + 3, f.w, sw, bw);
+  for (int q = q_lo + tid; q < q_hi; q += kSelUnroll * kSelThreads) {
+    float4 f[kSelUnroll];
+    uint32_t sw[kSelUnroll], bw[kSelUnroll];
+#pragma unroll
+    for (int u = 0; u < kSelUnroll; ++u) {
+      const int qq = q + u * kSelThreads;
+      if (qq < q_hi) {
+        f[u] = x4[qq];
+        sw[u] = __ldg(p.suppress_mask + (qq >> 3));
+        bw[u] = use_blank ? __ldg(p.blank_mask + (qq >> 3)) : 0u;
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < kSelUnroll; ++u) {
+      const int qq = q + u * kSelThreads;
+      if (qq < q_hi) {
+        const int v = qq << 2;
+        acc2(v, f[u].x, sw[u], bw[u]);
+        acc2(v + 1, f[u].y, sw[u], bw[u]);
+        acc2(v + 2, f[u].z, sw[u], bw[u]);
+        acc2(v + 3, f[u].w, sw[u], bw[u]);
+      }
+    }
   }
   if (has_tail && tid < (p.V & 3)) {
     const int v = (V4 << 2) + tid;
@@ -593,8 +625,8 @@ int launch_filter_topk(const FilterParams& p, int R, cudaStream_t s) {
   if (p.K < 1 || p.K > kMaxTopK) return 50;
   ProfileScope prof(PROF_SELECT, s);
   if ((reinterpret_cast<uintptr_t>(p.logits) & 15) || (p.ld & 3)) return 50;      // rows are read with 16-byte loads
-  if (R * kSelCluster <= sm_count()) {
-    // few rows: a cluster of CTAs per row
+  if (R * kSelCluster <= 2 * sm_count()) {
+    // few rows (one wave at two CTAs per SM): a cluster of CTAs per row
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(R * kSelCluster);
     cfg.blockDim = dim3(kSelThreads);
