@@ -25,7 +25,10 @@ DTYPES = [torch.float16, torch.bfloat16]
 # relative error per layer.
 # LOGIT_TOL is relative to the largest |logit| of the step (the synthetic models have heavy-tailed logits)
 LOGIT_TOL = {torch.float16: 2.5e-3, torch.bfloat16: 2.5e-2}
-TAU = {torch.float16: 0.12, torch.bfloat16: 1.0}
+# TAU (absolute logit units): a decision is only asserted where the oracle's margin exceeds twice the worst logit error a
+# correct 16-bit pipeline shows under teacher forcing - 1.5e-3 (fp16) / 1.5e-2 (bf16) of the largest |logit| (~40 for the
+# synthetic models), measured across the kernel forms (tile / few-rows / one-launch stack differ in summation order only)
+TAU = {torch.float16: 0.12, torch.bfloat16: 1.5}
 FEAT_TOL = {torch.float16: 0.02, torch.bfloat16: 0.12}
 
 _MODELS = {}

@@ -482,9 +482,9 @@ constexpr int kDRThreads = (kDRComputeWarps + 1) * 32;
 constexpr int kDRMaxTiles = 3;                                  // 16-feature tiles per CTA and phase (N / grid <= 48)
 constexpr int kDRCols = kDRMaxTiles * 16;
 // scratch tail for NT 8-row operand tiles (R <= 8 NT): fp32 partial sums [warp][tile][16][8 NT], stored values
-// [8 NT][48], mean | rstd per row, three mbarriers
+// [8 NT][48], mean | rstd per row, four mbarriers
 __host__ __device__ constexpr int dr_red_floats(int nt) { return kDRComputeWarps * kDRMaxTiles * 16 * 8 * nt; }
-__host__ __device__ constexpr int dr_tail_bytes(int nt) { return (dr_red_floats(nt) + 8 * nt * kDRCols + 2 * 8 * nt) * 4 + 3 * 8 + 64; }
+__host__ __device__ constexpr int dr_tail_bytes(int nt) { return (dr_red_floats(nt) + 8 * nt * kDRCols + 2 * 8 * nt) * 4 + 4 * 8 + 64; }
 
 // ---- attention inside the few-rows kernel: one query row, keys in blocks of four per warp.  Lane = (key of the block
 // g = lane / 8, 16-byte chunk c = lane % 8 of the 64-wide head): every load instruction fetches four complete 128-byte K
@@ -592,6 +592,12 @@ __device__ __forceinline__ uint4 att_pack(const float (&o)[8], float inv) {
   return u;
 }
 
+// features of a CTA's share that fit the slab buffer (the region in front of the input rows) at once
+__host__ __device__ __forceinline__ int dr_slab_cols(int w_region_bytes, int K) {
+  const int c = w_region_bytes / (K * 2 + 16);
+  return c > kDRCols ? kDRCols : (c < 1 ? 1 : c);
+}
+
 template <typename T, int NT>
 __global__ void __launch_bounds__(kDRThreads, 1) dec_rows_kernel(const DLParams P) {
   constexpr int RMAX = 8 * NT;
@@ -605,8 +611,9 @@ __global__ void __launch_bounds__(kDRThreads, 1) dec_rows_kernel(const DLParams 
   float* s_out = s_red + dr_red_floats(NT);                         // [row][feature]: the values as stored
   float* s_stat = s_out + RMAX * kDRCols;                           // mean[RMAX] | rstd[RMAX]
   uint64_t* w_full = reinterpret_cast<uint64_t*>(s_stat + 2 * RMAX);
-  uint64_t* a_full = w_full + 1;
+  uint64_t* a_full = w_full + 1;      // the input rows of a Linear phase have landed
   uint64_t* w_empty = w_full + 2;
+  uint64_t* go = w_full + 3;          // phase p may start: the grid barrier behind phase p - 1 has opened
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, tid = threadIdx.x;
   const int grid = gridDim.x, cta = blockIdx.x;
   const int R = P.R;
@@ -614,6 +621,7 @@ __global__ void __launch_bounds__(kDRThreads, 1) dec_rows_kernel(const DLParams 
     mbar_init(w_full, 1);
     mbar_init(a_full, 1);
     mbar_init(w_empty, 1);
+    mbar_init(go, 1);
     mbar_fence_init();
   }
   __syncthreads();
@@ -630,19 +638,23 @@ __global__ void __launch_bounds__(kDRThreads, 1) dec_rows_kernel(const DLParams 
 
   if (warp == kDRComputeWarps) {
     // ===================== control warp: bulk copies and the grid barrier =====================
-    auto issue_w = [&](int p) {
+    // slab j of Linear phase p: the weight rows of this CTA's features [j * cap, (j + 1) * cap) - one slab per phase unless
+    // the CTA owns more features than the buffer holds (the logits: 351 features of K = 1280 -> 10 slabs)
+    auto issue_w = [&](int p, int j) {
       const DLPhase ph = phase(p);
       const int n0 = static_cast<int>(static_cast<long long>(cta) * ph.N / grid);
       const int nc = static_cast<int>(static_cast<long long>(cta + 1) * ph.N / grid) - n0;
       const uint32_t row_bytes = static_cast<uint32_t>(ph.K) * 2;
-      if (lane == 0) mbar_expect_tx(w_full, static_cast<uint32_t>(nc) * row_bytes);
+      const int cap = dr_slab_cols(P.dr_a_off, ph.K);
+      const int c0 = j * cap, ncc = min(cap, nc - c0);
+      if (lane == 0) mbar_expect_tx(w_full, static_cast<uint32_t>(ncc) * row_bytes);
       __syncwarp();
-      for (int i = lane; i < nc; i += 32)
-        bulk_load_1d(sW + static_cast<size_t>(i) * (row_bytes + 16), static_cast<const uint8_t*>(ph.w) + static_cast<size_t>(n0 + i) * row_bytes,
-                     row_bytes, w_full);
+      for (int i = lane; i < ncc; i += 32)
+        bulk_load_1d(sW + static_cast<size_t>(i) * (row_bytes + 16),
+                     static_cast<const uint8_t*>(ph.w) + static_cast<size_t>(n0 + c0 + i) * row_bytes, row_bytes, w_full);
     };
     int lin = next_linear(0);            // the Linear phase whose slab is in flight / resident
-    if (lin < P.n_phases) issue_w(lin);  // weights are constants: the first slab streams in under the tail of the previous kernel
+    if (lin < P.n_phases) issue_w(lin, 0);  // weights are constants: the first slab streams in under the tail of the previous kernel
     pdl_wait();
     if (P.skip_flag && *P.skip_flag) {
       if (lin < P.n_phases) dl_mbar_wait(w_full, 0);  // never leave with a copy into this CTA's shared memory in flight
@@ -660,11 +672,9 @@ __global__ void __launch_bounds__(kDRThreads, 1) dec_rows_kernel(const DLParams 
           if (++spins > (1ll << 23)) __trap();
         }
       }
-      if (p != lin) {                    // an attention phase: nothing to stage, just let the compute warps go
-        __syncwarp();
-        if (lane == 0) mbar_arrive(a_full);
-        continue;
-      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(go);    // the compute warps start on what needs no staging (LN statistics, residual rows, attention)
+      if (p != lin) continue;            // an attention / LayerNorm phase: nothing to stage
       const DLPhase ph = phase(p);
       fence_proxy_async_global();        // other CTAs' generic-proxy stores -> this lane's bulk (async-proxy) reads
       const uint32_t row_bytes = static_cast<uint32_t>(ph.K) * 2;
@@ -673,10 +683,19 @@ __global__ void __launch_bounds__(kDRThreads, 1) dec_rows_kernel(const DLParams 
       if (lane < R)                      // R <= 32: one input row per lane
         bulk_load_1d(sA + static_cast<size_t>(lane) * (row_bytes + 16), static_cast<const uint8_t*>(ph.a) + static_cast<size_t>(lane) * ph.lda * 2,
                      row_bytes, a_full);
+      {
+        const int nc = static_cast<int>(static_cast<long long>(cta + 1) * ph.N / grid) - static_cast<int>(static_cast<long long>(cta) * ph.N / grid);
+        const int cap = dr_slab_cols(P.dr_a_off, ph.K);
+        for (int j = 1; j * cap < nc; ++j) {   // further slabs of this phase, each once the previous one has been consumed
+          dl_mbar_wait(w_empty, slab & 1);
+          ++slab;
+          issue_w(p, j);
+        }
+      }
       lin = next_linear(p + 1);
       if (lin < P.n_phases) {
         dl_mbar_wait(w_empty, slab & 1); // every compute warp is done with the slab and the input rows of phase p
-        issue_w(lin);                    // streams in while phase p finishes and the attention phases in between run
+        issue_w(lin, 0);                 // streams in while phase p finishes and the attention phases in between run
       }
       ++slab;
     }
@@ -688,36 +707,16 @@ __global__ void __launch_bounds__(kDRThreads, 1) dec_rows_kernel(const DLParams 
   if (P.skip_flag && *P.skip_flag) return;
   const int g = lane >> 2, t4 = lane & 3;
   const int g4 = lane >> 3, c8 = lane & 7;                    // attention: key of the block, 16-byte chunk
-  int slab = 0;
+  int slab = 0, n_lin = 0;
   for (int p = 0; p < P.n_phases; ++p) {
     const DLPhase ph = phase(p);
     if (ph.type == DS_LINEAR) {
       const int n0 = static_cast<int>(static_cast<long long>(cta) * ph.N / grid);
       const int nc = static_cast<int>(static_cast<long long>(cta + 1) * ph.N / grid) - n0;
-      const int n_tiles = (nc + 15) >> 4;
+      const int cap = dr_slab_cols(P.dr_a_off, ph.K);            // features per slab (all of them except for the logits)
       const int stride = ph.K * 2 + 16;
       const bool fold = (ph.flags & DL_FOLD) != 0;
-      // ---- this thread's <= J output elements (row, feature) and their constants, before anything has to be waited for
-      const int n_out = nc * R;
-      int o_r[J], o_n[J];
-      float o_c1[J], o_c2[J];
-#pragma unroll
-      for (int j = 0; j < J; ++j) {
-        const int o = tid + j * 256;
-        o_r[j] = o < n_out ? o / nc : -1;
-        o_n[j] = o < n_out ? o - o_r[j] * nc : 0;
-        o_c1[j] = o_c2[j] = 0.f;
-        if (o_r[j] >= 0) {
-          const int n = n0 + o_n[j];
-          if (fold) {
-            o_c1[j] = __ldg(ph.c1 + n);
-            o_c2[j] = __ldg(ph.c2 + n);
-          } else {
-            o_c1[j] = Cvt<T>::to_f(__ldg(reinterpret_cast<const T*>(ph.bias) + n));
-          }
-        }
-      }
-      dl_mbar_wait(a_full, p & 1);         // the previous phase is complete grid-wide (the control warp saw the barrier open)
+      dl_mbar_wait(go, p & 1);           // the previous phase is complete grid-wide (the control warp saw the barrier open)
       // ---- LayerNorm statistics of rows warp, warp + 8, .. from the partials their producer left (model.py:39-41, eps 1e-5)
       if (fold) {
         const int slots = (p == 0 && P.ln_slots_in > 0) ? P.ln_slots_in : grid;
@@ -739,75 +738,100 @@ __global__ void __launch_bounds__(kDRThreads, 1) dec_rows_kernel(const DLParams 
           }
         }
       }
-      float o_x[J];
+      for (int c0 = 0; c0 == 0 || c0 < nc; c0 += cap) {          // one slab per pass (an empty share still consumes its slab)
+        const int ncc = max(0, min(cap, nc - c0));
+        const int n_tiles = (ncc + 15) >> 4;
+        // ---- this thread's <= J output elements (row, feature) of the slab and their constants
+        const int n_out = ncc * R;
+        int o_r[J], o_n[J];
+        float o_c1[J], o_c2[J], o_x[J];
 #pragma unroll
-      for (int j = 0; j < J; ++j) {
-        o_x[j] = 0.f;
-        if ((ph.flags & DL_RESID) && o_r[j] >= 0)
-          o_x[j] = Cvt<T>::to_f(__ldcg(reinterpret_cast<const T*>(ph.out) + o_r[j] * ph.ldo + n0 + o_n[j]));
-      }
-      // ---- main loop: this warp's eighth of K for every 16-feature tile
-      float acc[kDRMaxTiles][NT][4];
-#pragma unroll
-      for (int t = 0; t < kDRMaxTiles; ++t)
-#pragma unroll
-        for (int u = 0; u < NT; ++u)
-#pragma unroll
-          for (int i = 0; i < 4; ++i) acc[t][u][i] = 0.f;
-      dl_mbar_wait(w_full, slab & 1);
-      {
-        const int kw = ph.K / kDRComputeWarps;
-        // ldmatrix x4 on the slab: matrices (features 0-7, k 0-7), (8-15, k 0-7), (0-7, k 8-15), (8-15, k 8-15) = a0..a3
-        const uint8_t* wrow = sW + static_cast<size_t>((lane & 7) + ((lane >> 3) & 1) * 8) * stride + (lane >> 4) * 16;
-        // ldmatrix x2 on 8 input rows: (rows 0-7, k 0-7), (rows 0-7, k 8-15) = b0, b1
-        const uint8_t* arow = sA + static_cast<size_t>(lane & 7) * stride + ((lane >> 3) & 1) * 16;
-        for (int k0 = warp * kw; k0 < (warp + 1) * kw; k0 += 16) {
-          uint32_t b[NT][2];
-#pragma unroll
-          for (int u = 0; u < NT; ++u) ldmatrix_x2(b[u], arow + static_cast<size_t>(u) * 8 * stride + k0 * 2);
-#pragma unroll
-          for (int t = 0; t < kDRMaxTiles; ++t)
-            if (t < n_tiles) {
-              uint32_t a[4];
-              ldmatrix_x4(a, wrow + static_cast<size_t>(t) * 16 * stride + k0 * 2);
-#pragma unroll
-              for (int u = 0; u < NT; ++u) mma16816<T>(acc[t][u], a, b[u][0], b[u][1]);
+        for (int j = 0; j < J; ++j) {
+          const int o = tid + j * 256;
+          o_r[j] = o < n_out ? o / ncc : -1;
+          o_n[j] = o < n_out ? o - o_r[j] * ncc : 0;
+          o_c1[j] = o_c2[j] = o_x[j] = 0.f;
+          if (o_r[j] >= 0) {
+            const int n = n0 + c0 + o_n[j];
+            if (fold) {
+              o_c1[j] = __ldg(ph.c1 + n);
+              o_c2[j] = __ldg(ph.c2 + n);
+            } else if (ph.bias) {
+              o_c1[j] = Cvt<T>::to_f(__ldg(reinterpret_cast<const T*>(ph.bias) + n));
             }
-        }
-      }
-#pragma unroll
-      for (int t = 0; t < kDRMaxTiles; ++t)
-        if (t < n_tiles) {
-          float* dst = s_red + ((warp * kDRMaxTiles + t) * 16) * RMAX;
-#pragma unroll
-          for (int u = 0; u < NT; ++u) {
-            *reinterpret_cast<float2*>(dst + g * RMAX + u * 8 + 2 * t4) = make_float2(acc[t][u][0], acc[t][u][1]);
-            *reinterpret_cast<float2*>(dst + (g + 8) * RMAX + u * 8 + 2 * t4) = make_float2(acc[t][u][2], acc[t][u][3]);
+            if (ph.flags & DL_RESID) o_x[j] = Cvt<T>::to_f(__ldcg(reinterpret_cast<const T*>(ph.out) + o_r[j] * ph.ldo + n));
           }
         }
-      asm volatile("bar.sync 1, 256;" ::: "memory");
-      if (tid == 0) mbar_arrive(w_empty);
-      ++slab;
-      // ---- epilogue
+        // ---- main loop: this warp's eighth of K for every 16-feature tile of the slab
+        float acc[kDRMaxTiles][NT][4];
 #pragma unroll
-      for (int j = 0; j < J; ++j)
-        if (o_r[j] >= 0) {
-          const int r = o_r[j], nl = o_n[j];
-          const float* src = s_red + ((nl >> 4) * 16 + (nl & 15)) * RMAX + r;
-          float v = 0.f;
+        for (int t = 0; t < kDRMaxTiles; ++t)
 #pragma unroll
-          for (int w = 0; w < kDRComputeWarps; ++w) v += src[w * kDRMaxTiles * 16 * RMAX];
-          if (fold)
-            v = fmaf(s_stat[RMAX + r], v - s_stat[r] * o_c1[j], o_c2[j]);
-          else
-            v += o_c1[j];
-          if (ph.flags & DL_GELU) v = gelu_erf(round_to<T>(v));
-          if (ph.flags & DL_RESID) v = round_to<T>(v) + o_x[j];
-          const T tv = Cvt<T>::from_f(v);
-          reinterpret_cast<T*>(ph.out)[r * ph.ldo + n0 + nl] = tv;
-          s_out[r * kDRCols + nl] = Cvt<T>::to_f(tv);
+          for (int u = 0; u < NT; ++u)
+#pragma unroll
+            for (int i = 0; i < 4; ++i) acc[t][u][i] = 0.f;
+        if (c0 == 0) dl_mbar_wait(a_full, n_lin & 1);
+        dl_mbar_wait(w_full, slab & 1);
+        {
+          const int kw = ph.K / kDRComputeWarps;
+          // ldmatrix x4 on the slab: matrices (features 0-7, k 0-7), (8-15, k 0-7), (0-7, k 8-15), (8-15, k 8-15) = a0..a3
+          const uint8_t* wrow = sW + static_cast<size_t>((lane & 7) + ((lane >> 3) & 1) * 8) * stride + (lane >> 4) * 16;
+          // ldmatrix x2 on 8 input rows: (rows 0-7, k 0-7), (rows 0-7, k 8-15) = b0, b1
+          const uint8_t* arow = sA + static_cast<size_t>(lane & 7) * stride + ((lane >> 3) & 1) * 16;
+          for (int k0 = warp * kw; k0 < (warp + 1) * kw; k0 += 16) {
+            uint32_t b[NT][2];
+#pragma unroll
+            for (int u = 0; u < NT; ++u) ldmatrix_x2(b[u], arow + static_cast<size_t>(u) * 8 * stride + k0 * 2);
+#pragma unroll
+            for (int t = 0; t < kDRMaxTiles; ++t)
+              if (t < n_tiles) {
+                uint32_t a[4];
+                ldmatrix_x4(a, wrow + static_cast<size_t>(t) * 16 * stride + k0 * 2);
+#pragma unroll
+                for (int u = 0; u < NT; ++u) mma16816<T>(acc[t][u], a, b[u][0], b[u][1]);
+              }
+          }
         }
-      if (ph.flags & DL_STATS) {
+#pragma unroll
+        for (int t = 0; t < kDRMaxTiles; ++t)
+          if (t < n_tiles) {
+            float* dst = s_red + ((warp * kDRMaxTiles + t) * 16) * RMAX;
+#pragma unroll
+            for (int u = 0; u < NT; ++u) {
+              *reinterpret_cast<float2*>(dst + g * RMAX + u * 8 + 2 * t4) = make_float2(acc[t][u][0], acc[t][u][1]);
+              *reinterpret_cast<float2*>(dst + (g + 8) * RMAX + u * 8 + 2 * t4) = make_float2(acc[t][u][2], acc[t][u][3]);
+            }
+          }
+        asm volatile("bar.sync 1, 256;" ::: "memory");
+        if (tid == 0) mbar_arrive(w_empty);          // the next slab may land while the epilogue runs
+        ++slab;
+        // ---- epilogue
+#pragma unroll
+        for (int j = 0; j < J; ++j)
+          if (o_r[j] >= 0) {
+            const int r = o_r[j], nl = o_n[j];
+            const float* src = s_red + ((nl >> 4) * 16 + (nl & 15)) * RMAX + r;
+            float v = 0.f;
+#pragma unroll
+            for (int w = 0; w < kDRComputeWarps; ++w) v += src[w * kDRMaxTiles * 16 * RMAX];
+            if (fold)
+              v = fmaf(s_stat[RMAX + r], v - s_stat[r] * o_c1[j], o_c2[j]);
+            else
+              v += o_c1[j];
+            if (ph.flags & DL_GELU) v = gelu_erf(round_to<T>(v));
+            if (ph.flags & DL_RESID) v = round_to<T>(v) + o_x[j];
+            if (ph.flags & DL_OUTF32) {
+              reinterpret_cast<float*>(ph.out)[r * ph.ldo + n0 + c0 + nl] = v;
+            } else {
+              const T tv = Cvt<T>::from_f(v);
+              reinterpret_cast<T*>(ph.out)[r * ph.ldo + n0 + c0 + nl] = tv;
+              s_out[r * kDRCols + nl] = Cvt<T>::to_f(tv);
+            }
+          }
+        if (c0 + cap < nc) asm volatile("bar.sync 1, 256;" ::: "memory");   // the partial sums are re-used by the next slab
+      }
+      ++n_lin;
+      if (ph.flags & DL_STATS) {         // (single-slab phases only)
         asm volatile("bar.sync 1, 256;" ::: "memory");
         if (tid < R) {
           // statistics of the STORED (16-bit rounded) values: what the next LayerNorm would read
@@ -823,10 +847,60 @@ __global__ void __launch_bounds__(kDRThreads, 1) dec_rows_kernel(const DLParams 
           __stcg(P.ln_part + static_cast<long long>(cta) * P.ln_ld + tid, make_float4(static_cast<float>(nc), mean, m2, 0.f));
         }
       }
+    } else if (ph.type == DS_LN) {
+      // ---- LayerNorm of the rows (the decoder's final ln, model.py:243-245): a warp per row, fp32 statistics in two
+      //      passes like layernorm_kernel
+      dl_mbar_wait(go, p & 1);
+      for (int row = cta; row < R; row += grid) {
+        if (warp != 0) continue;
+        const T* xr = reinterpret_cast<const T*>(ph.a) + static_cast<long long>(row) * ph.lda;
+        T* yr = reinterpret_cast<T*>(ph.out) + static_cast<long long>(row) * ph.ldo;
+        const int d = ph.N;
+        float sum = 0.f;
+        for (int c = lane * 8; c < d; c += 256) {
+          const uint4 u = __ldcg(reinterpret_cast<const uint4*>(xr + c));
+          const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            const float2 f = Cvt<T>::unpack2(w[e]);
+            sum += f.x + f.y;
+          }
+        }
+        const float mean = warp_sum(sum) / static_cast<float>(d);
+        float sq = 0.f;
+        for (int c = lane * 8; c < d; c += 256) {
+          const uint4 u = __ldcg(reinterpret_cast<const uint4*>(xr + c));
+          const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            const float2 f = Cvt<T>::unpack2(w[e]);
+            sq += (f.x - mean) * (f.x - mean);
+            sq += (f.y - mean) * (f.y - mean);
+          }
+        }
+        const float rstd = rsqrtf(warp_sum(sq) / static_cast<float>(d) + 1e-5f);
+        for (int c = lane * 8; c < d; c += 256) {
+          const uint4 u = __ldcg(reinterpret_cast<const uint4*>(xr + c));
+          const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+          float o[8];
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            const float2 f = Cvt<T>::unpack2(w[e]);
+            o[2 * e] = (f.x - mean) * rstd * __ldg(ph.c1 + c + 2 * e) + __ldg(ph.c2 + c + 2 * e);
+            o[2 * e + 1] = (f.y - mean) * rstd * __ldg(ph.c1 + c + 2 * e + 1) + __ldg(ph.c2 + c + 2 * e + 1);
+          }
+          uint4 y;
+          y.x = Cvt<T>::pack2(o[0], o[1]);
+          y.y = Cvt<T>::pack2(o[2], o[3]);
+          y.z = Cvt<T>::pack2(o[4], o[5]);
+          y.w = Cvt<T>::pack2(o[6], o[7]);
+          *reinterpret_cast<uint4*>(yr + c) = y;
+        }
+      }
     } else if (ph.type == DS_SELF) {
       // ---- self-attention of the new position of every (row, head) over the row's lineage + kv append: model.py:124-127
       //      with the cache of model.py:327-333 read through the parent table (decoding.py:172-176)
-      dl_mbar_wait(a_full, p & 1);
+      dl_mbar_wait(go, p & 1);
       const int H = P.n_head, ctx = P.ctx, d = P.d;
       const int L = *P.len_ptr, pos_new = L - 1;
       const long long row_stride = static_cast<long long>(H) * ctx * 128;
@@ -878,7 +952,7 @@ __global__ void __launch_bounds__(kDRThreads, 1) dec_rows_kernel(const DLParams 
     } else if (ph.type == DS_CROSS) {
       // ---- cross-attention (model.py:101-109 + SDPA) of every (row, head) over a slice of the audio's keys; with one slice
       //      the output is final, otherwise (m, l, o) partials for the DS_COMBINE phase
-      dl_mbar_wait(a_full, p & 1);
+      dl_mbar_wait(go, p & 1);
       const int H = P.n_head, d = P.d, S = P.splits, Tn = P.T;
       for (int item = cta; item < R * H * S; item += grid) {
         const int pair = item / S, sp = item - pair * S;
@@ -890,11 +964,12 @@ __global__ void __launch_bounds__(kDRThreads, 1) dec_rows_kernel(const DLParams 
         const uint8_t* vb = kb + static_cast<long long>(H) * Tn * 128;
         AttAcc a;
         att_init(a);
-        for (int b = warp; k0 + b * 4 < k1; b += 4 * kDRComputeWarps) {    // four blocks of four keys in flight
-          uint4 kk[4], vv[4];
-          bool ok[4];
+        // eight blocks of four keys in flight per warp: 64 KB per CTA, what it takes to pull ~40 GB/s per SM out of HBM
+        for (int b = warp; k0 + b * 4 < k1; b += 8 * kDRComputeWarps) {
+          uint4 kk[8], vv[8];
+          bool ok[8];
 #pragma unroll
-          for (int u = 0; u < 4; ++u) {
+          for (int u = 0; u < 8; ++u) {
             const int key = k0 + (b + u * kDRComputeWarps) * 4 + g4;
             ok[u] = key < k1;
             kk[u] = vv[u] = make_uint4(0u, 0u, 0u, 0u);
@@ -904,7 +979,7 @@ __global__ void __launch_bounds__(kDRThreads, 1) dec_rows_kernel(const DLParams 
             }
           }
 #pragma unroll
-          for (int u = 0; u < 4; ++u) att_update<T>(a, q, kk[u], vv[u], ok[u]);
+          for (int u = 0; u < 8; ++u) att_update<T>(a, q, kk[u], vv[u], ok[u]);
         }
         att_park(a, s_red + warp * 68);
         asm volatile("bar.sync 1, 256;" ::: "memory");
@@ -928,7 +1003,7 @@ __global__ void __launch_bounds__(kDRThreads, 1) dec_rows_kernel(const DLParams 
       }
     } else {
       // ---- DS_COMBINE: merge the key slices of every (row, head); a warp per pair, two output features per lane
-      dl_mbar_wait(a_full, p & 1);
+      dl_mbar_wait(go, p & 1);
       const int H = P.n_head, d = P.d, S = P.splits;
       for (int pair = cta + warp * grid; pair < R * H; pair += grid * kDRComputeWarps) {
         const int row = pair / H, h = pair - row * H;
@@ -1074,7 +1149,7 @@ void dl_init_launch(DLLaunch& L, int dtype, int R, int grid, float4* ln_part, in
 // shared-memory layout of the few-rows form over a set of Linear phases; 0 if it does not fit
 static int dr_layout(const DLPhase* ph, int n, int R, int grid, int* a_off_out, int* tail_off_out) {
   const int nt = R <= 8 ? 1 : (R <= 16 ? 2 : 4);       // 8-row operand tiles of the input rows
-  long long w_bytes = 0, extent = 0, a_bytes = 0;
+  long long w_bytes = 0, a_bytes = 0;
   int n_linear = 0;
   for (int p = 0; p < n; ++p) {
     if (ph[p].type != DS_LINEAR) continue;
@@ -1082,13 +1157,23 @@ static int dr_layout(const DLPhase* ph, int n, int R, int grid, int* a_off_out, 
     if (ph[p].K % (16 * kDRComputeWarps) || ph[p].N < 1) return 0;
     const long long stride = ph[p].K * 2LL + 16;
     const int nc_max = (ph[p].N + grid - 1) / grid;
-    if (nc_max > kDRCols) return 0;
-    w_bytes = std::max(w_bytes, nc_max * stride);
-    extent = std::max(extent, ((nc_max + 15) / 16 * 16) * stride);     // ldmatrix reads whole 16-row tiles
+    // a share of more than 48 features (the logits) goes through the buffer in several slabs: it does not size it
+    if (nc_max <= kDRCols) w_bytes = std::max(w_bytes, nc_max * stride);
+    else if (ph[p].flags & DL_STATS) return 0;
     a_bytes = std::max(a_bytes, 8LL * nt * stride);
   }
   if (!n_linear) return 0;
+  if (w_bytes == 0) w_bytes = 64 * 1024;
   const long long a_off = (w_bytes + 127) / 128 * 128;
+  long long extent = 0;
+  for (int p = 0; p < n; ++p) {
+    if (ph[p].type != DS_LINEAR) continue;
+    const long long stride = ph[p].K * 2LL + 16;
+    const int nc_max = (ph[p].N + grid - 1) / grid;
+    const int cols = std::min(nc_max, dr_slab_cols(static_cast<int>(a_off), ph[p].K));
+    if (nc_max > kDRCols && cols < 16) return 0;                       // slabs too thin to be worth it
+    extent = std::max(extent, ((cols + 15) / 16 * 16) * stride);     // ldmatrix reads whole 16-row tiles
+  }
   const long long tail_off = (std::max(a_off + a_bytes, extent) + 127) / 128 * 128;
   const long long total = tail_off + dr_tail_bytes(nt) + 128;
   if (total > 227 * 1024) return 0;

@@ -10,10 +10,10 @@ constexpr int kDLMaxPhases = 4;
 constexpr int kDLUnit = 16;        // output columns per work unit (one tcgen05.ld .x16, one 16-row weight box)
 constexpr int kDLMaxUnits = 12;    // widest per-CTA tile: 192 columns
 
-enum { DL_FOLD = 1, DL_GELU = 2, DL_RESID = 4, DL_STATS = 8 };
+enum { DL_FOLD = 1, DL_GELU = 2, DL_RESID = 4, DL_STATS = 8, DL_OUTF32 = 16 };   // OUTF32: fp32 output (the logits)
 // phase kinds (few-rows form only; the tile form knows Linear phases): Linear, self-attention + kv append over the
 // rows' lineages, cross-attention partials over a slice of the audio keys, merge of those partials
-enum { DS_LINEAR = 0, DS_SELF = 1, DS_CROSS = 2, DS_COMBINE = 3 };
+enum { DS_LINEAR = 0, DS_SELF = 1, DS_CROSS = 2, DS_COMBINE = 3, DS_LN = 4 };   // LN: out = LayerNorm(a) with c1 = gamma, c2 = beta
 
 // One Linear of the chain.  DL_FOLD: the input is LayerNorm(x) - W holds W (.) gamma, c1 / c2 the fold vectors, the row
 // statistics come from the LN partials left by the producer of x.  DL_RESID: out is the residual stream,

@@ -325,7 +325,7 @@ static void dec_carve(const Model* m, const wb200_decode_config& c, Arena& ar, D
   o->ln_ld = static_cast<int>((R + 63) / 64 * 64);
   o->ln_part = static_cast<float4*>(ar.take(static_cast<size_t>(256) * o->ln_ld * sizeof(float4)));
   o->dl_sync = static_cast<unsigned int*>(ar.take(256));
-  o->stack_table = static_cast<DLPhase*>(ar.take((static_cast<size_t>(9) * NL + 2) * sizeof(DLPhase)));
+  o->stack_table = static_cast<DLPhase*>(ar.take((static_cast<size_t>(9) * NL + 4) * sizeof(DLPhase)));
 }
 
 size_t decoder_workspace_bytes(const Model* m, const wb200_decode_config* c) {
@@ -379,7 +379,32 @@ static int build_stack_plan(Decoder* D, cudaStream_t s) {
     if (splits > 1) attention(DS_COMBINE, nullptr, nullptr);
     for (int i = 0; i < D->dl_tail[l].p.n_phases; ++i) tab.push_back(D->dl_tail[l].p.ph[i]);
   }
-  if (tab.size() > static_cast<size_t>(9) * NL + 2) return 80;
+  {
+    // the decoder's final LayerNorm and the logits (model.py:243-247) close the table: the rows are normalised by one
+    // warp each, then every CTA runs its 1/148 of the vocabulary through the slab buffer in several passes
+    DLPhase ln = {};
+    ln.type = DS_LN;
+    ln.N = d;
+    ln.a = D->x;
+    ln.lda = d;
+    ln.out = D->ln;
+    ln.ldo = d;
+    ln.c1 = static_cast<const float*>(m->t[G_DEC_LN_W]);
+    ln.c2 = static_cast<const float*>(m->t[G_DEC_LN_B]);
+    tab.push_back(ln);
+    DLPhase lg = {};
+    lg.type = DS_LINEAR;
+    lg.N = m->dims.n_vocab;
+    lg.K = d;
+    lg.flags = DL_OUTF32;
+    lg.a = D->ln;
+    lg.lda = d;
+    lg.w = m->t[G_TOK_EMB16];
+    lg.out = D->logits;
+    lg.ldo = D->ldv;
+    tab.push_back(lg);
+  }
+  if (tab.size() > static_cast<size_t>(9) * NL + 4) return 80;
   DLLaunch& S = D->dl_stack;
   dl_init_launch(S, m->dtype, R, grid, D->ln_part, D->ln_ld, D->dl_sync, D->done_ptr, 1);
   if (!dl_plan_stack(S, tab.data(), static_cast<int>(tab.size()), D->stack_table)) return 0;
@@ -706,8 +731,10 @@ int decoder_step(Decoder* D, cudaStream_t s) {
   if (D->forward_only) return set_error(241, "step: this session was created with all_logits (forward-only)");
   if (dt == DT_BF16) launch_embed<__nv_bfloat16>(D, R, true, s); else launch_embed<__half>(D, R, true, s);
   WB_TRY(decoder_stack(D, R, true, s));
-  WB_TRY(launch_layernorm(dt, D->x, d, D->ln, d, (const float*)m->t[G_DEC_LN_W], (const float*)m->t[G_DEC_LN_B], R, d, s, D->done_ptr));
-  WB_TRY(linear(m, D->ln, d, R, m->t[G_TOK_EMB16], V, d, nullptr, nullptr, D->logits, D->ldv, 0, 1, s, D->done_ptr, D));
+  if (!(D->fused && D->stack_ready)) {      // (the one-launch stack ends with the final LayerNorm and the logits)
+    WB_TRY(launch_layernorm(dt, D->x, d, D->ln, d, (const float*)m->t[G_DEC_LN_W], (const float*)m->t[G_DEC_LN_B], R, d, s, D->done_ptr));
+    WB_TRY(linear(m, D->ln, d, R, m->t[G_TOK_EMB16], V, d, nullptr, nullptr, D->logits, D->ldv, 0, 1, s, D->done_ptr, D));
+  }
   D->logits_cur = D->logits;
   D->logits_row_div = 1;
   D->logits_rows = R;

@@ -100,8 +100,8 @@ struct Decoder {
   // theirs from the previous layer's tail), [out-proj, cross-query], [cross-out, fc1, fc2, next layer's QKV]
   bool fused = false;
   std::vector<DLLaunch> dl_head, dl_mid, dl_tail;
-  // few-rows sessions: the whole decoder stack of an iteration (every Linear chain AND both attentions of every layer) as
-  // ONE launch of dec_rows_kernel driven by a phase table in device memory
+  // few-rows sessions: the whole decoder stack of an iteration (every Linear chain AND both attentions of every layer, the
+  // final LayerNorm and the logits) as ONE launch of dec_rows_kernel driven by a phase table in device memory
   bool stack_ready = false;
   DLLaunch dl_stack;
   std::vector<DLPhase> stack_host;
