@@ -32,7 +32,7 @@ def main():
             continue
         if cur is None or "/*" not in line:
             continue
-        if re.search(r"/\*[0-9a-f]{4}\*/", line):
+        if re.search(r"/\*[0-9a-f]{4,}\*/", line):
             counts[cur]["instructions"] += 1
             for name, pat in PATTERNS:
                 if re.search(pat, line):

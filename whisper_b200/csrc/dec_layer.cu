@@ -462,7 +462,7 @@ dec_layer_kernel(const DLParams P, const __grid_constant__ DLMaps M) {
 // =================================================================================================
 // With a handful of rows the tile form above is all fixed cost: a 64-row UMMA tile holds <= 8 real rows, every K = 16
 // step still costs ~58 clk of tensor-pipe issue at N = 16, and a phase takes 6-18 us for 20-90 KB of weights per SM
-// (measured on the turbo batch-1 run, profiles/r2_launches_turbo_b1.csv: 46 us per launch, 9 launches per token).
+// (measured on the turbo batch-1 run, profiles/r2_launches_turbo_b1_tileform.csv: 46 us per launch, 9 launches per token).
 // This form keeps the phase structure, the LayerNorm folding and the grid barrier, and replaces the main loop by a
 // weight-stationary matrix-vector product on mma.sync with the operands swapped:
 //   * every CTA owns N / grid consecutive output features (8-35 weight rows); ONE bulk copy per weight row brings its
@@ -477,6 +477,11 @@ dec_layer_kernel(const DLParams P, const __grid_constant__ DLMaps M) {
 //     buffer holds and only ever reach accumulator entries nobody looks at.
 //   * epilogue per output element as in the tile form (fold / bias / erf-GELU / residual), LN partials per
 //     (row, CTA): count = this CTA's features, merged by the consumer with Chan's formula.
+// Whole stack in one launch: the phases may also come from a table in global memory that strings every layer's chains
+// together with its self-attention (kv append + attention over the row's lineage through the parent table), its
+// cross-attention ((row, head, key slice) items over all SMs + a merge phase), the final LayerNorm and the logits (a
+// Linear whose share of 351 features per CTA passes through the slab buffer in several slabs).  The control warp keeps
+// prefetching the slab of the next Linear through the attention phases, so the weights stream continuously.
 constexpr int kDRComputeWarps = 8;
 constexpr int kDRThreads = (kDRComputeWarps + 1) * 32;
 constexpr int kDRMaxTiles = 3;                                  // 16-feature tiles per CTA and phase (N / grid <= 48)
