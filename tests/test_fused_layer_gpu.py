@@ -27,10 +27,11 @@ def _set_rows(on: bool):
     assert _lib.lib().wb200_set_fused_decoder_rows(int(on)) == 0
 
 
-def _set_stack(on: bool):
+def _set_stack(mode):
+    """0: per-layer launches, 1 / True: one launch per iteration (default), 2: ... ending with the final LayerNorm + logits."""
     from whisper_b200 import _lib
 
-    assert _lib.lib().wb200_set_fused_decoder_stack(int(on)) == 0
+    assert _lib.lib().wb200_set_fused_decoder_stack(int(mode)) == 0
 
 
 def _teacher_forced_logits(model, g_feats, rec, n_audio, opts):
@@ -210,3 +211,46 @@ def test_few_rows_form_matches_tile_form_and_oracle(name, n_audio, opts, dtype):
           f"{worst_stack:.5f}, vs oracle {worst_ora:.5f} (of max |logit|), {len(rows)} steps")
     # the forms differ by the order of fp32 sums only (Linears: K split over warps; attention: keys split over warps / slices)
     assert worst_ora < LOGIT_TOL[dtype] and worst_pair < LOGIT_TOL[dtype] and worst_stack < LOGIT_TOL[dtype]
+
+
+@pytest.mark.parametrize("name,n_audio,opts", [("test-multi", 1, dict(sample_len=12)), ("tiny.en", 1, dict(beam_size=5, sample_len=10))])
+def test_stack_closing_with_layernorm_and_logits(name, n_audio, opts):
+    """Mode 2 of the one-launch stack: the table ends with the decoder's final LayerNorm (a warp per row) and the logits (a
+    Linear whose 1/148 share of the vocabulary passes through the slab buffer in several slabs, fp32 output) - against
+    the default (separate layernorm + tcgen05 GEMM launches) and the oracle."""
+    import whisper_b200 as wb
+    from oracle import audio as OA
+    from oracle import model as OM
+    from oracle import parity
+    from whisper_b200 import synthetic
+
+    dtype = torch.float16
+    meta, _ = load_model_fixture(name)
+    dims, sd, _ = fixture_inputs(meta)
+    audio = synthetic.synthetic_audio(n_audio, 480000, seed=31, kind="speechlike")
+    W = OM.to_weights(sd)
+    mel = torch.from_numpy(np.stack([OA.log_mel_spectrogram(a, dims["n_mels"]) for a in audio]))
+    rec = parity.oracle_record(W, dims, OM.encoder_forward(W, dims, mel), opts, n_audio)
+    G = opts.get("beam_size") or 1
+    model = wb.Whisper(wb.ModelDimensions(**dims), sd, device="cuda", dtype=dtype)
+    g_feats = model.embed_audio(torch.stack([wb.log_mel_spectrogram(torch.from_numpy(a).cuda(), dims["n_mels"]) for a in audio]))
+    try:
+        _set_stack(1)
+        model.clear_sessions()
+        base = _teacher_forced_logits(model, g_feats, rec, n_audio, opts)
+        _set_stack(2)
+        model.clear_sessions()
+        full = _teacher_forced_logits(model, g_feats, rec, n_audio, opts)
+    finally:
+        _set_stack(1)
+        model.clear_sessions()
+    worst_pair = worst_ora = 0.0
+    for i, (a, b) in enumerate(zip(base, full)):
+        assert bool(torch.isfinite(b).all())
+        ref = rec["raw_logits"][i]
+        ref = ref[::G] if i == 0 else ref
+        scale = float(ref.abs().max())
+        worst_pair = max(worst_pair, float((a - b).abs().max()) / scale)
+        worst_ora = max(worst_ora, float((b - ref).abs().max()) / scale)
+    print(f"{name} R={n_audio * G}: stack with LayerNorm + logits vs default {worst_pair:.6f}, vs oracle {worst_ora:.5f}")
+    assert worst_ora < LOGIT_TOL[dtype] and worst_pair < 1e-3      # same 16-bit inputs, fp32 sums in another order

@@ -133,8 +133,8 @@ int wb200_set_fused_decoder_rows(int enabled) {
   return 0;
 }
 
-int wb200_set_fused_decoder_stack(int enabled) {
-  g_fused_stack = enabled ? 1 : 0;
+int wb200_set_fused_decoder_stack(int mode) {
+  g_fused_stack = mode < 0 ? 0 : (mode > 2 ? 2 : mode);
   return 0;
 }
 

@@ -81,7 +81,7 @@ struct DLLaunch {
 constexpr int kDRMaxRows = 32;     // the few-rows form covers R <= 32 (1, 2 or 4 mma.sync n = 8 operand tiles) where shared memory allows
 
 extern int g_fused_layer;
-extern int g_fused_stack;          // few-rows sessions: whole stack in one launch (wb200_set_fused_decoder_stack / WB200_FUSED_STACK, default on)
+extern int g_fused_stack;          // few-rows sessions: whole stack in one launch (wb200_set_fused_decoder_stack / WB200_FUSED_STACK: 0 off, 1 default, 2 incl. logits)
 extern int g_fused_rows;           // few-rows form for R <= kDRMaxRows (wb200_set_fused_decoder_rows / WB200_FUSED_ROWS, default on)
 int dl_grid_size();
 bool dl_supported(int R, int d, int grid);

@@ -346,7 +346,7 @@ static int build_stack_plan(Decoder* D, cudaStream_t s) {
   D->stack_ready = false;
   if (g_fused_stack < 0) {
     const char* e = getenv("WB200_FUSED_STACK");
-    g_fused_stack = (e && e[0] == '0') ? 0 : 1;
+    g_fused_stack = (e && e[0] >= '0' && e[0] <= '2') ? e[0] - '0' : 1;
   }
   const int NL = m->dims.n_text_layer, H = m->dims.n_text_head, d = m->dims.n_text_state, ctx = m->dims.n_text_ctx;
   const int Ta = m->dims.n_audio_ctx, B = D->cfg.n_audio, G = D->cfg.n_group, R = B * G;
@@ -379,9 +379,12 @@ static int build_stack_plan(Decoder* D, cudaStream_t s) {
     if (splits > 1) attention(DS_COMBINE, nullptr, nullptr);
     for (int i = 0; i < D->dl_tail[l].p.n_phases; ++i) tab.push_back(D->dl_tail[l].p.ph[i]);
   }
-  {
-    // the decoder's final LayerNorm and the logits (model.py:243-247) close the table: the rows are normalised by one
-    // warp each, then every CTA runs its 1/148 of the vocabulary through the slab buffer in several passes
+  const size_t n_layers_phases = tab.size();
+  if (g_fused_stack >= 2) {
+    // opt-in (mode 2): the decoder's final LayerNorm and the logits (model.py:243-247) close the table - the rows are
+    // normalised by one warp each, then every CTA runs its 1/148 of the vocabulary through the slab buffer in several
+    // passes.  Measured on the turbo one-audio run: 48 us inside the stack (single-buffered slabs: load and compute of a
+    // slab alternate) against 6 + 42 us for the two separate launches - no gain, hence not the default.
     DLPhase ln = {};
     ln.type = DS_LN;
     ln.N = d;
@@ -407,7 +410,13 @@ static int build_stack_plan(Decoder* D, cudaStream_t s) {
   if (tab.size() > static_cast<size_t>(9) * NL + 4) return 80;
   DLLaunch& S = D->dl_stack;
   dl_init_launch(S, m->dtype, R, grid, D->ln_part, D->ln_ld, D->dl_sync, D->done_ptr, 1);
-  if (!dl_plan_stack(S, tab.data(), static_cast<int>(tab.size()), D->stack_table)) return 0;
+  D->stack_has_logits = tab.size() > n_layers_phases;
+  if (!dl_plan_stack(S, tab.data(), static_cast<int>(tab.size()), D->stack_table)) {
+    if (!D->stack_has_logits) return 0;
+    tab.resize(n_layers_phases);             // the logits slabs do not fit next to the input rows: the layers alone
+    D->stack_has_logits = false;
+    if (!dl_plan_stack(S, tab.data(), static_cast<int>(tab.size()), D->stack_table)) return 0;
+  }
   if (cudaMemcpyAsync(D->stack_table, tab.data(), tab.size() * sizeof(DLPhase), cudaMemcpyHostToDevice, s) != cudaSuccess) return 81;
   S.p.qkv = D->qkv;
   S.p.q = D->q;
@@ -731,7 +740,7 @@ int decoder_step(Decoder* D, cudaStream_t s) {
   if (D->forward_only) return set_error(241, "step: this session was created with all_logits (forward-only)");
   if (dt == DT_BF16) launch_embed<__nv_bfloat16>(D, R, true, s); else launch_embed<__half>(D, R, true, s);
   WB_TRY(decoder_stack(D, R, true, s));
-  if (!(D->fused && D->stack_ready)) {      // (the one-launch stack ends with the final LayerNorm and the logits)
+  if (!(D->fused && D->stack_ready && D->stack_has_logits)) {      // (mode 2 of the one-launch stack ends with both)
     WB_TRY(launch_layernorm(dt, D->x, d, D->ln, d, (const float*)m->t[G_DEC_LN_W], (const float*)m->t[G_DEC_LN_B], R, d, s, D->done_ptr));
     WB_TRY(linear(m, D->ln, d, R, m->t[G_TOK_EMB16], V, d, nullptr, nullptr, D->logits, D->ldv, 0, 1, s, D->done_ptr, D));
   }

@@ -100,9 +100,10 @@ struct Decoder {
   // theirs from the previous layer's tail), [out-proj, cross-query], [cross-out, fc1, fc2, next layer's QKV]
   bool fused = false;
   std::vector<DLLaunch> dl_head, dl_mid, dl_tail;
-  // few-rows sessions: the whole decoder stack of an iteration (every Linear chain AND both attentions of every layer, the
-  // final LayerNorm and the logits) as ONE launch of dec_rows_kernel driven by a phase table in device memory
+  // few-rows sessions: the whole decoder stack of an iteration (every Linear chain AND both attentions of every layer;
+  // optionally the final LayerNorm and the logits) as ONE launch of dec_rows_kernel driven by a phase table in device memory
   bool stack_ready = false;
+  bool stack_has_logits = false;    // the table ends with the final LayerNorm and the logits (mode 2)
   DLLaunch dl_stack;
   std::vector<DLPhase> stack_host;
   DLPhase* stack_table = nullptr;   // device copy of stack_host
