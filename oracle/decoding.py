@@ -123,7 +123,9 @@ def suppress_tokens(logits: torch.Tensor, suppress: Sequence[int]) -> None:
 
 
 def timestamp_rules(logits: torch.Tensor, tokens: List[List[int]], ids: TokenIds, sample_begin: int,
-                    max_initial_timestamp_index: Optional[int]) -> None:
+                    max_initial_timestamp_index: Optional[int], rule_gaps: Optional[List[float]] = None) -> None:
+    """ApplyTimestampRules (decoding.py:441-505).  rule_gaps (diagnostics for the margin-gated parity tests): per row, how
+    far the "timestamps outweigh every text token" decision of :498-505 was from flipping, in log-probability units."""
     tb = ids.timestamp_begin
     logits[:, ids.no_timestamps] = NEG_INF                              # decoding.py:454-455
     for k, row in enumerate(tokens):
@@ -147,6 +149,9 @@ def timestamp_rules(logits: torch.Tensor, tokens: List[List[int]], ids: TokenIds
     for k in range(len(tokens)):
         ts_lp = torch.logsumexp(logprobs[k, tb:], dim=-1)
         text_max = logprobs[k, :tb].max()
+        if rule_gaps is not None:
+            both = bool(torch.isfinite(ts_lp)) and bool(torch.isfinite(text_max))
+            rule_gaps.append(abs(float(ts_lp - text_max)) if both else float("inf"))
         if ts_lp > text_max:
             logits[k, :tb] = NEG_INF
 
@@ -348,14 +353,14 @@ def suppress_list(ids: TokenIds, opt: Options) -> Tuple[int, ...]:
 
 
 def apply_filters(logits: torch.Tensor, tokens: List[List[int]], ids: TokenIds, opt: Options, sample_begin: int,
-                  sup: Sequence[int], mits: Optional[int]) -> None:
+                  sup: Sequence[int], mits: Optional[int], rule_gaps: Optional[List[float]] = None) -> None:
     """The LogitFilter chain in the order DecodingTask builds it (decoding.py:554-570), in place."""
     if opt.suppress_blank:
         suppress_blank(logits, tokens, ids, sample_begin)
     if sup:
         suppress_tokens(logits, sup)
     if not opt.without_timestamps:
-        timestamp_rules(logits, tokens, ids, sample_begin, mits)
+        timestamp_rules(logits, tokens, ids, sample_begin, mits, rule_gaps)
 
 
 def filter_context(dims: Dict[str, int], opt: Options):
@@ -427,14 +432,21 @@ def decode(W: M.Weights, dims: Dict[str, int], mel_or_features: torch.Tensor, op
         if record is not None:
             record.setdefault("raw_logits", []).append(logits.clone())
             record.setdefault("tokens_in", []).append([list(t) for t in tokens])
-        apply_filters(logits, tokens, ids, opt, sample_begin, sup, mits)
+        rule_gaps: Optional[List[float]] = [] if record is not None else None
+        apply_filters(logits, tokens, ids, opt, sample_begin, sup, mits, rule_gaps)
         if record is not None:
             record.setdefault("filtered_logits", []).append(logits.clone())
             record.setdefault("sum_logprobs_in", []).append(sum_lp.clone())
         if record is not None:                 # decision margins: diagnostics for the margin-gated parity tests only
+            # the smaller of (a) the gap between the two best surviving logits and (b) the distance of the timestamp-vs-text
+            # rule (decoding.py:498-505) from flipping: a near-tie there removes or keeps the whole text vocabulary
             top2 = logits.topk(2, dim=-1).values.cpu()
             for r in range(R):
-                margins[r].append(float(top2[r, 0] - top2[r, 1]))
+                gap = float(top2[r, 0] - top2[r, 1])
+                if rule_gaps:
+                    gap = min(gap, rule_gaps[r])
+                margins[r].append(gap)
+            record.setdefault("rule_gaps", []).append(list(rule_gaps) if rule_gaps else None)
         if beam is None and opt.temperature > 0:
             tokens, completed, gaps = sample_update(tokens, logits, sum_lp, ids.eot, opt.temperature, opt.seed)
             if record is not None:
@@ -446,6 +458,10 @@ def decode(W: M.Weights, dims: Dict[str, int], mel_or_features: torch.Tensor, op
             cache.reorder(src)
             if record is not None:
                 record.setdefault("source_indices", []).append(list(src))
+                if rule_gaps:              # a flipped timestamp rule changes a beam's whole candidate set
+                    g_rule = min(rule_gaps)
+                    beam.step_gaps[-1] = min(beam.step_gaps[-1], g_rule)
+                    beam.min_gap = min(beam.min_gap, g_rule)
         if record is not None:
             record.setdefault("tokens_out", []).append([list(t) for t in tokens])
             record.setdefault("sum_logprobs_out", []).append(sum_lp.clone())

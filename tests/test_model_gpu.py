@@ -29,6 +29,14 @@ LOGIT_TOL = {torch.float16: 2.5e-3, torch.bfloat16: 2.5e-2}
 # correct 16-bit pipeline shows under teacher forcing - 1.5e-3 (fp16) / 1.5e-2 (bf16) of the largest |logit| (~40 for the
 # synthetic models), measured across the kernel forms (tile / few-rows / one-launch stack differ in summation order only)
 TAU = {torch.float16: 0.12, torch.bfloat16: 1.5}
+# ... and never less than twice the measured relative error times the model's own logit scale (tiny.en: max |logit| 258,
+# measured per-step error up to 0.5 in fp16 and 3.0 in bf16 under teacher forcing, profiles/r2_summary.md section 6)
+REL_ERR = {torch.float16: 2.0e-3, torch.bfloat16: 1.3e-2}
+
+
+def decision_gate(rec, dtype):
+    scale = max(float(l.abs().max()) for l in rec["raw_logits"])
+    return max(TAU[dtype], 2.0 * REL_ERR[dtype] * scale)
 FEAT_TOL = {torch.float16: 0.02, torch.bfloat16: 0.12}
 
 _MODELS = {}
@@ -315,14 +323,14 @@ def test_decode_end_to_end(name, case, dtype):
         assert o_res[a].tokens == ref["tokens"]                      # the oracle itself is pinned
         assert np.isfinite(g.avg_logprob), f"audio {a}: non-finite avg_logprob, tokens {g.tokens[:8]}"
         if beam:
-            risky = rec["beam_min_gap"] < TAU[dtype]
+            risky = rec["beam_min_gap"] < decision_gate(rec, dtype)
             if not risky:
                 assert g.tokens == ref["tokens"], f"audio {a}: beam tokens differ although min gap {rec['beam_min_gap']:.3f}"
             elif g.tokens != ref["tokens"]:
                 print(f"{name}/{case}/{dtype} audio {a}: beam result differs, oracle min gap {rec['beam_min_gap']:.4f} < TAU")
         else:
             margins = o_res[a].step_margins
-            k = _first_risky_step(margins, TAU[dtype])
+            k = _first_risky_step(margins, decision_gate(rec, dtype))
             if k is None:
                 assert g.tokens == ref["tokens"], f"audio {a}: tokens differ with all margins >= TAU"
                 assert abs(g.avg_logprob - ref["avg_logprob"]) < 0.02 * max(1.0, abs(ref["avg_logprob"]))

@@ -49,11 +49,13 @@ def test_decode_task_and_language_options_gpu(case):
             continue
         if g.language != ref["language"]:
             continue                                   # a near-tie in language detection changes the whole prompt
+        # the gate of tests/test_model_gpu.py: never below twice the measured fp16 error (2e-3 of the largest |logit|)
+        tau = max(TAU, 2.0 * 2.0e-3 * max(float(l.abs().max()) for l in rec["raw_logits"]))
         if c["options"].get("beam_size"):
-            if rec["beam_min_gap"] >= TAU:
+            if rec["beam_min_gap"] >= tau:
                 assert g.tokens == ref["tokens"]
         else:
-            k = _first_risky_step(o_res[a].step_margins, TAU)
+            k = _first_risky_step(o_res[a].step_margins, tau)
             if k is None:
                 assert g.tokens == ref["tokens"]
                 assert abs(g.avg_logprob - ref["avg_logprob"]) < 0.02 * max(1.0, abs(ref["avg_logprob"]))
