@@ -59,6 +59,8 @@ def test_tma_attention_matches_cp_async(which, name, opts, dtype):
         g_mel = torch.stack([wb.log_mel_spectrogram(torch.from_numpy(a).cuda(), dims["n_mels"]) for a in audio])
         g_feats = model.embed_audio(g_mel)
     try:
+        # few-rows sessions run their attention inside the one-launch decoder stack: keep the stand-alone kernels in play
+        _lib.lib().wb200_set_fused_decoder_stack(0)
         switch(0)
         model.clear_sessions()
         old = _logits_run(model, g_feats, rec, opts, n_audio)
@@ -66,7 +68,9 @@ def test_tma_attention_matches_cp_async(which, name, opts, dtype):
         model.clear_sessions()
         new = _logits_run(model, g_feats, rec, opts, n_audio)
     finally:
-        switch(1)
+        switch(1 if which == "cross" else 0)         # the defaults: TMA cross-attention on, beam-window self-attention off
+        _lib.lib().wb200_set_fused_decoder_stack(1)
+        model.clear_sessions()
     worst, worst_ora = 0.0, 0.0
     G = opts.get("beam_size") or 1
     for i, (a, b) in enumerate(zip(old, new)):

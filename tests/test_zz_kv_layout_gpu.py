@@ -2,8 +2,9 @@
 
 The layout only changes WHERE the two cp.async decode-attention kernels (and the cross-K/V projection's epilogue) put
 the same 16-bit values, and the order of every reduction is untouched, so with those kernels a decode in either layout
-must be equal bit for bit.  (The TMA attention kernels, which exist for the head-major layout only and reduce in
-another order, are switched off for this comparison; tests/test_xattn_tma_gpu.py covers them.)
+must be equal bit for bit.  (The TMA attention kernels and the one-launch decoder stack, which exist for the head-major
+layout only and reduce in another order, are switched off for this comparison; tests/test_xattn_tma_gpu.py and
+tests/test_fused_layer_gpu.py cover them.)
 """
 import numpy as np
 import pytest
@@ -46,6 +47,7 @@ def test_head_major_layout_is_bit_identical(name):
     try:
         _lib.lib().wb200_set_cross_attention_tma(0)
         _lib.lib().wb200_set_self_attention_tma(0)
+        _lib.lib().wb200_set_fused_decoder_stack(0)
         _lib.lib().wb200_set_kv_head_major(0)
         model.clear_sessions()
         base, base_logits, base_qk = run_all()
@@ -55,8 +57,8 @@ def test_head_major_layout_is_bit_identical(name):
     finally:
         _lib.lib().wb200_set_kv_head_major(1)
         _lib.lib().wb200_set_cross_attention_tma(1)
-        _lib.lib().wb200_set_self_attention_tma(1)
-        model.clear_sessions()
+        _lib.lib().wb200_set_fused_decoder_stack(1)
+        model.clear_sessions()                       # (the beam-window self-attention stays off: that is its default)
     assert hm == base
     assert torch.equal(hm_logits, base_logits)
     assert torch.equal(hm_qk, base_qk)
