@@ -72,7 +72,6 @@ struct alignas(64) DLMaps {
 struct DLLaunch {
   int dtype = 0;
   int grid = 0;
-  int max_k = 0, max_cols = 0;   // few-rows stack form: extremes over the table's Linear phases (shared-memory layout)
   int rows_smem = 0;      // > 0: launch the few-rows form (dec_rows_kernel) with this much dynamic shared memory
   DLParams p;
   DLMaps maps;
