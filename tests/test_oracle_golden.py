@@ -186,3 +186,31 @@ def test_gumbel_max_is_categorical():
     assert toks[1][-1] == 0 and float(sums[1]) == 0.0 and toks[0][-1] in live and len(gaps) == 2
     want = float(torch.log_softmax(lg[0], -1)[toks[0][-1]])
     assert abs(float(sums[0]) - want) < 1e-6
+
+
+def test_margins_include_the_timestamp_rule_distance():
+    """The diagnostic decision margins the GPU parity tests gate on must see a near-tie of ApplyTimestampRules' "timestamps
+    outweigh every text token" comparison (reference decoding.py:498-505): a flip there masks the whole text vocabulary
+    while the top-2 gap of the filtered logits stays large (found on hardware: step margin 47.8, decision flipped)."""
+    from oracle import decoding as OD
+
+    ids = OD.token_ids(51864)
+    tb = ids.timestamp_begin
+    sample_begin = 3
+    tokens = [[ids.sot, 50362, 50363, 1000, 1001]]          # two text tokens sampled: text and timestamps both allowed
+    base = torch.full((1, 51864), -30.0)
+    base[0, 2000] = 5.0                                      # best text token
+    for eps, flips in ((+0.02, True), (-0.02, False)):
+        logits = base.clone()
+        logits[0, tb + 10] = 5.0 + eps                       # one dominant timestamp: lse(ts) ~ 5 + eps vs text max 5
+        gaps = []
+        OD.timestamp_rules(logits, tokens, ids, sample_begin, None, gaps)
+        assert len(gaps) == 1 and gaps[0] < 0.05             # the decision was close ...
+        assert bool(torch.isinf(logits[0, 2000])) == flips   # ... and it decides whether any text token survives
+        top2 = logits.topk(2, dim=-1).values[0]
+        assert float(top2[0] - top2[1]) > 10.0 or not flips  # while the filtered top-2 gap looks perfectly safe
+    far = base.clone()
+    far[0, tb + 10] = -5.0
+    gaps = []
+    OD.timestamp_rules(far, tokens, ids, sample_begin, None, gaps)
+    assert gaps[0] > 5.0
