@@ -356,6 +356,28 @@ def test_batched_beam_equals_per_audio():
         assert alone.tokens == both[a].tokens and abs(alone.avg_logprob - both[a].avg_logprob) < 2e-3
 
 
+def test_checkpoint_file_round_trip(tmp_path):
+    """A checkpoint file in the reference's format ({"dims", "model_state_dict"}, whisper/__init__.py:147-156) through
+    load_model(path): same decode, bit for bit, as the model built from the same state dict in memory - the fp32 -> 16-bit
+    repack (pack_weights, LayerNorm-folded decoder weights included) sees the same values either way."""
+    import whisper_b200 as wb
+    from whisper_b200.decoding import DecodingOptions
+
+    meta, _ = load_model_fixture("test-en")
+    dims, sd, _ = fixture_inputs(meta)
+    path = tmp_path / "test-en.pt"
+    torch.save({"dims": dict(dims), "model_state_dict": {k: torch.from_numpy(np.ascontiguousarray(v)) for k, v in sd.items()}}, path)
+    loaded = wb.load_model(str(path), dtype=torch.float16)
+    assert loaded.dims == wb.ModelDimensions(**dims) and not loaded.is_multilingual
+    built = gpu_model("test-en", torch.float16)
+    mel = gpu_mel("test-en")
+    for opt in (DecodingOptions(language="en", sample_len=24), DecodingOptions(language="en", beam_size=5, sample_len=24)):
+        a, b = loaded.decode(mel, opt), built.decode(mel, opt)
+        assert [r.tokens for r in a] == [r.tokens for r in b]
+        assert [r.avg_logprob for r in a] == [r.avg_logprob for r in b]
+    assert torch.equal(loaded.embed_audio(mel), built.embed_audio(mel))
+
+
 def test_detect_language():
     meta, arrays = load_model_fixture("test-multi")
     model = gpu_model("test-multi", torch.float16)
