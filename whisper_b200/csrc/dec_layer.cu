@@ -487,9 +487,9 @@ constexpr int kDRThreads = (kDRComputeWarps + 1) * 32;
 constexpr int kDRMaxTiles = 3;                                  // 16-feature tiles per CTA and phase (N / grid <= 48)
 constexpr int kDRCols = kDRMaxTiles * 16;
 // scratch tail for NT 8-row operand tiles (R <= 8 NT): fp32 partial sums [warp][tile][16][8 NT], stored values
-// [8 NT][48], mean | rstd per row, four mbarriers
+// [8 NT][48], mean | rstd per row, six mbarriers
 __host__ __device__ constexpr int dr_red_floats(int nt) { return kDRComputeWarps * kDRMaxTiles * 16 * 8 * nt; }
-__host__ __device__ constexpr int dr_tail_bytes(int nt) { return (dr_red_floats(nt) + 8 * nt * kDRCols + 2 * 8 * nt) * 4 + 4 * 8 + 64; }
+__host__ __device__ constexpr int dr_tail_bytes(int nt) { return (dr_red_floats(nt) + 8 * nt * kDRCols + 2 * 8 * nt) * 4 + 6 * 8 + 64; }
 
 // ---- attention inside the few-rows kernel: one query row, keys in blocks of four per warp.  Lane = (key of the block
 // g = lane / 8, 16-byte chunk c = lane % 8 of the 64-wide head): every load instruction fetches four complete 128-byte K
@@ -602,6 +602,20 @@ __host__ __device__ __forceinline__ int dr_slab_cols(int w_region_bytes, int K) 
   const int c = w_region_bytes / (K * 2 + 16);
   return c > kDRCols ? kDRCols : (c < 1 ? 1 : c);
 }
+// A Linear whose per-CTA share exceeds 48 features (the logits) goes through the buffer in SEVERAL slabs; those use the
+// two halves of the region alternately, so that slab j + 1 streams in while slab j is multiplied.
+struct DRSlabs {
+  bool multi;
+  int half;      // byte offset of the second half (multi only)
+  int cap;       // features per slab
+};
+__host__ __device__ __forceinline__ DRSlabs dr_slabs(int w_region_bytes, int N, int K, int grid) {
+  DRSlabs g;
+  g.multi = (N + grid - 1) / grid > kDRCols;
+  g.half = (w_region_bytes / 2) & ~127;
+  g.cap = dr_slab_cols(g.multi ? g.half : w_region_bytes, K);
+  return g;
+}
 
 template <typename T, int NT>
 __global__ void __launch_bounds__(kDRThreads, 1) dec_rows_kernel(const DLParams P) {
@@ -615,17 +629,19 @@ __global__ void __launch_bounds__(kDRThreads, 1) dec_rows_kernel(const DLParams 
   float* s_red = reinterpret_cast<float*>(smem + P.dr_tail_off);   // [warp][tile][16 features][RMAX rows]; attention: [warp][68]
   float* s_out = s_red + dr_red_floats(NT);                         // [row][feature]: the values as stored
   float* s_stat = s_out + RMAX * kDRCols;                           // mean[RMAX] | rstd[RMAX]
-  uint64_t* w_full = reinterpret_cast<uint64_t*>(s_stat + 2 * RMAX);
-  uint64_t* a_full = w_full + 1;      // the input rows of a Linear phase have landed
-  uint64_t* w_empty = w_full + 2;
-  uint64_t* go = w_full + 3;          // phase p may start: the grid barrier behind phase p - 1 has opened
+  uint64_t* w_full = reinterpret_cast<uint64_t*>(s_stat + 2 * RMAX);   // [2]: a weight slab has landed (buffer 0 / second half)
+  uint64_t* w_empty = w_full + 2;     // [2]: ... and has been multiplied
+  uint64_t* a_full = w_full + 4;      // the input rows of a Linear phase have landed
+  uint64_t* go = w_full + 5;          // phase p may start: the grid barrier behind phase p - 1 has opened
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, tid = threadIdx.x;
   const int grid = gridDim.x, cta = blockIdx.x;
   const int R = P.R;
   if (tid == 0) {
-    mbar_init(w_full, 1);
+    mbar_init(&w_full[0], 1);
+    mbar_init(&w_full[1], 1);
+    mbar_init(&w_empty[0], 1);
+    mbar_init(&w_empty[1], 1);
     mbar_init(a_full, 1);
-    mbar_init(w_empty, 1);
     mbar_init(go, 1);
     mbar_fence_init();
   }
@@ -643,29 +659,46 @@ __global__ void __launch_bounds__(kDRThreads, 1) dec_rows_kernel(const DLParams 
 
   if (warp == kDRComputeWarps) {
     // ===================== control warp: bulk copies and the grid barrier =====================
-    // slab j of Linear phase p: the weight rows of this CTA's features [j * cap, (j + 1) * cap) - one slab per phase unless
-    // the CTA owns more features than the buffer holds (the logits: 351 features of K = 1280 -> 10 slabs)
+    // slab j of Linear phase p: the weight rows of this CTA's features [j * cap, (j + 1) * cap) - one slab per phase (buffer
+    // 0, the whole region) unless the CTA owns more features than fit (the logits: 351 features of K = 1280 -> 20 slabs
+    // alternating between the two halves of the region).  A buffer is re-used once its previous slab has been multiplied.
+    int issued0 = 0, issued1 = 0, waited0 = 0, waited1 = 0;      // per buffer (scalars: no local-memory arrays)
+    auto ensure_free = [&](int b) {
+      if (b == 0) {
+        if (waited0 < issued0) {
+          dl_mbar_wait(&w_empty[0], waited0 & 1);
+          ++waited0;
+        }
+      } else if (waited1 < issued1) {
+        dl_mbar_wait(&w_empty[1], waited1 & 1);
+        ++waited1;
+      }
+    };
     auto issue_w = [&](int p, int j) {
       const DLPhase ph = phase(p);
       const int n0 = static_cast<int>(static_cast<long long>(cta) * ph.N / grid);
       const int nc = static_cast<int>(static_cast<long long>(cta + 1) * ph.N / grid) - n0;
       const uint32_t row_bytes = static_cast<uint32_t>(ph.K) * 2;
-      const int cap = dr_slab_cols(P.dr_a_off, ph.K);
-      const int c0 = j * cap, ncc = min(cap, nc - c0);
-      if (lane == 0) mbar_expect_tx(w_full, static_cast<uint32_t>(ncc) * row_bytes);
+      const DRSlabs g = dr_slabs(P.dr_a_off, ph.N, ph.K, grid);
+      const int b = g.multi ? (j & 1) : 0;
+      ensure_free(b);
+      if (!g.multi) ensure_free(1);      // a whole-region slab also covers the second half
+      const int c0 = j * g.cap, ncc = max(0, min(g.cap, nc - c0));
+      uint8_t* dst = sW + (b ? g.half : 0);
+      if (lane == 0) mbar_expect_tx(&w_full[b], static_cast<uint32_t>(ncc) * row_bytes);
       __syncwarp();
       for (int i = lane; i < ncc; i += 32)
-        bulk_load_1d(sW + static_cast<size_t>(i) * (row_bytes + 16),
-                     static_cast<const uint8_t*>(ph.w) + static_cast<size_t>(n0 + c0 + i) * row_bytes, row_bytes, w_full);
+        bulk_load_1d(dst + static_cast<size_t>(i) * (row_bytes + 16),
+                     static_cast<const uint8_t*>(ph.w) + static_cast<size_t>(n0 + c0 + i) * row_bytes, row_bytes, &w_full[b]);
+      if (b == 0) ++issued0; else ++issued1;
     };
     int lin = next_linear(0);            // the Linear phase whose slab is in flight / resident
     if (lin < P.n_phases) issue_w(lin, 0);  // weights are constants: the first slab streams in under the tail of the previous kernel
     pdl_wait();
     if (P.skip_flag && *P.skip_flag) {
-      if (lin < P.n_phases) dl_mbar_wait(w_full, 0);  // never leave with a copy into this CTA's shared memory in flight
+      if (lin < P.n_phases) dl_mbar_wait(&w_full[0], 0);  // never leave with a copy into this CTA's shared memory in flight
       return;
     }
-    int slab = 0;
     for (int p = 0; p < P.n_phases; ++p) {
       if (p > 0) {
         const unsigned int target = static_cast<unsigned int>(p) * static_cast<unsigned int>(grid);
@@ -690,19 +723,11 @@ __global__ void __launch_bounds__(kDRThreads, 1) dec_rows_kernel(const DLParams 
                      row_bytes, a_full);
       {
         const int nc = static_cast<int>(static_cast<long long>(cta + 1) * ph.N / grid) - static_cast<int>(static_cast<long long>(cta) * ph.N / grid);
-        const int cap = dr_slab_cols(P.dr_a_off, ph.K);
-        for (int j = 1; j * cap < nc; ++j) {   // further slabs of this phase, each once the previous one has been consumed
-          dl_mbar_wait(w_empty, slab & 1);
-          ++slab;
-          issue_w(p, j);
-        }
+        const int cap = dr_slabs(P.dr_a_off, ph.N, ph.K, grid).cap;
+        for (int j = 1; j * cap < nc; ++j) issue_w(p, j);   // further slabs of this phase, each into the half that is free
       }
       lin = next_linear(p + 1);
-      if (lin < P.n_phases) {
-        dl_mbar_wait(w_empty, slab & 1); // every compute warp is done with the slab and the input rows of phase p
-        issue_w(lin, 0);                 // streams in while phase p finishes and the attention phases in between run
-      }
-      ++slab;
+      if (lin < P.n_phases) issue_w(lin, 0);   // streams in while phase p finishes and the attention phases in between run
     }
     return;
   }
@@ -712,13 +737,14 @@ __global__ void __launch_bounds__(kDRThreads, 1) dec_rows_kernel(const DLParams 
   if (P.skip_flag && *P.skip_flag) return;
   const int g = lane >> 2, t4 = lane & 3;
   const int g4 = lane >> 3, c8 = lane & 7;                    // attention: key of the block, 16-byte chunk
-  int slab = 0, n_lin = 0;
+  int used0 = 0, used1 = 0, n_lin = 0;     // slabs consumed per buffer, Linear phases done
   for (int p = 0; p < P.n_phases; ++p) {
     const DLPhase ph = phase(p);
     if (ph.type == DS_LINEAR) {
       const int n0 = static_cast<int>(static_cast<long long>(cta) * ph.N / grid);
       const int nc = static_cast<int>(static_cast<long long>(cta + 1) * ph.N / grid) - n0;
-      const int cap = dr_slab_cols(P.dr_a_off, ph.K);            // features per slab (all of them except for the logits)
+      const DRSlabs sl = dr_slabs(P.dr_a_off, ph.N, ph.K, grid);
+      const int cap = sl.cap;            // features per slab (all of them except for the logits)
       const int stride = ph.K * 2 + 16;
       const bool fold = (ph.flags & DL_FOLD) != 0;
       dl_mbar_wait(go, p & 1);           // the previous phase is complete grid-wide (the control warp saw the barrier open)
@@ -743,7 +769,9 @@ __global__ void __launch_bounds__(kDRThreads, 1) dec_rows_kernel(const DLParams 
           }
         }
       }
-      for (int c0 = 0; c0 == 0 || c0 < nc; c0 += cap) {          // one slab per pass (an empty share still consumes its slab)
+      for (int c0 = 0, js = 0; c0 == 0 || c0 < nc; c0 += cap, ++js) {   // one slab per pass (an empty share still consumes its slab)
+        const int wb = sl.multi ? (js & 1) : 0;
+        const uint8_t* sWs = sW + (wb ? sl.half : 0);
         const int ncc = max(0, min(cap, nc - c0));
         const int n_tiles = (ncc + 15) >> 4;
         // ---- this thread's <= J output elements (row, feature) of the slab and their constants
@@ -776,11 +804,11 @@ __global__ void __launch_bounds__(kDRThreads, 1) dec_rows_kernel(const DLParams 
 #pragma unroll
             for (int i = 0; i < 4; ++i) acc[t][u][i] = 0.f;
         if (c0 == 0) dl_mbar_wait(a_full, n_lin & 1);
-        dl_mbar_wait(w_full, slab & 1);
+        dl_mbar_wait(&w_full[wb], (wb ? used1 : used0) & 1);
         {
           const int kw = ph.K / kDRComputeWarps;
           // ldmatrix x4 on the slab: matrices (features 0-7, k 0-7), (8-15, k 0-7), (0-7, k 8-15), (8-15, k 8-15) = a0..a3
-          const uint8_t* wrow = sW + static_cast<size_t>((lane & 7) + ((lane >> 3) & 1) * 8) * stride + (lane >> 4) * 16;
+          const uint8_t* wrow = sWs + static_cast<size_t>((lane & 7) + ((lane >> 3) & 1) * 8) * stride + (lane >> 4) * 16;
           // ldmatrix x2 on 8 input rows: (rows 0-7, k 0-7), (rows 0-7, k 8-15) = b0, b1
           const uint8_t* arow = sA + static_cast<size_t>(lane & 7) * stride + ((lane >> 3) & 1) * 16;
           for (int k0 = warp * kw; k0 < (warp + 1) * kw; k0 += 16) {
@@ -808,8 +836,8 @@ __global__ void __launch_bounds__(kDRThreads, 1) dec_rows_kernel(const DLParams 
             }
           }
         asm volatile("bar.sync 1, 256;" ::: "memory");
-        if (tid == 0) mbar_arrive(w_empty);          // the next slab may land while the epilogue runs
-        ++slab;
+        if (tid == 0) mbar_arrive(&w_empty[wb]);     // the buffer may be refilled while the epilogue runs
+        if (wb) ++used1; else ++used0;
         // ---- epilogue
 #pragma unroll
         for (int j = 0; j < J; ++j)
@@ -1175,9 +1203,10 @@ static int dr_layout(const DLPhase* ph, int n, int R, int grid, int* a_off_out, 
     if (ph[p].type != DS_LINEAR) continue;
     const long long stride = ph[p].K * 2LL + 16;
     const int nc_max = (ph[p].N + grid - 1) / grid;
-    const int cols = std::min(nc_max, dr_slab_cols(static_cast<int>(a_off), ph[p].K));
-    if (nc_max > kDRCols && cols < 16) return 0;                       // slabs too thin to be worth it
-    extent = std::max(extent, ((cols + 15) / 16 * 16) * stride);     // ldmatrix reads whole 16-row tiles
+    const DRSlabs g = dr_slabs(static_cast<int>(a_off), ph[p].N, ph[p].K, grid);
+    const int cols = std::min(nc_max, g.cap);
+    if (g.multi && cols < 16) return 0;                                // slabs too thin to be worth it
+    extent = std::max(extent, (g.multi ? g.half : 0) + ((cols + 15) / 16 * 16) * stride);     // ldmatrix reads whole 16-row tiles
   }
   const long long tail_off = (std::max(a_off + a_bytes, extent) + 127) / 128 * 128;
   const long long total = tail_off + dr_tail_bytes(nt) + 128;
