@@ -85,7 +85,8 @@ int wb200_set_fused_decoder_rows(int enabled);
  * over the rows' lineages through the parent table, whisper/model.py:124-127,327-333 + decoding.py:172-176) and its
  * cross-attention (key slices + merge) as further grid-barrier phases.  mode 1 (default) for sessions created AFTER the
  * call; 0 (or WB200_FUSED_STACK=0): three few-rows launches per layer around the two attention kernels; 2: the table
- * also ends with the decoder's final LayerNorm and the logits (measured: no gain over the two separate launches). */
+ * also ends with the decoder's final LayerNorm and the logits (measured: identical tokens, no gain over the two
+ * separate launches). */
 int wb200_set_fused_decoder_stack(int mode);
 /* Layout of the decoder's kv caches for sessions created AFTER the call (default 1, or WB200_KV_HEAD_MAJOR=0 in
  * the environment).  1: head-major - cross-attention K/V [n_audio, 2H, 1500, 64] (written that way by the K/V

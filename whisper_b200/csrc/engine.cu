@@ -382,9 +382,10 @@ static int build_stack_plan(Decoder* D, cudaStream_t s) {
   const size_t n_layers_phases = tab.size();
   if (g_fused_stack >= 2) {
     // opt-in (mode 2): the decoder's final LayerNorm and the logits (model.py:243-247) close the table - the rows are
-    // normalised by one warp each, then every CTA runs its 1/148 of the vocabulary through the slab buffer in several
-    // passes.  Measured on the turbo one-audio run: 48 us inside the stack (single-buffered slabs: load and compute of a
-    // slab alternate) against 6 + 42 us for the two separate launches - no gain, hence not the default.
+    // normalised by one warp each, then every CTA runs its 1/148 of the vocabulary through the slab buffer in ~20 slabs
+    // that alternate between the two halves of the buffer.  Measured on the turbo one-audio decode
+    // (tools/time_stack_modes.py): 300-308 us per iteration against 302 us with the two separate launches (LayerNorm
+    // 6 us + tcgen05 GEMM 42 us) - identical tokens, no gain, hence not the default.
     DLPhase ln = {};
     ln.type = DS_LN;
     ln.N = d;
