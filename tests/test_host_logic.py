@@ -2,6 +2,7 @@
 suppress lists, hypothesis finalisation / ranking, window splitting, padding, id tables."""
 import json
 import os
+import sys
 from types import SimpleNamespace
 
 import numpy as np
@@ -538,3 +539,41 @@ def test_decoding_task_run_host_logic(opts, monkeypatch):
     res = task.run(feats, initial_tokens=init)
     assert len(res) == 7 and _FakeSession.log[0][0] == 7 and len(_FakeSession.log) == 1
     assert all(np.isfinite(r.avg_logprob) for r in res)
+
+
+def test_official_checkpoint_table_and_sha256_gate(tmp_path):
+    """load_model(<official name>) only accepts the cached file the reference would accept: right file name, SHA-256 equal
+    to the digest in the reference's download URL (whisper/__init__.py:17-32, 63-71); the alignment-head dumps are the
+    reference's (:36-51)."""
+    import base64
+    import gzip
+
+    import whisper_b200 as wb
+
+    table = wb._checkpoint_table()
+    assert set(table) == {n for n in wb.available_models()}
+    assert table["turbo"]["file"] == "large-v3-turbo.pt" and table["large"]["file"] == "large-v3.pt"
+    assert all(len(e["sha256"]) == 64 and int(e["sha256"], 16) >= 0 for e in table.values())
+    # every dump decodes to an (n_text_layer x n_text_head) mask with at least one head (model.py:278-285)
+    for name, e in table.items():
+        if e["alignment_heads"]:
+            d = wb.dims_dict(name)
+            mask = np.frombuffer(gzip.decompress(base64.b85decode(e["alignment_heads"].encode())), dtype=bool)
+            assert mask.size == d["n_text_layer"] * d["n_text_head"] and mask.any()
+    if os.path.isdir("/root/reference/whisper"):      # in the build container: the table IS the reference's
+        sys.path.insert(0, "/root/reference")
+        try:
+            import whisper as ref
+            for name, url in ref._MODELS.items():
+                assert table[name]["file"] == os.path.basename(url) and table[name]["sha256"] == url.split("/")[-2]
+                assert (table[name]["alignment_heads"] or "").encode() == ref._ALIGNMENT_HEADS.get(name, b"")
+        finally:
+            sys.path.remove("/root/reference")
+    # a file under the official name with other contents is refused before anything touches the GPU
+    (tmp_path / "tiny.en.pt").write_bytes(b"not the official checkpoint")
+    with pytest.raises(RuntimeError, match="SHA256"):
+        wb.load_model("tiny.en", download_root=str(tmp_path))
+    # no file and no synthetic weights: the reference would download; here it is an error that says so
+    with pytest.raises(RuntimeError, match="no network"):
+        wb.load_model("base.en", download_root=str(tmp_path))
+    assert wb._resolve_official("base.en", str(tmp_path)) is None
